@@ -1,0 +1,281 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see geokerr.cc header).
+// CPU restatement of the per-pixel driver and its orchestration:
+//   grtrans_driver.f90:57-466 (grtrans_driver), :468-513 (convert_model, grtrans_compute_intensity),
+//   emis.f90:461-571 (calc_emissivity copy-out), :786-847 (calc_opt_depth, rotate_emis,
+//   invariant_emis/intensity), pgrtrans.f90:12-253 (grtrans_main: frequency/mdot/mu grids, camera
+//   indexing, the OpenMP `schedule(static,1)` pixel loop and its wall-clock bracket).
+#include <omp.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "oracle.h"
+
+namespace orc {
+
+// pgrtrans.f90:88-106
+void compute_freqs(const RunArgs &a, std::vector<double> &freqs, std::vector<double> &mdots,
+                   std::vector<double> &mu0) {
+  freqs.resize(a.nfreq);
+  mdots.resize(a.nmdot);
+  mu0.resize(a.nmu);
+  if (a.nfreq == 1)
+    freqs[0] = a.fmin;
+  else
+    for (int i = 0; i < a.nfreq; i++) freqs[i] = a.fmin * std::exp(i * std::log(a.fmax / a.fmin) / (a.nfreq - 1));
+  if (a.nmdot == 1)
+    mdots[0] = a.mdotmin;
+  else
+    for (int i = 0; i < a.nmdot; i++)
+      mdots[i] = a.mdotmin * std::exp(i * std::log(a.mdotmax / a.mdotmin) / (a.nmdot - 1));
+  if (a.nmu == 1)
+    mu0[0] = a.mumin;
+  else
+    for (int i = 0; i < a.nmu; i++) mu0[i] = a.mumin + (a.mumax - a.mumin) / (a.nmu - 1) * i;
+}
+
+static int iflag_from_name(const std::string &iname) {  // rad_trans.f90:30-38
+  if (iname == "lsoda") return 0;
+  if (iname == "delo") return 1;
+  if (iname == "formal") return 2;
+  if (iname == "lsodasph") return 3;
+  return 0;
+}
+
+namespace {
+struct RayWork {
+  Geo g;
+  std::vector<FluidPt> f;
+  std::vector<double> s2xi, c2xi, ang, rshift, cosne, ncgs, ncgsnth, bcgs, tcgs;
+  std::vector<double> ej, eK, j, K, tau, intensity, absK;
+};
+}  // namespace
+
+// Process one geodesic index for all (mdot, freq).  out[(m*nfreq+k)*nvals + s] in cgs (double).
+static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &gargs, int i,
+                      const std::vector<double> &freqs, const std::vector<double> &mdots, double *out,
+                      long long *npoints, RayDump *dump) {
+  const int nfreq = (int)freqs.size(), nparams = (int)mdots.size(), nvals = A.nvals;
+  for (int q = 0; q < nparams * nfreq * nvals; q++) out[q] = 0.0;
+  RayWork w;
+  Geo &g = w.g;
+  int status;
+  initialize_geodesic(g, gargs, i, status);
+  if (dump) {
+    dump->npts = g.npts;
+    dump->status = status;
+    dump->ncase = g.ncase;
+  }
+  if (!(status == 1 && g.npts > 0)) return;
+  int npts = g.npts;
+  if (npoints) *npoints += npts;
+  int eneq;
+  int etype = emis_type_from_name(A.ename, eneq);
+  int enk = 1 + eneq * (eneq - 1) / 2;
+  get_fluid_vars(fd, g, w.f);
+  w.s2xi.assign(npts, 0); w.c2xi.assign(npts, 0); w.ang.assign(npts, 0); w.rshift.assign(npts, 0); w.cosne.assign(npts, 0);
+  for (int p = 0; p < npts; p++)
+    comoving_ortho(g.x[p].d[1], g.x[p].d[2], g.a, g.alpha, g.beta, g.mu0, w.f[p].u, w.f[p].b, g.k[p].d, w.s2xi[p],
+                   w.c2xi[p], w.ang[p], w.rshift[p], w.cosne[p]);
+  int rneq = nvals;
+  int rnk = 1 + rneq * (rneq - 1) / 2;
+  int iflag = iflag_from_name(A.iname);
+  int rnpts = npts;
+  RtOptions opt;
+  if (getenv("ORC_LSODA_INTENDED")) opt.lsoda_neighbor_as_written = false;  // experiment switch
+  if (getenv("ORC_RT_TIGHT")) { opt.ortol = 1e-9; opt.oatol = 1e-11; }
+  w.ej.assign((size_t)npts * 4, 0.0);
+  w.eK.assign((size_t)npts * 7, 0.0);
+  w.j.assign((size_t)npts * rneq, 0.0);
+  w.K.assign((size_t)npts * rnk, 0.0);
+  w.tau.assign(npts, 0.0);
+  w.absK.assign(npts, 0.0);
+  w.intensity.assign((size_t)npts * rneq, 0.0);
+  if (dump) {
+    dump->lambda = g.lambda;
+    dump->tpm = g.tpmarr;
+    dump->tpr = g.tprarr;
+    for (int p = 0; p < npts; p++) {
+      dump->t.push_back(g.x[p].d[0]); dump->r.push_back(g.x[p].d[1]); dump->th.push_back(g.x[p].d[2]);
+      dump->ph.push_back(g.x[p].d[3]);
+      dump->kt.push_back(g.k[p].d[0]); dump->kr.push_back(g.k[p].d[1]); dump->kth.push_back(g.k[p].d[2]);
+      dump->kph.push_back(g.k[p].d[3]);
+      dump->rho.push_back(w.f[p].rho); dump->p.push_back(w.f[p].p); dump->bmag.push_back(w.f[p].bmag);
+      for (int c = 0; c < 4; c++) {
+        dump->u.push_back(w.f[p].u[c]);
+        dump->b.push_back(w.f[p].b[c]);
+      }
+    }
+    dump->s2xi = w.s2xi; dump->c2xi = w.c2xi; dump->ang = w.ang; dump->rshift = w.rshift; dump->cosne = w.cosne;
+    dump->stokes.assign((size_t)nfreq * nvals, 0.0);
+  }
+  for (int m = 0; m < nparams; m++) {
+    SourceParams sp;
+    sp.mdot = mdots[m]; sp.mbh = A.mbh; sp.nfac = A.ftscl; sp.bfac = A.frscl; sp.jetalphaval = A.jetalpha;
+    sp.gminval = A.gmin; sp.muval = A.muval; sp.gmax = A.gmax; sp.p1 = A.p1; sp.p2 = A.p2; sp.sigcut = A.sigcut;
+    double MBH = sp.mbh;
+    double LBH = pc::G * MBH * pc::msun / pc::c2;
+    convert_fluid_vars(fd, w.f, sp, w.ncgs, w.ncgsnth, w.bcgs, w.tcgs);
+    // emis_params are single precision in the reference (emis.f90:32-40): gmin, gmax, p1 pass through real(4)
+    double e_gmin = (double)(float)sp.gminval, e_gmax = (double)(float)A.gmax, e_p = (double)(float)A.p1;
+    if (dump && m == 0) {
+      dump->ncgs = w.ncgs; dump->ncgsnth = w.ncgsnth; dump->bcgs = w.bcgs; dump->tcgs = w.tcgs;
+    }
+    std::fill(w.eK.begin(), w.eK.end(), 0.0);
+    for (int k = 0; k < nfreq; k++) {
+      // ---- calc_emissivity (emis.f90:461-571)
+      for (int p = 0; p < npts; p++) {
+        double nu = freqs[k] / w.rshift[p];
+        double K11[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        switch (etype) {
+          case E_POLSYNCHTH: polsynchth(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], K11); break;
+          case E_POLSYNCHPL: polsynchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, K11); break;
+          case E_SYNCHPL: synchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, K11); break;
+          case E_SYNCHTHAV: synchemis(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], K11); break;
+          case E_BB: K11[0] = bnu(w.tcgs[p], nu); break;
+          case E_BBPOL: {
+            double fcol = 1.8;
+            K11[0] = std::pow(fcol, -4.0) * bnu(w.tcgs[p] * fcol, nu);
+            float cI, cdel;
+            interp_chandra_tab24((float)w.cosne[p], cI, cdel);
+            K11[0] = K11[0] * (double)cI;
+            K11[1] = K11[0] * (double)cdel;
+          } break;
+          default: break;
+        }
+        double *ej = &w.ej[(size_t)p * 4], *eK = &w.eK[(size_t)p * 7];
+        if (eneq == 4) {
+          for (int c = 0; c < 4; c++) ej[c] = K11[c];
+          for (int c = 0; c < 7; c++)
+            if (A.coefindx[c] == 1) eK[c] = K11[4 + c];
+        } else {
+          ej[0] = K11[0];
+          eK[0] = K11[4];
+        }
+      }
+      double fac = 0.0;
+      if (npts > 1) {
+        for (int p = 0; p < npts; p++) fac += w.ej[(size_t)p * 4] * (g.lambda[0] - g.lambda[p]);
+      } else {
+        for (int p = 0; p < npts; p++) fac += w.ej[(size_t)p * 4] / npts;
+      }
+      double *o = out + ((size_t)m * nfreq + k) * nvals;
+      if (fac / 1e16 > 0.0) {
+        if (eneq == 4) {  // rotate_emis emis.f90:797-829
+          for (int p = 0; p < npts; p++) {
+            double *ej = &w.ej[(size_t)p * 4], *eK = &w.eK[(size_t)p * 7];
+            double jq = ej[1], ju = ej[2], aq = eK[1], au = eK[2], rhoq = eK[4], rhou = eK[5];
+            double c2 = w.c2xi[p], s2 = w.s2xi[p];
+            ej[1] = c2 * jq - s2 * ju;
+            ej[2] = s2 * jq + c2 * ju;
+            eK[1] = c2 * aq - s2 * au;
+            eK[2] = s2 * aq + c2 * au;
+            eK[4] = c2 * rhoq - s2 * rhou;
+            eK[5] = s2 * rhoq + c2 * rhou;
+          }
+        }
+        if (npts != 1) {
+          for (int p = 0; p < npts; p++) {
+            double gg = w.rshift[p];
+            double *ej = &w.ej[(size_t)p * 4], *eK = &w.eK[(size_t)p * 7];
+            for (int c = 0; c < eneq; c++) ej[c] = ej[c] * gg * gg;  // invariant_emis
+            for (int c = 0; c < enk; c++) eK[c] = eK[c] / gg;
+            for (int c = 0; c < eneq; c++) ej[c] = ej[c] / fac;
+            for (int c = 0; c < enk; c++) eK[c] = eK[c] * LBH;
+            w.absK[p] = std::fabs(eK[0]);
+          }
+          tsum(npts, g.lambda.data(), w.absK.data(), w.tau.data());
+          for (int p = 0; p < npts; p++) w.tau[p] = -w.tau[p];
+          // pack to the integrator's width (A21: nvals and the emissivity's neq are independent)
+          for (int p = 0; p < npts; p++) {
+            for (int c = 0; c < rneq; c++) w.j[(size_t)p * rneq + c] = (c < eneq) ? w.ej[(size_t)p * 4 + c] : 0.0;
+            for (int c = 0; c < rnk; c++) w.K[(size_t)p * rnk + c] = (c < enk) ? w.eK[(size_t)p * 7 + c] : 0.0;
+          }
+          rnpts = rt_integrate(iflag, rneq, npts, g.lambda.data(), w.j.data(), w.K.data(), w.tau.data(),
+                               w.intensity.data(), opt);
+          if (rnpts >= 1)
+            for (int c = 0; c < rneq; c++) o[c] = w.intensity[(size_t)(rnpts - 1) * rneq + c] * fac * LBH;
+        } else {
+          // invariant_intensity(e,rshift,3); grtrans_compute_intensity
+          double g3 = std::pow(w.rshift[0], 3);
+          for (int c = 0; c < std::min(rneq, eneq); c++) o[c] = w.ej[c] * g3;
+        }
+      }
+      if (dump && m == 0) {
+        for (int c = 0; c < nvals; c++) dump->stokes[(size_t)k * nvals + c] = o[c];
+        if (k == nfreq - 1) {
+          dump->j = w.ej;
+          dump->K = w.eK;
+          dump->tau = w.tau;
+        }
+      }
+    }
+  }
+}
+
+void grtrans_ray_dump(const RunArgs &args, const FluidData &fd, const GeokerrArgs &gargs, int i,
+                      const std::vector<double> &freqs, RayDump &d) {
+  std::vector<double> mdots(1, args.mdotmin);
+  std::vector<double> out((size_t)freqs.size() * args.nvals);
+  d = RayDump();
+  drive_ray(args, fd, gargs, i, freqs, mdots, out.data(), nullptr, &d);
+}
+
+// pgrtrans.f90:12-253
+void grtrans_main(const RunArgs &A, RunResult &res) {
+  std::vector<double> freqs, mdots, mu0;
+  compute_freqs(A, freqs, mdots, mu0);
+  int nro = A.nn[0], nphi = A.nn[1], nup = A.nn[2];
+  int npix = nro * nphi;
+  int nparams = A.nmdot, nfreq = A.nfreq;
+  int ncams = A.nmdot * A.nfreq * A.nmu * A.nt;
+  res.nvals = A.nvals;
+  res.npix = npix;
+  res.ncams = ncams;
+  res.freqs = freqs;
+  res.pixvals.assign((size_t)ncams * npix * A.nvals, 0.f);
+  res.pixloc.assign((size_t)npix * 2, 0.f);
+  res.loop_seconds = 0;
+  res.npoints = 0;
+  FluidData fd;
+  FluidArgs fa = A.fargs;
+  fa.mbh = A.mbh;
+  load_fluid_model(fd, A.fname, A.spin, fa);
+  int i1 = A.i1, i2 = (A.i2 < 0) ? npix : A.i2;
+  int nth = A.nthreads > 0 ? A.nthreads : omp_get_max_threads();
+  for (int jm = 0; jm < A.nmu; jm++) {
+    GeokerrArgs gargs;
+    initialize_pixels(gargs, A.standard, mu0[jm], A.phi0, A.spin, A.uout, A.uin, A.rcut, A.nrotype, A.gridvals[0],
+                      A.gridvals[1], A.gridvals[2], A.gridvals[3], nro, nphi, nup);
+    auto t0 = std::chrono::steady_clock::now();
+    long long npoints = 0;
+    for (int lt = 0; lt < A.nt; lt++) {
+      int l = jm * A.nt + lt;  // 0-based (j-1)*nt+l-1
+#pragma omp parallel num_threads(nth) reduction(+ : npoints)
+      {
+        std::vector<double> out((size_t)nparams * nfreq * A.nvals);
+#pragma omp for schedule(static, 1)
+        for (int i = i1; i <= i2; i++) {
+          drive_ray(A, fd, gargs, i, freqs, mdots, out.data(), &npoints, nullptr);
+          for (int m = 0; m < nparams; m++)
+            for (int k = 0; k < nfreq; k++) {
+              size_t cam = (size_t)l * nfreq * nparams + (size_t)m * nfreq + k;
+              for (int c = 0; c < A.nvals; c++)
+                res.pixvals[(cam * npix + (i - 1)) * A.nvals + c] = (float)out[((size_t)m * nfreq + k) * A.nvals + c];
+            }
+          if (l == 0) {
+            res.pixloc[(size_t)(i - 1) * 2] = (float)gargs.alpha[i - 1];
+            res.pixloc[(size_t)(i - 1) * 2 + 1] = (float)gargs.beta[i - 1];
+          }
+        }
+      }
+    }
+    res.loop_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    res.npoints += npoints;
+  }
+}
+
+}  // namespace orc

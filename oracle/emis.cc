@@ -1,0 +1,330 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see geokerr.cc header).
+// CPU restatement of the emissivity stage of the hot path:
+//   polsynchemis.f90 (polsynchth :700-863, polsynchpl :527-631, synchpl :633-698, synchemis
+//   :865-904, bnu :1014-1032, table lookups :62-92), bessel.f90 (NR polynomial K0,K1,I0,I1 + K_n
+//   recurrence), chandra_tab24.f90, emis.f90:294-367 (name -> type).
+// Output layout e11[0..10] = (jI,jQ,jU,jV, aI,aQ,aU,aV, rhoQ,rhoU,rhoV) like the reference's K(:,11).
+#include <cmath>
+#include <mutex>
+
+#include "oracle.h"
+#include "ref_tables.h"
+
+namespace orc {
+
+using pc::pi;
+
+// ------------------------------------------------------------------ bessel.f90
+static double poly(double x, const double *c, int m) {
+  double p = c[m - 1];
+  for (int i = m - 2; i >= 0; i--) p = x * p + c[i];
+  return p;
+}
+static double besseli0(double x) {
+  static const double p[7] = {1.00, 3.51562290, 3.08994240, 1.20674920, 0.26597320, 0.360768e-10, 0.45813e-20};
+  static const double q[9] = {0.398942280,   0.1328592e-10, 0.225319e-20,   -0.157565e-20, 0.916281e-20,
+                              -0.2057706e-10, 0.2635537e-10, -0.1647633e-10, 0.392377e-20};
+  double ax = std::fabs(x);
+  if (ax < 3.75) {
+    double t = x / 3.750;
+    return poly(t * t, p, 7);
+  }
+  double y = 3.750 / ax;
+  return (std::exp(ax) / std::sqrt(ax)) * poly(y, q, 9);
+}
+static double besseli1(double x) {
+  static const double p[7] = {0.50, 0.878905940, 0.514988690, 0.150849340, 0.2658733e-10, 0.301532e-20, 0.32411e-30};
+  static const double q[9] = {0.398942280,  -0.3988024e-10, -0.362018e-20, 0.163801e-20, -0.1031555e-10,
+                              0.2282967e-10, -0.2895312e-10, 0.1787654e-10, -0.420059e-20};
+  double ax = std::fabs(x), r;
+  if (ax < 3.75) {
+    double t = x / 3.750;
+    r = ax * poly(t * t, p, 7);
+  } else {
+    double y = 3.750 / ax;
+    r = (std::exp(ax) / std::sqrt(ax)) * poly(y, q, 9);
+  }
+  if (x < 0.0) r = -r;
+  return r;
+}
+double besselk0(double x) {
+  static const double p[7] = {-0.57721566, 0.42278420, 0.23069756, 0.3488590e-1, 0.262698e-2, 0.10750e-3, 0.74e-5};
+  static const double q[7] = {1.25331414, -0.7832358e-1, 0.2189568e-1, -0.1062446e-1, 0.587872e-2, -0.251540e-2, 0.53208e-3};
+  if (x <= 2.0) {
+    double y = x * x / 4.0;
+    return (-std::log(x / 2.0) * besseli0(x)) + poly(y, p, 7);
+  }
+  double y = (2.0 / x);
+  return (std::exp(-x) / std::sqrt(x)) * poly(y, q, 7);
+}
+double besselk1(double x) {
+  static const double p[7] = {1.0, 0.15443144, -0.67278579, -0.18156897, -0.1919402e-1, -0.110404e-2, -0.4686e-4};
+  static const double q[7] = {1.25331414, 0.23498619, -0.3655620e-1, 0.1504268e-1, -0.780353e-2, 0.325614e-2, -0.68245e-3};
+  if (x <= 2.0) {
+    double y = x * x / 4.0;
+    return (std::log(x / 2.0) * besseli1(x)) + (1.0 / x) * poly(y, p, 7);
+  }
+  double y = 2.0 / x;
+  return (std::exp(-x) / std::sqrt(x)) * poly(y, q, 7);
+}
+double besselkn(int n, double x) {
+  double tox = 2.0 / x;
+  double bkm = besselk0(x), bk = besselk1(x);
+  for (int j = 1; j <= n - 1; j++) {
+    double bkp = bkm + j * tox * bk;
+    bkm = bk;
+    bk = bkp;
+  }
+  return bk;
+}
+
+// ------------------------------------------------------------------ bnu  polsynchemis.f90:1014-1032
+double bnu(double T, double nu) {
+  double b;
+  if (pc::h * nu / pc::k / T < 1e-6)
+    b = 2.0 * nu * nu * pc::k * T / pc::c2;
+  else
+    b = 2.0 * pc::h * nu / pc::c2 * nu * nu / (std::exp(pc::h * nu / pc::k / T) - 1.0);
+  if (b == 0) b = 2.220446049250313e-16;  // epsilon(T)
+  return b;
+}
+
+// ------------------------------------------------------------------ polsynchth
+static inline double iix(double x) {
+  return 2.5651 * (1.0 + 1.92 / std::pow(x, 1.0 / 3.0) + .9977 / std::pow(x, 2.0 / 3.0)) * std::exp(-1.8899 * std::pow(x, 1.0 / 3.0));
+}
+static inline double iqx(double x) {
+  return 2.5651 * (1.0 + .93193 / std::pow(x, 1.0 / 3.0) + .499873 / std::pow(x, 2.0 / 3.0)) *
+         std::exp(-1.8899 * std::pow(x, 1.0 / 3.0));
+}
+static inline double ivx(double x) {
+  return (1.81384 / x + 3.42319 / std::pow(x, 2.0 / 3.0) + 0.0292545 / std::sqrt(x) + 2.03773 / std::pow(x, 1.0 / 3.0)) *
+         std::exp(-1.8899 * std::pow(x, 1.0 / 3.0));
+}
+static inline double jffunc(double x) {
+  double extraterm = (.011 * std::exp(-x / 47.2) - std::pow(2.0, -1.0 / 3.0) / std::pow(3.0, 23.0 / 6.0) * pi * 1e4 *
+                                                       std::pow(x + 1e-16, -8.0 / 3.0)) *
+                     (0.5 + 0.5 * std::tanh((std::log(x) - std::log(120.0)) / 0.1));
+  return 2.011 * std::exp(-std::pow(x, 1.035) / 4.7) - std::cos(x / 2.0) * std::exp(-std::pow(x, 1.2) / 2.73) -
+         .011 * std::exp(-x / 47.2) + extraterm;
+}
+static inline double shgmfunc(double x) {
+  // single-precision literals as written: 0.43793091*log(1d0+0.00185777*x**1.50316886)
+  return (double)0.43793091f * std::log(1.0 + (double)0.00185777f * std::pow(x, (double)1.50316886f));
+}
+
+void polsynchth(double nu, double n, double b, double t, double theta, double *e) {
+  using namespace pc;
+  const double ec = pc::e;
+  const double nucminval = 1.0, thetaemin = 1e-10;
+  double thetae = k * t / m / c / c + thetaemin;
+  double nuc = 3.0 * ec * b * std::sin(theta) / 4.0 / pi / m / c * thetae * thetae + nucminval;
+  double xm = nu / nuc;
+  double ji = ec * ec / c / std::sqrt(3.0) / 2.0 * n / (thetae * thetae) * nu * iix(xm);
+  double jq = ec * ec / c / std::sqrt(3.0) / 2.0 * n / (thetae * thetae) * nu * iqx(xm);
+  double jv = 4.0 * ec * ec / c / 3.0 / std::sqrt(3.0) / std::tan(theta) * n / 2.0 / std::pow(thetae, 3.0) * nu * ivx(xm);
+  double ju = 0.0;
+  double bnutnu = bnu(t, nu);
+  double ai = ji / bnutnu, aq = jq / bnutnu, av = jv / bnutnu, au = ju / bnutnu;
+  double rhou = au;
+  double wp2 = 4.0 * pi * n * ec * ec / m;
+  double omega0 = ec * b / m / c;
+  double xarg = thetae * std::sqrt(std::sqrt(2.0) * std::sin(theta) * (1e3 * omega0 / 2.0 / pi / nu));
+  double eps11m22, eps12;
+  double w4 = std::pow(2.0 * pi * nu, 4), w3 = std::pow(2.0 * pi * nu, 3);
+  if (thetae > 1e-2) {
+    double k2 = besselkn(2, 1.0 / thetae);
+    eps11m22 = jffunc(xarg) * wp2 * omega0 * omega0 / w4 * (besselk1(1.0 / thetae) / k2 + 6.0 * thetae) *
+               std::sin(theta) * std::sin(theta);
+    double step = 0.5 + 0.5 * std::tanh((thetae - 1.0) / 0.05);
+    eps12 = wp2 * omega0 / w3 * (besselk0(1.0 / thetae) - step * shgmfunc(xarg)) / k2 * std::cos(theta);
+  } else {
+    eps11m22 = jffunc(xarg) * wp2 * omega0 * omega0 / w4 * (1.0 + 6.0 * thetae) * std::sin(theta) * std::sin(theta);
+    eps12 = wp2 * omega0 / w3 * std::cos(theta);
+  }
+  double rhov = 2.0 * pi * nu / c * eps12;
+  double rhoq = 2.0 * pi * nu / 2.0 / c * eps11m22;
+  e[0] = ji; e[1] = jq; e[2] = ju; e[3] = jv; e[4] = ai; e[5] = aq; e[6] = au; e[7] = av;
+  e[8] = rhoq; e[9] = rhou; e[10] = rhov;
+}
+
+// ------------------------------------------------------------------ power-law tables
+struct PlTables {
+  double gxvals[181], gyvals[543], xvals[81], yavals[243], ypvals[243], yvvals[243], yapvals[243], yavvals[243];
+  PlTables() {
+    for (int i = 0; i < 181; i++) gxvals[i] = std::log(GRT_PL_GXVALS_RAW[i]);
+    for (int i = 0; i < 543; i++) gyvals[i] = std::log(GRT_PL_GYVALS_RAW[i]);
+    for (int i = 0; i < 81; i++) xvals[i] = std::log(GRT_PL_XVALS_RAW[i]);
+    for (int i = 0; i < 243; i++) {
+      yavals[i] = std::log(GRT_PL_YAVALS_RAW[i]);
+      ypvals[i] = std::log(GRT_PL_YPVALS_RAW[i]);
+      yvvals[i] = std::log(GRT_PL_YVVALS_RAW[i]);
+      yapvals[i] = std::log(GRT_PL_YAPVALS_RAW[i]);
+      yavvals[i] = std::log(GRT_PL_YAVVALS_RAW[i]);
+    }
+  }
+};
+static const PlTables &pltab() {
+  static PlTables t;
+  return t;
+}
+
+// polsynchemis.f90:62-74 ; xv is 0-based storage of the 1-based Fortran array
+static void find_inds_gxp(double x, double p, const double *xv, int nx, int &ix, int &iy) {
+  double xx = std::log(x);
+  ix = (int)((xx - xv[0]) / (xv[nx - 1] - xv[0]) * (nx));
+  ix = (ix < (nx - 1)) ? ((ix > 1) ? ix : 1) : (nx - 1);
+  iy = (p < 5.0) ? ((p > 3.2) ? 1 : 0) : 2;
+}
+// polsynchemis.f90:76-92
+static double interp_gxp(double x, int ix, int iy, const double *xv, int nx, const double *yv) {
+  double xx = std::log(x);
+  int indx = iy * nx + ix;  // 1-based
+  double yix = yv[indx - 1], yix1 = yv[indx], xix1 = xv[ix], xix = xv[ix - 1];
+  double slope = (yix1 - yix) / (xix1 - xix);
+  double yy = yix + slope * (xx - xix);
+  return std::exp(yy);
+}
+
+// polsynchemis.f90:527-631
+void polsynchpl(double nu, double nnth, double b, double th, double p, double gmin, double gmax, double *e) {
+  using namespace pc;
+  const double ec = pc::e;
+  const PlTables &T = pltab();
+  const double nufloor = 1e-10, thsafe = 1e-10;
+  double tanth = std::tan(th) + (std::signbit(std::cos(th)) ? -1.0 : 1.0) * thsafe;
+  double sinth = std::sin(th) + thsafe;
+  double nubperp = ec * b / m / c / 2.0 / pi * sinth + nufloor;
+  double nucmin = 3.0 / 2.0 * nubperp * gmin * gmin, nucmax = 3.0 / 2.0 * nubperp * gmax * gmax;
+  double omega0 = nubperp * 2.0 * pi, omega = nu * 2.0 * pi;
+  double xmin = nu / nucmin, xmax = nu / nucmax;
+  double A = (p - 1.0) * nnth / (std::pow(gmin, 1.0 - p) - std::pow(gmax, 1.0 - p));
+  int ix1, ix2, iy1, iy2;
+  find_inds_gxp(xmax, p, T.gxvals, 181, ix2, iy2);
+  find_inds_gxp(xmin, p, T.gxvals, 181, ix1, iy1);
+  double gxfac = interp_gxp(xmax, ix2, iy2, T.gxvals, 181, T.gyvals) - interp_gxp(xmin, ix1, iy1, T.gxvals, 181, T.gyvals);
+  find_inds_gxp(xmax, p, T.xvals, 81, ix2, iy2);
+  find_inds_gxp(xmin, p, T.xvals, 81, ix1, iy1);
+  auto dif = [&](const double *yv) {
+    return interp_gxp(xmax, ix2, iy2, T.xvals, 81, yv) - interp_gxp(xmin, ix1, iy1, T.xvals, 81, yv);
+  };
+  double gafac = dif(T.yavals), gpfac = dif(T.ypvals), gapfac = dif(T.yapvals), gvfac = dif(T.yvvals),
+         gavfac = dif(T.yavvals);
+  double jfac = A * ec * ec / c * std::sqrt(3.0) / 4.0 * std::pow(3.0 * nubperp / 2.0 / nu, (p - 1.0) / 2.0) * nubperp;
+  double ji = jfac * gxfac;
+  double jq = jfac * gpfac;
+  double jv = jfac * 4.0 / 3.0 / tanth * std::sqrt(3.0 * nubperp / 2.0 / nu) * gvfac;
+  double alpha = (p - 1) / 2.0;
+  double kperp = A * ec * ec / m / c / nubperp;
+  double nui = gmin * gmin * nubperp;
+  double kstaralphaq = 1.0;
+  double kstaralphav = 2.0 * (alpha + 3.0 / 2.0) / (alpha + 1);
+  double kstarq = kstaralphaq * kperp * std::pow(nubperp / nu, 3.0) * std::pow(gmin, -2.0 * alpha + 1.0) *
+                  (1.0 - std::pow(nui / nu, alpha - 1.0 / 2.0)) * std::pow(alpha - 1.0 / 2.0, -1.0);
+  double kstarv = kstaralphav * kperp * std::pow(nubperp / nu, 2.0) * std::log(gmin) * std::pow(gmin, -2 * (alpha + 1)) / tanth;
+  double afac = std::pow(2.0 * pi, 3) * A * ec * ec * std::sqrt(3.0) * omega0 * (p + 2.0) / 32.0 / (pi * pi) / m / c /
+                (omega * omega) * std::pow(2.0 * omega / 3.0 / omega0, -p / 2.0);
+  double ai = afac * gafac;
+  double aq = afac * gapfac;
+  double av = afac * 4.0 / 3.0 / tanth * gavfac * std::pow(2.0 * omega / 3.0 / omega0, -1.0 / 2.0);
+  e[0] = ji; e[1] = jq; e[2] = 0.0; e[3] = jv; e[4] = ai; e[5] = aq; e[6] = 0.0; e[7] = av;
+  e[8] = kstarq; e[9] = 0.0; e[10] = kstarv;
+}
+
+// polsynchemis.f90:633-698
+void synchpl(double nu, double nnth, double b, double th, double p, double gmin, double gmax, double *e) {
+  using namespace pc;
+  const double ec = pc::e;
+  const PlTables &T = pltab();
+  const double nufloor = 1e-10;
+  for (int i = 0; i < 11; i++) e[i] = 0.0;
+  double nubperp = ec * b / m / c / 2.0 / pi * std::sin(th) + nufloor;
+  double nucmin = 3.0 / 2.0 * nubperp * gmin * gmin, nucmax = 3.0 / 2.0 * nubperp * gmax * gmax;
+  double omega0 = nubperp * 2.0 * pi, omega = nu * 2.0 * pi;
+  double xmin = nu / nucmin, xmax = nu / nucmax;
+  double A = (p - 1.0) * nnth / (std::pow(gmin, 1.0 - p) - std::pow(gmax, 1.0 - p));
+  int ix1, ix2, iy1, iy2;
+  find_inds_gxp(xmax, p, T.gxvals, 181, ix2, iy2);
+  find_inds_gxp(xmin, p, T.gxvals, 181, ix1, iy1);
+  double gxfac = interp_gxp(xmax, ix2, iy2, T.gxvals, 181, T.gyvals) - interp_gxp(xmin, ix1, iy1, T.gxvals, 181, T.gyvals);
+  find_inds_gxp(xmin, p, T.xvals, 81, ix1, iy1);
+  find_inds_gxp(xmax, p, T.xvals, 81, ix2, iy2);
+  double gafac = interp_gxp(xmax, ix2, iy2, T.xvals, 81, T.yavals) - interp_gxp(xmin, ix1, iy1, T.xvals, 81, T.yavals);
+  // jfac=A*ec*ec/c*sqrt(3.)/4.*...  : sqrt(3.) is single precision in the reference
+  double jfac = A * ec * ec / c * (double)std::sqrt(3.f) / 4. * std::pow(3.0 * nubperp / 2.0 / nu, (p - 1) / 2.0) * nubperp;
+  double ji = jfac * gxfac;
+  double afac = std::pow(2.0 * pi, 3) * A * ec * ec * std::sqrt(3.0) * omega0 * (p + 2.0) / 32.0 / (pi * pi) / m / c /
+                (omega * omega) * std::pow(2.0 * omega / 3.0 / omega0, -p / 2.0);
+  double ai = afac * gafac;
+  e[0] = ji;
+  e[4] = ai;
+}
+
+// polsynchemis.f90:865-904
+void synchemis(double nu, double n, double B, double T, double *e) {
+  using namespace pc;
+  const double ec = pc::e;
+  const double nucminval = 1.0, thetaemin = 1e-10;
+  for (int i = 0; i < 11; i++) e[i] = 0.0;
+  double thetae = k * T / m / c2 + thetaemin;
+  double nucrit = 3.0 * ec * B / (4 * pi * m * c) * std::pow(thetae, 2.0) + nucminval;
+  double xm = nu / nucrit;
+  double ipx = 4.0505 / std::exp(std::log(xm) / 6.) * (1 + .40 / std::sqrt(std::sqrt(xm)) + 0.5316 / std::sqrt(xm)) *
+               std::exp(-1.8899 * std::exp(std::log(xm) / 3.));
+  double jnu = 4.43e-30 / 2.0 * nu * n * ipx / (thetae * thetae);
+  double anu;
+  if (std::fabs(jnu) > 0.)
+    anu = jnu / bnu(T, nu);
+  else
+    anu = 0.0;
+  e[0] = jnu;
+  e[4] = anu;
+}
+
+// ------------------------------------------------------------------ chandra_tab24.f90:29-38
+void interp_chandra_tab24(float mu, float &I, float &del) {
+  static float ch_mu[22], ch_I[22], ch_delta[22];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (int i = 1; i <= 21; i++) {
+      ch_mu[i] = (float)GRT_CH24_MU[i - 1];
+      ch_I[i] = (float)GRT_CH24_I[i - 1];
+      ch_delta[i] = (float)GRT_CH24_DELTA[i - 1];
+    }
+  });
+  // get_weight_arr: locate (bisection) for the first element; npts==1 on this path
+  int n = 21, jl = 0, ju = n + 1;
+  bool ascnd = (ch_mu[n] >= ch_mu[1]);
+  while (ju - jl > 1) {
+    int jm = (ju + jl) / 2;
+    if (ascnd == (mu >= ch_mu[jm]))
+      jl = jm;
+    else
+      ju = jm;
+  }
+  int indx;
+  if (mu == ch_mu[1])
+    indx = 1;
+  else if (mu == ch_mu[n])
+    indx = n - 1;
+  else
+    indx = jl;
+  int j = indx < 1 ? 1 : (indx > n - 1 ? n - 1 : indx);  // guard
+  float weight = (mu - ch_mu[j]) / (ch_mu[j + 1] - ch_mu[j]);
+  I = (1.f - weight) * ch_I[j] + weight * ch_I[j + 1];
+  del = (1.f - weight) * ch_delta[j] + weight * ch_delta[j + 1];
+}
+
+// emis.f90:294-367
+int emis_type_from_name(const std::string &ename, int &neq) {
+  if (ename == "POLSYNCHTH") { neq = 4; return E_POLSYNCHTH; }
+  if (ename == "SYNCHTHAV") { neq = 1; return E_SYNCHTHAV; }
+  if (ename == "POLSYNCHPL") { neq = 4; return E_POLSYNCHPL; }
+  if (ename == "SYNCHPL") { neq = 1; return E_SYNCHPL; }
+  if (ename == "BB") { neq = 1; return E_BB; }
+  if (ename == "BBPOL") { neq = 4; return E_BBPOL; }
+  neq = 1;
+  return -1;
+}
+
+}  // namespace orc

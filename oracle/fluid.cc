@@ -1,0 +1,769 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see geokerr.cc header).
+// CPU restatement of the fluid sampling stage of the hot path:
+//   fluid.f90 (get_*_fluidvars, convert_fluidvars_*, scale_sim_units, monika_e, nonthermale_b2,
+//   andrew_sigcut), fluid_model_{thindisk,sphacc,ffjet,harm,harm3d}.f90, interpolate.f90, hunt.f,
+//   math.f90:zbrent.  Single/double precision placement follows the reference declarations
+//   (real vs real(kind=8)) and Fortran's mixed-mode promotion rules.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "oracle.h"
+#include "ref_tables.h"
+
+namespace orc {
+
+using pc::pi;
+
+// ------------------------------------------------------------------ hunt.f (float)
+// returns 1-based jlo; jlo may be 0 or n when x is out of range
+static void hunt(const float *xx /*1-based*/, int n, float x, int &jlo) {
+  bool ascnd = (xx[n] >= xx[1]);
+  int jhi, inc;
+  if (jlo <= 0 || jlo > n) {
+    jlo = 0;
+    jhi = n + 1;
+  } else {
+    inc = 1;
+    if ((x >= xx[jlo]) == ascnd) {
+      for (;;) {
+        jhi = jlo + inc;
+        if (jhi > n) {
+          jhi = n + 1;
+          break;
+        } else {
+          if ((x < xx[jhi]) == ascnd) break;
+          jlo = jhi;
+          inc = inc + inc;
+        }
+      }
+    } else {
+      jhi = jlo;
+      for (;;) {
+        jlo = jhi - inc;
+        if (jlo < 1) {
+          jlo = 0;
+          break;
+        } else {
+          if ((x >= xx[jlo]) == ascnd) break;
+          jhi = jlo;
+          inc = inc + inc;
+        }
+      }
+    }
+  }
+  for (;;) {
+    if (jhi - jlo <= 1) {
+      if (x == xx[n]) jlo = n - 1;
+      if (x == xx[1]) jlo = 1;
+      break;
+    } else {
+      int jm = (jhi + jlo) / 2;
+      if ((x >= xx[jm]) == ascnd)
+        jlo = jm;
+      else
+        jhi = jm;
+    }
+  }
+}
+
+// interpolate.f90:76-84
+static void get_weight(const float *xx, int n, float x, int &jlo, float &weight) {
+  hunt(xx, n, x, jlo);
+  int j = std::min(std::max(jlo, 1), n - 1);  // guard (the reference reads out of bounds)
+  jlo = j;
+  weight = (x - xx[j]) / (xx[j + 1] - xx[j]);
+}
+
+// ------------------------------------------------------------------ math.f90:56-135
+template <class F>
+static double zbrent(F func, double x1, double x2, double tol) {
+  const int itmax = 100;
+  const double eps = 2.220446049250313e-16;
+  double a = x1, b = x2, c, d = 0, e = 0, fa, fb, fc, p, q, r, s, tol1, xm;
+  fa = func(a);
+  fb = func(b);
+  if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) {
+    // 'ROOT MUST BE BRACKETED FOR ZBRENT' (the reference STOPs)
+    return std::nan("");
+  }
+  c = b;
+  fc = fb;
+  for (int iter = 1; iter <= itmax; iter++) {
+    if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
+      c = a;
+      fc = fa;
+      d = b - a;
+      e = d;
+    }
+    if (std::fabs(fc) < std::fabs(fb)) {
+      a = b;
+      b = c;
+      c = a;
+      fa = fb;
+      fb = fc;
+      fc = fa;
+    }
+    tol1 = 2.0 * eps * std::fabs(b) + 0.5 * tol;
+    xm = 0.5 * (c - b);
+    if (std::fabs(xm) <= tol1 || fb == 0.0) return b;
+    if (std::fabs(e) >= tol1 && std::fabs(fa) > std::fabs(fb)) {
+      s = fb / fa;
+      if (a == c) {
+        p = 2.0 * xm * s;
+        q = 1.0 - s;
+      } else {
+        q = fa / fc;
+        r = fb / fc;
+        p = s * (2.0 * xm * q * (q - r) - (b - a) * (r - 1.0));
+        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      p = std::fabs(p);
+      if (2.0 * p < std::min(3.0 * xm * q - std::fabs(tol1 * q), std::fabs(e * q))) {
+        e = d;
+        d = p / q;
+      } else {
+        d = xm;
+        e = d;
+      }
+    } else {
+      d = xm;
+      e = d;
+    }
+    a = b;
+    fa = fb;
+    b = b + ((std::fabs(d) > tol1) ? d : (std::signbit(xm) ? -std::fabs(tol1) : std::fabs(tol1)));
+    fb = func(b);
+  }
+  return b;
+}
+
+// ------------------------------------------------------------------ kerr.f90:147-162 bl2ks
+static double bl2ks_time(double r, double x, double a) {
+  return x + std::log(r * r - 2 * r + a * a) +
+         1. / (2.0 * std::sqrt(1. - a * a)) * std::log((r - 1. - std::sqrt(1. - a * a)) / (r - 1 + std::sqrt(1. - a * a)));
+}
+static double bl2ks_phi(double r, double x, double a) {
+  return x + a / (2.0 * std::sqrt(1. - a * a)) * std::log((r - 1. - std::sqrt(1. - a * a)) / (r - 1. + std::sqrt(1. - a * a)));
+}
+
+// ------------------------------------------------------------------ THINDISK
+// kerr.f90:102-129 krolikc (real(4) variables, mixed-mode arithmetic as written)
+static float krolikc(float r, float a) {
+  float pif = std::acos(-1.f);
+  float rms = calc_rms(a);
+  float y = std::sqrt(r);
+  float yms = std::sqrt(rms);
+  float y1 = (float)(2.0 * (double)std::cos(1.f / 3.f * (std::acos(a) - pif)));
+  float y2 = (float)(2.0 * (double)std::cos(1.f / 3.f * (std::acos(a) + pif)));
+  float y3 = (float)(-2.0 * (double)std::cos(1.f / 3.f * std::acos(a)));
+  float arg1 = (float)((double)(3.f * a) / (2.0 * (double)y));
+  float arg2 = (float)((double)3.f * std::pow((double)(y1 - a), 2.0) / (double)(y * y1 * (y1 - y2) * (y1 - y3)));
+  float arg3 = (float)((double)3.f * std::pow((double)(y2 - a), 2.0) / (double)(y * y2 * (y2 - y1) * (y2 - y3)));
+  float arg4 = (float)((double)3.f * std::pow((double)(y3 - a), 2.0) / (double)(y * y3 * (y3 - y1) * (y3 - y2)));
+  float kc = 1.f - yms / y - arg1 * std::log(y / yms) - arg2 * std::log((y - y1) / (yms - y1)) -
+             arg3 * std::log((y - y2) / (yms - y2)) - arg4 * std::log((y - y3) / (yms - y3));
+  return kc;
+}
+
+// fluid_model_thindisk.f90:51-84
+static void thindisk_vals(const FluidData &fd, float &rin_state, float r, float th, float a, float &T, float &omega) {
+  float MBH = fd.td_mbh, Mdot = fd.td_mdot;
+  float lbh = (float)((double)MBH * pc::msun * pc::G / pc::c2);
+  float b = 1.f - 3.f / r + 2.f * a / std::pow(r, 3.f / 2.f);
+  float rms = calc_rms(a);
+  rin_state = std::max(rms, rin_state);
+  float kc = krolikc(r, a);
+  float d = r * r - 2.f * r + a * a;
+  float lc = (rms * rms - 2.f * a * std::sqrt(rms) + a * a) / (std::pow(rms, 1.5f) - 2.f * std::sqrt(rms) + a);
+  float hc = (2.f * r - a * lc) / d;
+  float ar = std::pow(r * r + a * a, 2.f) - a * a * d * std::pow(std::sin(th), 2.f);
+  float om = 2.f * a * r / ar;
+  // ledd(m)=4.*pi*G*m*msun*mp*c/sigt  (double result), Mdotedd=ledd(MBH)/c2 -> real(4)
+  double leddval = 4. * pi * pc::G * (double)MBH * pc::msun * pc::mp * pc::c / pc::sigt;
+  float Mdotedd = (float)(leddval / pc::c2);
+  float T0 = (float)std::pow(3.0 / 8.0 / pi * pc::G * (double)MBH * pc::msun * (double)Mdot * (double)Mdotedd /
+                                 (double)lbh / (double)lbh / (double)lbh / pc::sigb,
+                             (double).25f);
+  if (r > rms)
+    omega = std::max(1.f / (std::pow(r, 3.f / 2.f) + a), om);
+  else
+    omega = std::max((lc + a * hc) / (r * r + 2.f * r * (1.f + hc)), om);
+  if (r > rin_state && r < fd.td_rout)
+    T = T0 * std::pow(kc / b / std::pow(r, 3.f), 1.f / 4.f);
+  else
+    T = (float)((double)T0 / 1e5);
+}
+
+// fluid.f90:586-620
+static void get_thindisk_fluidvars(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) {
+  float a = (float)g.a;
+  float rin_state = fd.td_rin;
+  for (int i = 0; i < g.npts; i++) {
+    float T, omega;
+    float r = (float)g.x[i].d[1], th = (float)g.x[i].d[2];
+    thindisk_vals(fd, rin_state, r, th, a, T, omega);
+    f[i].rho = T;
+    float metric[10];
+    blmetric_cov_real(r, th, a, metric);
+    // f%u%data(1)=sqrt(-1./(metric(:,1)+2d0*metric(:,4)*omega+metric(:,10)*omega*omega))
+    double den = (double)metric[0] + 2.0 * (double)metric[3] * (double)omega + (double)(metric[9] * omega * omega);
+    f[i].u[0] = std::sqrt(-1. / den);
+    f[i].u[1] = 0.;
+    f[i].u[2] = 0.;
+    f[i].u[3] = (double)omega * f[i].u[0];
+    calc_polvec(g.x[i].d[1], std::cos(g.x[i].d[2]), g.k[i].d, (double)a, std::asin(1.0), f[i].b);
+  }
+}
+
+// ------------------------------------------------------------------ SPHACC
+static void init_sphacc(FluidData &fd) {
+  fd.uvals.assign(499, 0.f);
+  fd.vvals.assign(499, 0.f);
+  fd.rvals.assign(462, 0.f);
+  fd.tvals.assign(462, 0.f);
+  for (int I = 1; I <= 498; I++) fd.uvals[I] = (float)(I - 1) * .001f + 1.f / 399.f;
+  for (int I = 1; I <= 461; I++) {
+    fd.tvals[I] = (float)GRT_SPHACC_TVALS[I - 1];
+    fd.rvals[I] = (float)GRT_SPHACC_RVALS[I - 1];
+  }
+  for (int I = 1; I <= 498; I++) fd.vvals[I] = (float)GRT_SPHACC_VVALS[I - 1];
+}
+
+// fluid_model_sphacc.f90:450-497 + fluid.f90:1215-1247
+static void get_sphacc_fluidvars(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) {
+  float gamma = (float)(5.0 / 3.0), alpha = (float)(1.0 / 4.0), ninf = 1.f, Tinf = (float).917e-9, us = (float).94;
+  static thread_local std::vector<float> uv;
+  if (uv.size() != 462) {
+    uv.assign(462, 0.f);
+    for (int i = 1; i <= 461; i++) uv[i] = (float)(1.0 / (double)fd.rvals[i]);
+  }
+  int lindx_v = 1, lindx_t = 1;
+  for (int i = 0; i < g.npts; i++) {
+    float u = (float)(1. / g.x[i].d[1]);
+    float n = (float)((double)(ninf * alpha / 4.f / us) * std::pow((double)(2 * gamma * Tinf), -1.5) *
+                      std::pow(2.0 * (double)u, 1.5));
+    float w;
+    get_weight(uv.data(), 461, u, lindx_t, w);
+    float T = (float)((1.0 - (double)w) * (double)fd.tvals[lindx_t] + (double)(w * fd.tvals[lindx_t + 1]));
+    float B = (float)std::sqrt(8. * pi * (double)n * pc::mp / 2. * pc::c2 * (double)u);
+    get_weight(fd.uvals.data(), 498, u, lindx_v, w);
+    float ur = (float)((1.0 - (double)w) * (double)fd.vvals[lindx_v] + (double)(w * fd.vvals[lindx_v + 1]));
+    float g00 = -(1.f - 2.f * u);
+    float grr = (float)(-1.0 / (double)g00);
+    FluidPt &p = f[i];
+    p.u[1] = -(double)ur;
+    p.u[2] = 0.0;
+    p.u[3] = 0.0;
+    p.u[0] = std::sqrt((-(double)grr * p.u[1] * p.u[1] - 1) / (double)g00);
+    p.b[2] = 0.0;
+    p.b[3] = 0.0;
+    double B2 = (double)(B * B);
+    p.b[0] = std::sqrt(p.u[1] * p.u[1] * (double)grr * B2 /
+                       (p.u[1] * p.u[1] * (double)g00 * (double)grr + p.u[0] * p.u[0] * (double)g00 * (double)g00));
+    p.b[1] = -std::sqrt((double)((B * B) / grr) - p.b[0] * p.b[0] * (double)g00 / (double)grr);
+    p.rho = n;
+    p.p = T;
+    p.bmag = B;
+  }
+}
+
+// ------------------------------------------------------------------ gridded models: shared tail
+// b.b with float32 metric, LNRF^-1 velocities, u^i = u^t v^i  (fluid_model_ffjet.f90:133-162 etc.)
+static void finish_grid_point(FluidPt &p, float zr, float th, float a, float vrl0, float vtl0, float vpl0,
+                              double bfac) {
+  float metric[10];
+  blmetric_cov_real(zr, th, a, metric);
+  double m[10];
+  for (int i = 0; i < 10; i++) m[i] = (double)metric[i];
+  float bmag = (float)dot4(m, p.b, p.b);
+  bmag = ((double)bmag >= 0.0) ? bmag : 0.f;
+  bmag = std::sqrt(bmag);
+  p.bmag = (float)((double)bmag * bfac);
+  float vr0, vth0, vph0;
+  lnrf_frame_inv_real(vrl0, vtl0, vpl0, zr, a, th, vr0, vth0, vph0);
+  p.u[1] = p.u[0] * (double)vr0;
+  p.u[2] = p.u[0] * (double)vth0;
+  p.u[3] = p.u[0] * (double)vph0;
+}
+
+static inline float bilin(const float *v, float xd, float yd) {  // interpolate.f90:171-182
+  float w1 = v[0] * (1.f - yd) + v[1] * yd;
+  float w2 = v[2] * (1.f - yd) + v[3] * yd;
+  return w1 * (1.f - xd) + w2 * xd;
+}
+static inline float trilin(const float *v, float xd, float yd, float zd) {  // interpolate.f90:184-201
+  float i1 = v[0] * (1.f - zd) + v[1] * zd;
+  float i2 = v[2] * (1.f - zd) + v[3] * zd;
+  float j1 = v[4] * (1.f - zd) + v[5] * zd;
+  float j2 = v[6] * (1.f - zd) + v[7] * zd;
+  float w1 = i1 * (1.f - yd) + i2 * yd;
+  float w2 = j1 * (1.f - yd) + j2 * yd;
+  return w1 * (1.f - xd) + w2 * xd;
+}
+static inline float quadlin(const float *v, float td, float xd, float yd, float zd) {  // interpolate.f90:203-232
+  float i1 = v[0] * (1.f - zd) + v[1] * zd, i2 = v[2] * (1.f - zd) + v[3] * zd;
+  float j1 = v[4] * (1.f - zd) + v[5] * zd, j2 = v[6] * (1.f - zd) + v[7] * zd;
+  float k1 = v[8] * (1.f - zd) + v[9] * zd, k2 = v[10] * (1.f - zd) + v[11] * zd;
+  float l1 = v[12] * (1.f - zd) + v[13] * zd, l2 = v[14] * (1.f - zd) + v[15] * zd;
+  float m1 = i1 * (1.f - yd) + i2 * yd, m2 = j1 * (1.f - yd) + j2 * yd;
+  float n1 = k1 * (1.f - yd) + k2 * yd, n2 = l1 * (1.f - yd) + l2 * yd;
+  float w1 = m1 * (1.f - xd) + m2 * xd, w2 = n1 * (1.f - xd) + n2 * xd;
+  return w1 * (1.f - td) + w2 * td;
+}
+
+// ------------------------------------------------------------------ FFJET
+// fluid_model_ffjet.f90:181-210 (Fortran sequential unformatted, 4-byte record markers)
+static bool load_ffjet(FluidData &fd, const std::string &dfile) {
+  FILE *fp = fopen(dfile.c_str(), "rb");
+  if (!fp) return false;
+  auto rec = [&](std::vector<char> &buf) -> bool {
+    int n1 = 0, n2 = 0;
+    if (fread(&n1, 4, 1, fp) != 1) return false;
+    buf.resize(n1);
+    if (n1 && fread(buf.data(), 1, n1, fp) != (size_t)n1) return false;
+    if (fread(&n2, 4, 1, fp) != 1) return false;
+    return n1 == n2;
+  };
+  std::vector<char> b;
+  if (!rec(b)) { fclose(fp); return false; }
+  float aa;
+  int nx;
+  memcpy(&aa, b.data(), 4);
+  memcpy(&nx, b.data() + 4, 4);
+  fd.asim = aa;
+  int n1d = (int)std::sqrt((float)nx);
+  fd.nx1 = n1d;
+  fd.nx2 = n1d;
+  auto take = [&](const char *&p, std::vector<float> &v) {
+    v.resize(nx);
+    memcpy(v.data(), p, 4 * (size_t)nx);
+    p += 4 * (size_t)nx;
+  };
+  std::vector<float> dummy;
+  const char *p;
+  if (!rec(b)) { fclose(fp); return false; }
+  p = b.data();
+  take(p, fd.r_arr); take(p, fd.th_arr); take(p, fd.rho_arr);
+  if (!rec(b)) { fclose(fp); return false; }
+  p = b.data();
+  take(p, dummy); take(p, fd.b0_arr); take(p, fd.br_arr); take(p, fd.bth_arr); take(p, fd.bph_arr);
+  if (!rec(b)) { fclose(fp); return false; }
+  p = b.data();
+  take(p, fd.u0_arr); take(p, fd.vrl_arr); take(p, fd.vtl_arr); take(p, fd.vpl_arr);
+  fclose(fp);
+  fd.p_arr.assign(nx, 0.f);  // allocated but never read by the reference (garbage there)
+  return true;
+}
+
+// fluid_model_ffjet.f90:42-171
+static void ffjet_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) {
+  float a = (float)g.a;
+  int nx1 = fd.nx1, nx2 = nx1;
+  std::vector<float> uniqr(nx1 + 1), uniqx1(nx1 + 1), uniqx2(nx1 + 1);
+  for (int i = 1; i <= nx1; i++) {
+    uniqr[i] = fd.r_arr[i - 1];
+    uniqx2[i] = fd.th_arr[(i - 1) * nx1];
+    uniqx1[i] = std::log(uniqr[i]);
+  }
+  const float *uniqth = uniqx2.data();
+  for (int i = 0; i < g.npts; i++) {
+    float theta = (float)g.x[i].d[2];
+    float zm = std::cos(theta);
+    float x2 = std::acos(std::fabs(zm));
+    theta = x2;
+    float zr = (float)g.x[i].d[1];
+    float x1 = std::log(zr);
+    int lx1 = (int)((x1 - uniqx1[1]) / (uniqx1[nx1] - uniqx1[1]) * (float)(nx1 - 1)) + 1;
+    int ux1 = lx1 + 1;
+    int lx2 = (int)((x2 - uniqx2[1]) / (uniqx2[nx2] - uniqx2[1]) * (float)(nx2 - 1)) + 1;
+    lx2 = (lx2 <= (nx2 - 1)) ? ((lx2 >= 1) ? lx2 : 1) : (nx2 - 1);
+    int ux2 = lx2 + 1;
+    // guard the radial indices (the reference reads out of bounds and discards via merge)
+    int lx1s = std::min(std::max(lx1, 1), nx1 - 1), ux1s = lx1s + 1;
+    float td = (theta - uniqth[lx2]) / (uniqth[ux2] - uniqth[lx2]);
+    float rd = (zr - uniqr[lx1s]) / (uniqr[ux1s] - uniqr[lx1s]);
+    (void)ux1;
+    int x1l = lx1s - 1, x1u = ux1s - 1, x2l = (lx2 - 1) * nx1, x2u = (ux2 - 1) * nx1;
+    int idx[4] = {x1l + x2l, x1l + x2u, x1u + x2l, x1u + x2u};  // 0-based
+    auto gat = [&](const std::vector<float> &arr) {
+      float v[4] = {arr[idx[0]], arr[idx[1]], arr[idx[2]], arr[idx[3]]};
+      return bilin(v, rd, td);
+    };
+    bool in = x1 > uniqx1[1];
+    FluidPt &p = f[i];
+    p.rho = in ? gat(fd.rho_arr) : 0.f;
+    p.p = in ? gat(fd.p_arr) : 1.f;
+    float vrl0 = in ? gat(fd.vrl_arr) : 0.f;
+    float vtl0 = in ? gat(fd.vtl_arr) : 1.f;
+    p.b[0] = in ? gat(fd.b0_arr) : 1.f;
+    p.b[1] = in ? gat(fd.br_arr) : 1.f;
+    p.b[2] = in ? gat(fd.bth_arr) : 1.f;
+    p.b[3] = in ? gat(fd.bph_arr) : 1.f;
+    p.u[0] = in ? (double)gat(fd.u0_arr) : 1.0;
+    float vpl0 = in ? gat(fd.vpl_arr) : 0.f;
+    finish_grid_point(p, zr, (float)g.x[i].d[2], a, vrl0, vtl0, vpl0, 1.0);
+  }
+}
+
+// ------------------------------------------------------------------ HARM (2-D)
+// fluid_model_harm.f90:100-265
+static void harm_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) {
+  float a = (float)g.a;
+  int nx1 = fd.nx1, nx2 = fd.nx2;
+  float h = fd.h;
+  std::vector<float> uniqx1(nx1 + 1), uniqr(nx1 + 1), uniqx2(nx2 + 1), uniqth(nx2 + 1);
+  for (int i = 1; i <= nx2; i++) {
+    uniqx2[i] = fd.x2_arr[i - 1];
+    uniqth[i] = (float)(pi * (double)uniqx2[i] + (double)((1.f - h) / 2.f) * std::sin(2. * pi * (double)uniqx2[i]));
+  }
+  for (int i = 1; i <= nx1; i++) {
+    uniqx1[i] = fd.x1_arr[(i - 1) * nx2];
+    uniqr[i] = std::exp(uniqx1[i]);
+  }
+  float rh = 1.f + std::sqrt(1.f - std::pow(a, 2.f));
+  for (int i = 0; i < g.npts; i++) {
+    float theta = (float)g.x[i].d[2];
+    float zr = (float)g.x[i].d[1];
+    float x1 = std::log(zr);
+    double thd = (double)theta, hd = (double)h;
+    float x2 = (float)zbrent([&](double x) { return thd - pi * x - .5 * (1 - hd) * std::sin(2. * pi * x); }, 0.0, 1.0, 1e-6);
+    int lx1 = (int)std::floor((x1 - uniqx1[1]) / (uniqx1[nx1] - uniqx1[1]) * (float)(nx1 - 1)) + 1;
+    int ux1 = lx1 + 1;
+    int lx2 = (int)std::floor((x2 - uniqx2[1]) / (uniqx2[nx2] - uniqx2[1]) * (float)(nx2 - 1)) + 1;
+    int ux2 = lx2 + 1;
+    lx2 = (lx2 >= 1) ? lx2 : 1;
+    ux2 = (ux2 <= nx2) ? ux2 : nx2;
+    float dth = (ux2 != lx2) ? (uniqth[ux2] - uniqth[lx2]) : uniqth[1];
+    float td = std::fabs(theta - uniqth[lx2]) / dth;
+    int lx1s = std::min(std::max(lx1, 1), nx1 - 1), ux1s = lx1s + 1;  // guard
+    (void)ux1;
+    float rd = (zr - uniqr[lx1s]) / (uniqr[ux1s] - uniqr[lx1s]);
+    if (uniqr[lx1s] <= rh) rd = 1.f;
+    int x2l = lx2 - 1, x2u = ux2 - 1, x1l = (lx1s - 1) * nx2, x1u = (ux1s - 1) * nx2;
+    // nt=1: tindx=0 and the "second time slice" wraps onto the first (indx-n), rttd=0
+    int idx[8] = {x1l + x2l, x1l + x2u, x1u + x2l, x1u + x2u, x1l + x2l, x1l + x2u, x1u + x2l, x1u + x2u};
+    auto gat = [&](const std::vector<float> &arr) {
+      float v[8];
+      for (int q = 0; q < 8; q++) v[q] = arr[idx[q]];
+      return trilin(v, 0.f, rd, td);
+    };
+    bool in = x1 > uniqx1[1];
+    FluidPt &p = f[i];
+    p.rho = in ? gat(fd.rho_arr) : 0.f;
+    p.p = in ? gat(fd.p_arr) : 1.f;
+    float vrl0 = in ? gat(fd.vrl_arr) : 0.f;
+    float vtl0 = in ? gat(fd.vtl_arr) : 1.f;
+    p.b[0] = in ? gat(fd.b0_arr) : 1.f;
+    p.b[1] = in ? gat(fd.br_arr) : 1.f;
+    p.b[2] = in ? gat(fd.bth_arr) : 1.f;
+    p.b[3] = in ? gat(fd.bph_arr) : 1.f;
+    p.u[0] = in ? (double)gat(fd.u0_arr) : 1.0;
+    float vpl0 = in ? gat(fd.vpl_arr) : 0.f;
+    finish_grid_point(p, zr, (float)g.x[i].d[2], a, vrl0, vtl0, vpl0, 1.0);
+  }
+}
+
+// ------------------------------------------------------------------ HARM3D
+// fluid_model_harm3d.f90:107-327
+static void harm3d_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) {
+  float a = (float)g.a;
+  int nx1 = fd.nx1, nx2 = fd.nx2, nx3 = fd.nx3;
+  std::vector<float> uniqx1(nx1 + 1), uniqr(nx1 + 1), uniqx2(nx2 + 1), uniqth(nx2 + 1), uniqx3(nx3 + 1);
+  for (int i = 1; i <= nx3; i++) uniqx3[i] = fd.x3_arr[i - 1];
+  for (int i = 1; i <= nx2; i++) {
+    uniqx2[i] = fd.x2_arr[(i - 1) * nx3];
+    uniqth[i] = (float)(pi * (double)uniqx2[i]);
+  }
+  for (int i = 1; i <= nx1; i++) {
+    uniqx1[i] = fd.x1_arr[(size_t)(i - 1) * nx3 * nx2];
+    uniqr[i] = std::exp(uniqx1[i]);
+  }
+  const float *uniqph = uniqx3.data();
+  float rh = 1.f + std::sqrt(1.f - std::pow(a, 2.f));
+  for (int i = 0; i < g.npts; i++) {
+    float theta = (float)g.x[i].d[2];
+    float zr = (float)g.x[i].d[1];
+    float zpp = (float)g.x[i].d[3];
+    float zphi = (float)bl2ks_phi((double)zr, (double)zpp, (double)a);
+    zphi = (float)std::fmod((double)zphi, 2. * pi);
+    if (zphi < 0.f) zphi = (float)((double)zphi + 2. * pi);
+    float x1 = std::log(zr);
+    float x3 = zphi;
+    float x2 = (float)((double)theta / pi);
+    int lx1 = (int)std::floor((x1 - uniqx1[1]) / (uniqx1[nx1] - uniqx1[1]) * (float)(nx1 - 1)) + 1;
+    int lx2 = (int)std::floor((x2 - uniqx2[1]) / (uniqx2[nx2] - uniqx2[1]) * (float)(nx2 - 1)) + 1;
+    int ux2 = lx2 + 1;
+    int lx3 = (int)std::floor((x3 - uniqx3[1]) / (uniqx3[nx3] - uniqx3[1]) * (float)(nx3 - 1)) + 1;
+    int ux3 = lx3 + 1;
+    lx2 = (lx2 <= (nx2 - 1)) ? ((lx2 >= 1) ? lx2 : 1) : (nx2 - 1);
+    lx1 = (lx1 >= 1) ? lx1 : 1;
+    int ux1 = lx1 + 1;
+    lx2 = (lx2 >= 1) ? lx2 : 1;
+    lx2 = (lx2 <= nx2) ? lx2 : nx2;
+    ux2 = (ux2 >= 1) ? ux2 : 1;
+    ux2 = (ux2 <= nx2) ? ux2 : nx2;
+    float dth = (ux2 != lx2) ? (uniqth[ux2] - uniqth[lx2]) : (uniqth[1] * 2);
+    // periodic in phi
+    int lx3s = std::min(std::max(lx3, 1), nx3);  // guard for the read below when lx3<1
+    float minph = uniqph[lx3s];
+    if (ux3 > nx3) ux3 = 1;
+    if (lx3 < 1) {
+      lx3 = nx3;
+      minph = (float)((double)uniqph[lx3] - 2. * pi);
+    }
+    float pd = (zphi - minph) / (uniqph[2] - uniqph[1]);
+    float td = std::fabs(theta - uniqth[lx2]) / dth;
+    int ux1s = std::min(ux1, nx1);  // guard (reference reads out of bounds beyond the outer edge)
+    int lx1s = std::min(lx1, nx1);
+    float rd = (zr - uniqr[lx1s]) / (uniqr[ux1s] - uniqr[lx1s]);
+    double pfac, nfac, bfac;
+    if (uniqr[lx1s] <= std::max(uniqr[1], rh)) {
+      rd = 1.f;
+      pfac = 1e-6; nfac = 1e-6; bfac = 1e-6;
+    } else {
+      pfac = 1.0; nfac = 1.0; bfac = 1.0;
+    }
+    size_t x3l = lx3 - 1, x3u = ux3 - 1, x2l = (size_t)(lx2 - 1) * nx3, x2u = (size_t)(ux2 - 1) * nx3;
+    size_t x1l = (size_t)(lx1s - 1) * nx2 * nx3, x1u = (size_t)(ux1s - 1) * nx2 * nx3;
+    size_t idx[16] = {x1l + x2l + x3l, x1l + x2u + x3l, x1u + x2l + x3l, x1u + x2u + x3l,
+                      x1l + x2l + x3u, x1l + x2u + x3u, x1u + x2l + x3u, x1u + x2u + x3u};
+    for (int q = 0; q < 8; q++) idx[8 + q] = idx[q];  // nt=1: second slice wraps to the first
+    auto gat = [&](const std::vector<float> &arr) {
+      float v[16];
+      for (int q = 0; q < 16; q++) v[q] = arr[idx[q]];
+      return quadlin(v, 0.f, pd, rd, td);
+    };
+    bool in = x1 > uniqx1[1];
+    FluidPt &p = f[i];
+    p.rho = (float)((double)gat(fd.rho_arr) * nfac);
+    p.p = (float)((double)gat(fd.p_arr) * pfac);
+    float vrl0 = in ? gat(fd.vrl_arr) : 0.f;
+    float vtl0 = in ? gat(fd.vtl_arr) : 0.f;
+    p.b[0] = in ? gat(fd.b0_arr) : 1.f;
+    p.b[1] = in ? gat(fd.br_arr) : 1.f;
+    p.b[2] = in ? gat(fd.bth_arr) : 1.f;
+    p.b[3] = in ? gat(fd.bph_arr) : 1.f;
+    p.u[0] = in ? (double)gat(fd.u0_arr) : 1.0;
+    float vpl0 = in ? gat(fd.vpl_arr) : 0.f;
+    finish_grid_point(p, zr, (float)g.x[i].d[2], a, vrl0, vtl0, vpl0, bfac);
+  }
+}
+
+// ------------------------------------------------------------------ HARM data ingestion
+// umksh2uks + uks2ubl + lnrf_frame (fluid_model_harm.f90:73-98,380-386,468-485; kerr.f90:131-144).
+// Inputs are per-cell MKS contravariant components as the dump stores them.  For the 3-D model
+// dthdx2 = pi (fluid_model_harm3d.f90:96).
+void harm_transform_and_store(FluidData &fd, const std::vector<double> &rho, const std::vector<double> &uu,
+                              const std::vector<double> &ucon, const std::vector<double> &bcon) {
+  size_t n = rho.size();
+  fd.rho_arr.resize(n); fd.p_arr.resize(n); fd.u0_arr.resize(n); fd.vrl_arr.resize(n); fd.vtl_arr.resize(n);
+  fd.vpl_arr.resize(n); fd.b0_arr.resize(n); fd.br_arr.resize(n); fd.bth_arr.resize(n); fd.bph_arr.resize(n);
+  bool is3d = (fd.model == F_HARM3D);
+  for (size_t i = 0; i < n; i++) {
+    float r = fd.r_arr[i], x2 = fd.x2_arr[i], th = fd.th_arr[i];
+    float dthdx2 = is3d ? (float)pi : (float)(pi * (1. + (double)(1.f - fd.h) * std::cos(2. * pi * (double)x2)));
+    double asim = (double)fd.asim;
+    double rr = (double)r;
+    double delta = rr * rr - 2.0 * rr + asim * asim;
+    double u[4], b[4];
+    for (int c = 0; c < 2; c++) {
+      const double *src = (c == 0 ? ucon.data() : bcon.data()) + 4 * i;
+      double v[4] = {src[0], rr * src[1], src[2] * (double)dthdx2, src[3]};
+      double *dst = c == 0 ? u : b;
+      dst[0] = v[0] - 2.0 * rr / delta * v[1];
+      dst[1] = v[1];
+      dst[2] = v[2];
+      dst[3] = v[3] - asim / delta * v[1];
+    }
+    float vrl, vtl, vpl;
+    lnrf_frame_real((float)(u[1] / u[0]), (float)(u[2] / u[0]), (float)(u[3] / u[0]), r, fd.asim, th, vrl, vtl, vpl);
+    fd.rho_arr[i] = (float)rho[i];
+    fd.p_arr[i] = (float)(uu[i] * (double)(fd.gam - 1.f));
+    fd.b0_arr[i] = (float)b[0]; fd.br_arr[i] = (float)b[1]; fd.bth_arr[i] = (float)b[2]; fd.bph_arr[i] = (float)b[3];
+    fd.u0_arr[i] = (float)u[0];
+    fd.vrl_arr[i] = vrl; fd.vtl_arr[i] = vtl; fd.vpl_arr[i] = vpl;
+  }
+}
+
+// fluid_model_harm.f90:275-408  (ASCII header: 26 numbers; rows of 34 columns)
+static bool load_harm(FluidData &fd, const FluidArgs &fa, double a) {
+  std::ifstream hf(fa.hfile);
+  if (!hf) return false;
+  double header[26];
+  for (int i = 0; i < 26; i++)
+    if (!(hf >> header[i])) return false;
+  fd.nx1 = (int)header[1];
+  fd.nx2 = (int)header[2];
+  fd.asim = (float)header[9];
+  fd.gam = (float)header[10];
+  fd.h = (float)header[24];
+  fd.nx3 = 1;
+  if (std::fabs(fd.asim - (float)a) > 1e-4f) {
+    fprintf(stderr, "ERROR -- Different simulation and grtrans spin values!\n");
+    return false;
+  }
+  char append[16];
+  snprintf(append, sizeof append, "%03d", fa.indf);
+  std::ifstream df(fa.dfile + append);
+  if (!df) return false;
+  for (int i = 0; i < 26; i++)
+    if (!(df >> header[i])) return false;
+  size_t n = (size_t)fd.nx1 * fd.nx2;
+  fd.x1_arr.resize(n); fd.x2_arr.resize(n); fd.r_arr.resize(n); fd.th_arr.resize(n);
+  std::vector<double> rho(n), uu(n), ucon(4 * n), bcon(4 * n);
+  for (size_t i = 0; i < n; i++) {
+    double row[34];
+    for (int c = 0; c < 34; c++)
+      if (!(df >> row[c])) return false;
+    fd.x1_arr[i] = (float)row[0]; fd.x2_arr[i] = (float)row[1]; fd.r_arr[i] = (float)row[2]; fd.th_arr[i] = (float)row[3];
+    rho[i] = row[4];
+    uu[i] = row[5];
+    for (int c = 0; c < 4; c++) {
+      ucon[4 * i + c] = row[13 + c];
+      bcon[4 * i + c] = row[21 + c];
+    }
+  }
+  harm_transform_and_store(fd, rho, uu, ucon, bcon);
+  return true;
+}
+
+// Synthetic 3-D snapshot container used by config 5 (binary, little endian):
+//   int32 nx1,nx2,nx3; float32 asim,gam,h; then float32[n] x1,x2,x3,r,th,ph; float64[n] rho,u;
+//   float64[4n] ucon, bcon (MKS components, index (ix1*nx2+ix2)*nx3+ix3).
+static bool load_harm3d(FluidData &fd, const FluidArgs &fa, double a) {
+  FILE *fp = fopen(fa.dfile.c_str(), "rb");
+  if (!fp) return false;
+  int dims[3];
+  float par[3];
+  if (fread(dims, 4, 3, fp) != 3 || fread(par, 4, 3, fp) != 3) { fclose(fp); return false; }
+  fd.nx1 = dims[0]; fd.nx2 = dims[1]; fd.nx3 = dims[2];
+  fd.asim = par[0]; fd.gam = par[1]; fd.h = par[2];
+  if (std::fabs(fd.asim - (float)a) > 1e-4f) { fclose(fp); return false; }
+  size_t n = (size_t)fd.nx1 * fd.nx2 * fd.nx3;
+  std::vector<float> *fl[6] = {&fd.x1_arr, &fd.x2_arr, &fd.x3_arr, &fd.r_arr, &fd.th_arr, &fd.ph_arr};
+  for (auto v : fl) {
+    v->resize(n);
+    if (fread(v->data(), 4, n, fp) != n) { fclose(fp); return false; }
+  }
+  std::vector<double> rho(n), uu(n), ucon(4 * n), bcon(4 * n);
+  bool ok = fread(rho.data(), 8, n, fp) == n && fread(uu.data(), 8, n, fp) == n &&
+            fread(ucon.data(), 8, 4 * n, fp) == 4 * n && fread(bcon.data(), 8, 4 * n, fp) == 4 * n;
+  fclose(fp);
+  if (!ok) return false;
+  harm_transform_and_store(fd, rho, uu, ucon, bcon);
+  return true;
+}
+
+// fluid.f90:163-243
+bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa) {
+  fd = FluidData();
+  if (fname == "SPHACC") {
+    fd.model = F_SPHACC;
+    init_sphacc(fd);
+  } else if (fname == "FFJET") {
+    fd.model = F_FFJET;
+    fd.ok = load_ffjet(fd, fa.dfile);
+  } else if (fname == "THINDISK") {
+    fd.model = F_THINDISK;
+    fd.td_mdot = (float)fa.mdot; fd.td_mbh = (float)fa.mbh; fd.td_rin = (float)fa.rin; fd.td_rout = (float)fa.rout;
+  } else if (fname == "HARM") {
+    fd.model = F_HARM;
+    fd.ok = load_harm(fd, fa, a);
+  } else if (fname == "HARM3D") {
+    fd.model = F_HARM3D;
+    fd.ok = load_harm3d(fd, fa, a);
+  } else {
+    fd.model = F_DUMMY;
+  }
+  return fd.ok;
+}
+
+// fluid.f90:473-526
+void get_fluid_vars(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) {
+  f.assign(g.npts, FluidPt());
+  switch (fd.model) {
+    case F_SPHACC: get_sphacc_fluidvars(fd, g, f); break;
+    case F_FFJET: ffjet_vals(fd, g, f); break;
+    case F_THINDISK: get_thindisk_fluidvars(fd, g, f); break;
+    case F_HARM: harm_vals(fd, g, f); break;
+    case F_HARM3D: harm3d_vals(fd, g, f); break;
+    default: break;
+  }
+}
+
+// fluid.f90:765-790
+static void scale_sim_units(double mbh, double mdotcgs, double mdot, float rho, float p, float bmag, double &ncgs,
+                            double &bcgs, double &tempcgs) {
+  double lcgs = pc::G * mbh * pc::msun / (pc::c * pc::c), tcgs = lcgs / pc::c;
+  double rhocgs = mdotcgs / mdot / (lcgs * lcgs * lcgs) * tcgs * (double)rho;
+  ncgs = rhocgs / pc::mp;
+  double pcgs = (double)p * rhocgs / (double)rho * std::pow(pc::c, 2.0);
+  tempcgs = pcgs / ncgs / pc::k;
+  bcgs = (double)bmag * std::sqrt(rhocgs / (double)rho) * pc::c;
+  bcgs = bcgs * std::sqrt(4.0 * pi);
+}
+
+// fluid.f90:870-892
+static double monika_e(float rho, float p, float b, double rlow, double rhigh) {
+  (void)rho;
+  double beta = (double)(p / (b * b)) / 0.5;
+  double b2 = beta * beta;
+  if ((double)b > 0.0) return rhigh * b2 / (1.0 + b2) + rlow / (1.0 + b2);
+  return rhigh;
+}
+
+// fluid.f90:528-584 and the per-model converters (:957-993, :1164-1172, :1190-1196, :1249-1259)
+void convert_fluid_vars(const FluidData &fd, const std::vector<FluidPt> &f, const SourceParams &sp,
+                        std::vector<double> &ncgs, std::vector<double> &ncgsnth, std::vector<double> &bcgs,
+                        std::vector<double> &tcgs) {
+  size_t n = f.size();
+  ncgs.assign(n, 0.0); ncgsnth.assign(n, 0.0); bcgs.assign(n, 0.0); tcgs.assign(n, 0.0);
+  for (size_t i = 0; i < n; i++) {
+    const FluidPt &p = f[i];
+    switch (fd.model) {
+      case F_SPHACC:
+        ncgs[i] = p.rho; bcgs[i] = p.bmag; tcgs[i] = p.p; ncgsnth[i] = 0.;
+        break;
+      case F_FFJET:
+        ncgsnth[i] = (double)p.rho * sp.nfac; bcgs[i] = (double)p.bmag * sp.bfac; ncgs[i] = 0.; tcgs[i] = 0.;
+        break;
+      case F_THINDISK:
+        tcgs[i] = p.rho; ncgs[i] = 1.;
+        break;
+      case F_HARM: {
+        double mdot = .003;
+        scale_sim_units(sp.mbh, sp.mdot, mdot, p.rho, p.p, p.bmag, ncgs[i], bcgs[i], tcgs[i]);
+        double trat = monika_e(p.rho, p.p, p.bmag, sp.muval, sp.muval / sp.gminval);
+        tcgs[i] = tcgs[i] * trat;
+        ncgsnth[i] = ncgs[i];
+      } break;
+      case F_HARM3D: {
+        double mdot = pc::G * sp.mbh * pc::msun / (pc::c * pc::c * pc::c);
+        scale_sim_units(sp.mbh, sp.mdot, mdot, p.rho, p.p, p.bmag, ncgs[i], bcgs[i], tcgs[i]);
+        double trat = monika_e(p.rho, p.p, p.bmag, 1.0 / sp.muval - 1.0, sp.gminval * (1.0 / sp.muval - 1.0));
+        tcgs[i] = tcgs[i] / (1.0 + trat);
+        // nonthermale_b2 (fluid.f90:914-923)
+        double bmagrho = std::pow((double)p.bmag, 2.0) / (double)p.rho;
+        if (bmagrho > 1.0)
+          ncgsnth[i] = sp.jetalphaval * std::pow(bcgs[i], 2.0) / 8.0 / pi / sp.gminval * (sp.p1 - 2.0) / (sp.p1 - 1.0) / 8.2e-7;
+        else
+          ncgsnth[i] = 0.0;
+        // andrew_sigcut (fluid.f90:792-810)
+        double rhocgs = ncgs[i] * pc::mp;
+        double sigmacgs = (bcgs[i] * bcgs[i]) / (rhocgs * 8.988e20 * 4.0 * pi);
+        if (sigmacgs >= sp.sigcut) {
+          ncgs[i] = 0.0;
+          tcgs[i] = 1e9;
+        }
+      } break;
+      default: break;
+    }
+  }
+}
+
+}  // namespace orc
