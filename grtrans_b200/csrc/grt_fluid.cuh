@@ -1,0 +1,421 @@
+// grtrans_b200 -- fluid sampling device functions (one geodesic point per thread).
+//
+// Replaces fluid.f90:473-526 (get_fluid_vars_arr) and the *_vals routines of
+// fluid_model_thindisk.f90:51-84, fluid_model_sphacc.f90:450-497, fluid_model_ffjet.f90:42-171,
+// fluid_model_harm.f90:100-265, fluid_model_harm3d.f90:107-327 with interpolate.f90 / hunt.f /
+// math.f90:zbrent, plus the unit conversions fluid.f90:765-810, 870-892, 914-993, 1164-1259.
+//
+// Snapshot layout in HBM: the reference keeps ten float32 SoA arrays (rho,p,u0,vrl,vtl,vpl,b0,br,bth,
+// bph).  Every sample needs all ten fields at the same 4/8 corners, so the snapshot is re-packed as
+// an array of 48-byte cells {rho,p,vrl,vtl | vpl,b0,br,bth | bph,u0,-,-}: one corner = three
+// 128-bit read-only loads instead of ten scattered 32-bit loads.  Index and weight arithmetic stays in
+// float32 exactly where the reference has `real` variables so the gathered cells are the same.
+#pragma once
+#include "grt_kerr.cuh"
+
+namespace grt {
+
+enum { FL_DUMMY = 0, FL_SPHACC = 1, FL_THINDISK = 2, FL_HARM = 12, FL_FFJET = 13, FL_HARM3D = 19 };
+
+struct Cell {  // 48 bytes, 16-byte aligned
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, pad0, pad1;
+};
+
+struct FluidDev {
+  int model, nx1, nx2, nx3;
+  float h, rh_dummy;
+  float td_mbh, td_mdot, td_rin, td_rout;
+  const float *ax1;   // uniqx1 (log r for HARM/FFJET)          [nx1]
+  const float *axr;   // uniqr                                   [nx1]
+  const float *ax2;   // uniqx2                                  [nx2]
+  const float *axth;  // uniqth                                  [nx2]
+  const float *ax3;   // uniqx3 / uniqph                         [nx3]
+  const Cell *cells;  // [n] packed snapshot
+  // SPHACC tables
+  const float *uvals, *vvals, *uv, *tvals;  // 498, 498, 461 (=1/rvals), 461
+};
+
+struct FluidSample {
+  float rho, p, bmag;
+  double u[4], b[4];
+};
+
+struct Field10 {
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0;
+};
+
+GRT_HD Field10 load_cell(const Cell *cells, size_t idx) {
+  Field10 f;
+#if defined(__CUDA_ARCH__)
+  const float4 *q = reinterpret_cast<const float4 *>(cells + idx);
+  float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  f.rho = a.x; f.p = a.y; f.vrl = a.z; f.vtl = a.w; f.vpl = b.x; f.b0 = b.y; f.br = b.z; f.bth = b.w; f.bph = c.x; f.u0 = c.y;
+#else
+  const Cell &c = cells[idx];
+  f.rho = c.rho; f.p = c.p; f.vrl = c.vrl; f.vtl = c.vtl; f.vpl = c.vpl; f.b0 = c.b0; f.br = c.br; f.bth = c.bth;
+  f.bph = c.bph; f.u0 = c.u0;
+#endif
+  return f;
+}
+
+#define GRT_FOR_FIELDS(OP) OP(rho) OP(p) OP(vrl) OP(vtl) OP(vpl) OP(b0) OP(br) OP(bth) OP(bph) OP(u0)
+
+// bilinear blend of four corners (interpolate.f90:171-182), all float32
+GRT_HD Field10 blend4(const Field10 &c0, const Field10 &c1, const Field10 &c2, const Field10 &c3, float xd, float yd) {
+  Field10 o;
+#define OP(f) { float w1 = c0.f * (1.f - yd) + c1.f * yd; float w2 = c2.f * (1.f - yd) + c3.f * yd; o.f = w1 * (1.f - xd) + w2 * xd; }
+  GRT_FOR_FIELDS(OP)
+#undef OP
+  return o;
+}
+
+// finish a gridded sample: b.b with the float32 metric, LNRF^-1 velocity, u^i = u^t v^i
+GRT_HD void finish_grid(FluidSample &s, const Field10 &v, bool in, float fill_vtl, float zr, float th, float a,
+                        double bfac) {
+  float vrl0 = in ? v.vrl : 0.f, vtl0 = in ? v.vtl : fill_vtl, vpl0 = in ? v.vpl : 0.f;
+  s.b[0] = in ? v.b0 : 1.f;
+  s.b[1] = in ? v.br : 1.f;
+  s.b[2] = in ? v.bth : 1.f;
+  s.b[3] = in ? v.bph : 1.f;
+  s.u[0] = in ? (double)v.u0 : 1.0;
+  MetricF mf = bl_metric_f(zr, th, a);
+  Metric m;
+  m.tt = mf.tt; m.tp = mf.tp; m.rr = mf.rr; m.hh = mf.hh; m.pp = mf.pp;
+  float bm = (float)mdot(m, s.b, s.b);
+  bm = ((double)bm >= 0.0) ? bm : 0.f;
+  bm = sqrtf(bm);
+  s.bmag = (float)((double)bm * bfac);
+  float vr0, vt0, vp0;
+  lnrf_inv_f(vrl0, vtl0, vpl0, zr, a, th, vr0, vt0, vp0);
+  s.u[1] = s.u[0] * (double)vr0;
+  s.u[2] = s.u[0] * (double)vt0;
+  s.u[3] = s.u[0] * (double)vp0;
+}
+
+// ---- Brent root finder specialised to the HARM theta(x2) map (math.f90:56-135, tol=1e-6) ---------
+GRT_HD double harm_x2_of_theta(double theta, double h) {
+  const double pi = GRT_PI, eps = 2.220446049250313e-16, tol = 1e-6;
+#define GRT_F(x) (theta - pi * (x) - .5 * (1 - h) * sin(2. * pi * (x)))
+  double a = 0.0, b = 1.0, c, d = 0, e = 0, fa = GRT_F(a), fb = GRT_F(b), fc, p, q, r, s, tol1, xm;
+  if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) return nan("");
+  c = b;
+  fc = fb;
+  for (int iter = 0; iter < 100; iter++) {
+    if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
+      c = a; fc = fa; d = b - a; e = d;
+    }
+    if (fabs(fc) < fabs(fb)) {
+      a = b; b = c; c = a; fa = fb; fb = fc; fc = fa;
+    }
+    tol1 = 2.0 * eps * fabs(b) + 0.5 * tol;
+    xm = 0.5 * (c - b);
+    if (fabs(xm) <= tol1 || fb == 0.0) return b;
+    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+      s = fb / fa;
+      if (a == c) {
+        p = 2.0 * xm * s;
+        q = 1.0 - s;
+      } else {
+        q = fa / fc;
+        r = fb / fc;
+        p = s * (2.0 * xm * q * (q - r) - (b - a) * (r - 1.0));
+        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      p = fabs(p);
+      if (2.0 * p < dmin(3.0 * xm * q - fabs(tol1 * q), fabs(e * q))) {
+        e = d;
+        d = p / q;
+      } else {
+        d = xm;
+        e = d;
+      }
+    } else {
+      d = xm;
+      e = d;
+    }
+    a = b;
+    fa = fb;
+    b = b + ((fabs(d) > tol1) ? d : (signbit(xm) ? -fabs(tol1) : fabs(tol1)));
+    fb = GRT_F(b);
+  }
+#undef GRT_F
+  return b;
+}
+
+// bracket search equivalent to NR hunt/locate for an in-range x (1-based result clamped to [1,n-1])
+GRT_HD int bracket(const float *xx /*0-based*/, int n, float x) {
+  bool ascnd = xx[n - 1] >= xx[0];
+  int jl = 0, ju = n + 1;
+  while (ju - jl > 1) {
+    int jm = (ju + jl) >> 1;
+    if (ascnd == (x >= xx[jm - 1]))
+      jl = jm;
+    else
+      ju = jm;
+  }
+  if (x == xx[0]) jl = 1;
+  if (x == xx[n - 1]) jl = n - 1;
+  if (jl < 1) jl = 1;
+  if (jl > n - 1) jl = n - 1;
+  return jl;
+}
+
+GRT_HD float krolik_c(float r, float a) {
+  float pif = acosf(-1.f);
+  float rms = isco_radius_f(a);
+  float y = sqrtf(r), yms = sqrtf(rms);
+  float ac = acosf(a);
+  float y1 = (float)(2.0 * (double)cosf(1.f / 3.f * (ac - pif)));
+  float y2 = (float)(2.0 * (double)cosf(1.f / 3.f * (ac + pif)));
+  float y3 = (float)(-2.0 * (double)cosf(1.f / 3.f * ac));
+  float arg1 = (float)((double)(3.f * a) / (2.0 * (double)y));
+  float arg2 = (float)(3.0 * sq((double)(y1 - a)) / (double)(y * y1 * (y1 - y2) * (y1 - y3)));
+  float arg3 = (float)(3.0 * sq((double)(y2 - a)) / (double)(y * y2 * (y2 - y1) * (y2 - y3)));
+  float arg4 = (float)(3.0 * sq((double)(y3 - a)) / (double)(y * y3 * (y3 - y1) * (y3 - y2)));
+  return 1.f - yms / y - arg1 * logf(y / yms) - arg2 * logf((y - y1) / (yms - y1)) - arg3 * logf((y - y2) / (yms - y2)) -
+         arg4 * logf((y - y3) / (yms - y3));
+}
+
+// ---- the sampler ---------------------------------------------------------------------------------
+GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, double phh, const double *k4,
+                          FluidSample &s) {
+  const double pi = GRT_PI;
+  // reference constants (phys_constants.f90)
+  const double pcG = 6.67e-8, pcc = 2.99792458e10, pcc2 = pcc * pcc, pcmsun = 1.998e33, pcmp = 1.67262158e-24,
+               pcsigt = 6.6523e-25, pcsigb = 5.6704e-5;
+  float a = (float)ad;
+  s.rho = s.p = s.bmag = 0.f;
+  for (int i = 0; i < 4; i++) s.u[i] = s.b[i] = 0.0;
+  switch (F.model) {
+    case FL_THINDISK: {
+      float r = (float)rr, th = (float)thh;
+      float MBH = F.td_mbh, Mdot = F.td_mdot;
+      float lbh = (float)((double)MBH * pcmsun * pcG / pcc2);
+      float b = 1.f - 3.f / r + 2.f * a / powf(r, 1.5f);
+      float rms = isco_radius_f(a);
+      float rin = fmaxf(rms, F.td_rin);
+      float kc = krolik_c(r, a);
+      float d = r * r - 2.f * r + a * a;
+      float lc = (rms * rms - 2.f * a * sqrtf(rms) + a * a) / (powf(rms, 1.5f) - 2.f * sqrtf(rms) + a);
+      float hc = (2.f * r - a * lc) / d;
+      float sn = sinf(th);
+      float ar = (r * r + a * a) * (r * r + a * a) - a * a * d * (sn * sn);
+      float om = 2.f * a * r / ar;
+      float Mdotedd = (float)(4. * pi * pcG * (double)MBH * pcmsun * pcmp * pcc / pcsigt / pcc2);
+      float T0 = (float)pow(3.0 / 8.0 / pi * pcG * (double)MBH * pcmsun * (double)Mdot * (double)Mdotedd / (double)lbh /
+                                (double)lbh / (double)lbh / pcsigb,
+                            0.25);
+      float omega;
+      if (r > rms)
+        omega = fmaxf(1.f / (powf(r, 1.5f) + a), om);
+      else
+        omega = fmaxf((lc + a * hc) / (r * r + 2.f * r * (1.f + hc)), om);
+      float T;
+      if (r > rin && r < F.td_rout)
+        T = T0 * powf(kc / b / powf(r, 3.f), 0.25f);
+      else
+        T = (float)((double)T0 / 1e5);
+      s.rho = T;
+      MetricF m = bl_metric_f(r, th, a);
+      double den = (double)m.tt + 2.0 * (double)m.tp * (double)omega + (double)(m.pp * omega * omega);
+      s.u[0] = sqrt(-1. / den);
+      s.u[3] = (double)omega * s.u[0];
+      disk_polvec(rr, cos(thh), k4, (double)a, asin(1.0), s.b);
+    } break;
+    case FL_SPHACC: {
+      float gamma = (float)(5.0 / 3.0), alpha = 0.25f, ninf = 1.f, Tinf = (float).917e-9, us = (float).94;
+      float u = (float)(1. / rr);
+      float n = (float)((double)(ninf * alpha / 4.f / us) * pow((double)(2 * gamma * Tinf), -1.5) * pow(2.0 * (double)u, 1.5));
+      int j = bracket(F.uv, 461, u);
+      float w = (u - F.uv[j - 1]) / (F.uv[j] - F.uv[j - 1]);
+      float T = (float)((1.0 - (double)w) * (double)F.tvals[j - 1] + (double)(w * F.tvals[j]));
+      float B = (float)sqrt(8. * pi * (double)n * pcmp / 2. * pcc2 * (double)u);
+      j = bracket(F.uvals, 498, u);
+      w = (u - F.uvals[j - 1]) / (F.uvals[j] - F.uvals[j - 1]);
+      float ur = (float)((1.0 - (double)w) * (double)F.vvals[j - 1] + (double)(w * F.vvals[j]));
+      float g00 = -(1.f - 2.f * u);
+      float grr = (float)(-1.0 / (double)g00);
+      s.u[1] = -(double)ur;
+      s.u[0] = sqrt((-(double)grr * s.u[1] * s.u[1] - 1) / (double)g00);
+      double B2 = (double)(B * B);
+      s.b[0] = sqrt(s.u[1] * s.u[1] * (double)grr * B2 /
+                    (s.u[1] * s.u[1] * (double)g00 * (double)grr + s.u[0] * s.u[0] * (double)g00 * (double)g00));
+      s.b[1] = -sqrt((double)((B * B) / grr) - s.b[0] * s.b[0] * (double)g00 / (double)grr);
+      s.rho = n;
+      s.p = T;
+      s.bmag = B;
+    } break;
+    case FL_FFJET: {
+      const int nx1 = F.nx1, nx2 = F.nx2;
+      float theta = (float)thh;
+      float zm = cosf(theta);
+      float x2 = acosf(fabsf(zm));
+      theta = x2;
+      float zr = (float)rr;
+      float x1 = logf(zr);
+      int lx1 = (int)((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
+      int lx2 = (int)((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;
+      lx2 = (lx2 <= (nx2 - 1)) ? ((lx2 >= 1) ? lx2 : 1) : (nx2 - 1);
+      int ux2 = lx2 + 1;
+      lx1 = lx1 < 1 ? 1 : (lx1 > nx1 - 1 ? nx1 - 1 : lx1);  // guard: reference discards these through merge()
+      int ux1 = lx1 + 1;
+      float td = (theta - F.axth[lx2 - 1]) / (F.axth[ux2 - 1] - F.axth[lx2 - 1]);
+      float rd = (zr - F.axr[lx1 - 1]) / (F.axr[ux1 - 1] - F.axr[lx1 - 1]);
+      int x1l = lx1 - 1, x1u = ux1 - 1, x2l = (lx2 - 1) * nx1, x2u = (ux2 - 1) * nx1;  // r fastest
+      Field10 v = blend4(load_cell(F.cells, x1l + x2l), load_cell(F.cells, x1l + x2u), load_cell(F.cells, x1u + x2l),
+                         load_cell(F.cells, x1u + x2u), rd, td);
+      bool in = x1 > F.ax1[0];
+      s.rho = in ? v.rho : 0.f;
+      s.p = in ? v.p : 1.f;
+      finish_grid(s, v, in, 1.f, zr, (float)thh, a, 1.0);
+    } break;
+    case FL_HARM: {
+      const int nx1 = F.nx1, nx2 = F.nx2;
+      float theta = (float)thh, zr = (float)rr;
+      float x1 = logf(zr);
+      float x2 = (float)harm_x2_of_theta((double)theta, (double)F.h);
+      int lx1 = (int)floorf((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
+      int lx2 = (int)floorf((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;
+      int ux2 = lx2 + 1;
+      lx2 = (lx2 >= 1) ? lx2 : 1;
+      ux2 = (ux2 <= nx2) ? ux2 : nx2;
+      float dth = (ux2 != lx2) ? (F.axth[ux2 - 1] - F.axth[lx2 - 1]) : F.axth[0];
+      float td = fabsf(theta - F.axth[lx2 - 1]) / dth;
+      lx1 = lx1 < 1 ? 1 : (lx1 > nx1 - 1 ? nx1 - 1 : lx1);  // guard
+      int ux1 = lx1 + 1;
+      float rd = (zr - F.axr[lx1 - 1]) / (F.axr[ux1 - 1] - F.axr[lx1 - 1]);
+      float rh = 1.f + sqrtf(1.f - a * a);
+      if (F.axr[lx1 - 1] <= rh) rd = 1.f;
+      int x2l = lx2 - 1, x2u = ux2 - 1, x1l = (lx1 - 1) * nx2, x1u = (ux1 - 1) * nx2;  // theta fastest
+      // trilinear with time weight 0 (rttd=0.) reduces to the first time slice: y=w1*(1-0)+w2*0
+      Field10 v = blend4(load_cell(F.cells, x1l + x2l), load_cell(F.cells, x1l + x2u), load_cell(F.cells, x1u + x2l),
+                         load_cell(F.cells, x1u + x2u), rd, td);
+#define OP(f) v.f = v.f * (1.f - 0.f) + v.f * 0.f;
+      GRT_FOR_FIELDS(OP)
+#undef OP
+      bool in = x1 > F.ax1[0];
+      s.rho = in ? v.rho : 0.f;
+      s.p = in ? v.p : 1.f;
+      finish_grid(s, v, in, 1.f, zr, (float)thh, a, 1.0);
+    } break;
+    case FL_HARM3D: {
+      const int nx1 = F.nx1, nx2 = F.nx2, nx3 = F.nx3;
+      float theta = (float)thh, zr = (float)rr, zpp = (float)phh;
+      double sq1 = sqrt(1. - (double)a * (double)a);
+      float zphi = (float)((double)zpp + (double)a / (2.0 * sq1) * log(((double)zr - 1. - sq1) / ((double)zr - 1. + sq1)));
+      zphi = (float)fmod((double)zphi, 2. * pi);
+      if (zphi < 0.f) zphi = (float)((double)zphi + 2. * pi);
+      float x1 = logf(zr), x3 = zphi;
+      float x2 = (float)((double)theta / pi);
+      int lx1 = (int)floorf((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
+      int lx2 = (int)floorf((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;
+      int ux2 = lx2 + 1;
+      int lx3 = (int)floorf((x3 - F.ax3[0]) / (F.ax3[nx3 - 1] - F.ax3[0]) * (float)(nx3 - 1)) + 1;
+      int ux3 = lx3 + 1;
+      lx2 = (lx2 <= (nx2 - 1)) ? ((lx2 >= 1) ? lx2 : 1) : (nx2 - 1);
+      lx1 = (lx1 >= 1) ? lx1 : 1;
+      int ux1 = lx1 + 1;
+      ux2 = (ux2 >= 1) ? ux2 : 1;
+      ux2 = (ux2 <= nx2) ? ux2 : nx2;
+      float dth = (ux2 != lx2) ? (F.axth[ux2 - 1] - F.axth[lx2 - 1]) : (F.axth[0] * 2);
+      int lx3s = lx3 < 1 ? 1 : (lx3 > nx3 ? nx3 : lx3);
+      float minph = F.ax3[lx3s - 1];
+      if (ux3 > nx3) ux3 = 1;
+      if (lx3 < 1) {
+        lx3 = nx3;
+        minph = (float)((double)F.ax3[lx3 - 1] - 2. * pi);
+      }
+      float pd = (zphi - minph) / (F.ax3[1] - F.ax3[0]);
+      float td = fabsf(theta - F.axth[lx2 - 1]) / dth;
+      if (ux1 > nx1) ux1 = nx1;  // guard beyond the outer edge
+      if (lx1 > nx1) lx1 = nx1;
+      float rd = (zr - F.axr[lx1 - 1]) / (F.axr[ux1 - 1] - F.axr[lx1 - 1]);
+      float rh = 1.f + sqrtf(1.f - a * a);
+      double fac = 1.0;
+      if (F.axr[lx1 - 1] <= fmaxf(F.axr[0], rh)) {
+        rd = 1.f;
+        fac = 1e-6;
+      }
+      size_t x3l = lx3 - 1, x3u = ux3 - 1, x2l = (size_t)(lx2 - 1) * nx3, x2u = (size_t)(ux2 - 1) * nx3;
+      size_t x1l = (size_t)(lx1 - 1) * nx2 * nx3, x1u = (size_t)(ux1 - 1) * nx2 * nx3;
+      // quadlininterp(vv, td=0, xd=pd, yd=rd, zd=td): theta, then r, then phi
+      Field10 lo = blend4(load_cell(F.cells, x1l + x2l + x3l), load_cell(F.cells, x1l + x2u + x3l),
+                          load_cell(F.cells, x1u + x2l + x3l), load_cell(F.cells, x1u + x2u + x3l), rd, td);
+      Field10 hi = blend4(load_cell(F.cells, x1l + x2l + x3u), load_cell(F.cells, x1l + x2u + x3u),
+                          load_cell(F.cells, x1u + x2l + x3u), load_cell(F.cells, x1u + x2u + x3u), rd, td);
+      Field10 v;
+#define OP(f) { float w1 = lo.f * (1.f - pd) + hi.f * pd; v.f = w1 * (1.f - 0.f) + w1 * 0.f; }
+      GRT_FOR_FIELDS(OP)
+#undef OP
+      bool in = x1 > F.ax1[0];
+      s.rho = (float)((double)v.rho * fac);
+      s.p = (float)((double)v.p * fac);
+      finish_grid(s, v, in, 0.f, zr, (float)thh, a, fac);
+    } break;
+    default:
+      break;
+  }
+}
+
+// ---- code units -> cgs (convert_fluid_vars_arr and the per-model converters) -----------------------
+struct SourceDev {
+  double nfac, bfac, mbh, mdot, p1, p2, gmax, gminval, jetalphaval, muval, sigcut;
+};
+struct CgsVars {
+  double ncgs, ncgsnth, bcgs, tcgs;
+};
+
+GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bmag, CgsVars &o) {
+  const double pi = GRT_PI;
+  const double pcG = 6.67e-8, pcc = 2.99792458e10, pcmsun = 1.998e33, pcmp = 1.67262158e-24, pck = 1.38e-16;
+  o.ncgs = o.ncgsnth = o.bcgs = o.tcgs = 0.0;
+  switch (model) {
+    case FL_SPHACC:
+      o.ncgs = rho; o.bcgs = bmag; o.tcgs = p;
+      break;
+    case FL_FFJET:
+      o.ncgsnth = (double)rho * sp.nfac; o.bcgs = (double)bmag * sp.bfac;
+      break;
+    case FL_THINDISK:
+      o.tcgs = rho; o.ncgs = 1.;
+      break;
+    case FL_HARM:
+    case FL_HARM3D: {
+      double mdot = (model == FL_HARM) ? .003 : pcG * sp.mbh * pcmsun / (pcc * pcc * pcc);
+      double lcgs = pcG * sp.mbh * pcmsun / (pcc * pcc), tcg = lcgs / pcc;
+      double rhocgs = sp.mdot / mdot / (lcgs * lcgs * lcgs) * tcg * (double)rho;
+      o.ncgs = rhocgs / pcmp;
+      double pcgs = (double)p * rhocgs / (double)rho * (pcc * pcc);
+      o.tcgs = pcgs / o.ncgs / pck;
+      o.bcgs = (double)bmag * sqrt(rhocgs / (double)rho) * pcc;
+      o.bcgs = o.bcgs * sqrt(4.0 * pi);
+      double beta = (double)(p / (bmag * bmag)) / 0.5;
+      double b2 = beta * beta;
+      if (model == FL_HARM) {
+        double rlow = sp.muval, rhigh = sp.muval / sp.gminval;
+        double trat = ((double)bmag > 0.0) ? rhigh * b2 / (1.0 + b2) + rlow / (1.0 + b2) : rhigh;
+        o.tcgs = o.tcgs * trat;
+        o.ncgsnth = o.ncgs;
+      } else {
+        double rlow = 1.0 / sp.muval - 1.0, rhigh = sp.gminval * (1.0 / sp.muval - 1.0);
+        double trat = ((double)bmag > 0.0) ? rhigh * b2 / (1.0 + b2) + rlow / (1.0 + b2) : rhigh;
+        o.tcgs = o.tcgs / (1.0 + trat);
+        double bmagrho = sq((double)bmag) / (double)rho;
+        o.ncgsnth = (bmagrho > 1.0)
+                        ? sp.jetalphaval * sq(o.bcgs) / 8.0 / pi / sp.gminval * (sp.p1 - 2.0) / (sp.p1 - 1.0) / 8.2e-7
+                        : 0.0;
+        double rc2 = o.ncgs * pcmp;
+        double sigmacgs = (o.bcgs * o.bcgs) / (rc2 * 8.988e20 * 4.0 * pi);
+        if (sigmacgs >= sp.sigcut) {
+          o.ncgs = 0.0;
+          o.tcgs = 1e9;
+        }
+      }
+    } break;
+    default:
+      break;
+  }
+}
+
+}  // namespace grt

@@ -1,0 +1,57 @@
+// grtrans_b200 -- host-side declarations shared by the engine (CUDA) and the I/O layer.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/grtrans_b200.h"
+
+namespace grt_host {
+
+// ---- camera (R1): geokerr_wrapper.f:1-354 INITIALIZE_CAMERA_GEOKERR + geodesics.f90:64-111 -----------
+struct Camera {
+  int standard = 1, nro = 0, nphi = 0, nup = 0;
+  int usegeor = 0, phit = 1, mufill = 0, kext = 0, next = 0;
+  double a = 0, mu0 = 0, phi0 = 0, uout = 0, u0 = 0, offset = 0.5;
+  std::vector<double> alpha, beta, q2, l, su, sm, uf, muf;
+  std::vector<int> tpm, tpr;
+  int maxpts() const { return nup + next - 2 * kext; }
+};
+void build_camera(Camera &c, int standard, double mu0, double phi0, double a, double uout, double rcut, int nrotype,
+                  const double gridvals[4], int nro, int nphi, int nup);
+
+// ---- fluid snapshot on the host (reference module state of fluid_model_*.f90) --------------------------
+struct HostCell {
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, pad0, pad1;
+};
+struct FluidHost {
+  int model = 0, nx1 = 0, nx2 = 0, nx3 = 1;
+  float h = 0, asim = 0, gam = 0;
+  float td_mbh = 0, td_mdot = 0, td_rin = 0, td_rout = 0;
+  std::vector<float> ax1, axr, ax2, axth, ax3;
+  std::vector<HostCell> cells;
+  std::vector<float> uvals, vvals, uv, tvals;
+};
+// returns GRT_OK / GRT_ERR_IO / GRT_ERR_BAD_ARG
+int load_fluid(FluidHost &f, const grt_args &a);
+
+// emissivity tables (log of the tabulated G(x) integrals; Chandrasekhar table)
+struct EmisTablesHost {
+  std::vector<double> gx, gy, xv, ya, yp, yv, yap, yav;
+  std::vector<float> ch_mu, ch_I, ch_del;
+};
+void build_emis_tables(EmisTablesHost &t);
+
+int fluid_model_id(const std::string &fname);                 // fluid.f90:283-377 (supported subset)
+int emis_type_id(const std::string &ename, int *neq);         // emis.f90:294-367
+int integrator_flag(const std::string &iname);                // rad_trans.f90:30-38
+
+void make_grids(const grt_args &a, std::vector<double> &freqs, std::vector<double> &mdots, std::vector<double> &mu0);
+
+// ---- namelists / output -----------------------------------------------------------------------------
+int read_inputs_file(const char *ifile, grt_args *a);                      // read_inputs.f90:47-100
+int read_files_in(const char *path, std::string &ifile, std::string &ofile);  // grtrans_program.f90
+// camera.f90:156-344 kwrite_raytrace_camera for all cameras; pixvals [ncams][npix][nv] float32
+int write_output(const grt_args &a, const char *outfile, int nx, int ny, int nv, int ncams, const float *pixloc,
+                 const float *pixvals, const std::vector<double> &freqs);
+
+}  // namespace grt_host

@@ -1,0 +1,312 @@
+// grtrans_b200 -- device math primitives for the Kerr geodesic kernels (sm_100a, FP64).
+//
+// Carlson symmetric elliptic integrals R_F, R_C, R_D, R_J by the duplication theorem, Jacobi
+// sn/cn/dn by the descending Landen/AGM recurrence and a small complex type for Laguerre root
+// polishing.  Tolerances and series coefficients are the ones the reference uses
+// (geokerr_wrapper.f:3277-3346 SNCNDN CA=3e-8, :3444 rf ERRTOL=.0025, :3608 rc .0012,
+// :3648 rd .0015, :3697 rj .0015) so iteration counts -- and therefore results -- agree to
+// round-off with the Fortran.
+//
+// Everything here is __host__ __device__ so the same kernel code can be driven on the CPU by
+// tests/host_emul (a debugging harness; the product only ever launches the CUDA kernels).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define GRT_HD __host__ __device__ __forceinline__
+#define GRT_HDN __host__ __device__ __noinline__
+#else
+#define GRT_HD inline
+#define GRT_HDN
+#endif
+
+namespace grt {
+
+GRT_HD double dmax(double a, double b) { return a > b ? a : b; }
+GRT_HD double dmin(double a, double b) { return a < b ? a : b; }
+GRT_HD double sgn(double b) { return signbit(b) ? -1.0 : 1.0; }      // Fortran SIGN(1d0,b)
+GRT_HD double pm1(int n) { return (n & 1) ? -1.0 : 1.0; }            // (-1)**n
+GRT_HD double sq(double x) { return x * x; }
+
+// ---- Carlson R_F ------------------------------------------------------------------------------
+GRT_HDN double rf(double x, double y, double z) {
+  double ave, dx, dy, dz;
+  do {
+    double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
+    double lam = sx * (sy + sz) + sy * sz;
+    x = 0.25 * (x + lam);
+    y = 0.25 * (y + lam);
+    z = 0.25 * (z + lam);
+    ave = (1.0 / 3.0) * (x + y + z);
+    if (ave == 0.0) {
+      dx = dy = dz = 0.0;
+    } else {
+      dx = (ave - x) / ave;
+      dy = (ave - y) / ave;
+      dz = (ave - z) / ave;
+    }
+  } while (dmax(dmax(fabs(dx), fabs(dy)), fabs(dz)) > 0.0025);
+  double e2 = dx * dy - dz * dz, e3 = dx * dy * dz;
+  return (1.0 + ((1.0 / 24.0) * e2 - 0.1 - (3.0 / 44.0) * e3) * e2 + (1.0 / 14.0) * e3) / sqrt(ave);
+}
+
+// ---- Carlson R_C ------------------------------------------------------------------------------
+GRT_HDN double rc(double x, double y) {
+  double w = 1.0;
+  if (!(y > 0.0)) {
+    double xt = x - y;
+    w = sqrt(x) / sqrt(xt);
+    x = xt;
+    y = -y;
+  }
+  double ave, s;
+  do {
+    double lam = 2.0 * sqrt(x) * sqrt(y) + y;
+    x = 0.25 * (x + lam);
+    y = 0.25 * (y + lam);
+    ave = (1.0 / 3.0) * (x + y + y);
+    s = (y - ave) / ave;
+  } while (fabs(s) > 0.0012);
+  return w * (1.0 + s * s * (0.3 + s * ((1.0 / 7.0) + s * (0.375 + s * (9.0 / 22.0))))) / sqrt(ave);
+}
+
+// ---- Carlson R_D ------------------------------------------------------------------------------
+GRT_HDN double rd(double x, double y, double z) {
+  const double C1 = 3.0 / 14.0, C2 = 1.0 / 6.0, C3 = 9.0 / 22.0, C4 = 3.0 / 26.0, C5 = 0.25 * C3, C6 = 1.5 * C4;
+  double sum = 0.0, fac = 1.0, ave, dx, dy, dz;
+  do {
+    double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
+    double lam = sx * (sy + sz) + sy * sz;
+    sum += fac / (sz * (z + lam));
+    fac *= 0.25;
+    x = 0.25 * (x + lam);
+    y = 0.25 * (y + lam);
+    z = 0.25 * (z + lam);
+    ave = 0.2 * (x + y + 3.0 * z);
+    dx = (ave - x) / ave;
+    dy = (ave - y) / ave;
+    dz = (ave - z) / ave;
+  } while (dmax(dmax(fabs(dx), fabs(dy)), fabs(dz)) > 0.0015);
+  double ea = dx * dy, eb = dz * dz, ec = ea - eb, ed = ea - 6.0 * eb, ee = ed + ec + ec;
+  return 3.0 * sum +
+         fac * (1.0 + ed * (-C1 + C5 * ed - C6 * dz * ee) + dz * (C2 * ee + dz * (-C3 * ec + dz * C4 * ea))) /
+             (ave * sqrt(ave));
+}
+
+// ---- Carlson R_J (p<=0 handled through the Cauchy principal value transformation) ---------------
+GRT_HDN double rj(double x, double y, double z, double p) {
+  const double C1 = 3.0 / 14.0, C2 = 1.0 / 3.0, C3 = 3.0 / 22.0, C4 = 3.0 / 26.0, C5 = 0.75 * C3, C6 = 1.5 * C4,
+               C7 = 0.5 * C2, C8 = C3 + C3;
+  double a = 0.0, b = 0.0, rcx = 0.0;
+  const bool neg = !(p > 0.0);
+  if (neg) {
+    double lo = dmin(dmin(x, y), z), hi = dmax(dmax(x, y), z);
+    double mid = x + y + z - lo - hi;
+    a = 1.0 / (mid - p);
+    b = a * (hi - mid) * (mid - lo);
+    double pt = mid + b;
+    rcx = rc(lo * hi / mid, p * pt / mid);
+    x = lo;
+    y = mid;
+    z = hi;
+    p = pt;
+  }
+  double sum = 0.0, fac = 1.0, ave, dx, dy, dz, dp;
+  do {
+    double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
+    double lam = sx * (sy + sz) + sy * sz;
+    double al = sq(p * (sx + sy + sz) + sx * sy * sz);
+    double be = p * sq(p + lam);
+    sum += fac * rc(al, be);
+    fac *= 0.25;
+    x = 0.25 * (x + lam);
+    y = 0.25 * (y + lam);
+    z = 0.25 * (z + lam);
+    p = 0.25 * (p + lam);
+    ave = 0.2 * (x + y + z + p + p);
+    dx = (ave - x) / ave;
+    dy = (ave - y) / ave;
+    dz = (ave - z) / ave;
+    dp = (ave - p) / ave;
+  } while (dmax(dmax(fabs(dx), fabs(dy)), dmax(fabs(dz), fabs(dp))) > 0.0015);
+  double ea = dx * (dy + dz) + dy * dz, eb = dx * dy * dz, ec = dp * dp, ed = ea - 3.0 * ec,
+         ee = eb + 2.0 * dp * (ea - ec);
+  double r = 3.0 * sum + fac *
+                             (1.0 + ed * (-C1 + C5 * ed - C6 * ee) + eb * (C7 + dp * (-C8 + dp * C4)) +
+                              dp * ea * (C2 - dp * C3) - C2 * dp * ec) /
+                             (ave * sqrt(ave));
+  if (neg) r = a * (b * r + 3.0 * (rcx - rf(x, y, z)));
+  return r;
+}
+
+// ---- Jacobi elliptic functions sn, cn, dn for parameter complement emmc = 1-k^2 ------------------
+GRT_HDN void sncndn(double u, double emc, double &sn, double &cn, double &dn) {
+  if (emc == 0.0) {
+    cn = 1.0 / cosh(u);
+    dn = cn;
+    sn = tanh(u);
+    return;
+  }
+  double em[13], en[13];
+  const bool bo = emc < 0.0;
+  double d = 1.0;
+  if (bo) {
+    d = 1.0 - emc;
+    emc = -emc / d;
+    d = sqrt(d);
+    u = d * u;
+  }
+  double a = 1.0, c = 0.0;
+  dn = 1.0;
+  int l = 0;
+  for (int i = 0; i < 13; i++) {
+    l = i;
+    em[i] = a;
+    emc = sqrt(emc);
+    en[i] = emc;
+    c = 0.5 * (a + emc);
+    if (fabs(a - emc) <= 3.e-8 * a) break;
+    emc = a * emc;
+    a = c;
+  }
+  u = c * u;
+  sn = sin(u);
+  cn = cos(u);
+  if (sn != 0.0) {
+    a = cn / sn;
+    c = a * c;
+    for (int i = l; i >= 0; i--) {
+      double b = em[i];
+      a = c * a;
+      c = dn * c;
+      dn = (en[i] + a) / (b + a);
+      a = c / b;
+    }
+    a = 1.0 / sqrt(c * c + 1.0);
+    sn = (sn < 0.0) ? -a : a;
+    cn = c * sn;
+  }
+  if (bo) {
+    a = dn;
+    dn = cn;
+    cn = a;
+    sn = sn / d;
+  }
+}
+
+// ---- minimal complex arithmetic (naive multiply, Smith divide: Fortran rules) --------------------
+struct cpx {
+  double re, im;
+};
+GRT_HD cpx cmk(double r, double i) {
+  cpx z;
+  z.re = r;
+  z.im = i;
+  return z;
+}
+GRT_HD cpx cadd(cpx a, cpx b) { return cmk(a.re + b.re, a.im + b.im); }
+GRT_HD cpx csub(cpx a, cpx b) { return cmk(a.re - b.re, a.im - b.im); }
+GRT_HD cpx cmul(cpx a, cpx b) { return cmk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+GRT_HD cpx cscale(cpx a, double s) { return cmk(a.re * s, a.im * s); }
+GRT_HD double cabs_(cpx a) { return hypot(a.re, a.im); }
+GRT_HD cpx cdiv(cpx a, cpx b) {
+  if (fabs(b.re) >= fabs(b.im)) {
+    double r = b.im / b.re, den = b.re + r * b.im;
+    return cmk((a.re + a.im * r) / den, (a.im - a.re * r) / den);
+  }
+  double r = b.re / b.im, den = b.im + r * b.re;
+  return cmk((a.re * r + a.im) / den, (a.im * r - a.re) / den);
+}
+GRT_HD cpx csqrt_(cpx z) {  // principal branch
+  double m = cabs_(z);
+  if (m == 0.0) return cmk(0.0, 0.0);
+  double t = sqrt(0.5 * (m + fabs(z.re)));
+  if (z.re >= 0.0) return cmk(t, z.im / (2.0 * t));
+  return cmk(fabs(z.im) / (2.0 * t), (signbit(z.im) ? -t : t));
+}
+
+// Laguerre iteration on a polynomial with coefficients A[0..M] (A[0] constant term)
+// (Numerical-Recipes LAGUER as used by the reference, geokerr_wrapper.f:3533-3606)
+GRT_HDN void laguer(const cpx *A, int M, cpx &X) {
+  const double frac[9] = {0., 0.5, 0.25, 0.75, 0.13, 0.38, 0.62, 0.88, 1.0};
+  for (int it = 1; it <= 80; it++) {
+    cpx B = A[M], D = cmk(0., 0.), F = cmk(0., 0.);
+    double err = cabs_(B), abx = cabs_(X);
+    for (int j = M - 1; j >= 0; j--) {
+      F = cadd(cmul(X, F), D);
+      D = cadd(cmul(X, D), B);
+      B = cadd(cmul(X, B), A[j]);
+      err = cabs_(B) + abx * err;
+    }
+    err *= 1.e-15;
+    if (cabs_(B) <= err) return;
+    cpx G = cdiv(D, B);
+    cpx G2 = cmul(G, G);
+    cpx H = csub(G2, cscale(cdiv(F, B), 2.0));
+    cpx SQ = csqrt_(cscale(csub(cscale(H, (double)M), G2), (double)(M - 1)));
+    cpx GP = cadd(G, SQ), GM = csub(G, SQ);
+    double abp = cabs_(GP), abm = cabs_(GM);
+    if (abp < abm) GP = GM;
+    cpx DX;
+    if (dmax(abp, abm) > 0.0) {
+      DX = cdiv(cmk((double)M, 0.0), GP);
+    } else {
+      float mag = expf((float)log(1.0 + abx));
+      DX = cmk((double)(mag * cosf((float)it)), (double)(mag * sinf((float)it)));
+    }
+    cpx X1 = csub(X, DX);
+    if (X.re == X1.re && X.im == X1.im) return;
+    if (it % 10 != 0)
+      X = X1;
+    else
+      X = csub(X, cscale(DX, frac[it / 10]));
+  }
+}
+
+// All roots of a real-coefficient polynomial of degree M<=6, sorted by real part
+// (ZROOTS with polishing, geokerr_wrapper.f:3348-3441, including its start-point heuristic).
+GRT_HDN void zroots(const double *coef, int M, cpx *roots) {
+  cpx A[7], AD[7];
+  for (int j = 0; j <= M; j++) {
+    A[j] = cmk(coef[j], 0.0);
+    AD[j] = A[j];
+  }
+  cpx xstart = cmk(0., 0.);
+  int ncc = 0;
+  for (int j = M; j >= 1; j--) {  // j = current degree; root index j-1
+    cpx X = xstart;
+    if (j < M) {
+      if (roots[j].im != 0.0 && ncc == 0) {
+        xstart = cmk(roots[j].re, -roots[j].re);
+        ncc = 1;
+      } else {
+        xstart = cmk(0., 0.);
+        ncc = 0;
+      }
+    } else {
+      xstart = cmk(0., 0.);
+      ncc = 0;
+    }
+    laguer(AD, j, X);
+    if (fabs(X.im) <= 2.0 * 1e-6 * 1e-6 * fabs(X.re)) X.im = 0.0;
+    roots[j - 1] = X;
+    cpx B = AD[j];
+    for (int jj = j - 1; jj >= 0; jj--) {
+      cpx C = AD[jj];
+      AD[jj] = B;
+      B = cadd(cmul(X, B), C);
+    }
+  }
+  for (int j = 0; j < M; j++) laguer(A, M, roots[j]);
+  for (int j = 1; j < M; j++) {  // insertion sort on the real part
+    cpx X = roots[j];
+    int i = j - 1;
+    while (i >= 0 && roots[i].re > X.re) {
+      roots[i + 1] = roots[i];
+      i--;
+    }
+    roots[i + 1] = X;
+  }
+}
+
+}  // namespace grt

@@ -1,0 +1,156 @@
+// grtrans_b200 -- per-ray / per-point stage bodies shared by the CUDA kernels (grt_engine.cu) and the
+// CPU debugging harness (tests/host_emul).  See grt_engine.cu for the pipeline description.
+#pragma once
+#include "grt_geokerr.cuh"
+#include "grt_transfer.cuh"
+
+namespace grt {
+
+struct PointArrays {  // raw geokerr outputs, [ray][maxpts]
+  double *u, *mu, *dt, *dphi, *lam;
+  signed char *tpm, *tpr;
+};
+
+struct RayMeta {  // per ray after finalize
+  int i1, npts, status;
+  double lamN, dt1;
+};
+
+struct StageDump {  // optional per-point outputs for parity tests (device pointers or null)
+  double *lambda, *t, *r, *th, *ph, *kt, *kr, *kth, *kph, *u, *b, *s2xi, *c2xi, *ang, *rshift, *cosne, *ncgs, *ncgsnth,
+      *bcgs, *tcgs;
+  float *rho, *p, *bmag;
+};
+
+struct FluidKernelArgs {
+  FluidDev F;
+  SourceDev sp[8];
+  int nparams, etype, maxpts;
+  EmisTables tab;
+};
+
+GRT_HD void point_store(const RayInv &c, int nup, int slot, size_t idx, PointArrays pa) {
+  GeoPoint p;
+  bool ok = slot < c.npts && geo_point(c, nup, slot, p);
+  if (!ok) {
+    p.u = 0.0; p.mu = 0.0; p.dt = 0.0; p.dphi = 0.0; p.lam = 0.0; p.tpm = 0; p.tpr = 0;
+  }
+  pa.u[idx] = p.u; pa.mu[idx] = p.mu; pa.dt[idx] = p.dt; pa.dphi[idx] = p.dphi; pa.lam[idx] = p.lam;
+  pa.tpm[idx] = (signed char)p.tpm; pa.tpr[idx] = (signed char)p.tpr;
+}
+
+// geodesics.f90:294-323 (trim u<0 ends, standard=2 only), :255 (status), :343-347 (reference values)
+GRT_HD void ray_finalize(int npts, size_t i, int maxpts, int usegeor, PointArrays pa, RayMeta &m) {
+  const double *u = pa.u + i * maxpts;
+  int i1 = 1, i2 = npts;
+  if (usegeor && npts > 1) {
+    if (u[0] < 0.0)
+      for (int ii = 2; ii <= npts; ii++)
+        if (u[ii - 1] >= 0.0) {
+          i1 = ii;
+          break;
+        }
+    if (u[npts - 1] < 0.0)
+      for (int ii = 1; ii <= npts - 1; ii++)
+        if (u[npts - ii - 1] >= 0.0) {
+          i2 = npts - ii;
+          break;
+        }
+    npts = i2 - i1 + 1;
+  }
+  double sumr = 0.0;
+  for (int k = 0; k < npts; k++) sumr += 1.0 / u[i1 - 1 + k];
+  m.i1 = i1;
+  m.npts = npts;
+  m.status = (sumr < 0.0) ? -1 : 1;
+  // (sic) LAMBDAI(g%npts): the trimmed COUNT indexes the untrimmed array
+  m.lamN = (npts >= 1) ? pa.lam[i * maxpts + (npts - 1)] : 0.0;
+  m.dt1 = pa.dt[i * maxpts];
+}
+
+// x^mu, k^mu, fluid sample, comoving frame, unit conversion and the 128-byte point record(s)
+GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernelArgs &A, int ray, int slot, int nrays,
+                         PointArrays pa, double *rec, StageDump sd) {
+  const int maxpts = A.maxpts;
+  if (m.status != 1 || slot >= m.npts) return;
+  size_t src = (size_t)ray * maxpts + (m.i1 - 1) + slot;
+  double u = pa.u[src], mu = pa.mu[src];
+  double r = 1.0 / u, th = acos(mu);
+  // g%gk%phi0 = acos(-1.)*phi0 : pi in SINGLE precision (geodesics.f90:218)
+  double ph = (double)acosf(-1.f) * r0.phi0 - pa.dphi[src];
+  if (fabs(r0.mu0) == 1.0) ph += sgn(r0.mu0) * atan2(r0.beta, r0.alpha);
+  double lam, t;
+  int tpm, tpr;
+  if (m.npts != 1) {
+    lam = m.lamN - pa.lam[src];
+    t = m.dt1 - pa.dt[src] - r0.t0;
+    tpm = pa.tpm[src];
+    tpr = pa.tpr[src];
+  } else {
+    size_t s1 = (size_t)ray * maxpts;
+    lam = pa.lam[s1];
+    t = pa.dt[s1];
+    tpm = pa.tpm[s1];
+    tpr = pa.tpr[s1];
+  }
+  double k4[4];
+  null_momentum(r0.q2, r0.l, r0.a, r, cos(th), r0.su * pm1(tpr), r0.sm * pm1(tpm), k4);
+  FluidSample fs;
+  fluid_sample(A.F, r0.a, r, th, ph, k4, fs);
+  OrthoOut oo;
+  comoving_ortho(r, th, r0.a, r0.alpha, r0.beta, r0.mu0, fs.u, fs.b, k4, oo);
+  size_t dst = (size_t)ray * maxpts + slot;
+  for (int mm = 0; mm < A.nparams; mm++) {
+    CgsVars cg;
+    to_cgs(A.F.model, A.sp[mm], fs.rho, fs.p, fs.bmag, cg);
+    double *q = rec + ((size_t)mm * nrays * maxpts + dst) * GRT_NREC;
+    double o[GRT_NREC];
+    for (int i = 0; i < GRT_NREC; i++) o[i] = 0.0;
+    o[0] = lam; o[1] = oo.g; o[2] = oo.s2xi; o[3] = oo.c2xi;
+    switch (A.etype) {
+      case EM_POLSYNCHTH: {
+        ThermalPoint T;
+        thermal_point(cg.ncgs, cg.bcgs, cg.tcgs, oo.ang, T);
+        o[4] = T.n; o[5] = T.b; o[6] = T.t; o[7] = T.sinth; o[8] = T.costh; o[9] = T.k0; o[10] = T.k1ok2; o[11] = T.ik2;
+        o[12] = T.step; o[13] = T.tanth;
+      } break;
+      case EM_POLSYNCHPL:
+      case EM_SYNCHPL:
+        o[4] = cg.ncgsnth; o[5] = cg.bcgs; o[6] = oo.ang;
+        break;
+      case EM_SYNCHTHAV:
+        o[4] = cg.ncgs; o[5] = cg.bcgs; o[6] = cg.tcgs;
+        break;
+      case EM_BB:
+        o[6] = cg.tcgs;
+        break;
+      case EM_BBPOL: {
+        float cI, cdel;
+        chandra_interp(A.tab, (float)oo.cosne, cI, cdel);
+        o[6] = cg.tcgs; o[7] = (double)cI; o[8] = (double)cdel;
+      } break;
+    }
+#if defined(__CUDA_ARCH__)
+    double2 *q2 = reinterpret_cast<double2 *>(q);
+#pragma unroll
+    for (int i = 0; i < GRT_NREC / 2; i++) q2[i] = make_double2(o[2 * i], o[2 * i + 1]);
+#else
+    for (int i = 0; i < GRT_NREC; i++) q[i] = o[i];
+#endif
+    if (mm == 0 && sd.ncgs) {
+      sd.ncgs[dst] = cg.ncgs; sd.ncgsnth[dst] = cg.ncgsnth; sd.bcgs[dst] = cg.bcgs; sd.tcgs[dst] = cg.tcgs;
+    }
+  }
+  if (sd.lambda) {
+    sd.lambda[dst] = lam; sd.t[dst] = t; sd.r[dst] = r; sd.th[dst] = th; sd.ph[dst] = ph;
+    sd.kt[dst] = k4[0]; sd.kr[dst] = k4[1]; sd.kth[dst] = k4[2]; sd.kph[dst] = k4[3];
+    for (int i = 0; i < 4; i++) {
+      sd.u[dst * 4 + i] = fs.u[i];
+      sd.b[dst * 4 + i] = fs.b[i];
+    }
+    sd.s2xi[dst] = oo.s2xi; sd.c2xi[dst] = oo.c2xi; sd.ang[dst] = oo.ang; sd.rshift[dst] = oo.g; sd.cosne[dst] = oo.cosne;
+    sd.rho[dst] = fs.rho; sd.p[dst] = fs.p; sd.bmag[dst] = fs.bmag;
+  }
+}
+
+}  // namespace grt

@@ -131,6 +131,11 @@ void grt_session_destroy(grt_session *s);
 /* launch the whole per-pixel path for this rank's rays on the session stream (asynchronous) */
 int grt_session_launch(grt_session *s);
 int grt_session_sync(grt_session *s);
+/* host->device half of an end-to-end step: re-copy camera constants, fluid snapshot and frequency grid from the
+ * session's host buffers; *bytes = bytes copied */
+int grt_session_upload(grt_session *s, long long *bytes);
+/* nsteps back-to-back passes bracketed by CUDA events on the session stream; *ms = elapsed device time */
+int grt_session_run_timed(grt_session *s, int nsteps, float *ms);
 /* one launch bracketed by CUDA events on the session stream; ms for the whole path and per stage
  * (stage_ms[0..3] = ray setup, geodesic points, fluid+ortho, emissivity+transfer) */
 int grt_session_time(grt_session *s, float *total_ms, float stage_ms[4]);

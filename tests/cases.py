@@ -1,0 +1,82 @@
+"""Shared test configurations (BASELINE.json configs at oracle-affordable sizes)."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+FFJET_BIN = os.path.join(HERE, "data", "m87bl09rfp10xi5a998fluidvars.bin")
+SNAPDIR = os.environ.get("GRT_SNAPDIR", "/tmp/grt_snap")
+
+
+def snapshots():
+    import make_snapshot as ms
+    os.makedirs(SNAPDIR, exist_ok=True)
+    p2 = os.path.join(SNAPDIR, "dump040")
+    if not os.path.exists(p2):
+        ms.write_harm2d(os.path.join(SNAPDIR, "dump"), indf=40)
+    p3 = os.path.join(SNAPDIR, "h3d_small.bin")
+    if not os.path.exists(p3):
+        ms.write_harm3d(p3)
+    return os.path.join(SNAPDIR, "dump"), p2, p3
+
+
+def cfg_thindisk(n=60, nfreq=5, **kw):
+    d = dict(standard=2, nn=[n, n, 1], nmu=1, mumin=.5, mumax=.5, spin=.998, nfreq=nfreq, fmin=2.41e17, fmax=6.31e18,
+             mbh=10., fname='THINDISK', ename='BB', nvals=1)
+    d.update(kw)
+    return d
+
+
+def cfg_sphacc(n=40, nup=100, nfreq=5, iname='delo', **kw):
+    d = dict(fname='SPHACC', nfreq=nfreq, nmu=1, fmin=2.41e11, fmax=6.31e14, ename='POLSYNCHTH', nvals=4, spin=0., mbh=10.,
+             standard=1, nn=[n, n, nup], uout=.04, mumin=.5, mumax=.5, gridvals=[-15., 15., -15., 15.], iname=iname)
+    d.update(kw)
+    return d
+
+
+def cfg_ffjet(n=40, nup=100, nfreq=3, iname='delo', **kw):
+    d = dict(fname='FFJET', fdfile=FFJET_BIN, nfreq=nfreq, nmu=1, fmin=2.41e10, fmax=6.31e14, ename='POLSYNCHPL', nvals=4,
+             spin=0.998, standard=1, nn=[n, n, nup], uout=0.01, mbh=6.4e9, mumin=.906, mumax=.906,
+             gridvals=[-40., 20., -20., 40.], ntscl=2., nrscl=70., iname=iname)
+    d.update(kw)
+    return d
+
+
+def cfg_harm(n=40, nup=100, nfreq=2, iname='delo', **kw):
+    pre, dump, _ = snapshots()
+    d = dict(fname='HARM', ename='POLSYNCHTH', nvals=4, iname=iname, spin=.9375, standard=1, nn=[n, n, nup], uout=.04, mbh=4e6,
+             mdotmin=1.57e15, mdotmax=1.57e15, nmu=1, mumin=.6428, mumax=.6428, gridvals=[-13., 13., -13., 13.], nfreq=nfreq,
+             fmin=2.3e11, fmax=1e12, muval=.25, gmin=1., fdfile=pre, fhfile=dump, findf=40)
+    d.update(kw)
+    return d
+
+
+def cfg_harm3d(n=40, nup=100, nfreq=4, iname='delo', **kw):
+    _, _, p3 = snapshots()
+    d = dict(fname='HARM3D', ename='POLSYNCHTH', nvals=4, iname=iname, spin=.9375, standard=1, nn=[n, n, nup], uout=.04,
+             mbh=4e6, mdotmin=1e20, mdotmax=1e20, nmu=1, mumin=.6428, mumax=.6428, gridvals=[-13., 13., -13., 13.],
+             nfreq=nfreq, fmin=1e10, fmax=1e13, muval=.25, gmin=1., fdfile=p3)
+    d.update(kw)
+    return d
+
+
+def image_errors(got, ref):
+    """got/ref: ivals[nvals,npix,ncams].  Returns (max rel dI over pixels with I > 1e-4 Imax per camera, flux error,
+    max |dQUV|/Imax, nan masks equal)."""
+    import numpy as np
+    nanok = np.array_equal(np.isnan(got), np.isnan(ref))
+    g = np.nan_to_num(got); r = np.nan_to_num(ref)
+    relI = 0.; flux = 0.; quv = 0.
+    for k in range(r.shape[2]):
+        I = r[0, :, k]
+        Imax = np.abs(I).max()
+        if Imax == 0.:
+            assert np.abs(g[0, :, k]).max() == 0.
+            continue
+        w = np.abs(I) > 1e-4 * Imax
+        relI = max(relI, np.max(np.abs(g[0, w, k] - I[w]) / np.abs(I[w])))
+        flux = max(flux, abs(g[0, :, k].sum() - I.sum()) / abs(I.sum()))
+        if r.shape[0] == 4:
+            quv = max(quv, np.abs(g[1:, :, k] - r[1:, :, k]).max() / Imax)
+    return relI, flux, quv, nanok

@@ -1,0 +1,105 @@
+// Debug/test harness: drives the product's __host__ __device__ stage bodies (grt_pipeline.cuh) on the
+// CPU, with the product's own host layer (grt_io.cpp), to compare kernel logic with the oracle without a
+// GPU.  NOT part of the product; never loaded by grtrans_b200.  Built by tests/test_host_emul.py.
+#include <cstring>
+#include <vector>
+
+#include "../../grtrans_b200/csrc/grt_host.h"
+#include "../../grtrans_b200/csrc/grt_pipeline.cuh"
+
+using namespace grt;
+
+extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncams][n][nvals]*/, int *npts_out,
+                         double *stage /* optional [n][maxpts][8]: lam,r,th,ph,s2xi,c2xi,ang,rshift */) {
+  int eneq = 1;
+  int etype = grt_host::emis_type_id(a->ename, &eneq), iflag = grt_host::integrator_flag(a->iname);
+  if (etype < 0 || iflag < 0) return 2;
+  grt_host::FluidHost fh;
+  int rc = grt_host::load_fluid(fh, *a);
+  if (rc) return rc;
+  std::vector<double> freqs, mdots, mu0;
+  grt_host::make_grids(*a, freqs, mdots, mu0);
+  grt_host::EmisTablesHost th;
+  grt_host::build_emis_tables(th);
+  FluidKernelArgs fk;
+  memset(&fk, 0, sizeof(fk));
+  FluidDev &F = fk.F;
+  F.model = fh.model; F.nx1 = fh.nx1; F.nx2 = fh.nx2; F.nx3 = fh.nx3; F.h = fh.h;
+  F.td_mbh = fh.td_mbh; F.td_mdot = fh.td_mdot; F.td_rin = fh.td_rin; F.td_rout = fh.td_rout;
+  F.ax1 = fh.ax1.data(); F.axr = fh.axr.data(); F.ax2 = fh.ax2.data(); F.axth = fh.axth.data(); F.ax3 = fh.ax3.data();
+  F.cells = reinterpret_cast<const Cell *>(fh.cells.data());
+  F.uvals = fh.uvals.data(); F.vvals = fh.vvals.data(); F.uv = fh.uv.data(); F.tvals = fh.tvals.data();
+  TransferParams P;
+  memset(&P, 0, sizeof(P));
+  EmisTables &tb = P.tab;
+  tb.gx = th.gx.data(); tb.gy = th.gy.data(); tb.xv = th.xv.data(); tb.ya = th.ya.data(); tb.yp = th.yp.data();
+  tb.yv = th.yv.data(); tb.yap = th.yap.data(); tb.yav = th.yav.data();
+  tb.ch_mu = th.ch_mu.data(); tb.ch_I = th.ch_I.data(); tb.ch_del = th.ch_del.data();
+  fk.tab = tb;
+  int nparams = a->nmdot, nfreq = a->nfreq, nv = a->nvals;
+  fk.nparams = nparams; fk.etype = etype;
+  for (int m = 0; m < nparams; m++) {
+    SourceDev &sp = fk.sp[m];
+    sp.mdot = mdots[m]; sp.mbh = a->mbh; sp.nfac = a->ftscl; sp.bfac = a->frscl; sp.jetalphaval = a->jetalpha;
+    sp.gminval = a->gmin; sp.muval = a->muval; sp.gmax = a->gmax; sp.p1 = a->p1; sp.p2 = a->p2; sp.sigcut = a->sigcut;
+  }
+  P.etype = etype; P.eneq = eneq; P.rneq = nv; P.iflag = iflag; P.model = fh.model; P.npts_is_one = (a->nn[2] == 1);
+  for (int i = 0; i < 7; i++) P.coefindx[i] = a->epcoefindx[i];
+  P.LBH = pc::G * a->mbh * pc::msun / pc::c2;
+  P.gmin = (double)(float)a->gmin; P.gmax = (double)(float)a->gmax; P.p = (double)(float)a->p1;
+  P.max_tau = 10.0; P.hmax = 0.1; P.ortol = 1e-6; P.oatol = 1e-8; P.thin = 1e-2; P.maxsteps = 100000;
+  int n = i2 - i1 + 1;
+  for (int jm = 0; jm < a->nmu; jm++) {
+    grt_host::Camera c;
+    grt_host::build_camera(c, a->standard, mu0[jm], a->phi0, a->spin, a->uout, a->rcut, a->nrotype, a->gridvals, a->nn[0],
+                           a->nn[1], a->nn[2]);
+    int mp = c.maxpts();
+    fk.maxpts = mp;
+    GeoFlags fl{a->nn[2], c.kext, c.next, c.mufill, c.usegeor, 1};
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int q = 0; q < n; q++) {
+      int ix = i1 - 1 + q;
+      RayConst r;
+      r.a = c.a; r.mu0 = c.mu0; r.u0 = c.u0; r.uout = c.uout; r.alpha = c.alpha[ix]; r.beta = c.beta[ix]; r.q2 = c.q2[ix];
+      r.l = c.l[ix]; r.su = c.su[ix]; r.sm = c.sm[ix]; r.uf = c.uf[ix]; r.muf = c.muf[ix]; r.offset = c.offset;
+      r.phi0 = c.phi0; r.t0 = 0; r.tpm = c.tpm[ix]; r.tpr = c.tpr[ix];
+      RayInv inv;
+      geo_setup(r, fl, inv);
+      std::vector<double> bu(mp), bmu(mp), bdt(mp), bdp(mp), bl(mp), rec((size_t)nparams * mp * GRT_NREC, 0.0);
+      std::vector<signed char> btm(mp), btr(mp);
+      PointArrays pa{bu.data(), bmu.data(), bdt.data(), bdp.data(), bl.data(), btm.data(), btr.data()};
+      for (int s = 0; s < mp; s++) point_store(inv, fl.nup, s, (size_t)s, pa);
+      RayMeta m;
+      ray_finalize(inv.npts, 0, mp, fl.usegeor, pa, m);
+      StageDump sd;
+      memset(&sd, 0, sizeof(sd));
+      std::vector<double> sdl(mp), sdt(mp), sdr(mp), sdth(mp), sdph(mp), sk0(mp), sk1(mp), sk2(mp), sk3(mp), su(4 * mp),
+          sb(4 * mp), s2(mp), c2(mp), an(mp), rs(mp), cn(mp), n1(mp), n2(mp), n3(mp), n4(mp);
+      std::vector<float> fr(mp), fp(mp), fb(mp);
+      if (stage && jm == 0) {
+        sd.lambda = sdl.data(); sd.t = sdt.data(); sd.r = sdr.data(); sd.th = sdth.data(); sd.ph = sdph.data();
+        sd.kt = sk0.data(); sd.kr = sk1.data(); sd.kth = sk2.data(); sd.kph = sk3.data(); sd.u = su.data(); sd.b = sb.data();
+        sd.s2xi = s2.data(); sd.c2xi = c2.data(); sd.ang = an.data(); sd.rshift = rs.data(); sd.cosne = cn.data();
+        sd.ncgs = n1.data(); sd.ncgsnth = n2.data(); sd.bcgs = n3.data(); sd.tcgs = n4.data();
+        sd.rho = fr.data(); sd.p = fp.data(); sd.bmag = fb.data();
+      }
+      for (int s = 0; s < mp; s++) point_record(r, m, fk, 0, s, 1, pa, rec.data(), sd);
+      if (jm == 0) npts_out[q] = (m.status == 1) ? m.npts : 0;
+      if (stage && jm == 0)
+        for (int s = 0; s < mp; s++) {
+          double *o = stage + ((size_t)q * mp + s) * 8;
+          bool v = m.status == 1 && s < m.npts;
+          o[0] = v ? sdl[s] : 0; o[1] = v ? sdr[s] : 0; o[2] = v ? sdth[s] : 0; o[3] = v ? sdph[s] : 0; o[4] = v ? s2[s] : 0;
+          o[5] = v ? c2[s] : 0; o[6] = v ? an[s] : 0; o[7] = v ? rs[s] : 0;
+        }
+      for (int mm = 0; mm < nparams; mm++)
+        for (int f = 0; f < nfreq; f++) {
+          double out[4] = {0, 0, 0, 0};
+          if (m.status == 1 && m.npts > 0) ray_transfer(P, rec.data() + (size_t)mm * mp * GRT_NREC, m.npts, freqs[f], out);
+          int cam = jm * nparams * nfreq + mm * nfreq + f;
+          for (int k = 0; k < nv; k++) image[((size_t)cam * n + q) * nv + k] = (float)out[k];
+        }
+    }
+  }
+  return 0;
+}

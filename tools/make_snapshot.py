@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Seeded synthetic GRMHD-like snapshots in the reference's input formats.
+
+The reference's HARM test input `dump040` is missing from the checkout (.MISSING_LARGE_BLOBS), so
+configs 4 and 5 run on analytic torus-like fluids written in
+
+  * the HARM 2-D ASCII dump layout read by fluid_model_harm.f90:275-408 (26-number header; rows of 34
+    columns: x1,x2,r,theta = cols 1-4, rho = col 5, u = col 6, u^mu = cols 14-17, b^mu = cols 22-25,
+    gdet = col 34), and
+  * a small binary container for the 3-D model (harm3d has no bundled reader input): int32 nx1,nx2,nx3;
+    float32 asim,gam,h; float32[n] x1,x2,x3,r,th,ph; float64[n] rho,u; float64[4n] ucon, bcon (modified
+    Kerr-Schild components), index (ix1*nx2+ix2)*nx3+ix3.
+
+The flow is a valid (u.u=-1, u.b=0) field in Kerr-Schild coordinates: the normal-observer infall plus a
+sub-Keplerian rotation, a Gaussian torus in (r, theta) with m=1,2 azimuthal perturbations in 3-D, and a
+toroidal + radial magnetic field.  Everything is a closed-form function of (seed, grid), so the same file
+is regenerated on the GPU box.
+"""
+import numpy as np
+
+
+def _ks_metric(r, th, a):
+    s2 = np.sin(th) ** 2
+    rho2 = r ** 2 + a ** 2 * np.cos(th) ** 2
+    psi = 2. * r / rho2
+    g = {}
+    g['tt'] = -(1. - psi); g['tr'] = psi; g['tp'] = -a * s2 * psi; g['rr'] = 1. + psi
+    g['rp'] = -a * s2 * (1. + psi); g['hh'] = rho2; g['pp'] = s2 * (rho2 + a ** 2 * (1. + psi) * s2)
+    return g
+
+
+def _fluid(r, th, ph, a, seed, threed):
+    rng = np.random.RandomState(seed)
+    amp1, amp2, ph1, ph2 = 0.3 * rng.rand() + 0.2, 0.2 * rng.rand() + 0.1, 2 * np.pi * rng.rand(), 2 * np.pi * rng.rand()
+    g = _ks_metric(r, th, a)
+    psi = g['tr']
+    vr = -psi / (1. + psi)                       # normal observer dr/dt in KS
+    om = 0.8 / (r ** 1.5 + a)                    # sub-Keplerian dphi/dt
+    for _ in range(40):                           # shrink the rotation until the 4-velocity is timelike
+        norm = g['tt'] + 2 * g['tr'] * vr + 2 * g['tp'] * om + g['rr'] * vr ** 2 + 2 * g['rp'] * vr * om + g['pp'] * om ** 2
+        bad = norm > -1e-3
+        if not bad.any():
+            break
+        om = np.where(bad, 0.5 * om, om)
+    norm = g['tt'] + 2 * g['tr'] * vr + 2 * g['tp'] * om + g['rr'] * vr ** 2 + 2 * g['rp'] * vr * om + g['pp'] * om ** 2
+    ut = 1. / np.sqrt(-norm)
+    u = np.stack([ut, ut * vr, np.zeros_like(r), ut * om], -1)
+    # density: Gaussian torus + floor, azimuthal m=1,2 modes
+    r0, w, hh = 8.0, 5.0, 0.45
+    rho = np.exp(-((r - r0) / w) ** 2) * np.exp(-(np.cos(th) / hh) ** 2) + 1e-4 * (r / r0) ** -1.5
+    if threed:
+        rho = rho * (1. + amp1 * np.cos(ph - ph1) + amp2 * np.cos(2. * ph - ph2))
+    uu = rho * 0.02 * (r / r0) ** -1.0           # internal energy density (code units)
+    # magnetic field: toroidal + radial pieces, b^t from u.b = 0
+    b0 = 0.05 * np.sqrt(rho)
+    br = 0.3 * b0 / r
+    bp = b0 / r * (1. + (0.2 * np.sin(ph) if threed else 0.))
+    bth = 0.1 * b0 / r * np.cos(th)
+    u_t = g['tt'] * u[..., 0] + g['tr'] * u[..., 1] + g['tp'] * u[..., 3]
+    u_r = g['tr'] * u[..., 0] + g['rr'] * u[..., 1] + g['rp'] * u[..., 3]
+    u_h = g['hh'] * u[..., 2]
+    u_p = g['tp'] * u[..., 0] + g['rp'] * u[..., 1] + g['pp'] * u[..., 3]
+    bt = -(u_r * br + u_h * bth + u_p * bp) / u_t
+    b = np.stack([bt, br, bth, bp], -1)
+    return rho, uu, u, b
+
+
+def _to_mks(v, r, dthdx2):
+    o = v.copy()
+    o[..., 1] = v[..., 1] / r
+    o[..., 2] = v[..., 2] / dthdx2
+    return o
+
+
+def harm2d_arrays(nx1=96, nx2=64, a=0.9375, hslope=0.3, rin=1.1, rout=40.0, seed=12345):
+    dx1 = np.log(rout / rin) / nx1
+    x1 = np.log(rin) + (np.arange(nx1) + 0.5) * dx1
+    x2 = (np.arange(nx2) + 0.5) / nx2
+    X1, X2 = np.meshgrid(x1, x2, indexing='ij')          # theta fastest
+    r = np.exp(X1)
+    th = np.pi * X2 + 0.5 * (1. - hslope) * np.sin(2. * np.pi * X2)
+    dthdx2 = np.pi * (1. + (1. - hslope) * np.cos(2. * np.pi * X2))
+    rho, uu, u, b = _fluid(r, th, np.zeros_like(r), a, seed, False)
+    return dict(nx1=nx1, nx2=nx2, a=a, h=hslope, dx1=dx1, dx2=1. / nx2, startx1=np.log(rin), startx2=0., x1=X1, x2=X2,
+                r=r, th=th, rho=rho, u=uu, ucon=_to_mks(u, r, dthdx2), bcon=_to_mks(b, r, dthdx2), gam=4. / 3.)
+
+
+def write_harm2d(prefix, indf=40, **kw):
+    """Writes `<prefix>%03d` (dump, also usable as the header file).  Returns the path."""
+    d = harm2d_arrays(**kw)
+    path = "%s%03d" % (prefix, indf)
+    hdr = np.zeros(26)
+    hdr[0] = 0.0; hdr[1] = d['nx1']; hdr[2] = d['nx2']; hdr[3] = d['startx1']; hdr[4] = d['startx2']; hdr[5] = d['dx1']
+    hdr[6] = d['dx2']; hdr[9] = d['a']; hdr[10] = d['gam']; hdr[24] = d['h']
+    n = d['nx1'] * d['nx2']
+    rows = np.zeros((n, 34))
+    rows[:, 0] = d['x1'].ravel(); rows[:, 1] = d['x2'].ravel(); rows[:, 2] = d['r'].ravel(); rows[:, 3] = d['th'].ravel()
+    rows[:, 4] = d['rho'].ravel(); rows[:, 5] = d['u'].ravel()
+    rows[:, 13:17] = d['ucon'].reshape(n, 4); rows[:, 21:25] = d['bcon'].reshape(n, 4)
+    rows[:, 33] = (d['r'] ** 2 * np.sin(d['th'])).ravel()
+    with open(path, 'w') as f:
+        f.write(" ".join("%.17g" % v for v in hdr) + "\n")
+        for row in rows:
+            f.write(" ".join("%.17g" % v for v in row) + "\n")
+    return path
+
+
+def harm3d_arrays(nx1=64, nx2=32, nx3=32, a=0.9375, rin=1.1, rout=40.0, seed=12345):
+    dx1 = np.log(rout / rin) / nx1
+    x1 = np.log(rin) + (np.arange(nx1) + 0.5) * dx1
+    x2 = (np.arange(nx2) + 0.5) / nx2
+    x3 = (np.arange(nx3) + 0.5) * 2. * np.pi / nx3
+    X1, X2, X3 = np.meshgrid(x1, x2, x3, indexing='ij')  # phi fastest
+    r = np.exp(X1); th = np.pi * X2; ph = X3
+    rho, uu, u, b = _fluid(r, th, ph, a, seed, True)
+    dth = np.pi * np.ones_like(r)
+    return dict(nx1=nx1, nx2=nx2, nx3=nx3, a=a, x1=X1, x2=X2, x3=X3, r=r, th=th, ph=ph, rho=rho, u=uu,
+                ucon=_to_mks(u, r, dth), bcon=_to_mks(b, r, dth), gam=4. / 3.)
+
+
+def write_harm3d(path, **kw):
+    d = harm3d_arrays(**kw)
+    with open(path, 'wb') as f:
+        np.array([d['nx1'], d['nx2'], d['nx3']], np.int32).tofile(f)
+        np.array([d['a'], d['gam'], 0.0], np.float32).tofile(f)
+        for k in ['x1', 'x2', 'x3', 'r', 'th', 'ph']:
+            d[k].astype(np.float32).ravel().tofile(f)
+        d['rho'].astype(np.float64).ravel().tofile(f)
+        d['u'].astype(np.float64).ravel().tofile(f)
+        d['ucon'].astype(np.float64).ravel().tofile(f)
+        d['bcon'].astype(np.float64).ravel().tofile(f)
+    return path
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) >= 3 and sys.argv[1] == "harm2d":
+        print(write_harm2d(sys.argv[2]))
+    elif len(sys.argv) >= 3 and sys.argv[1] == "harm3d":
+        print(write_harm3d(sys.argv[2]))
+    else:
+        print("usage: make_snapshot.py harm2d <prefix> | harm3d <path>")
