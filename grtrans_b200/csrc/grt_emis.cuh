@@ -76,65 +76,130 @@ GRT_HD double planck_bnu(double T, double nu) {
 }
 
 // ---- thermal polarised synchrotron ------------------------------------------------------------------
-// Frequency-independent part (per geodesic point) hoisted out of the frequency loop.
-struct ThermalPoint {
-  double thetae, n, b, t, sinth, costh, tanth, k0, k1ok2, ik2, step, nucfac;
+// polsynchth (polsynchemis.f90:700-863) is evaluated for every (geodesic point, frequency) pair, i.e. ~3e10 times for
+// the headline workload, so it is split into
+//   thermal_point()  per geodesic point: everything that does not depend on frequency, with the redshift g and the
+//                    length unit LBH of the invariant scaling (emis.f90:831-838, grtrans_driver.f90:217) folded in;
+//   thermal_eval()   per (point, frequency): 11 exp, 1 log, 1 cos, 1 sqrt, 1 reciprocal and ~90 multiply-adds.
+// Every power x**p of the reference becomes exp(p*log x) with the logarithm assembled from per-point and per-frequency
+// logarithms; divisions by constants-of-the-point are pre-inverted.  The algebra is otherwise the reference's, term by term
+// (fits iix/iqx/ivx :831-861, jffunc/shgmfunc :737-761, Kirchhoff alpha=j/B_nu), so results agree to round-off (~1e-13).
+//
+// Output of thermal_eval are the INVARIANT coefficients of frequency nu_obs: j*g^2 and K/g*LBH evaluated at the comoving
+// frequency nu = nu_obs/g (for the unit-level surface g = LBH = 1 gives the plain comoving polsynchth values).
+struct ThermalPoint {  // 12 doubles, stored in the point record
+  double lnu_off;      // -log(g) - log(nu_c'):  log(nu/nu_c') = log(nu_obs) + lnu_off
+  double AI, AV;       // comoving j_{I,Q} = AI nu {iix,iqx},  j_V = AV nu ivx   (nu = nu_obs/g)
+  double hkT_g;        // h/(k T g): h nu/(k T) = hkT_g nu_obs
+  double lAx;          // log of (xarg sqrt(nu_obs))
+  double RQ;           // rho_Q LBH/g = RQ jff / nu_obs^3
+  double RV0, RV1;     // rho_V LBH/g = (RV0 - RV1 shgm) / nu_obs^2
+  double g, ig;        // redshift and 1/g
 };
-GRT_HD void thermal_point(double n, double b, double t, double theta, ThermalPoint &P) {
-  P.n = n; P.b = b; P.t = t;
-  P.thetae = pc::k * t / pc::m / pc::c / pc::c + 1e-10;
-  P.sinth = sin(theta);
-  P.costh = cos(theta);
-  P.tanth = tan(theta);
-  P.nucfac = 3.0 * pc::e * b * P.sinth / 4.0 / GRT_PI / pc::m / pc::c * P.thetae * P.thetae + 1.0;
-  if (P.thetae > 1e-2) {
-    double x = 1.0 / P.thetae;
-    double k0 = bess_k0(x), k1 = bess_k1(x);
-    double k2 = k0 + 1.0 * (2.0 / x) * k1;  // besselk(2,x): one step of the upward recurrence
-    P.k0 = k0;
-    P.k1ok2 = k1 / k2;
-    P.ik2 = 1.0 / k2;
-    P.step = 0.5 + 0.5 * tanh((P.thetae - 1.0) / 0.05);
-  } else {
-    P.k0 = P.k1ok2 = P.ik2 = P.step = 0.0;
-  }
+
+struct FreqConst {  // per observed frequency
+  double nu, lnu, inu2, inu3;
+};
+GRT_HD FreqConst freq_const(double nu_obs) {
+  FreqConst f;
+  f.nu = nu_obs;
+  f.lnu = log(nu_obs);
+  double i = 1.0 / nu_obs;
+  f.inu2 = i * i;
+  f.inu3 = f.inu2 * i;
+  return f;
 }
 
-GRT_HD void polsynchth_eval(const ThermalPoint &P, double nu, double *e) {
+GRT_HD void thermal_point(double n, double b, double t, double theta, double g, double lbh, ThermalPoint &P) {
   const double ec = pc::e, c = pc::c, m = pc::m, pi = GRT_PI;
-  double xm = nu / P.nucfac;
-  double x13 = pow(xm, 1.0 / 3.0), x23 = pow(xm, 2.0 / 3.0);
-  double ex = exp(-1.8899 * x13);
-  double iix = 2.5651 * (1.0 + 1.92 / x13 + .9977 / x23) * ex;
-  double iqx = 2.5651 * (1.0 + .93193 / x13 + .499873 / x23) * ex;
-  double ivx = (1.81384 / xm + 3.42319 / x23 + 0.0292545 / sqrt(xm) + 2.03773 / x13) * ex;
-  double th2 = P.thetae * P.thetae;
-  double ji = ec * ec / c / sqrt(3.0) / 2.0 * P.n / th2 * nu * iix;
-  double jq = ec * ec / c / sqrt(3.0) / 2.0 * P.n / th2 * nu * iqx;
-  double jv = 4.0 * ec * ec / c / 3.0 / sqrt(3.0) / P.tanth * P.n / 2.0 / (th2 * P.thetae) * nu * ivx;
-  double bn = planck_bnu(P.t, nu);
-  double wp2 = 4.0 * pi * P.n * ec * ec / m;
-  double omega0 = ec * P.b / m / c;
-  double xarg = P.thetae * sqrt(sqrt(2.0) * P.sinth * (1e3 * omega0 / 2.0 / pi / nu));
-  double extraterm = (.011 * exp(-xarg / 47.2) - pow(2.0, -1.0 / 3.0) / pow(3.0, 23.0 / 6.0) * pi * 1e4 * pow(xarg + 1e-16, -8.0 / 3.0)) *
-                     (0.5 + 0.5 * tanh((log(xarg) - log(120.0)) / 0.1));
-  double jff = 2.011 * exp(-pow(xarg, 1.035) / 4.7) - cos(xarg / 2.0) * exp(-pow(xarg, 1.2) / 2.73) - .011 * exp(-xarg / 47.2) +
-               extraterm;
-  double w = 2.0 * pi * nu, w3 = w * w * w, w4 = w3 * w;
-  double eps11m22, eps12;
-  if (P.thetae > 1e-2) {
-    double shgm = (double)0.43793091f * log(1.0 + (double)0.00185777f * pow(xarg, (double)1.50316886f));
-    eps11m22 = jff * wp2 * omega0 * omega0 / w4 * (P.k1ok2 + 6.0 * P.thetae) * P.sinth * P.sinth;
-    eps12 = wp2 * omega0 / w3 * (P.k0 - P.step * shgm) * P.ik2 * P.costh;
+  double thetae = pc::k * t / pc::m / pc::c / pc::c + 1e-10;
+  double sinth = sin(theta), costh = cos(theta), tanth = tan(theta);
+  double nucfac = 3.0 * pc::e * b * sinth / 4.0 / GRT_PI / pc::m / pc::c * thetae * thetae + 1.0;
+  double th2 = thetae * thetae;
+  P.lnu_off = -log(g) - log(nucfac);
+  P.AI = ec * ec / c / sqrt(3.0) / 2.0 * n / th2;
+  P.AV = 4.0 * ec * ec / c / 3.0 / sqrt(3.0) / tanth * n / 2.0 / (th2 * thetae);
+  P.hkT_g = pc::h / pc::k / t / g;
+  double wp2 = 4.0 * pi * n * ec * ec / m;
+  double omega0 = ec * b / m / c;
+  // xarg = thetae*sqrt(sqrt(2) sin(theta) 1e3 omega0/(2 pi nu)),  nu = nu_obs/g
+  P.lAx = log(thetae * sqrt(sqrt(2.0) * sinth * (1e3 * omega0 / 2.0 / pi) * g));
+  double X, Z0, Z1;
+  if (thetae > 1e-2) {
+    double x = 1.0 / thetae;
+    double k0 = bess_k0(x), k1 = bess_k1(x);
+    double k2 = k0 + 1.0 * (2.0 / x) * k1;  // besselk(2,x): one step of the upward recurrence
+    X = k1 / k2 + 6.0 * thetae;
+    Z0 = k0 / k2;
+    Z1 = (0.5 + 0.5 * tanh((thetae - 1.0) / 0.05)) / k2;
   } else {
-    eps11m22 = jff * wp2 * omega0 * omega0 / w4 * (1.0 + 6.0 * P.thetae) * P.sinth * P.sinth;
-    eps12 = wp2 * omega0 / w3 * P.costh;
+    X = 1.0 + 6.0 * thetae;
+    Z0 = 1.0;
+    Z1 = 0.0;
   }
-  e[0] = ji; e[1] = jq; e[2] = 0.0; e[3] = jv;
-  e[4] = ji / bn; e[5] = jq / bn; e[6] = 0.0 / bn; e[7] = jv / bn;
-  e[8] = 2.0 * pi * nu / 2.0 / c * eps11m22;
-  e[9] = e[6];
-  e[10] = 2.0 * pi * nu / c * eps12;
+  P.RQ = wp2 * omega0 * omega0 * X * sinth * sinth / (16.0 * pi * pi * pi * c) * g * g * lbh;
+  double rvc = wp2 * omega0 * costh / (4.0 * pi * pi * c) * g * lbh;
+  P.RV0 = rvc * Z0;
+  P.RV1 = rvc * Z1;
+  P.g = g;
+  P.ig = 1.0 / g;
+}
+
+// e = (jI,jQ,jU,jV, aI,aQ,aU,aV, rhoQ,rhoU,rhoV) in invariant form (see above); jraw = comoving j_I.  kcl = c^2 LBH / (2 h).
+// The emissivities are formed in the reference's order -- comoving j first, then j g^2 and alpha = j/B_nu scaled by LBH/g --
+// so that they underflow (exp(-1.89 x^(1/3)) reaches 1e-320 in cold, weakly magnetised zones) where the reference's do: a
+// DELO step divides by alpha_I, and "j_inv == 0 but alpha_I != 0" must stay distinguishable from "both 0".
+GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, double *e, double &jraw) {
+  const double lxm = F.lnu + P.lnu_off;
+  const double x13 = exp(lxm * (1.0 / 3.0));
+  const double i13 = 1.0 / x13, i23 = i13 * i13;
+  const double ex = exp(-1.8899 * x13);
+  const double iix = 2.5651 * (1.0 + 1.92 * i13 + .9977 * i23) * ex;
+  const double iqx = 2.5651 * (1.0 + .93193 * i13 + .499873 * i23) * ex;
+  const double ivx = (1.81384 * (i23 * i13) + 3.42319 * i23 + 0.0292545 * (i13 * sqrt(i13)) + 2.03773 * i13) * ex;
+  const double nuc = F.nu * P.ig;
+  const double ji = P.AI * nuc * iix, jq = P.AI * nuc * iqx, jv = P.AV * nuc * ivx;
+  jraw = ji;
+  // 1/B_nu (bnu, polsynchemis.f90:1014-1032): Rayleigh-Jeans below h nu/kT = 1e-6; B_nu == 0 is replaced by epsilon
+  const double xh = P.hkT_g * F.nu;
+  const double g2 = P.g * P.g;
+  double ka;  // alpha_S LBH/g = j_S * ka
+  if (xh < 1e-6)
+    ka = kcl * g2 * xh * F.inu3;
+  else if (xh < 600.0)
+    ka = kcl * g2 * (exp(xh) - 1.0) * F.inu3;
+  else {  // deep Wien tail: follow the reference literally (B_nu underflowing to 0 is replaced by epsilon)
+    double bn = 2.0 * pc::h * nuc / pc::c2 * nuc * nuc / (exp(xh) - 1.0);
+    if (bn == 0.0) bn = 2.220446049250313e-16;
+    ka = P.ig * (kcl * 2.0 * pc::h / pc::c2) / bn;
+  }
+  e[0] = ji * g2; e[1] = jq * g2; e[2] = 0.0; e[3] = jv * g2;
+  e[4] = ji * ka; e[5] = jq * ka; e[6] = 0.0; e[7] = jv * ka;
+  // Faraday rotation / conversion (Shcherbakov 2008 fits)
+  const double lx = P.lAx - 0.5 * F.lnu;
+  const double xarg = exp(lx);
+  const double e1 = .011 * exp(xarg * (-1.0 / 47.2));
+  double jff = 2.011 * exp(exp(1.035 * lx) * (-1.0 / 4.7)) - cos(0.5 * xarg) * exp(exp(1.2 * lx) * (-1.0 / 2.73)) - e1;
+  const double z2 = (lx - 4.787491742782046) * 20.0;  // 2 (log(xarg) - log(120)) / 0.1
+  if (z2 > -40.0) {                                   // below: 0.5 + 0.5 tanh(z) == 0 exactly in FP64
+    double ez = exp(z2);
+    double sw = (z2 < 80.0) ? ez / (1.0 + ez) : 1.0;
+    const double c83 = 0.7937005259840998 / 67.44733739010397 * GRT_PI * 1e4;  // 2^(-1/3) / 3^(23/6) pi 1e4
+    jff += (e1 - c83 * exp((-8.0 / 3.0) * log(xarg + 1e-16))) * sw;
+  }
+  e[8] = P.RQ * jff * F.inu3;
+  e[9] = 0.0;
+  double rv = P.RV0;
+  if (P.RV1 != 0.0) rv -= P.RV1 * ((double)0.43793091f * log(1.0 + (double)0.00185777f * exp((double)1.50316886f * lx)));
+  e[10] = rv * F.inu2;
+}
+
+// plain comoving polsynchth values at frequency nu (the polsynchemis f2py surface): g = LBH = 1
+GRT_HD void polsynchth_eval(double nu, double n, double b, double t, double theta, double *e) {
+  ThermalPoint P;
+  thermal_point(n, b, t, theta, 1.0, 1.0, P);
+  double jraw;
+  thermal_eval(P, freq_const(nu), pc::c2 / (2.0 * pc::h), e, jraw);
 }
 
 // ---- power-law synchrotron ------------------------------------------------------------------------

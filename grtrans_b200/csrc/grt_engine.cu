@@ -1,4 +1,5 @@
-// grtrans_b200 -- CUDA engine (sm_100a): kernels, resident session and the C ABI.
+// grtrans_b200 -- CUDA engine (sm_100a): resident session and the C ABI (kernels: grt_k_geo.cu, grt_k_fluid.cu,
+// grt_k_transfer.cu, launched through grt_kernels.h).
 //
 // Pipeline per tile of rays:
 //   k_ray_setup      thread / ray            geo_setup()            -> RayInv              (R2 once-per-ray part)
@@ -20,7 +21,7 @@
 #include <vector>
 
 #include "grt_host.h"
-#include "grt_pipeline.cuh"
+#include "grt_kernels.h"
 
 using namespace grt;
 
@@ -32,191 +33,6 @@ using namespace grt;
       return GRT_ERR_CUDA;                                                                \
     }                                                                                     \
   } while (0)
-
-// ======================================================================================== kernels
-__global__ void __launch_bounds__(128) k_ray_setup(const RayConst *__restrict__ rc, GeoFlags fl, RayInv *__restrict__ inv, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  RayConst r = rc[i];
-  RayInv c;
-  geo_setup(r, fl, c);
-  inv[i] = c;
-}
-
-__global__ void __launch_bounds__(128) k_geo_points(const RayInv *__restrict__ inv, int nup, int maxpts, long long total, PointArrays pa) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int ray = (int)(idx / maxpts), slot = (int)(idx % maxpts);
-  point_store(inv[ray], nup, slot, (size_t)idx, pa);
-}
-
-__global__ void __launch_bounds__(128) k_ray_finalize(const RayInv *__restrict__ inv, int maxpts, int usegeor, int n, PointArrays pa,
-                               RayMeta *__restrict__ meta) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  RayMeta m;
-  ray_finalize(inv[i].npts, (size_t)i, maxpts, usegeor, pa, m);
-  meta[i] = m;
-}
-
-__global__ void __launch_bounds__(128) k_fluid_ortho(const RayConst *__restrict__ rc, const RayInv *__restrict__ inv,
-                                                     const RayMeta *__restrict__ meta, FluidKernelArgs A, long long total,
-                                                     int nrays, PointArrays pa, double *__restrict__ rec, StageDump sd) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int ray = (int)(idx / A.maxpts), slot = (int)(idx % A.maxpts);
-  point_record(rc[ray], meta[ray], A, ray, slot, nrays, pa, rec, sd);
-}
-
-// image layout: [cam][ray_local][nvals] float32, cam = (mu_index*nparams + m)*nfreq + k
-__global__ void __launch_bounds__(128) k_transfer(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
-                                                  const double *__restrict__ freqs, int nfreq, int nparams, int nrays, int maxpts,
-                                                  const double *__restrict__ rec, float *__restrict__ image, long long ray_off,
-                                                  long long nlocal, int cam0) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)nrays * nparams * nfreq;
-  if (idx >= total) return;
-  int f = (int)(idx % nfreq);
-  int mm = (int)((idx / nfreq) % nparams);
-  int ray = (int)(idx / ((long long)nfreq * nparams));
-  RayMeta m = meta[ray];
-  double out[4] = {0, 0, 0, 0};
-  if (m.status == 1 && m.npts > 0) {
-    P.LBH = lbh_m[mm];
-    const double *rr = rec + ((size_t)mm * nrays * maxpts + (size_t)ray * maxpts) * GRT_NREC;
-    ray_transfer(P, rr, m.npts, freqs[f], out);
-  }
-  int cam = cam0 + mm * nfreq + f;
-  float *dst = image + ((size_t)cam * nlocal + (ray_off + ray)) * P.rneq;
-  if (P.rneq == 4)
-    *reinterpret_cast<float4 *>(dst) = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
-  else
-    for (int i = 0; i < P.rneq; i++) dst[i] = (float)out[i];
-}
-
-// small stand-alone kernels for the unit-level C ABI
-__global__ void k_polsynchth(int n, const double *nu, const double *nc, const double *b, const double *t, const double *th, double *e) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  ThermalPoint T;
-  thermal_point(nc[i], b[i], t[i], th[i], T);
-  polsynchth_eval(T, nu[i], e + 11 * (size_t)i);
-}
-__global__ void k_polsynchpl(int n, EmisTables tab, const double *nu, const double *nnth, const double *b, const double *th,
-                             const double *p, const double *gmin, double gmax, double *e) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  synchpl_eval<true>(tab, nu[i], nnth[i], b[i], th[i], p[i], gmin[i], gmax, e + 11 * (size_t)i);
-}
-__global__ void k_synchemis(int n, const double *nu, const double *nc, const double *b, const double *t, double *e) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  synchemis_eval(nu[i], nc[i], b[i], t[i], e + 11 * (size_t)i);
-}
-
-// generic-coefficient integration (radtrans_integrate f2py surface): one thread per ray
-__global__ void k_rt_integrate(int iflag, int neq, int nrays, int npts, const double *s, const double *j, const double *K,
-                               const double *tau, double *intensity, int *nptsout, TransferParams P) {
-  int ray = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray >= nrays) return;
-  const int nk = 1 + neq * (neq - 1) / 2;
-  const double *ss = s + (size_t)ray * npts, *jj = j + (size_t)ray * npts * neq, *KK = K + (size_t)ray * npts * nk,
-               *tt = tau + (size_t)ray * npts;
-  double *I = intensity + (size_t)ray * npts * neq;
-  for (int i = 0; i < npts * neq; i++) I[i] = 0.0;
-  auto load = [&](int k, Coef &c) {  // k 0-based node
-    for (int i = 0; i < 4; i++) c.j[i] = (i < neq) ? jj[(size_t)k * neq + i] : 0.0;
-    for (int i = 0; i < 7; i++) c.K[i] = (i < nk) ? KK[(size_t)k * nk + i] : 0.0;
-  };
-  if (iflag != 0 && neq == 4) {
-    double Ip[4] = {0, 0, 0, 0}, In[4];
-    Coef c0, c1;
-    load(npts - 1, c1);
-    for (int k = npts - 2; k >= 0; k--) {
-      load(k, c0);
-      double dx = ss[k] - ss[k + 1];
-      if (iflag == 1)
-        delo_step(c0, c1, dx, tt[k + 1] - tt[k], P.thin, Ip, In);
-      else {
-        double v[4];
-        for (int i = 0; i < 4; i++) v[i] = c0.j[i] * dx + Ip[i];
-        formal_apply(c0.K, dx, v, In);
-      }
-      int col = npts - 1 - k;
-      for (int i = 0; i < 4; i++) {
-        Ip[i] = In[i];
-        I[(size_t)col * 4 + i] = In[i];
-      }
-      c1 = c0;
-    }
-    nptsout[ray] = npts;
-    return;
-  }
-  if (iflag != 0) {
-    double acc = 0.0, yprev = jj[0] * exp(-tt[0]);
-    I[0] = 0.0;
-    for (int k = 1; k < npts; k++) {
-      double y = jj[(size_t)k * neq] * exp(-tt[k]);
-      acc += (ss[k] - ss[k - 1]) * (yprev + y) / 2.0;
-      I[(size_t)k * neq] = -acc;
-      yprev = y;
-    }
-    nptsout[ray] = npts;
-    return;
-  }
-  // lsoda replacement
-  int lamdex = npts, i1 = 1, i2 = 0;
-  double maxtau = tt[0];
-  for (int k = 1; k < npts; k++) maxtau = dmax(maxtau, tt[k]);
-  if (maxtau > P.max_tau) {
-    for (int k = 0; k < npts; k++)
-      if (tt[k] > P.max_tau) {
-        lamdex = k + 1;
-        break;
-      }
-  }
-  if (jj[0] == 0.0)
-    for (int ii = 2; ii <= npts; ii++)
-      if (jj[(size_t)(ii - 1) * neq] != 0.0) {
-        i1 = ii;
-        break;
-      }
-  if (jj[(size_t)(lamdex - 1) * neq] == 0.0) {
-    for (int ii = 1; ii <= lamdex - 1; ii++)
-      if (jj[(size_t)(lamdex - ii - 1) * neq] != 0.0) {
-        i2 = lamdex - ii;
-        break;
-      }
-  } else
-    i2 = lamdex;
-  nptsout[ray] = i2;
-  if (i2 <= i1) return;
-  double y[4] = {0, 0, 0, 0}, h = P.hmax;
-  Coef ca, cb;
-  bool ok = true;
-  for (int m = 1; m <= i2 - i1; m++) {
-    int indx = i2 - m + 1;
-    load(indx - 1, ca);
-    load(((indx + 1 <= npts) ? indx + 1 : npts) - 1, cb);
-    double la = ss[indx - 1], lb = ss[indx - 2];
-    if (lb > la) ok = ck_interval(neq, ca, cb, la, lb, y, h, P);
-    if (!ok) break;
-    for (int i = 0; i < neq; i++) I[(size_t)(i1 - 1 + m) * neq + i] = y[i];
-  }
-  if (!ok)
-    for (int i = 0; i < npts * neq; i++) I[i] = 0.0;
-}
-
-// FP64 FMA peak micro-benchmark: 8 independent chains per thread
-__global__ void k_dfma(double *out, int iters) {
-  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-  const double b = 1.0000001, c = 1e-9;
-  for (int i = 0; i < iters; i++) {
-    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
-    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
-  }
-  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-}
 
 // ======================================================================================== session
 template <class T>
@@ -439,21 +255,17 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
 extern "C" void grt_session_destroy(grt_session *s) { session_free(s); }
 
 static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump sd, bool time_stages) {
-  const int B = 128;
   long long total = (long long)n * s->maxpts;
   if (time_stages) cudaEventRecord(s->ev[0], s->stream);
-  k_ray_setup<<<(n + B - 1) / B, B, 0, s->stream>>>(s->d_rc[jmu] + off, s->fl, s->d_inv, n);
+  launch_ray_setup(s->d_rc[jmu] + off, s->fl, s->d_inv, n, s->stream);
   if (time_stages) cudaEventRecord(s->ev[1], s->stream);
-  k_geo_points<<<(unsigned)((total + B - 1) / B), B, 0, s->stream>>>(s->d_inv, s->fl.nup, s->maxpts, total, s->pa);
-  k_ray_finalize<<<(n + B - 1) / B, B, 0, s->stream>>>(s->d_inv, s->maxpts, s->fl.usegeor, n, s->pa, s->d_meta);
+  launch_geo_points(s->d_inv, s->fl.nup, s->maxpts, total, s->pa, s->stream);
+  launch_ray_finalize(s->d_inv, s->maxpts, s->fl.usegeor, n, s->pa, s->d_meta, s->stream);
   if (time_stages) cudaEventRecord(s->ev[2], s->stream);
-  k_fluid_ortho<<<(unsigned)((total + B - 1) / B), B, 0, s->stream>>>(s->d_rc[jmu] + off, s->d_inv, s->d_meta, s->fk, total, n,
-                                                                     s->pa, s->d_rec, sd);
+  launch_fluid_ortho(s->d_rc[jmu] + off, s->d_inv, s->d_meta, s->fk, total, n, s->pa, s->d_rec, sd, s->stream);
   if (time_stages) cudaEventRecord(s->ev[3], s->stream);
-  long long tt = (long long)n * s->nparams * s->nfreq;
-  k_transfer<<<(unsigned)((tt + B - 1) / B), B, 0, s->stream>>>(s->d_meta, s->tp, s->d_lbh, s->d_freqs, s->nfreq, s->nparams, n,
-                                                              s->maxpts, s->d_rec, s->d_image, off, s->nlocal,
-                                                              jmu * s->nparams * s->nfreq);
+  launch_transfer(s->d_meta, s->tp, s->d_lbh, s->d_freqs, s->nfreq, s->nparams, n, s->maxpts, s->d_rec, s->d_image, off,
+                  s->nlocal, jmu * s->nparams * s->nfreq, s->stream);
   if (time_stages) cudaEventRecord(s->ev[4], s->stream);
   return (cudaGetLastError() == cudaSuccess) ? GRT_OK : GRT_ERR_CUDA;
 }
@@ -565,11 +377,10 @@ extern "C" int grt_session_counts(grt_session *s, long long *nrays_local, long l
     std::vector<RayMeta> hm(s->tile);
     for (long long off = 0; off < s->nlocal; off += s->tile) {
       int n = (int)std::min<long long>(s->tile, s->nlocal - off);
-      const int B = 128;
       long long total = (long long)n * s->maxpts;
-      k_ray_setup<<<(n + B - 1) / B, B, 0, s->stream>>>(s->d_rc[0] + off, s->fl, s->d_inv, n);
-      k_geo_points<<<(unsigned)((total + B - 1) / B), B, 0, s->stream>>>(s->d_inv, s->fl.nup, s->maxpts, total, s->pa);
-      k_ray_finalize<<<(n + B - 1) / B, B, 0, s->stream>>>(s->d_inv, s->maxpts, s->fl.usegeor, n, s->pa, s->d_meta);
+      launch_ray_setup(s->d_rc[0] + off, s->fl, s->d_inv, n, s->stream);
+      launch_geo_points(s->d_inv, s->fl.nup, s->maxpts, total, s->pa, s->stream);
+      launch_ray_finalize(s->d_inv, s->maxpts, s->fl.usegeor, n, s->pa, s->d_meta, s->stream);
       CK(cudaMemcpyAsync(hm.data(), s->d_meta, n * sizeof(RayMeta), cudaMemcpyDeviceToHost, s->stream));
       CK(cudaStreamSynchronize(s->stream));
       for (int i = 0; i < n; i++)
@@ -821,10 +632,9 @@ extern "C" int grt_geokerr_rays(int standard, double mu0, double phi0, double a,
   CK(dalloc(&dinv, (size_t)n)); CK(dalloc(&dmeta, (size_t)n));
   CK(dalloc(&pa.u, NP)); CK(dalloc(&pa.mu, NP)); CK(dalloc(&pa.dt, NP)); CK(dalloc(&pa.dphi, NP)); CK(dalloc(&pa.lam, NP));
   CK(dalloc(&pa.tpm, NP)); CK(dalloc(&pa.tpr, NP));
-  const int B = 128;
-  k_ray_setup<<<(n + B - 1) / B, B>>>(drc, fl, dinv, n);
-  k_geo_points<<<(unsigned)((NP + B - 1) / B), B>>>(dinv, nup, mp, (long long)NP, pa);
-  k_ray_finalize<<<(n + B - 1) / B, B>>>(dinv, mp, fl.usegeor, n, pa, dmeta);
+  launch_ray_setup(drc, fl, dinv, n, 0);
+  launch_geo_points(dinv, nup, mp, (long long)NP, pa, 0);
+  launch_ray_finalize(dinv, mp, fl.usegeor, n, pa, dmeta, 0);
   CK(cudaDeviceSynchronize());
   std::vector<double> hu(NP), hmu(NP), hdt(NP), hdp(NP), hl(NP);
   std::vector<signed char> htm(NP), htr(NP);
@@ -906,13 +716,12 @@ static int run_emis(int which, int n, const double *const *in, int nin, double g
   EmisTables tb;
   if (rc == GRT_OK && which == 1) rc = emis_tables_device(tb, owned);
   if (rc == GRT_OK) {
-    const int B = 128;
     if (which == 0)
-      k_polsynchth<<<(n + B - 1) / B, B>>>(n, d[0], d[1], d[2], d[3], d[4], de);
+      launch_polsynchth(n, d[0], d[1], d[2], d[3], d[4], de);
     else if (which == 1)
-      k_polsynchpl<<<(n + B - 1) / B, B>>>(n, tb, d[0], d[1], d[2], d[3], d[4], d[5], gmax, de);
+      launch_polsynchpl(n, tb, d[0], d[1], d[2], d[3], d[4], d[5], gmax, de);
     else
-      k_synchemis<<<(n + B - 1) / B, B>>>(n, d[0], d[1], d[2], d[3], de);
+      launch_synchemis(n, d[0], d[1], d[2], d[3], de);
     if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(e, de, (size_t)n * 88, cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = GRT_ERR_CUDA;
   }
@@ -951,8 +760,7 @@ extern "C" int grt_rt_integrate(int iflag, int neq, int nrays, int npts, const d
   TransferParams P;
   memset(&P, 0, sizeof(P));
   P.max_tau = max_tau; P.hmax = hmax; P.oatol = oatol; P.ortol = ortol; P.thin = thin; P.maxsteps = maxsteps;
-  const int B = 64;
-  k_rt_integrate<<<(nrays + B - 1) / B, B>>>(iflag, neq, nrays, npts, ds, dj, dK, dt, dI, dn, P);
+  launch_rt_integrate(iflag, neq, nrays, npts, ds, dj, dK, dt, dI, dn, P);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(intensity, dI, NP * neq * 8, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(nptsout, dn, (size_t)nrays * 4, cudaMemcpyDeviceToHost));
@@ -974,7 +782,7 @@ extern "C" int grt_dfma_peak(int device, double *tflops) {
   double best = 0.0;
   for (int rep = 0; rep < 6; rep++) {
     cudaEventRecord(e0);
-    k_dfma<<<blocks, threads>>>(d, iters);
+    launch_dfma(d, blocks, threads, iters);
     cudaEventRecord(e1);
     CK(cudaEventSynchronize(e1));
     float ms;

@@ -162,19 +162,19 @@ GRT_HD int bracket(const float *xx /*0-based*/, int n, float x) {
 }
 
 GRT_HD float krolik_c(float r, float a) {
-  float pif = acosf(-1.f);
+  float pif = r4acos(-1.f);
   float rms = isco_radius_f(a);
   float y = sqrtf(r), yms = sqrtf(rms);
-  float ac = acosf(a);
-  float y1 = (float)(2.0 * (double)cosf(1.f / 3.f * (ac - pif)));
-  float y2 = (float)(2.0 * (double)cosf(1.f / 3.f * (ac + pif)));
-  float y3 = (float)(-2.0 * (double)cosf(1.f / 3.f * ac));
+  float ac = r4acos(a);
+  float y1 = (float)(2.0 * (double)r4cos(1.f / 3.f * (ac - pif)));
+  float y2 = (float)(2.0 * (double)r4cos(1.f / 3.f * (ac + pif)));
+  float y3 = (float)(-2.0 * (double)r4cos(1.f / 3.f * ac));
   float arg1 = (float)((double)(3.f * a) / (2.0 * (double)y));
   float arg2 = (float)(3.0 * sq((double)(y1 - a)) / (double)(y * y1 * (y1 - y2) * (y1 - y3)));
   float arg3 = (float)(3.0 * sq((double)(y2 - a)) / (double)(y * y2 * (y2 - y1) * (y2 - y3)));
   float arg4 = (float)(3.0 * sq((double)(y3 - a)) / (double)(y * y3 * (y3 - y1) * (y3 - y2)));
-  return 1.f - yms / y - arg1 * logf(y / yms) - arg2 * logf((y - y1) / (yms - y1)) - arg3 * logf((y - y2) / (yms - y2)) -
-         arg4 * logf((y - y3) / (yms - y3));
+  return 1.f - yms / y - arg1 * r4log(y / yms) - arg2 * r4log((y - y1) / (yms - y1)) - arg3 * r4log((y - y2) / (yms - y2)) -
+         arg4 * r4log((y - y3) / (yms - y3));
 }
 
 // ---- the sampler ---------------------------------------------------------------------------------
@@ -192,14 +192,14 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       float r = (float)rr, th = (float)thh;
       float MBH = F.td_mbh, Mdot = F.td_mdot;
       float lbh = (float)((double)MBH * pcmsun * pcG / pcc2);
-      float b = 1.f - 3.f / r + 2.f * a / powf(r, 1.5f);
+      float b = 1.f - 3.f / r + 2.f * a / r4pow(r, 1.5f);
       float rms = isco_radius_f(a);
       float rin = fmaxf(rms, F.td_rin);
       float kc = krolik_c(r, a);
       float d = r * r - 2.f * r + a * a;
-      float lc = (rms * rms - 2.f * a * sqrtf(rms) + a * a) / (powf(rms, 1.5f) - 2.f * sqrtf(rms) + a);
+      float lc = (rms * rms - 2.f * a * sqrtf(rms) + a * a) / (r4pow(rms, 1.5f) - 2.f * sqrtf(rms) + a);
       float hc = (2.f * r - a * lc) / d;
-      float sn = sinf(th);
+      float sn = r4sin(th);
       float ar = (r * r + a * a) * (r * r + a * a) - a * a * d * (sn * sn);
       float om = 2.f * a * r / ar;
       float Mdotedd = (float)(4. * pi * pcG * (double)MBH * pcmsun * pcmp * pcc / pcsigt / pcc2);
@@ -208,12 +208,12 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
                             0.25);
       float omega;
       if (r > rms)
-        omega = fmaxf(1.f / (powf(r, 1.5f) + a), om);
+        omega = fmaxf(1.f / (r4pow(r, 1.5f) + a), om);
       else
         omega = fmaxf((lc + a * hc) / (r * r + 2.f * r * (1.f + hc)), om);
       float T;
       if (r > rin && r < F.td_rout)
-        T = T0 * powf(kc / b / powf(r, 3.f), 0.25f);
+        T = T0 * r4pow(kc / b / r4pow(r, 3.f), 0.25f);
       else
         T = (float)((double)T0 / 1e5);
       s.rho = T;
@@ -249,11 +249,11 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
     case FL_FFJET: {
       const int nx1 = F.nx1, nx2 = F.nx2;
       float theta = (float)thh;
-      float zm = cosf(theta);
-      float x2 = acosf(fabsf(zm));
+      float zm = r4cos(theta);
+      float x2 = r4acos(fabsf(zm));
       theta = x2;
       float zr = (float)rr;
-      float x1 = logf(zr);
+      float x1 = r4log(zr);
       int lx1 = (int)((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
       int lx2 = (int)((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;
       lx2 = (lx2 <= (nx2 - 1)) ? ((lx2 >= 1) ? lx2 : 1) : (nx2 - 1);
@@ -273,7 +273,7 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
     case FL_HARM: {
       const int nx1 = F.nx1, nx2 = F.nx2;
       float theta = (float)thh, zr = (float)rr;
-      float x1 = logf(zr);
+      float x1 = r4log(zr);
       float x2 = (float)harm_x2_of_theta((double)theta, (double)F.h);
       int lx1 = (int)floorf((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
       int lx2 = (int)floorf((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;
@@ -306,7 +306,7 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       float zphi = (float)((double)zpp + (double)a / (2.0 * sq1) * log(((double)zr - 1. - sq1) / ((double)zr - 1. + sq1)));
       zphi = (float)fmod((double)zphi, 2. * pi);
       if (zphi < 0.f) zphi = (float)((double)zphi + 2. * pi);
-      float x1 = logf(zr), x3 = zphi;
+      float x1 = r4log(zr), x3 = zphi;
       float x2 = (float)((double)theta / pi);
       int lx1 = (int)floorf((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
       int lx2 = (int)floorf((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;

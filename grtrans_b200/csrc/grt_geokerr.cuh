@@ -22,7 +22,6 @@
 
 namespace grt {
 
-#define GRT_PI 3.141592653589793238462643383279502884
 
 struct RayConst {  // one pixel of the camera (geodesics.f90:12-21 geokerr_args, per-ray slice)
   double a, mu0, u0, uout, alpha, beta, q2, l, su, sm, uf, muf, offset, phi0, t0;

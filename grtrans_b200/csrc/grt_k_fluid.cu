@@ -1,0 +1,27 @@
+// grtrans_b200 -- fluid sampling + comoving frame + unit conversion kernel.
+//   k_fluid_ortho    thread / (ray, point)   x^mu, k^mu, fluid gather, tetrad, cgs conversion -> 128-byte point record per mdot
+// THIS FILE IS COMPILED WITH -fmad=false.  The reference does its cell-index, weight, metric and LNRF arithmetic in
+// real(4) (fluid_model_*.f90, kerr.f90:361-379,427-500); gfortran/x86-64 code does not fuse multiply-adds, and several of
+// those expressions cancel strongly (b.b with the float32 metric, u^t normalisation), so a fused fmaf changes the result by
+// far more than one ulp.  Unfused float32 arithmetic + correctly rounded float32 libm calls (r4sin, r4log, ... in
+// grt_math.cuh) make this stage bit-faithful to the CPU evaluation order.
+#include "grt_kernels.h"
+
+namespace grt {
+
+__global__ void __launch_bounds__(128) k_fluid_ortho(const RayConst *__restrict__ rc, const RayInv *__restrict__ inv,
+                                                     const RayMeta *__restrict__ meta, FluidKernelArgs A, long long total,
+                                                     int nrays, PointArrays pa, double *__restrict__ rec, StageDump sd) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ray = (int)(idx / A.maxpts), slot = (int)(idx % A.maxpts);
+  point_record(rc[ray], meta[ray], A, ray, slot, nrays, pa, rec, sd);
+}
+
+void launch_fluid_ortho(const RayConst *rc, const RayInv *inv, const RayMeta *meta, const FluidKernelArgs &A, long long total,
+                        int nrays, PointArrays pa, double *rec, StageDump sd, cudaStream_t st) {
+  const int B = 128;
+  k_fluid_ortho<<<(unsigned)((total + B - 1) / B), B, 0, st>>>(rc, inv, meta, A, total, nrays, pa, rec, sd);
+}
+
+}  // namespace grt

@@ -1,0 +1,47 @@
+// grtrans_b200 -- geodesic kernels (SURVEY.md 8a rows R2, R3 bookkeeping).
+//   k_ray_setup      thread / ray            geo_setup()   -> RayInv  (per-ray invariants: roots, NCASE, u0/mu0 integrals)
+//   k_geo_points     thread / (ray, point)   geo_point()   -> u, mu, dt, dphi, lambda, tpm, tpr
+//   k_ray_finalize   thread / ray            trim / status / lambda_N, t_1
+#include "grt_kernels.h"
+
+namespace grt {
+
+__global__ void __launch_bounds__(128) k_ray_setup(const RayConst *__restrict__ rc, GeoFlags fl, RayInv *__restrict__ inv, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RayConst r = rc[i];
+  RayInv c;
+  geo_setup(r, fl, c);
+  inv[i] = c;
+}
+
+__global__ void __launch_bounds__(128) k_geo_points(const RayInv *__restrict__ inv, int nup, int maxpts, long long total, PointArrays pa) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int ray = (int)(idx / maxpts), slot = (int)(idx % maxpts);
+  point_store(inv[ray], nup, slot, (size_t)idx, pa);
+}
+
+__global__ void __launch_bounds__(128) k_ray_finalize(const RayInv *__restrict__ inv, int maxpts, int usegeor, int n, PointArrays pa,
+                               RayMeta *__restrict__ meta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RayMeta m;
+  ray_finalize(inv[i].npts, (size_t)i, maxpts, usegeor, pa, m);
+  meta[i] = m;
+}
+
+void launch_ray_setup(const RayConst *rc, GeoFlags fl, RayInv *inv, int n, cudaStream_t st) {
+  const int B = 128;
+  k_ray_setup<<<(n + B - 1) / B, B, 0, st>>>(rc, fl, inv, n);
+}
+void launch_geo_points(const RayInv *inv, int nup, int maxpts, long long total, PointArrays pa, cudaStream_t st) {
+  const int B = 128;
+  k_geo_points<<<(unsigned)((total + B - 1) / B), B, 0, st>>>(inv, nup, maxpts, total, pa);
+}
+void launch_ray_finalize(const RayInv *inv, int maxpts, int usegeor, int n, PointArrays pa, RayMeta *meta, cudaStream_t st) {
+  const int B = 128;
+  k_ray_finalize<<<(n + B - 1) / B, B, 0, st>>>(inv, maxpts, usegeor, n, pa, meta);
+}
+
+}  // namespace grt

@@ -1,0 +1,211 @@
+// grtrans_b200 -- emissivity + polarised transfer kernels and the unit-surface kernels.
+//   k_transfer       thread / (ray, mdot, nu)  emissivity + DELO/FORMAL/quadrature/RK march -> float32 Stokes image
+#include "grt_kernels.h"
+
+namespace grt {
+
+// image layout: [cam][ray_local][nvals] float32, cam = (mu_index*nparams + m)*nfreq + k.
+// Thread = (ray, mdot, frequency), frequency fastest: the 32 lanes of a warp march the SAME ray at 32 frequencies, so the
+// 128-byte point record is one broadcast load per step and the lanes never diverge on npts.
+template <int ET, int MODE>
+__global__ void __launch_bounds__(128) k_transfer(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
+                                                  const double *__restrict__ freqs, int nfreq, int nparams, int nrays, int maxpts,
+                                                  const double *__restrict__ rec, float *__restrict__ image, long long ray_off,
+                                                  long long nlocal, int cam0) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)nrays * nparams * nfreq;
+  if (idx >= total) return;
+  int f = (int)(idx % nfreq);
+  int mm = (int)((idx / nfreq) % nparams);
+  int ray = (int)(idx / ((long long)nfreq * nparams));
+  RayMeta m = meta[ray];
+  constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
+  double out[4] = {0, 0, 0, 0};
+  if (m.status == 1 && m.npts > 0) {
+    P.LBH = lbh_m[mm];
+    const double *rr = rec + ((size_t)mm * nrays * maxpts + (size_t)ray * maxpts) * GRT_NREC;
+    ray_transfer_t<ET, MODE>(P, rr, m.npts, freqs[f], out);
+  }
+  int cam = cam0 + mm * nfreq + f;
+  float *dst = image + ((size_t)cam * nlocal + (ray_off + ray)) * neq;
+  if (neq == 4)
+    *reinterpret_cast<float4 *>(dst) = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
+  else
+    dst[0] = (float)out[0];
+}
+
+// small stand-alone kernels for the unit-level C ABI
+__global__ void k_polsynchth(int n, const double *nu, const double *nc, const double *b, const double *t, const double *th, double *e) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  polsynchth_eval(nu[i], nc[i], b[i], t[i], th[i], e + 11 * (size_t)i);
+}
+__global__ void k_polsynchpl(int n, EmisTables tab, const double *nu, const double *nnth, const double *b, const double *th,
+                             const double *p, const double *gmin, double gmax, double *e) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  synchpl_eval<true>(tab, nu[i], nnth[i], b[i], th[i], p[i], gmin[i], gmax, e + 11 * (size_t)i);
+}
+__global__ void k_synchemis(int n, const double *nu, const double *nc, const double *b, const double *t, double *e) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  synchemis_eval(nu[i], nc[i], b[i], t[i], e + 11 * (size_t)i);
+}
+
+// generic-coefficient integration (radtrans_integrate f2py surface): one thread per ray
+__global__ void k_rt_integrate(int iflag, int neq, int nrays, int npts, const double *s, const double *j, const double *K,
+                               const double *tau, double *intensity, int *nptsout, TransferParams P) {
+  int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= nrays) return;
+  const int nk = 1 + neq * (neq - 1) / 2;
+  const double *ss = s + (size_t)ray * npts, *jj = j + (size_t)ray * npts * neq, *KK = K + (size_t)ray * npts * nk,
+               *tt = tau + (size_t)ray * npts;
+  double *I = intensity + (size_t)ray * npts * neq;
+  for (int i = 0; i < npts * neq; i++) I[i] = 0.0;
+  auto load = [&](int k, Coef &c) {  // k 0-based node
+    for (int i = 0; i < 4; i++) c.j[i] = (i < neq) ? jj[(size_t)k * neq + i] : 0.0;
+    for (int i = 0; i < 7; i++) c.K[i] = (i < nk) ? KK[(size_t)k * nk + i] : 0.0;
+  };
+  if (iflag != 0 && neq == 4) {
+    double Ip[4] = {0, 0, 0, 0}, In[4];
+    Coef c0, c1;
+    load(npts - 1, c1);
+    for (int k = npts - 2; k >= 0; k--) {
+      load(k, c0);
+      double dx = ss[k] - ss[k + 1];
+      if (iflag == 1)
+        delo_step(c0, c1, dx, tt[k + 1] - tt[k], P.thin, Ip, In);
+      else {
+        double v[4];
+        for (int i = 0; i < 4; i++) v[i] = c0.j[i] * dx + Ip[i];
+        formal_apply(c0.K, dx, v, In);
+      }
+      int col = npts - 1 - k;
+      for (int i = 0; i < 4; i++) {
+        Ip[i] = In[i];
+        I[(size_t)col * 4 + i] = In[i];
+      }
+      c1 = c0;
+    }
+    nptsout[ray] = npts;
+    return;
+  }
+  if (iflag != 0) {
+    double acc = 0.0, yprev = jj[0] * exp(-tt[0]);
+    I[0] = 0.0;
+    for (int k = 1; k < npts; k++) {
+      double y = jj[(size_t)k * neq] * exp(-tt[k]);
+      acc += (ss[k] - ss[k - 1]) * (yprev + y) / 2.0;
+      I[(size_t)k * neq] = -acc;
+      yprev = y;
+    }
+    nptsout[ray] = npts;
+    return;
+  }
+  // lsoda replacement
+  int lamdex = npts, i1 = 1, i2 = 0;
+  double maxtau = tt[0];
+  for (int k = 1; k < npts; k++) maxtau = dmax(maxtau, tt[k]);
+  if (maxtau > P.max_tau) {
+    for (int k = 0; k < npts; k++)
+      if (tt[k] > P.max_tau) {
+        lamdex = k + 1;
+        break;
+      }
+  }
+  if (jj[0] == 0.0)
+    for (int ii = 2; ii <= npts; ii++)
+      if (jj[(size_t)(ii - 1) * neq] != 0.0) {
+        i1 = ii;
+        break;
+      }
+  if (jj[(size_t)(lamdex - 1) * neq] == 0.0) {
+    for (int ii = 1; ii <= lamdex - 1; ii++)
+      if (jj[(size_t)(lamdex - ii - 1) * neq] != 0.0) {
+        i2 = lamdex - ii;
+        break;
+      }
+  } else
+    i2 = lamdex;
+  nptsout[ray] = i2;
+  if (i2 <= i1) return;
+  double y[4] = {0, 0, 0, 0}, h = P.hmax;
+  Coef ca, cb;
+  bool ok = true;
+  for (int m = 1; m <= i2 - i1; m++) {
+    int indx = i2 - m + 1;
+    load(indx - 1, ca);
+    load(((indx + 1 <= npts) ? indx + 1 : npts) - 1, cb);
+    double la = ss[indx - 1], lb = ss[indx - 2];
+    if (lb > la) ok = ck_interval(neq, ca, cb, la, lb, y, h, P);
+    if (!ok) break;
+    for (int i = 0; i < neq; i++) I[(size_t)(i1 - 1 + m) * neq + i] = y[i];
+  }
+  if (!ok)
+    for (int i = 0; i < npts * neq; i++) I[i] = 0.0;
+}
+
+// FP64 FMA peak micro-benchmark: 8 independent chains per thread
+__global__ void k_dfma(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+template <int ET>
+static void launch_transfer_e(int mode, unsigned grid, cudaStream_t st, const RayMeta *meta, const TransferParams &P,
+                              const double *lbh_m, const double *freqs, int nfreq, int nparams, int nrays, int maxpts,
+                              const double *rec, float *image, long long ray_off, long long nlocal, int cam0) {
+  const int B = 128;
+#define GRT_LAUNCH(M) \
+  k_transfer<ET, M><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0)
+  switch (mode) {
+    case MODE_DELO: GRT_LAUNCH(MODE_DELO); break;
+    case MODE_FORMAL: GRT_LAUNCH(MODE_FORMAL); break;
+    case MODE_QUAD: GRT_LAUNCH(MODE_QUAD); break;
+    case MODE_RK4: GRT_LAUNCH(MODE_RK4); break;
+    default: GRT_LAUNCH(MODE_RK1); break;
+  }
+#undef GRT_LAUNCH
+}
+
+void launch_transfer(const RayMeta *meta, const TransferParams &P, const double *lbh_m, const double *freqs, int nfreq,
+                     int nparams, int nrays, int maxpts, const double *rec, float *image, long long ray_off, long long nlocal,
+                     int cam0, cudaStream_t st) {
+  const int B = 128;
+  long long tt = (long long)nrays * nparams * nfreq;
+  unsigned grid = (unsigned)((tt + B - 1) / B);
+  const int mode = transfer_mode(P);
+  switch (P.etype) {
+#define OP(E) \
+  case E: launch_transfer_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0); break;
+    GRT_FOR_ETYPES(OP)
+#undef OP
+    default: break;
+  }
+}
+void launch_polsynchth(int n, const double *nu, const double *nc, const double *b, const double *t, const double *th, double *e) {
+  const int B = 128;
+  k_polsynchth<<<(n + B - 1) / B, B>>>(n, nu, nc, b, t, th, e);
+}
+void launch_polsynchpl(int n, EmisTables tab, const double *nu, const double *nnth, const double *b, const double *th,
+                       const double *p, const double *gmin, double gmax, double *e) {
+  const int B = 128;
+  k_polsynchpl<<<(n + B - 1) / B, B>>>(n, tab, nu, nnth, b, th, p, gmin, gmax, e);
+}
+void launch_synchemis(int n, const double *nu, const double *nc, const double *b, const double *t, double *e) {
+  const int B = 128;
+  k_synchemis<<<(n + B - 1) / B, B>>>(n, nu, nc, b, t, e);
+}
+void launch_rt_integrate(int iflag, int neq, int nrays, int npts, const double *s, const double *j, const double *K,
+                         const double *tau, double *intensity, int *nptsout, const TransferParams &P) {
+  const int B = 64;
+  k_rt_integrate<<<(nrays + B - 1) / B, B>>>(iflag, neq, nrays, npts, s, j, K, tau, intensity, nptsout, P);
+}
+void launch_dfma(double *out, int blocks, int threads, int iters) { k_dfma<<<blocks, threads>>>(out, iters); }
+
+}  // namespace grt

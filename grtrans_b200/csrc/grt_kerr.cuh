@@ -33,7 +33,7 @@ struct MetricF {
   float tt, tp, rr, hh, pp;
 };
 GRT_HD MetricF bl_metric_f(float r, float th, float a) {
-  float cth = cosf(th), sth = sinf(th);
+  float cth = r4cos(th), sth = r4sin(th);
   float delta = r * r - 2.f * r + a * a;
   float rho2 = r * r + a * a * cth * cth;
   float sigma = (r * r + a * a) * (r * r + a * a) - a * a * delta * sth * sth;
@@ -72,7 +72,7 @@ GRT_HD void null_momentum(double q2, double l, double a, double r, double mu, do
 
 // LNRF 3-velocity -> coordinate 3-velocity (single precision, as the reference stores fluid data)
 GRT_HD void lnrf_inv_f(float vr, float vt, float om_l, float r, float a, float th, float &vrc, float &vtc, float &vpc) {
-  float mu = cosf(th);
+  float mu = r4cos(th);
   float D = r * r - 2.f * r + a * a;
   float AR = (r * r + a * a) * (r * r + a * a) - a * a * D * (1.f - mu * mu);
   float RHO = r * r + a * a * mu * mu;
@@ -88,7 +88,7 @@ GRT_HD void lnrf_inv_f(float vr, float vt, float om_l, float r, float a, float t
 }
 
 GRT_HD void lnrf_fwd_f(float vr, float vt, float omega, float r, float a, float th, float &vrl, float &vtl, float &vpl) {
-  float mu = cosf(th);
+  float mu = r4cos(th);
   float D = r * r - 2.f * r + a * a;
   float AR = (r * r + a * a) * (r * r + a * a) - a * a * D * (1.f - mu * mu);
   float RHO = r * r + a * a * mu * mu;
@@ -104,7 +104,7 @@ GRT_HD void lnrf_fwd_f(float vr, float vt, float omega, float r, float a, float 
 }
 
 GRT_HD float isco_radius_f(float a) {
-  float z1 = 1.f + powf(1.f - a * a, 1.f / 3.f) * (powf(1.f + a, 1.f / 3.f) + powf(1.f - a, 1.f / 3.f));
+  float z1 = 1.f + r4pow(1.f - a * a, 1.f / 3.f) * (r4pow(1.f + a, 1.f / 3.f) + r4pow(1.f - a, 1.f / 3.f));
   float z2 = sqrtf(3.f * a * a + z1 * z1);
   float s = sqrtf((3.f - z1) * (3.f + z1 + 2.f * z2));
   return 3.f + z2 - (signbit(a) ? -fabsf(s) : fabsf(s));

@@ -14,11 +14,13 @@
 
 #if defined(__CUDACC__)
 #define GRT_HD __host__ __device__ __forceinline__
-#define GRT_HDN __host__ __device__ __noinline__
+#define GRT_HDN inline __host__ __device__ __noinline__
 #else
 #define GRT_HD inline
-#define GRT_HDN
+#define GRT_HDN inline
 #endif
+
+#define GRT_PI 3.141592653589793238462643383279502884
 
 namespace grt {
 
@@ -27,6 +29,27 @@ GRT_HD double dmin(double a, double b) { return a < b ? a : b; }
 GRT_HD double sgn(double b) { return signbit(b) ? -1.0 : 1.0; }      // Fortran SIGN(1d0,b)
 GRT_HD double pm1(int n) { return (n & 1) ? -1.0 : 1.0; }            // (-1)**n
 GRT_HD double sq(double x) { return x * x; }
+
+// ---- real(4) libm calls ---------------------------------------------------------------------------
+// The reference's real(4) code calls glibc's float functions, which are correctly rounded in all but
+// vanishingly rare cases.  CUDA's sinf/cosf/logf/powf/... are 1-2 ulp functions, and a 1-ulp difference
+// is amplified by the cancellations downstream (u^t normalisation, b.b), so on the device the float32
+// calls are evaluated in FP64 and rounded once -- the same value the CPU produces.
+#if defined(__CUDA_ARCH__)
+GRT_HD float r4sin(float x) { return (float)sin((double)x); }
+GRT_HD float r4cos(float x) { return (float)cos((double)x); }
+GRT_HD float r4log(float x) { return (float)log((double)x); }
+GRT_HD float r4exp(float x) { return (float)exp((double)x); }
+GRT_HD float r4acos(float x) { return (float)acos((double)x); }
+GRT_HD float r4pow(float x, float y) { return (float)pow((double)x, (double)y); }
+#else
+GRT_HD float r4sin(float x) { return sinf(x); }
+GRT_HD float r4cos(float x) { return cosf(x); }
+GRT_HD float r4log(float x) { return logf(x); }
+GRT_HD float r4exp(float x) { return expf(x); }
+GRT_HD float r4acos(float x) { return acosf(x); }
+GRT_HD float r4pow(float x, float y) { return powf(x, y); }
+#endif
 
 // ---- Carlson R_F ------------------------------------------------------------------------------
 GRT_HDN double rf(double x, double y, double z) {
@@ -251,8 +274,8 @@ GRT_HDN void laguer(const cpx *A, int M, cpx &X) {
     if (dmax(abp, abm) > 0.0) {
       DX = cdiv(cmk((double)M, 0.0), GP);
     } else {
-      float mag = expf((float)log(1.0 + abx));
-      DX = cmk((double)(mag * cosf((float)it)), (double)(mag * sinf((float)it)));
+      float mag = r4exp((float)log(1.0 + abx));
+      DX = cmk((double)(mag * r4cos((float)it)), (double)(mag * r4sin((float)it)));
     }
     cpx X1 = csub(X, DX);
     if (X.re == X1.re && X.im == X1.im) return;

@@ -77,7 +77,7 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
   double u = pa.u[src], mu = pa.mu[src];
   double r = 1.0 / u, th = acos(mu);
   // g%gk%phi0 = acos(-1.)*phi0 : pi in SINGLE precision (geodesics.f90:218)
-  double ph = (double)acosf(-1.f) * r0.phi0 - pa.dphi[src];
+  double ph = (double)r4acos(-1.f) * r0.phi0 - pa.dphi[src];
   if (fabs(r0.mu0) == 1.0) ph += sgn(r0.mu0) * atan2(r0.beta, r0.alpha);
   double lam, t;
   int tpm, tpr;
@@ -110,9 +110,9 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
     switch (A.etype) {
       case EM_POLSYNCHTH: {
         ThermalPoint T;
-        thermal_point(cg.ncgs, cg.bcgs, cg.tcgs, oo.ang, T);
-        o[4] = T.n; o[5] = T.b; o[6] = T.t; o[7] = T.sinth; o[8] = T.costh; o[9] = T.k0; o[10] = T.k1ok2; o[11] = T.ik2;
-        o[12] = T.step; o[13] = T.tanth;
+        thermal_point(cg.ncgs, cg.bcgs, cg.tcgs, oo.ang, oo.g, pc::G * A.sp[mm].mbh * pc::msun / pc::c2, T);
+        o[4] = T.lnu_off; o[5] = T.AI; o[6] = T.AV; o[7] = T.hkT_g; o[8] = T.lAx; o[9] = T.RQ; o[10] = T.RV0; o[11] = T.RV1;
+        o[12] = T.ig;
       } break;
       case EM_POLSYNCHPL:
       case EM_SYNCHPL:

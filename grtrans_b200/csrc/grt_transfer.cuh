@@ -23,6 +23,13 @@
 namespace grt {
 
 #define GRT_NREC 16  // doubles per point record (128 B)
+// record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
+//   POLSYNCHTH        [4..12] ThermalPoint (lnu_off, AI, AV, hkT_g, lAx, RQ, RV0, RV1, 1/g)
+//   POLSYNCHPL/SYNCHPL [4] n_nth, [5] B, [6] angle
+//   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
+
+// integration modes (rad_trans.f90:30-38 iflag x neq)
+enum { MODE_RK4 = 0, MODE_DELO = 1, MODE_FORMAL = 2, MODE_QUAD = 3, MODE_RK1 = 4 };
 
 struct TransferParams {
   int etype, eneq, rneq, iflag, model, npts_is_one;
@@ -33,53 +40,53 @@ struct TransferParams {
   EmisTables tab;
 };
 
+GRT_HD int transfer_mode(const TransferParams &P) {
+  if (P.iflag != 0) return (P.rneq == 4) ? ((P.iflag == 1) ? MODE_DELO : MODE_FORMAL) : MODE_QUAD;
+  return (P.rneq == 4) ? MODE_RK4 : MODE_RK1;
+}
+
 struct Coef {
   double j[4], K[7];
 };
 
-// record -> invariant, LBH-scaled coefficients at observed frequency nu_obs.  jI_raw returns the
-// comoving un-boosted j_I used for fac.
-GRT_HD void node_coef(const TransferParams &P, const double *rec, double nu_obs, Coef &c, double &jI_raw) {
+// record -> invariant, LBH-scaled coefficients at observed frequency F.nu.  jI_raw returns the comoving un-boosted j_I used
+// for the driver's `fac` (grtrans_driver.f90:183-187).  Replaces calc_emissivity + the e%j/e%K copy (emis.f90:461-571),
+// rotate_emis (:797-829), invariant_emis (:831-838) and the K*LBH scaling (grtrans_driver.f90:217).
+template <int ET>
+GRT_HD void node_coef(const TransferParams &P, const double *rec, const FreqConst &F, Coef &c, double &jI_raw) {
   const double g = rec[1];
-  double nu = nu_obs / g;
   double e[11];
-  switch (P.etype) {
-    case EM_POLSYNCHTH: {
-      ThermalPoint T;
-      T.n = rec[4]; T.b = rec[5]; T.t = rec[6]; T.sinth = rec[7]; T.costh = rec[8]; T.k0 = rec[9]; T.k1ok2 = rec[10];
-      T.ik2 = rec[11]; T.step = rec[12];
-      T.tanth = rec[13];
-      T.thetae = pc::k * T.t / pc::m / pc::c / pc::c + 1e-10;
-      T.nucfac = 3.0 * pc::e * T.b * T.sinth / 4.0 / GRT_PI / pc::m / pc::c * T.thetae * T.thetae + 1.0;
-      polsynchth_eval(T, nu, e);
-    } break;
-    case EM_POLSYNCHPL:
+  bool invariant = false;  // e already holds j g^2 and K LBH / g
+  if (ET == EM_POLSYNCHTH) {
+    ThermalPoint T;
+    T.lnu_off = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.lAx = rec[8]; T.RQ = rec[9]; T.RV0 = rec[10];
+    T.RV1 = rec[11]; T.ig = rec[12]; T.g = g;
+    thermal_eval(T, F, pc::c2 * P.LBH / (2.0 * pc::h), e, jI_raw);
+    invariant = true;
+  } else {
+    const double nu = F.nu / g;
+    if (ET == EM_POLSYNCHPL)
       synchpl_eval<true>(P.tab, nu, rec[4], rec[5], rec[6], P.p, P.gmin, P.gmax, e);
-      break;
-    case EM_SYNCHPL:
+    else if (ET == EM_SYNCHPL)
       synchpl_eval<false>(P.tab, nu, rec[4], rec[5], rec[6], P.p, P.gmin, P.gmax, e);
-      break;
-    case EM_SYNCHTHAV:
+    else if (ET == EM_SYNCHTHAV)
       synchemis_eval(nu, rec[4], rec[5], rec[6], e);
-      break;
-    case EM_BB:
+    else {
       for (int i = 0; i < 11; i++) e[i] = 0.0;
-      e[0] = planck_bnu(rec[6], nu);
-      break;
-    case EM_BBPOL: {
-      for (int i = 0; i < 11; i++) e[i] = 0.0;
-      const double fcol = 1.8;
-      e[0] = pow(fcol, -4.0) * planck_bnu(rec[6] * fcol, nu);
-      e[0] = e[0] * rec[7];
-      e[1] = e[0] * rec[8];
-    } break;
-    default:
-      for (int i = 0; i < 11; i++) e[i] = 0.0;
+      if (ET == EM_BB) e[0] = planck_bnu(rec[6], nu);
+      if (ET == EM_BBPOL) {
+        const double fcol = 1.8;
+        e[0] = pow(fcol, -4.0) * planck_bnu(rec[6] * fcol, nu);
+        e[0] = e[0] * rec[7];
+        e[1] = e[0] * rec[8];
+      }
+    }
+    jI_raw = e[0];
   }
-  jI_raw = e[0];
   for (int i = 0; i < 4; i++) c.j[i] = 0.0;
   for (int i = 0; i < 7; i++) c.K[i] = 0.0;
-  if (P.eneq == 4) {
+  constexpr bool POL = (ET == EM_POLSYNCHTH || ET == EM_POLSYNCHPL || ET == EM_BBPOL);
+  if (POL) {
     for (int i = 0; i < 4; i++) c.j[i] = e[i];
     for (int i = 0; i < 7; i++)
       if (P.coefindx[i] == 1) c.K[i] = e[4 + i];
@@ -96,11 +103,13 @@ GRT_HD void node_coef(const TransferParams &P, const double *rec, double nu_obs,
     c.K[0] = e[4];
   }
   if (!P.npts_is_one) {
-    for (int i = 0; i < 4; i++) c.j[i] = c.j[i] * g * g;
-    for (int i = 0; i < 7; i++) c.K[i] = c.K[i] / g * P.LBH;
-  } else {
-    double g3 = g * g * g;
-    for (int i = 0; i < 4; i++) c.j[i] = c.j[i] * g3;
+    if (!invariant) {
+      for (int i = 0; i < 4; i++) c.j[i] = c.j[i] * g * g;
+      for (int i = 0; i < 7; i++) c.K[i] = c.K[i] / g * P.LBH;
+    }
+  } else {  // single-point rays (thin disk): I = j g^3, no LBH (grtrans_driver.f90:293-297)
+    double s = invariant ? g : g * g * g;
+    for (int i = 0; i < 4; i++) c.j[i] = c.j[i] * s;
   }
   if (P.rneq == 1) {  // Stokes-I-only transfer of a polarised model (A21): keep j_I, alpha_I
     c.j[1] = c.j[2] = c.j[3] = 0.0;
@@ -116,56 +125,54 @@ GRT_HD void kmat_vec(const double *K, const double *x, double *y) {  // opacity_
   y[3] = K[3] * x[0] + K[5] * x[1] - K[4] * x[2] + K[0] * x[3];
 }
 
-// y = (c1*Id + c2*Kmat)^-1 x through the cofactor inverse of radtrans_integrate.f90:685-733
+// y = (c1*Id + c2*Kmat)^-1 x.  The reference inverts this 4x4 by cofactors (imatrix_4, radtrans_integrate.f90:685-733,
+// ~290 flops).  Kmat = [[aI, a^T], [a, aI - [r]x]] with a = (aQ,aU,aV) and r = (rQ,rU,rV), so with d = c1 + c2 aI,
+// a -> c2 a, r -> c2 r and B w = d w + w x r :
+//   B^-1 w = (d^2 w + d (r x w) + r (r.w)) / (d (d^2 + r^2)),   x0 = (y0 - a.B^-1 yv) / (d - a.B^-1 a),   xv = B^-1 (yv - a x0)
+// which is the same exact inverse (det = d^2 (d^2 + r^2 - a^2) - (a.r)^2) in ~70 flops and two reciprocals.
 GRT_HD void solve_delo(double c1, double c2, const double *K, const double *x, double *y) {
   const double d = c1 + c2 * K[0];
-  const double a12 = c2 * K[1], a13 = c2 * K[2], a14 = c2 * K[3];
-  const double a23 = c2 * K[6], a24 = -c2 * K[5], a34 = c2 * K[4];
-  const double a11 = d, a22 = d, a33 = d, a44 = d, a21 = a12, a31 = a13, a41 = a14, a32 = -a23, a42 = -a24, a43 = -a34;
-  double b11 = a22 * a33 * a44 + a23 * a34 * a42 + a24 * a32 * a43 - a22 * a34 * a43 - a23 * a32 * a44 - a24 * a33 * a42;
-  double b12 = a12 * a34 * a43 + a13 * a32 * a44 + a14 * a33 * a42 - a12 * a33 * a44 - a13 * a34 * a42 - a14 * a32 * a43;
-  double b13 = a12 * a23 * a44 + a13 * a24 * a42 + a14 * a22 * a43 - a12 * a24 * a43 - a13 * a22 * a44 - a14 * a23 * a42;
-  double b14 = a12 * a24 * a33 + a13 * a22 * a34 + a14 * a23 * a32 - a12 * a23 * a34 - a13 * a24 * a32 - a14 * a22 * a33;
-  double b21 = a21 * a34 * a43 + a23 * a31 * a44 + a24 * a33 * a41 - a21 * a33 * a44 - a23 * a34 * a41 - a24 * a31 * a43;
-  double b22 = a11 * a33 * a44 + a13 * a34 * a41 + a14 * a31 * a43 - a11 * a34 * a43 - a13 * a31 * a44 - a14 * a33 * a41;
-  double b23 = a11 * a24 * a43 + a13 * a21 * a44 + a14 * a23 * a41 - a11 * a23 * a44 - a13 * a24 * a41 - a14 * a21 * a43;
-  double b24 = a11 * a23 * a34 + a13 * a24 * a31 + a14 * a21 * a33 - a11 * a24 * a33 - a13 * a21 * a34 - a14 * a23 * a31;
-  double b31 = a21 * a32 * a44 + a22 * a34 * a41 + a24 * a31 * a42 - a21 * a34 * a42 - a22 * a31 * a44 - a24 * a32 * a41;
-  double b32 = a11 * a34 * a42 + a12 * a31 * a44 + a14 * a32 * a41 - a11 * a32 * a44 - a12 * a34 * a41 - a14 * a31 * a42;
-  double b33 = a11 * a22 * a44 + a12 * a24 * a41 + a14 * a21 * a42 - a11 * a24 * a42 - a12 * a21 * a44 - a14 * a22 * a41;
-  double b34 = a11 * a24 * a32 + a12 * a21 * a34 + a14 * a22 * a31 - a11 * a22 * a34 - a12 * a24 * a31 - a14 * a21 * a32;
-  double b41 = a21 * a33 * a42 + a22 * a31 * a43 + a23 * a32 * a41 - a21 * a32 * a43 - a22 * a33 * a41 - a23 * a31 * a42;
-  double b42 = a11 * a32 * a43 + a12 * a33 * a41 + a13 * a31 * a42 - a11 * a33 * a42 - a12 * a31 * a43 - a13 * a32 * a41;
-  double b43 = a11 * a23 * a42 + a12 * a21 * a43 + a13 * a22 * a41 - a11 * a22 * a43 - a12 * a23 * a41 - a13 * a21 * a42;
-  double b44 = a11 * a22 * a33 + a12 * a23 * a31 + a13 * a21 * a32 - a11 * a23 * a32 - a12 * a21 * a33 - a13 * a22 * a31;
-  double det = a11 * b11 + a21 * b12 + a31 * b13 + a41 * b14;
-  double id = 1.0 / det;
-  y[0] = (b11 * x[0] + b12 * x[1] + b13 * x[2] + b14 * x[3]) * id;
-  y[1] = (b21 * x[0] + b22 * x[1] + b23 * x[2] + b24 * x[3]) * id;
-  y[2] = (b31 * x[0] + b32 * x[1] + b33 * x[2] + b34 * x[3]) * id;
-  y[3] = (b41 * x[0] + b42 * x[1] + b43 * x[2] + b44 * x[3]) * id;
+  const double a1 = c2 * K[1], a2 = c2 * K[2], a3 = c2 * K[3];
+  const double r1 = c2 * K[4], r2 = c2 * K[5], r3 = c2 * K[6];
+  const double d2 = d * d;
+  const double rr = r1 * r1 + r2 * r2 + r3 * r3, aa = a1 * a1 + a2 * a2 + a3 * a3, ra = r1 * a1 + r2 * a2 + r3 * a3;
+  const double ry = r1 * x[1] + r2 * x[2] + r3 * x[3];
+  // p = d^2 yv + d (r x yv) + r (r.yv),  s = d^2 a + d (r x a) + r (r.a)
+  const double p1 = d2 * x[1] + d * (r2 * x[3] - r3 * x[2]) + r1 * ry;
+  const double p2 = d2 * x[2] + d * (r3 * x[1] - r1 * x[3]) + r2 * ry;
+  const double p3 = d2 * x[3] + d * (r1 * x[2] - r2 * x[1]) + r3 * ry;
+  const double s1 = d2 * a1 + d * (r2 * a3 - r3 * a2) + r1 * ra;
+  const double s2 = d2 * a2 + d * (r3 * a1 - r1 * a3) + r2 * ra;
+  const double s3 = d2 * a3 + d * (r1 * a2 - r2 * a1) + r3 * ra;
+  const double dn = d * (d2 + rr);
+  const double det = d2 * (d2 + rr - aa) - ra * ra;
+  const double x0 = (x[0] * dn - (a1 * p1 + a2 * p2 + a3 * p3)) / det;
+  const double q = 1.0 / dn;
+  y[0] = x0;
+  y[1] = (p1 - x0 * s1) * q;
+  y[2] = (p2 - x0 * s2) * q;
+  y[3] = (p3 - x0 * s3) * q;
 }
 
 // one DELO step from node k+1 (c1) to node k (c0): returns I at node k
 GRT_HD void delo_step(const Coef &c0, const Coef &c1, double dx, double delta, double thin, const double *iprev,
                       double *inew) {
   double rhs[4], t[4];
+  kmat_vec(c1.K, iprev, t);
   if (delta > thin) {
-    double E = exp(-delta), F = 1.0 - E, G = (1.0 - (1.0 + delta) * E) / delta;
-    // (E*Id - G*Kp1) iprev, Kp1 = K1/aI1 - Id
-    kmat_vec(c1.K, iprev, t);
-    for (int i = 0; i < 4; i++)
-      rhs[i] = (F - G) * (c0.j[i] / c0.K[0]) + G * (c1.j[i] / c1.K[0]) + (E * iprev[i] - G * (t[i] / c1.K[0] - iprev[i]));
+    const double E = exp(-delta), F = 1.0 - E, G = (1.0 - (1.0 + delta) * E) / delta;
+    const double i0 = 1.0 / c0.K[0], i1 = 1.0 / c1.K[0];
+    const double w0 = (F - G) * i0, w1 = G * i1;
+    // (F-G) S_k + G S_k+1 + (E*Id - G*Kp1) iprev,  S = j/aI,  Kp1 = K1/aI1 - Id
+    for (int i = 0; i < 4; i++) rhs[i] = w0 * c0.j[i] + w1 * c1.j[i] + ((E + G) * iprev[i] - w1 * t[i]);
     // matrix = Id + (F-G)*(K0/aI0 - Id) = (1-(F-G)) Id + ((F-G)/aI0) K0
-    solve_delo(1.0 - (F - G), (F - G) / c0.K[0], c0.K, rhs, inew);
+    solve_delo(1.0 - (F - G), w0, c0.K, rhs, inew);
   } else {
-    double ki = c0.K[0];
-    kmat_vec(c1.K, iprev, t);
-    double qa = 1.0 - 0.5 * dx * ki + 1.0 / 6.0 * dx * dx * ki * ki, qb = 0.5 * dx - 1.0 / 3.0 * dx * dx;
-    for (int i = 0; i < 4; i++)
-      rhs[i] = (0.5 * dx * c0.j[i] - 1.0 / 6.0 * dx * dx * ki * c0.j[i]) + (0.5 * c1.j[i] * dx - 1.0 / 3.0 * dx * dx * ki * c1.j[i]) +
-               (qa * iprev[i] - qb * t[i]);
-    solve_delo(1.0 - delta / 2.0 + delta * delta / 6.0, 0.5 * dx - 1.0 / 6.0 * dx * dx * ki, c0.K, rhs, inew);
+    const double ki = c0.K[0];
+    const double qa = 1.0 - 0.5 * dx * ki + 1.0 / 6.0 * dx * dx * ki * ki, qb = 0.5 * dx - 1.0 / 3.0 * dx * dx;
+    const double wa = 0.5 * dx - 1.0 / 6.0 * dx * dx * ki, wb = 0.5 * dx - 1.0 / 3.0 * dx * dx * ki;
+    for (int i = 0; i < 4; i++) rhs[i] = wa * c0.j[i] + wb * c1.j[i] + (qa * iprev[i] - qb * t[i]);
+    solve_delo(1.0 - delta / 2.0 + delta * delta / 6.0, wa, c0.K, rhs, inew);
   }
 }
 
@@ -279,15 +286,18 @@ GRT_HD bool ck_interval(int neq, const Coef &ca, const Coef &cb, double la, doub
 }
 
 // ---- the per-(ray, frequency) march ------------------------------------------------------------------
-// rec: [npts][GRT_NREC] records of this ray.  out: nvals Stokes values in cgs.
-GRT_HDN void ray_transfer(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
-  const int neq = P.rneq;
+// rec: [npts][GRT_NREC] records of this ray.  out: nvals Stokes values in cgs.  One instance per (emissivity, mode) so that
+// the hot loop of each kernel is a few thousand instructions (it has to live in the 32 KB L1.5 instruction cache).
+template <int ET, int MODE>
+GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
+  constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
   for (int i = 0; i < neq; i++) out[i] = 0.0;
   if (npts <= 0) return;
+  const FreqConst F = freq_const(nu_obs);
   double jraw;
   if (npts == 1) {
     Coef c;
-    node_coef(P, rec, nu_obs, c, jraw);
+    node_coef<ET>(P, rec, F, c, jraw);
     double fac = jraw / 1.0;
     if (fac / 1e16 > 0.0)
       for (int i = 0; i < neq; i++) out[i] = c.j[i];
@@ -295,47 +305,59 @@ GRT_HDN void ray_transfer(const TransferParams &P, const double *rec, int npts, 
   }
   const double lam0 = rec[0];
   double fac = 0.0;
-  if (P.iflag != 0 && neq == 4) {
-    // DELO / FORMAL: march from the deepest point to the camera
+  if (MODE == MODE_DELO || MODE == MODE_FORMAL) {
+    // march from the deepest point to the camera, I = 0 behind the last point
     double I[4] = {0, 0, 0, 0}, In[4];
     Coef c1, c0;
-    node_coef(P, rec + (size_t)(npts - 1) * GRT_NREC, nu_obs, c1, jraw);
-    fac += jraw * (lam0 - rec[(size_t)(npts - 1) * GRT_NREC]);
-    for (int k = npts - 2; k >= 0; k--) {
+    double lam1 = 0.0;
+#pragma unroll 1
+    for (int k = npts - 1; k >= 0; k--) {
       const double *rk = rec + (size_t)k * GRT_NREC;
-      node_coef(P, rk, nu_obs, c0, jraw);
-      fac += jraw * (lam0 - rk[0]);
-      double dx = rk[0] - rk[GRT_NREC];
-      if (P.iflag == 1) {
-        double delta = dx * 0.5 * (fabs(c0.K[0]) + fabs(c1.K[0]));
-        delo_step(c0, c1, dx, delta, P.thin, I, In);
-      } else {
-        double v[4];
-        for (int i = 0; i < 4; i++) v[i] = c0.j[i] * dx + I[i];
-        formal_apply(c0.K, dx, v, In);
+      const double lamk = rk[0];
+      node_coef<ET>(P, rk, F, c0, jraw);
+      fac += jraw * (lam0 - lamk);
+      if (k < npts - 1) {
+        const double dx = lamk - lam1;
+        if (MODE == MODE_DELO) {
+          double delta = dx * 0.5 * (fabs(c0.K[0]) + fabs(c1.K[0]));
+          delo_step(c0, c1, dx, delta, P.thin, I, In);
+        } else {
+          double v[4];
+          for (int i = 0; i < 4; i++) v[i] = c0.j[i] * dx + I[i];
+          formal_apply(c0.K, dx, v, In);
+        }
+#ifdef GRT_DEBUG_TRANSFER
+        if (In[0] != In[0] && I[0] == I[0]) printf("NaN at k=%d dx=%g j0=%g K0=%g j1=%g K1=%g I=%g rq=%g rv=%g aq=%g\n", k, dx, c0.j[0], c0.K[0], c1.j[0], c1.K[0], I[0], c0.K[4], c0.K[6], c0.K[1]);
+#endif
+        for (int i = 0; i < 4; i++) I[i] = In[i];
       }
-      for (int i = 0; i < 4; i++) I[i] = In[i];
       c1 = c0;
+      lam1 = lamk;
     }
     if (fac / 1e16 > 0.0)
       for (int i = 0; i < 4; i++) out[i] = I[i] * P.LBH;
     return;
   }
-  if (P.iflag != 0) {
+  if (MODE == MODE_QUAD) {
     // neq == 1 with delo/formal: quadrature  I = -tsum(s, j exp(-tau)), tau from the camera inwards
     Coef c;
-    node_coef(P, rec, nu_obs, c, jraw);
-    double tau = 0.0, acc = 0.0, yprev = c.j[0], kprev = fabs(c.K[0]);
-    for (int k = 1; k < npts; k++) {
+    double tau = 0.0, acc = 0.0, yprev = 0.0, kprev = 0.0, lprev = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < npts; k++) {
       const double *rk = rec + (size_t)k * GRT_NREC;
-      node_coef(P, rk, nu_obs, c, jraw);
-      fac += jraw * (lam0 - rk[0]);
-      double ds = rk[0] - rk[-GRT_NREC];
-      tau -= ds * (kprev + fabs(c.K[0])) / 2.0;
-      double y = c.j[0] * exp(-tau);
-      acc += ds * (yprev + y) / 2.0;
-      yprev = y;
+      node_coef<ET>(P, rk, F, c, jraw);
+      if (k > 0) {
+        fac += jraw * (lam0 - rk[0]);
+        double ds = rk[0] - lprev;
+        tau -= ds * (kprev + fabs(c.K[0])) / 2.0;
+        double y = c.j[0] * exp(-tau);
+        acc += ds * (yprev + y) / 2.0;
+        yprev = y;
+      } else {
+        yprev = c.j[0];
+      }
       kprev = fabs(c.K[0]);
+      lprev = rk[0];
     }
     if (fac / 1e16 > 0.0) out[0] = -acc * P.LBH;
     return;
@@ -344,15 +366,17 @@ GRT_HDN void ray_transfer(const TransferParams &P, const double *rec, int npts, 
   int lamdex = npts, i1 = 1, i2;
   {
     Coef c;
-    double tau = 0.0, kprev = 0.0;
+    double tau = 0.0, kprev = 0.0, lprev = 0.0;
     int firstnz = 0, lastnz_cut = 0;
     bool cut = false;
+#pragma unroll 1
     for (int k = 0; k < npts; k++) {
       const double *rk = rec + (size_t)k * GRT_NREC;
-      node_coef(P, rk, nu_obs, c, jraw);
+      node_coef<ET>(P, rk, F, c, jraw);
       fac += jraw * (lam0 - rk[0]);
-      if (k > 0) tau -= (rk[0] - rk[-GRT_NREC]) * (kprev + fabs(c.K[0])) / 2.0;
+      if (k > 0) tau -= (rk[0] - lprev) * (kprev + fabs(c.K[0])) / 2.0;
       kprev = fabs(c.K[0]);
+      lprev = rk[0];
       if (!cut && tau > P.max_tau) {  // locate(tau,MAX_TAU)+1 == first index with tau > MAX_TAU (1-based k+1)
         lamdex = k + 1;
         cut = true;
@@ -369,31 +393,48 @@ GRT_HDN void ray_transfer(const TransferParams &P, const double *rec, int npts, 
   {
     double y[4] = {0, 0, 0, 0};
     double h = P.hmax;
-    Coef cb, ca, ctmp;  // interval [s0(indx), s0(indx-1)] uses nodes (indx, indx+1) as written
-    auto norm = [&](Coef &c) {
-      for (int i = 0; i < 4; i++) c.j[i] /= fac;
-    };
-    int indx = i2;
-    node_coef(P, rec + (size_t)(indx - 1) * GRT_NREC, nu_obs, ca, jraw);
-    norm(ca);
-    int up = (indx + 1 <= npts) ? indx + 1 : npts;
-    node_coef(P, rec + (size_t)(up - 1) * GRT_NREC, nu_obs, cb, jraw);
-    norm(cb);
+    // interval [s0(indx), s0(indx-1)] uses nodes (indx, indx+1) as written (radtrans_aux :453-465 index map); the nodes
+    // are produced in the order up, i2, i2-1, ..., i1+1 by a single node_coef call site
+    Coef cb, ca;
+    for (int i = 0; i < 4; i++) ca.j[i] = 0.0;
+    for (int i = 0; i < 7; i++) ca.K[i] = 0.0;
     bool ok = true;
-    for (; indx >= i1 + 1; indx--) {
-      double la = rec[(size_t)(indx - 1) * GRT_NREC], lb = rec[(size_t)(indx - 2) * GRT_NREC];
-      if (lb > la) ok = ck_interval(neq, ca, cb, la, lb, y, h, P);
-      if (!ok) break;
-      // slide: next interval indx-1 uses nodes (indx-1, indx)
+    const int up = (i2 + 1 <= npts) ? i2 + 1 : npts;
+#pragma unroll 1
+    for (int s_ = i2 + 1; s_ >= i1 + 1 && ok; s_--) {
+      const int src = (s_ == i2 + 1) ? up : s_;
       cb = ca;
-      if (indx - 1 >= 1) {
-        node_coef(P, rec + (size_t)(indx - 2) * GRT_NREC, nu_obs, ctmp, jraw);
-        norm(ctmp);
-        ca = ctmp;
+      node_coef<ET>(P, rec + (size_t)(src - 1) * GRT_NREC, F, ca, jraw);
+      for (int i = 0; i < 4; i++) ca.j[i] /= fac;
+      if (s_ <= i2) {
+        double la = rec[(size_t)(s_ - 1) * GRT_NREC], lb = rec[(size_t)(s_ - 2) * GRT_NREC];
+        if (lb > la) ok = ck_interval(neq, ca, cb, la, lb, y, h, P);
       }
     }
     if (ok)
       for (int i = 0; i < neq; i++) out[i] = y[i] * fac * P.LBH;
+  }
+}
+
+// runtime dispatcher (host emulator / generic callers); the CUDA kernels are instantiated per (ET, MODE) directly
+#define GRT_FOR_ETYPES(OP) OP(EM_POLSYNCHTH) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL)
+template <int ET>
+GRT_HD void ray_transfer_e(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
+  switch (transfer_mode(P)) {
+    case MODE_DELO: ray_transfer_t<ET, MODE_DELO>(P, rec, npts, nu_obs, out); break;
+    case MODE_FORMAL: ray_transfer_t<ET, MODE_FORMAL>(P, rec, npts, nu_obs, out); break;
+    case MODE_QUAD: ray_transfer_t<ET, MODE_QUAD>(P, rec, npts, nu_obs, out); break;
+    case MODE_RK4: ray_transfer_t<ET, MODE_RK4>(P, rec, npts, nu_obs, out); break;
+    default: ray_transfer_t<ET, MODE_RK1>(P, rec, npts, nu_obs, out); break;
+  }
+}
+GRT_HDN void ray_transfer(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
+  switch (P.etype) {
+#define OP(E) case E: ray_transfer_e<E>(P, rec, npts, nu_obs, out); break;
+    GRT_FOR_ETYPES(OP)
+#undef OP
+    default:
+      for (int i = 0; i < P.rneq; i++) out[i] = 0.0;
   }
 }
 

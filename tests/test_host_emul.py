@@ -1,0 +1,78 @@
+"""CPU check of the product's kernel bodies.
+
+The CUDA kernels are thin wrappers around `__host__ __device__` stage functions (grtrans_b200/csrc/grt_pipeline.cuh).
+tests/host_emul compiles those same functions for the host and drives them ray by ray, so the kernel LOGIC (geodesic layout,
+fluid cell selection, emissivity algebra, DELO / FORMAL / RK marches) is compared with the oracle here, without a GPU.
+This is a debugging harness: nothing in the product imports it, and the GPU parity tests (test_gpu_parity.py) remain the
+parity tests proper."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import orc
+from grtrans_b200 import _lib, args_from_kwargs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BUILD = os.path.join(HERE, "host_emul", "_build")
+SO = os.path.join(BUILD, "libemul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    srcs = [os.path.join(HERE, "host_emul", "emul_full.cc"), os.path.join(HERE, "host_emul", "emul_geo.cc"),
+            os.path.join(ROOT, "grtrans_b200", "csrc", "grt_io.cpp")]
+    deps = srcs + [os.path.join(ROOT, "grtrans_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "grtrans_b200", "csrc"))
+                   if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        os.makedirs(BUILD, exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-shared", "-o", SO] + srcs)
+    return C.CDLL(SO)
+
+
+def run_emul(lib, kw, i1=None, i2=None):
+    a = args_from_kwargs(**kw)
+    npix = a.nn[0] * a.nn[1]
+    i1 = i1 or 1
+    i2 = i2 or npix
+    n = i2 - i1 + 1
+    ncams = a.nmdot * a.nfreq * a.nmu
+    img = np.zeros((ncams, n, a.nvals), np.float32)
+    npts = np.zeros(n, np.int32)
+    rc = lib.emul_full(C.byref(a), C.c_int(i1), C.c_int(i2), img.ctypes.data_as(C.c_void_p), npts.ctypes.data_as(C.c_void_p),
+                       None)
+    assert rc == 0
+    return np.ascontiguousarray(img.transpose(2, 1, 0)).astype(np.float64), npts
+
+
+EMUL_CASES = [
+    ("thindisk", dict(n=40, nfreq=5)),
+    ("thindisk", dict(n=30, nfreq=3, ename='BBPOL', nvals=4)),
+    ("sphacc", dict(n=24, nfreq=6, iname='delo')),
+    ("sphacc", dict(n=24, nfreq=6, iname='formal')),
+    ("sphacc", dict(n=20, nfreq=4, iname='delo', nvals=1)),
+    ("sphacc", dict(n=16, nfreq=3, iname='lsoda')),
+    ("ffjet", dict(n=24, nfreq=4, iname='delo')),
+    ("ffjet", dict(n=20, nfreq=3, iname='formal')),
+    ("harm", dict(n=24, nup=200, nfreq=2, iname='delo')),
+    ("harm3d", dict(n=24, nup=100, nfreq=4, iname='delo')),
+    ("harm3d", dict(n=16, nup=100, nfreq=2, iname='delo', nmdot=2, mdotmin=1e19, mdotmax=1e21)),
+]
+
+
+@pytest.mark.parametrize("cfg,over", EMUL_CASES)
+def test_kernel_bodies_match_oracle(emul, cfg, over):
+    kw = getattr(cases, "cfg_" + cfg)(**over)
+    got, npts = run_emul(emul, kw)
+    ref = orc.run(_args=args_from_kwargs(**kw))
+    relI, flux, quv, nanok = cases.image_errors(got, ref['ivals'])
+    lsoda = over.get('iname') == 'lsoda'
+    assert nanok
+    assert relI < (2e-4 if lsoda else 1e-4), (relI, flux, quv)
+    assert flux < (2e-5 if lsoda else 1e-5), flux
+    assert quv < 1e-3, quv
