@@ -85,7 +85,7 @@ struct UPiece {
 };
 
 template <bool PHIT>
-GRT_HD void upiece_eval(const RayInv &c, double y, double x, int kind, double sgnv, UPiece &o) {
+GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double sgnv, UPiece &o) {
   // kind: 1 row1 (u<=u2), 2 row2 (u>=u3), 3 cubic complex, 5 quartic complex, 6 double complex, 7 row7, 8 row8
   const double iup = 1.0 / c.uplus;
   if (kind == 1 || kind == 2) {
@@ -98,9 +98,11 @@ GRT_HD void upiece_eval(const RayInv &c, double y, double x, int kind, double sg
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
-      o.t2 = sgnv * F.m2(0.0, 1.0, r);
-      o.t3 = sgnv * F.m2(1.0, -iup, r);
-      o.t4 = sgnv * F.m2(1.0, -c.umi, r);
+      const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
+      double t[3];
+#pragma unroll 1
+      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   } else if (kind == 3) {
     CubicComplex F;
@@ -110,9 +112,11 @@ GRT_HD void upiece_eval(const RayInv &c, double y, double x, int kind, double sg
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
-      o.t2 = sgnv * F.m2(0.0, 1.0, r);
-      o.t3 = sgnv * F.m2(1.0, -iup, r);
-      o.t4 = sgnv * F.m2(1.0, -c.umi, r);
+      const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
+      double t[3];
+#pragma unroll 1
+      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   } else if (kind == 5) {
     QuarticComplex F;
@@ -121,9 +125,11 @@ GRT_HD void upiece_eval(const RayInv &c, double y, double x, int kind, double sg
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
-      o.t2 = sgnv * F.m2(0.0, 1.0, r);
-      o.t3 = sgnv * F.m2(1.0, -iup, r);
-      o.t4 = sgnv * F.m2(1.0, -c.umi, r);
+      const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
+      double t[3];
+#pragma unroll 1
+      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   } else if (kind == 6) {
     DoubleComplex F;
@@ -133,9 +139,11 @@ GRT_HD void upiece_eval(const RayInv &c, double y, double x, int kind, double sg
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
-      o.t2 = sgnv * F.m2(0.0, 1.0, r);
-      o.t3 = sgnv * F.m2(1.0, -iup, r);
-      o.t4 = sgnv * F.m2(1.0, -c.umi, r);
+      const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
+      double t[3];
+#pragma unroll 1
+      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   } else {
     QuarticReal F;
@@ -147,9 +155,11 @@ GRT_HD void upiece_eval(const RayInv &c, double y, double x, int kind, double sg
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
-      o.t2 = sgnv * F.m2(0.0, 1.0, r);
-      o.t3 = sgnv * F.m2(1.0, -iup, r);
-      o.t4 = sgnv * F.m2(1.0, -c.umi, r);
+      const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
+      double t[3];
+#pragma unroll 1
+      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   }
 }
@@ -176,7 +186,7 @@ struct MuPiece {
   double i2mu, tmuf, phimuf, sf;
 };
 template <bool PHIT>
-GRT_HD void mupiece_eval(const RayInv &c, double muf, MuPiece &o) {
+GRT_HDN void mupiece_eval(const RayInv &c, double muf, MuPiece &o) {
   const double mneg = c.mneg, mpos = c.mpos;
   double fac, m1, n, fac2, sf, phif;
   if (c.musym) {
@@ -297,13 +307,9 @@ GRT_HD int tpm_from_iu(double iu, double i1mu, double i3mu, double sm) {
   return (int)((iu + i1mu) / i3mu);
 }
 
-// mu_f and turning points from I_u (mu half of GEOMU) and, if PHIT, t_mu and phi_mu (mu half of
-// GEOPHITIME).  Returns muf.
-template <bool PHIT>
-GRT_HD double mu_from_iu(const RayInv &c, double iu, int &tpm, double &tmu, double &phimu) {
+// mu_f and the number of mu turning points from I_u (mu half of GEOMU).  Returns muf.
+GRT_HD double mu_of_iu(const RayInv &c, double iu, int &tpm) {
   double muf = 0.0;
-  tmu = 0.0;
-  phimu = 0.0;
   if (c.mumode == 0) {
     tpm = tpm_from_iu(iu, c.i1mu, c.i3mu, c.sm);
     double a2 = c.sm * pm1(tpm);
@@ -317,40 +323,52 @@ GRT_HD double mu_from_iu(const RayInv &c, double iu, int &tpm, double &tmu, doub
       sncndn(fabs(c.muplus) * iarg, c.mneg / c.mpos, sn, cn, dn);
       muf = c.muminus / dn;
     }
-    if (PHIT) {
-      MuPiece mp;
-      mupiece_eval<true>(c, muf, mp);
-      double b1 = c.sm, b2 = c.sm * pm1(tpm + 1), b3 = 2.0 * (int)((2 * tpm - c.sm + 1) / 4.0);
-      double tt = b1 * c.tmu1 + b2 * mp.tmuf + b3 * c.tmu3;
-      tmu = c.musym ? c.a * c.a * c.mneg * iu + tt : tt;
-      phimu = -c.l * iu + c.l * (b1 * c.phimu1 + b2 * mp.phimuf + b3 * c.phimu3);
-    }
-  } else if (c.mumode == 1) {  // a == 0 (geokerr_wrapper.f:948-967, 1941-1966)
+  } else if (c.mumode == 1) {  // a == 0 (geokerr_wrapper.f:948-967)
     tpm = tpm_from_iu(iu, c.i1mu, c.i3mu, c.sm);
     double a2 = c.sm * pm1(tpm);
     double a3 = 2.0 * (int)((2.0 * (double)tpm + 3.0 - c.sm) / 4.0) - 1.0;
     muf = -c.muplus * cos(sqrt(c.ql2) * (iu - c.sm * c.i1mu - a3 * c.i3mu) / a2);
-    if (PHIT) {
-      double mup = sqrt(c.q2 / c.ql2);  // (no mu0 clamp in GEOPHITIME)
-      double vfm = (muf - mup * mup) / (1.0 - muf) / mup;
-      double vfp = -(muf + mup * mup) / (1.0 + muf) / mup;
-      if (fabs(vfm) > 1.0) vfm = sgn(vfm);
-      if (fabs(vfp) > 1.0) vfp = sgn(vfp);
-      double vsm = ((c.mu0 - mup * mup) == 0.0) ? -1.0 : (c.mu0 - mup * mup) / (1.0 - c.mu0) / mup;
-      double vsp = ((c.mu0 + mup * mup) == 0.0) ? -1.0 : -(c.mu0 + mup * mup) / (1.0 + c.mu0) / mup;
-      if (fabs(vsp) > 1.0) vsp = sgn(vsp);
-      if (fabs(vsm) > 1.0) vsm = sgn(vsm);
-      double p1 = GRT_PI - asin(vsm) + asin(vsp);
-      double p2 = asin(vfm) - asin(vfp) + GRT_PI;
-      phimu = -c.l * iu + sgn(c.l) * 0.5 * (c.sm * p1 + a2 * p2 + a3 * 2.0 * GRT_PI);
-    }
-  } else if (c.mumode == 2) {  // q2 == 0 (:938-947, 1924-1940); tpm keeps its input value
+  } else if (c.mumode == 2) {  // q2 == 0 (:938-947); tpm keeps its input value
     double s1 = sgn(c.mu0);
     if (c.l2 < c.a * c.a && c.mu0 != 0.0) {
       double mup = s1 * sqrt(1.0 - c.l2 / c.a / c.a);
       muf = mup / cosh(fabs(c.a * mup) * iu - s1 * c.sm * asech_(c.mu0 / mup));
     }
-    if (PHIT && fabs(c.l) < fabs(c.a)) {
+  }
+  return muf;
+}
+
+// t_mu and phi_mu for an end point (muf, tpm) reached at I_u = I_mu = iu (mu half of GEOPHITIME :1924-2349).  One
+// out-of-line copy serves the inbound / return legs (muf from mu_of_iu) and the mu-driven points (standard=2, mu-fill).
+// mode2: evaluate the q2 == 0 closed forms (the mu-fill segment of the reference leaves them at 0).
+GRT_HDN void mu_tphi(const RayInv &c, double muf, int tpm, double iu, bool mode2, double &tmu, double &phimu) {
+  tmu = 0.0;
+  phimu = 0.0;
+  if (c.mumode == 0) {
+    MuPiece mp;
+    mupiece_eval<true>(c, muf, mp);
+    double b1 = c.sm, b2 = c.sm * pm1(tpm + 1), b3 = 2.0 * (int)((2 * tpm - c.sm + 1) / 4.0);
+    double tt = b1 * c.tmu1 + b2 * mp.tmuf + b3 * c.tmu3;
+    tmu = c.musym ? c.a * c.a * c.mneg * iu + tt : tt;
+    phimu = -c.l * iu + c.l * (b1 * c.phimu1 + b2 * mp.phimuf + b3 * c.phimu3);
+  } else if (c.mumode == 1) {  // a == 0 (:1941-1966)
+    double a2 = c.sm * pm1(tpm);
+    double a3 = 2.0 * (int)((2.0 * (double)tpm + 3.0 - c.sm) / 4.0) - 1.0;
+    double mup = sqrt(c.q2 / c.ql2);  // (no mu0 clamp in GEOPHITIME)
+    double vfm = (muf - mup * mup) / (1.0 - muf) / mup;
+    double vfp = -(muf + mup * mup) / (1.0 + muf) / mup;
+    if (fabs(vfm) > 1.0) vfm = sgn(vfm);
+    if (fabs(vfp) > 1.0) vfp = sgn(vfp);
+    double vsm = ((c.mu0 - mup * mup) == 0.0) ? -1.0 : (c.mu0 - mup * mup) / (1.0 - c.mu0) / mup;
+    double vsp = ((c.mu0 + mup * mup) == 0.0) ? -1.0 : -(c.mu0 + mup * mup) / (1.0 + c.mu0) / mup;
+    if (fabs(vsp) > 1.0) vsp = sgn(vsp);
+    if (fabs(vsm) > 1.0) vsm = sgn(vsm);
+    double p1 = GRT_PI - asin(vsm) + asin(vsp);
+    double p2 = asin(vfm) - asin(vfp) + GRT_PI;
+    phimu = -c.l * iu + sgn(c.l) * 0.5 * (c.sm * p1 + a2 * p2 + a3 * 2.0 * GRT_PI);
+  } else if (c.mumode == 2 && mode2) {  // q2 == 0 (:1924-1940)
+    if (fabs(c.l) < fabs(c.a)) {
+      double s1 = sgn(c.mu0);
       double b1 = s1 * c.sm, b2 = s1 * c.sm * pm1(tpm + 1);
       double mup = s1 * sqrt(1.0 - c.l2 / c.a / c.a);
       double sq1 = sqrt(1.0 - mup * mup), sg = sgn(mup * c.l / c.a);
@@ -361,6 +379,14 @@ GRT_HD double mu_from_iu(const RayInv &c, double iu, int &tpm, double &tmu, doub
       tmu = fabs(mup * c.a) * (b2 * sqrt(1.0 - muf * muf / (mup * mup)) + b1 * sqrt(1.0 - c.mu0 * c.mu0 / (mup * mup)));
     }
   }
+}
+
+template <bool PHIT>
+GRT_HD double mu_from_iu(const RayInv &c, double iu, int &tpm, double &tmu, double &phimu) {
+  tmu = 0.0;
+  phimu = 0.0;
+  double muf = mu_of_iu(c, iu, tpm);
+  if (PHIT) mu_tphi(c, muf, tpm, iu, true, tmu, phimu);
   return muf;
 }
 
@@ -459,7 +485,7 @@ GRT_HD double u_eval(const RayInv &c, double u0, double uf, int tpr, double &tu,
 }
 
 // u_f from I_mu (u half of GEOR, Table 2).  Returns false when no valid solution exists.
-GRT_HD bool u_from_imu(const RayInv &c, double imu, double &uf, int &tpr) {
+GRT_HDN bool u_from_imu(const RayInv &c, double imu, double &uf, int &tpr) {
   double sn, cn, dn;
   switch (c.ncase) {
     case 1: {
@@ -870,131 +896,84 @@ GRT_HDN void geo_setup(const RayConst &rc, const GeoFlags &fl, RayInv &c) {
 
 // ---- one point -----------------------------------------------------------------------------------
 // slot is the 0-based output slot of the ray.  Returns false for slots the reference leaves unset.
-GRT_HDN bool geo_point(const RayInv &c, int nup, int slot, GeoPoint &o) {
+// The four kinds of point (standard=2 disk-plane point, inbound leg, mu-fill, return leg) only differ in how the end point
+// is prescribed -- in u (legs) or in mu (standard=2, mu-fill) -- so they share ONE evaluation sequence
+//   [mu-driven: I_mu(mu_f) -> u_f]  ->  u integrals  ->  [u-driven: I_u -> mu_f]  ->  mu integrals
+// with a single call site per stage: the kernel's code has to stay small enough for the instruction cache.//
+// GRT_PHASE_BARRIER (__syncthreads() in grt_k_geo.cu, which defines GRT_USE_PHASE_BARRIER) re-aligns the warps of a thread block between the stages:
+// the stages together are ~100 KB of straight-line code, far more than the 32 KB L1.5 instruction cache, and warps that
+// drift apart (the Carlson loops have data-dependent trip counts) each stream the whole footprint from L2 on their own
+// (ncu: 64% of the stall samples were "no instruction").  With the barriers every warp of the SM is inside the same
+// <= 40 KB stage at the same time.  All threads of the block must therefore call geo_point (valid = false for padding).
+#if defined(GRT_USE_PHASE_BARRIER) && defined(__CUDA_ARCH__)
+#define GRT_PHASE_BARRIER() __syncthreads()
+#else
+#define GRT_PHASE_BARRIER() ((void)0)
+#endif
+GRT_HD bool geo_point(const RayInv &c, int nup, int slot, bool valid, GeoPoint &o) {
   o.u = o.mu = o.dt = o.dphi = o.lam = 0.0;
   o.tpm = o.tpr = 0;
   double tu = 0, phiu = 0, lamu = 0, tmu = 0, phimu = 0;
   const int nc = c.ncase;
-  if (c.usegeor) {
+  int tpm = 0, tpr = 0;
+  double un = -1.0, mun = 0.0, ustart = c.u0, ipar = 0.0;
+  bool mu_driven = false;
+  bool active = valid;  // false: nothing left to compute for this thread (result already final)
+  bool ret = valid;
+  if (!active) {
+  } else if (c.usegeor) {
     // standard=2: GEOR at equal steps in mu (geokerr_wrapper.f:421-461)
     int k = slot + 1;
-    double mun = c.mu0 + (k - c.offset) * (c.muf_target - c.mu0) / (double)nup;
-    int tpm = c.tpm_in, tpr = 0;
-    double uf = -1.0;
-    bool ok;
+    mun = c.mu0 + (k - c.offset) * (c.muf_target - c.mu0) / (double)nup;
+    tpm = c.tpm_in;
     if (c.equatorial) {  // IF(MU0.NE.0.OR.BETA.NE.0) ... ELSE UF=U0
       o.u = c.u0; o.mu = mun; o.tpm = tpm;
-      return true;
+      active = false;
     }
-    double imu = imu_from_mu(c, mun, tpm, ok);
-    if (ok && nc != 4) ok = u_from_imu(c, imu, uf, tpr);
-    if (!ok || nc == 4) {
-      o.u = -1.0;
-      o.mu = mun;
-      o.tpm = tpm;
-      return true;
-    }
-    u_eval<true>(c, c.u0, uf, tpr, tu, phiu, lamu);
-    int tdum = tpm;
-    // mu pieces for the prescribed mu_f: reuse mu_from_iu's PHIT half through a direct evaluation
-    if (c.mumode == 0) {
-      MuPiece mp;
-      mupiece_eval<true>(c, mun, mp);
-      double b1 = c.sm, b2 = c.sm * pm1(tpm + 1), b3 = 2.0 * (int)((2 * tpm - c.sm + 1) / 4.0);
-      double tt = b1 * c.tmu1 + b2 * mp.tmuf + b3 * c.tmu3;
-      tmu = c.musym ? c.a * c.a * c.mneg * imu + tt : tt;
-      phimu = -c.l * imu + c.l * (b1 * c.phimu1 + b2 * mp.phimuf + b3 * c.phimu3);
-    } else {
-      // a==0 / q2==0: closed forms depend on (muf, tpm, iu) only
-      RayInv cc = c;
-      (void)tdum;
-      double muf_chk;
-      int t2 = tpm;
-      // evaluate the closed forms with the prescribed mu_f by inverting nothing: copy of mu_from_iu's PHIT part
-      if (c.mumode == 1) {
-        double a2 = c.sm * pm1(tpm), a3 = 2.0 * (int)((2.0 * (double)tpm + 3.0 - c.sm) / 4.0) - 1.0;
-        double mup = sqrt(c.q2 / c.ql2);
-        double vfm = (mun - mup * mup) / (1.0 - mun) / mup, vfp = -(mun + mup * mup) / (1.0 + mun) / mup;
-        if (fabs(vfm) > 1.0) vfm = sgn(vfm);
-        if (fabs(vfp) > 1.0) vfp = sgn(vfp);
-        double vsm = ((c.mu0 - mup * mup) == 0.0) ? -1.0 : (c.mu0 - mup * mup) / (1.0 - c.mu0) / mup;
-        double vsp = ((c.mu0 + mup * mup) == 0.0) ? -1.0 : -(c.mu0 + mup * mup) / (1.0 + c.mu0) / mup;
-        if (fabs(vsp) > 1.0) vsp = sgn(vsp);
-        if (fabs(vsm) > 1.0) vsm = sgn(vsm);
-        double p1 = GRT_PI - asin(vsm) + asin(vsp), p2 = asin(vfm) - asin(vfp) + GRT_PI;
-        phimu = -c.l * imu + sgn(c.l) * 0.5 * (c.sm * p1 + a2 * p2 + a3 * 2.0 * GRT_PI);
-      } else if (c.mumode == 2 && fabs(c.l) < fabs(c.a)) {
-        double s1 = sgn(c.mu0), b1 = s1 * c.sm, b2 = s1 * c.sm * pm1(tpm + 1);
-        double mup = s1 * sqrt(1.0 - c.l2 / c.a / c.a);
-        double sq1 = sqrt(1.0 - mup * mup), sg = sgn(mup * c.l / c.a);
-        double t0 = tan(asin(c.mu0 / mup) / 2.0), tf = tan(asin(mun / mup) / 2.0);
-        phimu = b1 * sg * (atan((mup - t0) / sq1) + atan((mup + t0) / sq1)) +
-                b2 * sg * (atan((mup - tf) / sq1) + atan((mup + tf) / sq1));
-        tmu = fabs(mup * c.a) * (b2 * sqrt(1.0 - mun * mun / (mup * mup)) + b1 * sqrt(1.0 - c.mu0 * c.mu0 / (mup * mup)));
-      }
-      (void)cc; (void)muf_chk; (void)t2;
-    }
-    if (c.l == 0.0) phiu -= sgn(c.a) * GRT_PI * tpm;
-    o.u = uf; o.mu = mun; o.dt = tmu + tu; o.dphi = phimu + phiu; o.lam = lamu + tmu; o.tpm = tpm; o.tpr = tpr;
-    return true;
-  }
-  // ---- standard=1
-  int tpm = 0, tpr;
-  double un, mun;
-  if (slot < c.nkeep) {  // inbound leg
+    mu_driven = true;
+  } else if (slot < c.nkeep) {  // inbound leg
     int k = slot + 1;
     un = c.uout + (k - c.offset) * c.du;
     if ((nc == 1 || nc == 7) && un > c.u2) un = c.u2;
     if ((nc == 2 || nc == 8) && un < c.u3) un = c.u3;
-    tpr = 0;
-    double iu = u_eval<true>(c, c.u0, un, 0, tu, phiu, lamu);
-    mun = mu_from_iu<true>(c, iu, tpm, tmu, phimu);
   } else if (c.tpr == 1 && slot < c.nkeep + c.nfill) {  // mu-fill near the radial turning point
     int k = slot - c.nkeep + 1;
     indep_muf(c.fmuminus, c.fmuplus, c.fmu0, c.fmuf, c.ftpm0, c.ftpmf, c.sm, k, c.nfill, c.offset, mun, tpm);
-    bool ok;
-    double imu = imu_from_mu(c, mun, tpm, ok);
-    tpr = 1;
-    un = -1.0;
-    if (ok) ok = u_from_imu(c, imu, un, tpr);
-    if (!ok) {
-      o.u = -1.0; o.mu = mun; o.tpm = tpm; o.tpr = 0;
-      return true;
-    }
-    u_eval<true>(c, c.u0, un, tpr, tu, phiu, lamu);
-    if (c.mumode == 0) {
-      MuPiece mp;
-      mupiece_eval<true>(c, mun, mp);
-      double b1 = c.sm, b2 = c.sm * pm1(tpm + 1), b3 = 2.0 * (int)((2 * tpm - c.sm + 1) / 4.0);
-      double tt = b1 * c.tmu1 + b2 * mp.tmuf + b3 * c.tmu3;
-      tmu = c.musym ? c.a * c.a * c.mneg * imu + tt : tt;
-      phimu = -c.l * imu + c.l * (b1 * c.phimu1 + b2 * mp.phimuf + b3 * c.phimu3);
-    } else if (c.mumode == 1) {
-      double a2 = c.sm * pm1(tpm), a3 = 2.0 * (int)((2.0 * (double)tpm + 3.0 - c.sm) / 4.0) - 1.0;
-      double mup = sqrt(c.q2 / c.ql2);
-      double vfm = (mun - mup * mup) / (1.0 - mun) / mup, vfp = -(mun + mup * mup) / (1.0 + mun) / mup;
-      if (fabs(vfm) > 1.0) vfm = sgn(vfm);
-      if (fabs(vfp) > 1.0) vfp = sgn(vfp);
-      double vsm = ((c.mu0 - mup * mup) == 0.0) ? -1.0 : (c.mu0 - mup * mup) / (1.0 - c.mu0) / mup;
-      double vsp = ((c.mu0 + mup * mup) == 0.0) ? -1.0 : -(c.mu0 + mup * mup) / (1.0 + c.mu0) / mup;
-      if (fabs(vsp) > 1.0) vsp = sgn(vsp);
-      if (fabs(vsm) > 1.0) vsm = sgn(vsm);
-      double p1 = GRT_PI - asin(vsm) + asin(vsp), p2 = asin(vfm) - asin(vfp) + GRT_PI;
-      phimu = -c.l * imu + sgn(c.l) * 0.5 * (c.sm * p1 + a2 * p2 + a3 * 2.0 * GRT_PI);
-    }
+    mu_driven = true;
   } else if (c.tpr == 1) {  // return leg
     int k = slot + 1 - (c.nfill - 2 * (c.nfill ? c.kext : 0));
     un = 2.0 * c.ub - (c.uout + (k - c.offset) * c.du);
     if ((nc == 1 || nc == 7) && un > c.u2) un = c.u2;
     tpr = 1;
-    double iu = u_eval<true>(c, c.ufleg, un, 1, tu, phiu, lamu);
-    mun = mu_from_iu<true>(c, iu, tpm, tmu, phimu);
+    ustart = c.ufleg;
   } else {
-    return false;
+    active = false;
+    ret = false;
   }
-  if (c.l == 0.0) phiu -= sgn(c.a) * GRT_PI * tpm;
-  o.u = un; o.mu = mun; o.dt = tmu + tu; o.dphi = phimu + phiu; o.lam = lamu + tmu; o.tpm = tpm; o.tpr = tpr;
-  return true;
+  if (active && mu_driven) {
+    bool ok;
+    ipar = imu_from_mu(c, mun, tpm, ok);
+    if (ok) ok = u_from_imu(c, ipar, un, tpr);  // (false for ncase 4: no valid solution, uf = -1)
+    if (!ok) {
+      o.u = -1.0; o.mu = mun; o.tpm = tpm; o.tpr = 0;
+      active = false;
+    }
+  }
+  GRT_PHASE_BARRIER();
+  double iu = 0.0;
+  if (active) iu = u_eval<true>(c, ustart, un, tpr, tu, phiu, lamu);
+  GRT_PHASE_BARRIER();
+  if (active && !mu_driven) {
+    ipar = iu;
+    mun = mu_of_iu(c, iu, tpm);
+  }
+  GRT_PHASE_BARRIER();
+  if (active) {
+    mu_tphi(c, mun, tpm, ipar, !mu_driven || c.usegeor, tmu, phimu);
+    if (c.l == 0.0) phiu -= sgn(c.a) * GRT_PI * tpm;
+    o.u = un; o.mu = mun; o.dt = tmu + tu; o.dphi = phimu + phiu; o.lam = lamu + tmu; o.tpm = tpm; o.tpr = tpr;
+  }
+  return ret;
 }
 
 }  // namespace grt

@@ -2,6 +2,7 @@
 //   k_ray_setup      thread / ray            geo_setup()   -> RayInv  (per-ray invariants: roots, NCASE, u0/mu0 integrals)
 //   k_geo_points     thread / (ray, point)   geo_point()   -> u, mu, dt, dphi, lambda, tpm, tpr
 //   k_ray_finalize   thread / ray            trim / status / lambda_N, t_1
+#define GRT_USE_PHASE_BARRIER  // see geo_point (grt_geokerr.cuh)
 #include "grt_kernels.h"
 
 namespace grt {
@@ -15,11 +16,13 @@ __global__ void __launch_bounds__(128) k_ray_setup(const RayConst *__restrict__ 
   inv[i] = c;
 }
 
-__global__ void __launch_bounds__(128) k_geo_points(const RayInv *__restrict__ inv, int nup, int maxpts, long long total, PointArrays pa) {
+template <int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) k_geo_points(const RayInv *__restrict__ inv, int nup, int maxpts, long long total, PointArrays pa) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  const bool in_range = idx < total;  // no early exit: every thread of the block takes part in the phase barriers
+  if (!in_range) idx = total - 1;
   int ray = (int)(idx / maxpts), slot = (int)(idx % maxpts);
-  point_store(inv[ray], nup, slot, (size_t)idx, pa);
+  point_store(inv[ray], nup, slot, (size_t)idx, pa, in_range);
 }
 
 __global__ void __launch_bounds__(128) k_ray_finalize(const RayInv *__restrict__ inv, int maxpts, int usegeor, int n, PointArrays pa,
@@ -36,8 +39,11 @@ void launch_ray_setup(const RayConst *rc, GeoFlags fl, RayInv *inv, int n, cudaS
   k_ray_setup<<<(n + B - 1) / B, B, 0, st>>>(rc, fl, inv, n);
 }
 void launch_geo_points(const RayInv *inv, int nup, int maxpts, long long total, PointArrays pa, cudaStream_t st) {
-  const int B = 128;
-  k_geo_points<<<(unsigned)((total + B - 1) / B), B, 0, st>>>(inv, nup, maxpts, total, pa);
+  // 1024-thread blocks (one per SM, 64 registers): measured best of {128x6, 256x3, 384x2, 512x1, 768x1, 1024x1} -- the phase
+  // barriers of geo_point work per block, so one big block keeps all 32 warps of the SM inside the same code stage
+  // (nx=256 bench: 28.3 / 22.9 / 20.5 / 23.3 / 19.5 / 18.3 ms; 59.6 ms before the code was compacted and phased)
+  constexpr int BS = 1024;
+  k_geo_points<BS, 1><<<(unsigned)((total + BS - 1) / BS), BS, 0, st>>>(inv, nup, maxpts, total, pa);
 }
 void launch_ray_finalize(const RayInv *inv, int maxpts, int usegeor, int n, PointArrays pa, RayMeta *meta, cudaStream_t st) {
   const int B = 128;

@@ -29,9 +29,11 @@ struct FluidKernelArgs {
   EmisTables tab;
 };
 
-GRT_HD void point_store(const RayInv &c, int nup, int slot, size_t idx, PointArrays pa) {
+// in_range = false for the padding threads of the last block (they only take part in the phase barriers)
+GRT_HD void point_store(const RayInv &c, int nup, int slot, size_t idx, PointArrays pa, bool in_range = true) {
   GeoPoint p;
-  bool ok = slot < c.npts && geo_point(c, nup, slot, p);
+  bool ok = geo_point(c, nup, slot, in_range && slot < c.npts, p);
+  if (!in_range) return;
   if (!ok) {
     p.u = 0.0; p.mu = 0.0; p.dt = 0.0; p.dphi = 0.0; p.lam = 0.0; p.tpm = 0; p.tpr = 0;
   }

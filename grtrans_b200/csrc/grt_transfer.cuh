@@ -49,6 +49,16 @@ struct Coef {
   double j[4], K[7];
 };
 
+// the next point record (one 128-byte line) is pulled into L1 while the current node is evaluated: ncu showed 6.5% of the
+// stall samples on the first use of the record (long scoreboard) when it was only loaded at the top of the iteration
+GRT_HD void prefetch_record(const double *p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // record -> invariant, LBH-scaled coefficients at observed frequency F.nu.  jI_raw returns the comoving un-boosted j_I used
 // for the driver's `fac` (grtrans_driver.f90:183-187).  Replaces calc_emissivity + the e%j/e%K copy (emis.f90:461-571),
 // rotate_emis (:797-829), invariant_emis (:831-838) and the K*LBH scaling (grtrans_driver.f90:217).
@@ -313,6 +323,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
 #pragma unroll 1
     for (int k = npts - 1; k >= 0; k--) {
       const double *rk = rec + (size_t)k * GRT_NREC;
+      if (k > 0) prefetch_record(rk - GRT_NREC);
       const double lamk = rk[0];
       node_coef<ET>(P, rk, F, c0, jraw);
       fac += jraw * (lam0 - lamk);

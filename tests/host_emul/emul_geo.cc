@@ -21,7 +21,7 @@ int emul_geo(int n, int cap, int nup, int kext, int next, int mufill, int usegeo
     ncase[i] = inv.ncase;
     for (int s = 0; s < cap; s++) {
       grt::GeoPoint p;
-      bool ok = s < inv.npts && grt::geo_point(inv, nup, s, p);
+      bool ok = grt::geo_point(inv, nup, s, s < inv.npts, p);
       size_t q = (size_t)i * cap + s;
       if (!ok) { u[q] = mu[q] = dt[q] = dphi[q] = lam[q] = 0; tpmo[q] = tpro[q] = 0; continue; }
       u[q] = p.u; mu[q] = p.mu; dt[q] = p.dt; dphi[q] = p.dphi; lam[q] = p.lam; tpmo[q] = p.tpm; tpro[q] = p.tpr;

@@ -76,3 +76,29 @@ def test_kernel_bodies_match_oracle(emul, cfg, over):
     assert relI < (2e-4 if lsoda else 1e-4), (relI, flux, quv)
     assert flux < (2e-5 if lsoda else 1e-5), flux
     assert quv < 1e-3, quv
+
+
+@pytest.mark.parametrize("cfg,over", [("ffjet", dict(n=40, nup=100)), ("sphacc", dict(n=30, nup=100)),
+                                      ("harm", dict(n=24, nup=400)), ("thindisk", dict(n=50))])
+def test_geodesic_points_match_oracle(emul, cfg, over):
+    """Per-point geodesic + frame quantities of the kernel bodies against the oracle (same checks as the GPU tests)."""
+    kw = getattr(cases, "cfg_" + cfg)(**over)
+    a = args_from_kwargs(**kw)
+    npix = a.nn[0] * a.nn[1]
+    mp = _lib.maxpts_of(a)
+    ncams = a.nmdot * a.nfreq * a.nmu
+    img = np.zeros((ncams, npix, a.nvals), np.float32)
+    npts = np.zeros(npix, np.int32)
+    stage = np.zeros((npix, mp, 8))
+    rc = emul.emul_full(C.byref(a), C.c_int(1), C.c_int(npix), img.ctypes.data_as(C.c_void_p),
+                        npts.ctypes.data_as(C.c_void_p), stage.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    d = orc.ray_dump(1, npix, _args=args_from_kwargs(**kw))
+    ok = d['status'] == 1
+    assert np.array_equal(npts, np.where(ok, d['npts'], 0))      # bit-exact geodesic indexing
+    gv = np.asarray(a.gridvals[:4], float)
+    abmax = max(gv[0] ** 2, gv[1] ** 2) ** 2 + max(gv[2] ** 2, gv[3] ** 2) ** 2
+    ulp = np.finfo(float).eps / min(1e-4, 1. / (100. * abmax))
+    for i, k in enumerate(['lambda', 'r', 'th', 'ph', 's2xi', 'c2xi', 'ang', 'rshift']):
+        err = np.nanmax(np.abs(stage[:, :, i] - d[k]) - 1e-9 * np.abs(d[k]))
+        assert err < (16 * ulp if k == 'lambda' else 1e-9), (k, err)
