@@ -31,6 +31,10 @@ import numpy as np  # noqa: E402
 W_GEO = 5.8e3   # per (pixel, point): geodesic + geometry
 W_RT = 9.4e2    # per (pixel, point, freq): POLSYNCHTH emissivity + rotate/scale + DELO step
 B_GATHER = 320  # bytes per (pixel, point): 8 corners x 10 fields x 4 B (3-D)
+B_RECORD = 128  # bytes per (pixel, point) read by the transfer kernel (one point record)
+# from the ncu --set full capture of one k_transfer launch at this configuration (profiles/r1_ncu_summary.md):
+NCU_TRANSFER = {"dram_bytes_per_launch": 3.824378e9 + 0.110865e9, "fp64_pipe_busy_pct": 66.3, "issue_active_pct": 65.9,
+                "launch": "65536-ray tile (32768 blocks x 128 threads)", "source": "profiles/r1_ncu_summary.md"}
 
 
 def workload(nx, nfreq, snapdir, grid):
@@ -271,8 +275,12 @@ def main():
         k_s = stage_ms[3] * 1e-3
         flops = W_RT * float(npts_local) * args.nfreq
         ach = flops / k_s / 1e12 if k_s > 0 else None
-        roof = {"bound": "fp64", "kernel": "k_transfer", "achieved": ach, "peak": dfma, "unit": "TFLOP/s",
-                "frac": (ach / dfma) if (ach and dfma) else None, "traffic": None,
+        nlaunch = max(1, sess.launch_count() // 5)
+        roof = {"bound": "fp64", "kernel": "k_transfer<POLSYNCHTH,DELO>", "achieved": ach, "peak": dfma, "unit": "TFLOP/s",
+                "frac": (ach / dfma) if (ach and dfma) else None,
+                "traffic": NCU_TRANSFER["dram_bytes_per_launch"] if (args.nx == 1024 and world == 1) else None,
+                "algorithmic_bytes_per_launch": B_RECORD * float(npts_local) / nlaunch, "ncu": NCU_TRANSFER,
+                "launches_per_step": nlaunch, "avg_launch_ms": stage_ms[3] / nlaunch,
                 "peak_source": "FP64 DFMA micro-benchmark run in this process (grt_dfma_peak); no tensor-core / HBM bound applies: "
                                "the path has no dense contraction and moves ~0.1 byte per FP64 op",
                 "algorithmic_ops_per_point_freq": W_RT,

@@ -88,25 +88,38 @@ GRT_HD double planck_bnu(double T, double nu) {
 // Output of thermal_eval are the INVARIANT coefficients of frequency nu_obs: j*g^2 and K/g*LBH evaluated at the comoving
 // frequency nu = nu_obs/g (for the unit-level surface g = LBH = 1 gives the plain comoving polsynchth values).
 struct ThermalPoint {  // 12 doubles, stored in the point record
-  double lnu_off;      // -log(g) - log(nu_c'):  log(nu/nu_c') = log(nu_obs) + lnu_off
-  double AI, AV;       // comoving j_{I,Q} = AI nu {iix,iqx},  j_V = AV nu ivx   (nu = nu_obs/g)
+  double xp13;         // (g nu_c')^(-1/3):  (nu/nu_c')^(1/3) = nu_obs^(1/3) xp13
+  double AI, AV;       // comoving j_{I,Q} = AI nu_obs {iix,iqx},  j_V = AV nu_obs ivx   (the 1/g of nu = nu_obs/g folded in)
   double hkT_g;        // h/(k T g): h nu/(k T) = hkT_g nu_obs
-  double lAx;          // log of (xarg sqrt(nu_obs))
+  double Ax;           // xarg = Ax nu_obs^(-1/2)
+  double Ax1, Ax2, Ax3, Ax4;  // Ax^1.035, Ax^1.2, Ax^1.50316886, Ax^(-8/3)
   double RQ;           // rho_Q LBH/g = RQ jff / nu_obs^3
   double RV0, RV1;     // rho_V LBH/g = (RV0 - RV1 shgm) / nu_obs^2
-  double g, ig;        // redshift and 1/g
+  double g;            // redshift
 };
 
-struct FreqConst {  // per observed frequency
-  double nu, lnu, inu2, inu3;
+// Per observed frequency.  Every x**p of the reference with x = (per-point factor) * nu**q is evaluated as
+// (per-point factor)**p * nu**(p q): both powers are computed once (per point in k_fluid_ortho, per frequency here), the
+// hot loop only multiplies them.
+struct FreqConst {
+  double nu, inu2, inu3;
+  double n13;                   // nu^(1/3)
+  double nm12;                  // nu^(-1/2)
+  double nq1, nq2, nq3, nq4;    // nu^(-1.035/2), nu^(-1.2/2), nu^(-1.50316886/2), nu^(+4/3)
 };
 GRT_HD FreqConst freq_const(double nu_obs) {
   FreqConst f;
   f.nu = nu_obs;
-  f.lnu = log(nu_obs);
   double i = 1.0 / nu_obs;
   f.inu2 = i * i;
   f.inu3 = f.inu2 * i;
+  const double l = log(nu_obs);
+  f.n13 = exp(l * (1.0 / 3.0));
+  f.nm12 = exp(-0.5 * l);
+  f.nq1 = exp((-0.5 * 1.035) * l);
+  f.nq2 = exp((-0.5 * 1.2) * l);
+  f.nq3 = exp((-0.5 * (double)1.50316886f) * l);
+  f.nq4 = exp((4.0 / 3.0) * l);
   return f;
 }
 
@@ -116,14 +129,19 @@ GRT_HD void thermal_point(double n, double b, double t, double theta, double g, 
   double sinth = sin(theta), costh = cos(theta), tanth = tan(theta);
   double nucfac = 3.0 * pc::e * b * sinth / 4.0 / GRT_PI / pc::m / pc::c * thetae * thetae + 1.0;
   double th2 = thetae * thetae;
-  P.lnu_off = -log(g) - log(nucfac);
-  P.AI = ec * ec / c / sqrt(3.0) / 2.0 * n / th2;
-  P.AV = 4.0 * ec * ec / c / 3.0 / sqrt(3.0) / tanth * n / 2.0 / (th2 * thetae);
+  P.xp13 = exp((-log(g) - log(nucfac)) * (1.0 / 3.0));
+  P.AI = ec * ec / c / sqrt(3.0) / 2.0 * n / th2 / g;
+  P.AV = 4.0 * ec * ec / c / 3.0 / sqrt(3.0) / tanth * n / 2.0 / (th2 * thetae) / g;
   P.hkT_g = pc::h / pc::k / t / g;
   double wp2 = 4.0 * pi * n * ec * ec / m;
   double omega0 = ec * b / m / c;
   // xarg = thetae*sqrt(sqrt(2) sin(theta) 1e3 omega0/(2 pi nu)),  nu = nu_obs/g
-  P.lAx = log(thetae * sqrt(sqrt(2.0) * sinth * (1e3 * omega0 / 2.0 / pi) * g));
+  P.Ax = thetae * sqrt(sqrt(2.0) * sinth * (1e3 * omega0 / 2.0 / pi) * g);
+  const double lAx = log(P.Ax);
+  P.Ax1 = exp(1.035 * lAx);
+  P.Ax2 = exp(1.2 * lAx);
+  P.Ax3 = exp((double)1.50316886f * lAx);
+  P.Ax4 = exp((-8.0 / 3.0) * lAx);
   double X, Z0, Z1;
   if (thetae > 1e-2) {
     double x = 1.0 / thetae;
@@ -142,23 +160,22 @@ GRT_HD void thermal_point(double n, double b, double t, double theta, double g, 
   P.RV0 = rvc * Z0;
   P.RV1 = rvc * Z1;
   P.g = g;
-  P.ig = 1.0 / g;
 }
 
 // e = (jI,jQ,jU,jV, aI,aQ,aU,aV, rhoQ,rhoU,rhoV) in invariant form (see above); jraw = comoving j_I.  kcl = c^2 LBH / (2 h).
 // The emissivities are formed in the reference's order -- comoving j first, then j g^2 and alpha = j/B_nu scaled by LBH/g --
 // so that they underflow (exp(-1.89 x^(1/3)) reaches 1e-320 in cold, weakly magnetised zones) where the reference's do: a
 // DELO step divides by alpha_I, and "j_inv == 0 but alpha_I != 0" must stay distinguishable from "both 0".
+// Per call: 5 exp, 1 cos, 1 sqrt, 1 reciprocal (+ 1 log where the Faraday-rotation fit is switched on, + 1 division inside
+// the 16 < xarg < 6552 window of the high-frequency correction) and ~110 multiply-adds.
 GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, double *e, double &jraw) {
-  const double lxm = F.lnu + P.lnu_off;
-  const double x13 = exp(lxm * (1.0 / 3.0));
+  const double x13 = F.n13 * P.xp13;
   const double i13 = 1.0 / x13, i23 = i13 * i13;
-  const double ex = exp(-1.8899 * x13);
+  const double ex = exp_fast(-1.8899 * x13);
   const double iix = 2.5651 * (1.0 + 1.92 * i13 + .9977 * i23) * ex;
   const double iqx = 2.5651 * (1.0 + .93193 * i13 + .499873 * i23) * ex;
   const double ivx = (1.81384 * (i23 * i13) + 3.42319 * i23 + 0.0292545 * (i13 * sqrt(i13)) + 2.03773 * i13) * ex;
-  const double nuc = F.nu * P.ig;
-  const double ji = P.AI * nuc * iix, jq = P.AI * nuc * iqx, jv = P.AV * nuc * ivx;
+  const double ji = P.AI * F.nu * iix, jq = P.AI * F.nu * iqx, jv = P.AV * F.nu * ivx;
   jraw = ji;
   // 1/B_nu (bnu, polsynchemis.f90:1014-1032): Rayleigh-Jeans below h nu/kT = 1e-6; B_nu == 0 is replaced by epsilon
   const double xh = P.hkT_g * F.nu;
@@ -167,30 +184,35 @@ GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, 
   if (xh < 1e-6)
     ka = kcl * g2 * xh * F.inu3;
   else if (xh < 600.0)
-    ka = kcl * g2 * (exp(xh) - 1.0) * F.inu3;
+    ka = kcl * g2 * (exp_fast(xh) - 1.0) * F.inu3;
   else {  // deep Wien tail: follow the reference literally (B_nu underflowing to 0 is replaced by epsilon)
+    double ig = 1.0 / P.g, nuc = F.nu * ig;
     double bn = 2.0 * pc::h * nuc / pc::c2 * nuc * nuc / (exp(xh) - 1.0);
     if (bn == 0.0) bn = 2.220446049250313e-16;
-    ka = P.ig * (kcl * 2.0 * pc::h / pc::c2) / bn;
+    ka = ig * (kcl * 2.0 * pc::h / pc::c2) / bn;
   }
   e[0] = ji * g2; e[1] = jq * g2; e[2] = 0.0; e[3] = jv * g2;
   e[4] = ji * ka; e[5] = jq * ka; e[6] = 0.0; e[7] = jv * ka;
-  // Faraday rotation / conversion (Shcherbakov 2008 fits)
-  const double lx = P.lAx - 0.5 * F.lnu;
-  const double xarg = exp(lx);
-  const double e1 = .011 * exp(xarg * (-1.0 / 47.2));
-  double jff = 2.011 * exp(exp(1.035 * lx) * (-1.0 / 4.7)) - cos(0.5 * xarg) * exp(exp(1.2 * lx) * (-1.0 / 2.73)) - e1;
-  const double z2 = (lx - 4.787491742782046) * 20.0;  // 2 (log(xarg) - log(120)) / 0.1
-  if (z2 > -40.0) {                                   // below: 0.5 + 0.5 tanh(z) == 0 exactly in FP64
-    double ez = exp(z2);
-    double sw = (z2 < 80.0) ? ez / (1.0 + ez) : 1.0;
+  // Faraday rotation / conversion (Shcherbakov 2008 fits jffunc, shgmfunc)
+  const double xarg = P.Ax * F.nm12;
+  const double e1 = .011 * exp_fast(xarg * (-1.0 / 47.2));
+  double jff = 2.011 * exp_fast((P.Ax1 * F.nq1) * (-1.0 / 4.7)) - cos(0.5 * xarg) * exp_fast((P.Ax2 * F.nq2) * (-1.0 / 2.73)) - e1;
+  // extraterm * (0.5 + 0.5 tanh((log(xarg) - log(120))/0.1)) = extraterm * t^20/(1 + t^20), t = xarg/120; the switch is
+  // exactly 0 in FP64 below t = e^-2 and exactly 1 above t = e^4
+  const double t = xarg * (1.0 / 120.0);
+  if (t > 0.1353352832366127) {
+    double sw = 1.0;
+    if (t < 54.598150033144236) {
+      const double t2 = t * t, t4 = t2 * t2, t5 = t4 * t, t10 = t5 * t5, t20 = t10 * t10;
+      sw = t20 / (1.0 + t20);
+    }
     const double c83 = 0.7937005259840998 / 67.44733739010397 * GRT_PI * 1e4;  // 2^(-1/3) / 3^(23/6) pi 1e4
-    jff += (e1 - c83 * exp((-8.0 / 3.0) * log(xarg + 1e-16))) * sw;
+    jff += (e1 - c83 * (P.Ax4 * F.nq4)) * sw;  // (xarg + 1e-16)^(-8/3): the 1e-16 is below rounding for xarg > 16
   }
   e[8] = P.RQ * jff * F.inu3;
   e[9] = 0.0;
   double rv = P.RV0;
-  if (P.RV1 != 0.0) rv -= P.RV1 * ((double)0.43793091f * log(1.0 + (double)0.00185777f * exp((double)1.50316886f * lx)));
+  if (P.RV1 != 0.0) rv -= P.RV1 * ((double)0.43793091f * log(1.0 + (double)0.00185777f * (P.Ax3 * F.nq3)));
   e[10] = rv * F.inu2;
 }
 

@@ -11,6 +11,7 @@
 // tests/host_emul (a debugging harness; the product only ever launches the CUDA kernels).
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define GRT_HD __host__ __device__ __forceinline__
@@ -50,6 +51,59 @@ GRT_HD float r4exp(float x) { return expf(x); }
 GRT_HD float r4acos(float x) { return acosf(x); }
 GRT_HD float r4pow(float x, float y) { return powf(x, y); }
 #endif
+
+// ---- exp() for the transfer hot loop -------------------------------------------------------------
+// The emissivity + DELO loop calls exp() six times per (point, frequency).  libm's device exp spends two UMOV per
+// 64-bit polynomial coefficient (immediates travel through uniform registers) and a branch on the slow path: ~30% of the
+// instructions the loop issued were such moves (ncu, profiles/).  This version keeps the coefficients in constant memory
+// (they become c[bank][offset] operands of the DFMAs), has no branch, and scales by 2^k in two halves so results in the
+// subnormal range round like the reference's (the DELO step has to tell "underflowed to a subnormal" from 0).
+// e^r = 1 + r + r^2 q(r) on |r| <= ln2/2: degree-11 Chebyshev fit, max relative error 1.6e-17 (tools/fit_exp.py).
+// Domain: x <= 709 (callers guarantee it); x < -800 -> 0; NaN -> NaN.  Error <= 1 ulp like libm's.
+#define GRT_EXP_COEFS                                                                                                   \
+  2.510038549551032e-08, 2.7620088445409746e-07, 2.7557268459997064e-06, 2.4801521295954376e-05, 0.00019841269863053618, \
+      0.0013888888917213717, 0.008333333333330062, 0.04166666666662413, 0.16666666666666669, 0.5000000000000001, 1.0, 1.0
+#if defined(__CUDACC__)
+static __constant__ double grt_expc_dev[12] = {GRT_EXP_COEFS};
+#endif
+GRT_HD double exp_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  const double *C = grt_expc_dev;
+#else
+  const double C[12] = {GRT_EXP_COEFS};
+#endif
+  x = (x < -800.0) ? -800.0 : x;  // (keeps NaN)
+  double t = fma(x, 1.4426950408889634, 6755399441055744.0);  // round(x log2 e) in the low mantissa bits
+  int k;
+#if defined(__CUDA_ARCH__)
+  k = __double2loint(t);
+#else
+  {
+    long long b;
+    memcpy(&b, &t, 8);
+    k = (int)(unsigned)(b & 0xffffffffLL);
+  }
+#endif
+  double kf = t - 6755399441055744.0;
+  double r = fma(kf, -6.9314718055994529e-1, x);
+  r = fma(kf, -2.3190468138462996e-17, r);
+  double p = C[0];
+#pragma unroll
+  for (int i = 1; i < 12; i++) p = fma(p, r, C[i]);
+  int k1 = k >> 1, k2 = k - k1;
+  double s1, s2;
+#if defined(__CUDA_ARCH__)
+  s1 = __hiloint2double((k1 + 1023) << 20, 0);
+  s2 = __hiloint2double((k2 + 1023) << 20, 0);
+#else
+  {
+    long long b1 = (long long)(k1 + 1023) << 52, b2 = (long long)(k2 + 1023) << 52;
+    memcpy(&s1, &b1, 8);
+    memcpy(&s2, &b2, 8);
+  }
+#endif
+  return (p * s1) * s2;
+}
 
 // ---- Carlson R_F ------------------------------------------------------------------------------
 GRT_HDN double rf(double x, double y, double z) {

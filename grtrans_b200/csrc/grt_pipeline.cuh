@@ -113,8 +113,8 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
       case EM_POLSYNCHTH: {
         ThermalPoint T;
         thermal_point(cg.ncgs, cg.bcgs, cg.tcgs, oo.ang, oo.g, pc::G * A.sp[mm].mbh * pc::msun / pc::c2, T);
-        o[4] = T.lnu_off; o[5] = T.AI; o[6] = T.AV; o[7] = T.hkT_g; o[8] = T.lAx; o[9] = T.RQ; o[10] = T.RV0; o[11] = T.RV1;
-        o[12] = T.ig;
+        o[4] = T.xp13; o[5] = T.AI; o[6] = T.AV; o[7] = T.hkT_g; o[8] = T.Ax; o[9] = T.Ax1; o[10] = T.Ax2; o[11] = T.Ax3;
+        o[12] = T.Ax4; o[13] = T.RQ; o[14] = T.RV0; o[15] = T.RV1;
       } break;
       case EM_POLSYNCHPL:
       case EM_SYNCHPL:

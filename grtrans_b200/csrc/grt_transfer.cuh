@@ -24,7 +24,7 @@ namespace grt {
 
 #define GRT_NREC 16  // doubles per point record (128 B)
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
-//   POLSYNCHTH        [4..12] ThermalPoint (lnu_off, AI, AV, hkT_g, lAx, RQ, RV0, RV1, 1/g)
+//   POLSYNCHTH        [4..15] ThermalPoint (xp13, AI, AV, hkT_g, Ax, Ax^1.035, Ax^1.2, Ax^1.503, Ax^-8/3, RQ, RV0, RV1)
 //   POLSYNCHPL/SYNCHPL [4] n_nth, [5] B, [6] angle
 //   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
 
@@ -69,8 +69,8 @@ GRT_HD void node_coef(const TransferParams &P, const double *rec, const FreqCons
   bool invariant = false;  // e already holds j g^2 and K LBH / g
   if (ET == EM_POLSYNCHTH) {
     ThermalPoint T;
-    T.lnu_off = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.lAx = rec[8]; T.RQ = rec[9]; T.RV0 = rec[10];
-    T.RV1 = rec[11]; T.ig = rec[12]; T.g = g;
+    T.xp13 = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.Ax = rec[8]; T.Ax1 = rec[9]; T.Ax2 = rec[10];
+    T.Ax3 = rec[11]; T.Ax4 = rec[12]; T.RQ = rec[13]; T.RV0 = rec[14]; T.RV1 = rec[15]; T.g = g;
     thermal_eval(T, F, pc::c2 * P.LBH / (2.0 * pc::h), e, jI_raw);
     invariant = true;
   } else {
@@ -170,7 +170,7 @@ GRT_HD void delo_step(const Coef &c0, const Coef &c1, double dx, double delta, d
   double rhs[4], t[4];
   kmat_vec(c1.K, iprev, t);
   if (delta > thin) {
-    const double E = exp(-delta), F = 1.0 - E, G = (1.0 - (1.0 + delta) * E) / delta;
+    const double E = exp_fast(-delta), F = 1.0 - E, G = (1.0 - (1.0 + delta) * E) / delta;
     const double i0 = 1.0 / c0.K[0], i1 = 1.0 / c1.K[0];
     const double w0 = (F - G) * i0, w1 = G * i1;
     // (F-G) S_k + G S_k+1 + (E*Id - G*Kp1) iprev,  S = j/aI,  Kp1 = K1/aI1 - Id
