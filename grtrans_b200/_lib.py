@@ -21,7 +21,7 @@ ERRORS = {1: "no usable CUDA device (GRT_ERR_NO_DEVICE)", 2: "unsupported argume
 SYMBOLS = ["grt_args_defaults", "grt_main", "grt_get_ivals", "grt_get_ab", "grt_get_freqs", "grt_data_allocated",
            "grt_del_data", "grt_run", "grt_program", "grt_read_inputs", "grt_write_output", "grt_geokerr_camera",
            "grt_geokerr_rays", "grt_ray_stage_dump", "grt_polsynchth", "grt_polsynchpl", "grt_synchemis",
-           "grt_rt_integrate", "grt_session_create", "grt_session_destroy", "grt_session_launch", "grt_session_sync", "grt_session_upload", "grt_session_run_timed",
+           "grt_rt_integrate", "grt_session_create", "grt_session_destroy", "grt_session_launch", "grt_session_sync", "grt_session_launch_fetch", "grt_session_upload", "grt_session_run_timed",
            "grt_session_time", "grt_session_launch_count", "grt_session_counts", "grt_session_device_image",
            "grt_session_fetch", "grt_session_ncams", "grt_version", "grt_device_count", "grt_dfma_peak"]
 
@@ -189,6 +189,16 @@ class Session(object):
 
     def sync(self):
         check(lib().grt_session_sync(self._h), "grt_session_sync")
+
+    def launch_fetch(self):
+        """Launch and stream the image tile by tile into the session's pinned host buffer.  Returns (image view
+        [ncams, nlocal, nvals] float32 -- complete after sync(), owned by the session -- , bytes)."""
+        p = C.POINTER(C.c_float)(); b = C.c_longlong()
+        check(lib().grt_session_launch_fetch(self._h, C.byref(p), C.byref(b)), "grt_session_launch_fetch")
+        nl = self.nlocal()
+        if nl == 0:
+            return np.zeros((self.ncams, 0, self.nvals), np.float32), 0
+        return np.ctypeslib.as_array(p, shape=(self.ncams, nl, self.nvals)), b.value
 
     def upload(self):
         b = C.c_longlong()

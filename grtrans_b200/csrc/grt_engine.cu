@@ -50,8 +50,11 @@ static cudaError_t h2d(T **p, const std::vector<T> &v) {
 struct grt_session {
   grt_args args;
   int device = 0, rank = 0, nranks = 1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t tile_done = nullptr;
+  float *h_image = nullptr;            // pinned host image [ncams][nlocal][nvals] (grt_session_launch_fetch)
+  std::vector<void *> registered;      // host buffers pinned in place with cudaHostRegister
   std::vector<double> freqs, mdots, mu0;
   int nmu = 1, nparams = 1, nfreq = 1, nvals = 1, ncams = 1, maxpts = 1, npix = 0;
   std::vector<grt_host::Camera> cams;  // one per mu0
@@ -81,9 +84,13 @@ static int session_free(grt_session *s) {
   if (!s) return GRT_OK;
   cudaSetDevice(s->device);
   for (void *p : s->owned) cudaFree(p);
+  for (void *p : s->registered) cudaHostUnregister(p);
+  if (s->h_image) cudaFreeHost(s->h_image);
   for (auto &e : s->ev)
     if (e) cudaEventDestroy(e);
+  if (s->tile_done) cudaEventDestroy(s->tile_done);
   if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   delete s;
   return GRT_OK;
 }
@@ -248,6 +255,13 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   P.LBH = pc::G * a->mbh * pc::msun / pc::c2;
   P.gmin = (double)(float)a->gmin; P.gmax = (double)(float)a->gmax; P.p = (double)(float)a->p1;
   P.max_tau = 10.0; P.hmax = 0.1; P.ortol = 1e-6; P.oatol = 1e-8; P.thin = 1e-2; P.maxsteps = 100000;
+  // pin the host mirrors in place so grt_session_upload() runs at full PCIe rate (failure to pin is not an error)
+  auto pin = [&](void *p, size_t bytes) {
+    if (p && bytes && cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) s->registered.push_back(p);
+    else cudaGetLastError();
+  };
+  for (auto &v : s->h_rc) pin(v.data(), v.size() * sizeof(RayConst));
+  pin(s->fh.cells.data(), s->fh.cells.size() * sizeof(grt_host::HostCell));
   *out = s;
   return GRT_OK;
 }
@@ -270,20 +284,47 @@ static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump 
   return (cudaGetLastError() == cudaSuccess) ? GRT_OK : GRT_ERR_CUDA;
 }
 
-extern "C" int grt_session_launch(grt_session *s) {
+static int launch_all(grt_session *s, bool fetch) {
   if (!s) return GRT_ERR_BAD_ARG;
   if (cudaSetDevice(s->device) != cudaSuccess) return GRT_ERR_NO_DEVICE;
   StageDump sd;
   memset(&sd, 0, sizeof(sd));
   s->launches = 0;
+  const size_t rowb = (size_t)s->nvals * sizeof(float);
   for (int j = 0; j < s->nmu; j++)
     for (long long off = 0; off < s->nlocal; off += s->tile) {
       int n = (int)std::min<long long>(s->tile, s->nlocal - off);
       int rc = launch_tile(s, j, off, n, sd, false);
       if (rc != GRT_OK) return rc;
       s->launches += 5;
+      if (fetch) {
+        // this tile's pixels of the nparams*nfreq cameras of mu0 index j: a 2-D block of the [cam][ray][nvals] image
+        CK(cudaEventRecord(s->tile_done, s->stream));
+        CK(cudaStreamWaitEvent(s->copy_stream, s->tile_done, 0));
+        size_t cam0 = (size_t)j * s->nparams * s->nfreq;
+        size_t o = (cam0 * s->nlocal + off) * s->nvals;
+        CK(cudaMemcpy2DAsync(s->h_image + o, (size_t)s->nlocal * rowb, s->d_image + o, (size_t)s->nlocal * rowb, (size_t)n * rowb,
+                             (size_t)s->nparams * s->nfreq, cudaMemcpyDeviceToHost, s->copy_stream));
+      }
     }
   return GRT_OK;
+}
+
+extern "C" int grt_session_launch(grt_session *s) { return launch_all(s, false); }
+
+// Launch the whole path and stream every finished tile of the image to a pinned host buffer on a second stream, so the
+// device->host read-back overlaps the computation of the following tiles.  *host_image (owned by the session, valid until
+// the next call / destroy) is float32 [ncams][nrays_local][nvals]; it is complete after grt_session_sync().
+extern "C" int grt_session_launch_fetch(grt_session *s, const float **host_image, long long *bytes) {
+  if (!s) return GRT_ERR_BAD_ARG;
+  if (cudaSetDevice(s->device) != cudaSuccess) return GRT_ERR_NO_DEVICE;
+  size_t nel = (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nvals;
+  if (!s->h_image) CK(cudaHostAlloc((void **)&s->h_image, nel * sizeof(float), cudaHostAllocDefault));
+  if (!s->copy_stream) CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  if (!s->tile_done) CK(cudaEventCreateWithFlags(&s->tile_done, cudaEventDisableTiming));
+  if (host_image) *host_image = s->h_image;
+  if (bytes) *bytes = (long long)((size_t)s->ncams * s->nlocal * s->nvals * sizeof(float));
+  return launch_all(s, true);
 }
 
 // Re-copy this rank's host-resident inputs (per-ray camera constants, fluid snapshot, frequency grid) to the device:
@@ -328,6 +369,7 @@ extern "C" int grt_session_run_timed(grt_session *s, int nsteps, float *ms) {
 extern "C" int grt_session_sync(grt_session *s) {
   if (!s) return GRT_ERR_BAD_ARG;
   cudaError_t e = cudaStreamSynchronize(s->stream);
+  if (e == cudaSuccess && s->copy_stream) e = cudaStreamSynchronize(s->copy_stream);
   if (e != cudaSuccess) {
     fprintf(stderr, "grtrans_b200: %s\n", cudaGetErrorString(e));
     return GRT_ERR_CUDA;

@@ -131,6 +131,11 @@ void grt_session_destroy(grt_session *s);
 /* launch the whole per-pixel path for this rank's rays on the session stream (asynchronous) */
 int grt_session_launch(grt_session *s);
 int grt_session_sync(grt_session *s);
+/* launch + stream each finished tile of the image into a session-owned PINNED host buffer on a second stream (the
+ * device->host read-back overlaps the computation of the following tiles).  *host_image: float32
+ * [ncams][nrays_local][nvals], complete after grt_session_sync(), valid until the next call or grt_session_destroy;
+ * *bytes = its size */
+int grt_session_launch_fetch(grt_session *s, const float **host_image, long long *bytes);
 /* host->device half of an end-to-end step: re-copy camera constants, fluid snapshot and frequency grid from the
  * session's host buffers; *bytes = bytes copied */
 int grt_session_upload(grt_session *s, long long *bytes);

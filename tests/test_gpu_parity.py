@@ -282,3 +282,23 @@ def test_no_cpu_fallback_symbols_and_errors():
     a.fname = b"NOSUCHMODEL"
     with pytest.raises(_lib.GrtError):
         _lib.main(a)
+
+
+def test_session_pipelined_fetch_equals_fetch():
+    """grt_session_launch_fetch (tile-by-tile D2H into pinned memory on a second stream) returns the same image as
+    launch + fetch, also when the rays span several tiles and mu0 cameras."""
+    os.environ["GRT_TILE"] = "1000"
+    try:
+        kw = cases.cfg_sphacc(n=60, nfreq=3, nmu=2, mumin=.3, mumax=.7)
+        s = _lib.Session(args_from_kwargs(**kw))
+        s.upload()
+        s.launch(); s.sync()
+        img, idx = s.fetch()
+        view, nbytes = s.launch_fetch()
+        s.sync()
+        assert nbytes == img.nbytes and view.shape == img.shape
+        assert np.array_equal(np.asarray(view), img, equal_nan=True)
+        assert np.abs(img).max() > 0
+        s.close()
+    finally:
+        del os.environ["GRT_TILE"]
