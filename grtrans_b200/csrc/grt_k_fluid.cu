@@ -10,7 +10,7 @@
 namespace grt {
 
 __global__ void __launch_bounds__(128, 4) k_fluid_ortho(const RayConst *__restrict__ rc, const RayInv *__restrict__ inv,
-                                                     const RayMeta *__restrict__ meta, FluidKernelArgs A, long long total,
+                                                     const RayMeta *__restrict__ meta, const __grid_constant__ FluidKernelArgs A, long long total,
                                                      int nrays, PointArrays pa, double *__restrict__ rec, StageDump sd) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;

@@ -10,7 +10,7 @@
 //   FORMAL  :844-876 + calc_O :615-683 -- O(dx) applied to a vector without building M1..M4
 //   quadrature :878-882
 //   LSODA   :200-307 + radtrans_aux :453-465 -- same tau cut, zero-emissivity trim and (as written)
-//           neighbour-index coefficient model; ODEPACK is replaced by an embedded Cash-Karp 5(4)
+//           neighbour-index coefficient model; ODEPACK is replaced by an embedded Dormand-Prince 5(4)
 //           Runge-Kutta with the reference tolerances (rtol 1e-6, atol 1e-8 on fac-normalised
 //           intensities, hmax 0.1) that never steps across a tabulated node.
 // Because the transfer equation is linear and I_0 = 0, the reference's normalisation j/fac ... I*fac
@@ -231,17 +231,20 @@ GRT_HD void rt_rhs(int neq, const double *j, const double *K, const double *I, d
   }
 }
 
-// Cash-Karp 5(4) across one tabulated interval [la, lb] with coefficients linear between the node
-// values (ca at w=0, cb at w=1).  Returns false on step overflow / NaN.
+// Dormand-Prince 5(4) across one tabulated interval [la, lb] with coefficients linear between the node values (ca at
+// w=0, cb at w=1) -- the integrator north_star puts in LSODA's place, with the reference's tolerances (rtol 1e-6, atol
+// 1e-8 on fac-normalised intensities, hmax 0.1, maxsteps per output interval like mxstep).  Same tableau, error norm and
+// step controller as the oracle's restatement (oracle/radtrans.cc), which is the one pinned against ODEPACK's LSODA
+// (scipy.integrate.odeint, tests/test_oracle_integrators.py).  Returns false on step overflow / NaN (pixel zeroed, like
+// istate < 0 in odepack.f90:91-96).
 GRT_HD bool ck_interval(int neq, const Coef &ca, const Coef &cb, double la, double lb, double *y, double &h,
                         const TransferParams &P) {
-  const double b21 = 0.2, b31 = 3.0 / 40.0, b32 = 9.0 / 40.0, b41 = 0.3, b42 = -0.9, b43 = 1.2, b51 = -11.0 / 54.0,
-               b52 = 2.5, b53 = -70.0 / 27.0, b54 = 35.0 / 27.0, b61 = 1631.0 / 55296.0, b62 = 175.0 / 512.0,
-               b63 = 575.0 / 13824.0, b64 = 44275.0 / 110592.0, b65 = 253.0 / 4096.0;
-  const double c1 = 37.0 / 378.0, c3 = 250.0 / 621.0, c4 = 125.0 / 594.0, c6 = 512.0 / 1771.0;
-  const double d1 = c1 - 2825.0 / 27648.0, d3 = c3 - 18575.0 / 48384.0, d4 = c4 - 13525.0 / 55296.0, d5 = -277.0 / 14336.0,
-               d6 = c6 - 0.25;
-  const double a2 = 0.2, a3 = 0.3, a4 = 0.6, a5 = 1.0, a6 = 0.875;
+  const double c2 = 1. / 5, c3 = 3. / 10, c4 = 4. / 5, c5 = 8. / 9;
+  const double a21 = 1. / 5, a31 = 3. / 40, a32 = 9. / 40, a41 = 44. / 45, a42 = -56. / 15, a43 = 32. / 9,
+               a51 = 19372. / 6561, a52 = -25360. / 2187, a53 = 64448. / 6561, a54 = -212. / 729, a61 = 9017. / 3168,
+               a62 = -355. / 33, a63 = 46732. / 5247, a64 = 49. / 176, a65 = -5103. / 18656, a71 = 35. / 384,
+               a73 = 500. / 1113, a74 = 125. / 192, a75 = -2187. / 6784, a76 = 11. / 84;
+  const double e1 = 71. / 57600, e3 = -71. / 16695, e4 = 71. / 1920, e5 = -17253. / 339200, e6 = 22. / 525, e7 = -1. / 40;
   const double span = lb - la;
   double t = la;
   int steps = 0;
@@ -255,36 +258,38 @@ GRT_HD bool ck_interval(int neq, const Coef &ca, const Coef &cb, double la, doub
     if (++steps > P.maxsteps) return false;
     double hh = dmin(dmin(h, P.hmax), lb - t);
     bool last = hh >= lb - t;
-    double j[4], K[7], k1[4], k2[4], k3[4], k4[4], k5[4], k6[4], yt[4], yn[4];
+    double j[4], K[7], k1[4], k2[4], k3[4], k4[4], k5[4], k6[4], k7[4], yt[4], yn[4];
     coef(t, j, K);
     rt_rhs(neq, j, K, y, k1);
-    for (int i = 0; i < neq; i++) yt[i] = y[i] + hh * b21 * k1[i];
-    coef(t + a2 * hh, j, K);
+    for (int i = 0; i < neq; i++) yt[i] = y[i] + hh * a21 * k1[i];
+    coef(t + c2 * hh, j, K);
     rt_rhs(neq, j, K, yt, k2);
-    for (int i = 0; i < neq; i++) yt[i] = y[i] + hh * (b31 * k1[i] + b32 * k2[i]);
-    coef(t + a3 * hh, j, K);
+    for (int i = 0; i < neq; i++) yt[i] = y[i] + hh * (a31 * k1[i] + a32 * k2[i]);
+    coef(t + c3 * hh, j, K);
     rt_rhs(neq, j, K, yt, k3);
-    for (int i = 0; i < neq; i++) yt[i] = y[i] + hh * (b41 * k1[i] + b42 * k2[i] + b43 * k3[i]);
-    coef(t + a4 * hh, j, K);
+    for (int i = 0; i < neq; i++) yt[i] = y[i] + hh * (a41 * k1[i] + a42 * k2[i] + a43 * k3[i]);
+    coef(t + c4 * hh, j, K);
     rt_rhs(neq, j, K, yt, k4);
-    for (int i = 0; i < neq; i++) yt[i] = y[i] + hh * (b51 * k1[i] + b52 * k2[i] + b53 * k3[i] + b54 * k4[i]);
-    coef(t + a5 * hh, j, K);
+    for (int i = 0; i < neq; i++) yt[i] = y[i] + hh * (a51 * k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
+    coef(t + c5 * hh, j, K);
     rt_rhs(neq, j, K, yt, k5);
     for (int i = 0; i < neq; i++)
-      yt[i] = y[i] + hh * (b61 * k1[i] + b62 * k2[i] + b63 * k3[i] + b64 * k4[i] + b65 * k5[i]);
-    coef(t + a6 * hh, j, K);
+      yt[i] = y[i] + hh * (a61 * k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
+    coef(t + hh, j, K);
     rt_rhs(neq, j, K, yt, k6);
+    for (int i = 0; i < neq; i++)
+      yn[i] = y[i] + hh * (a71 * k1[i] + a73 * k3[i] + a74 * k4[i] + a75 * k5[i] + a76 * k6[i]);
+    rt_rhs(neq, j, K, yn, k7);
     double err = 0.0;
     for (int i = 0; i < neq; i++) {
-      yn[i] = y[i] + hh * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c6 * k6[i]);
-      double ei = hh * (d1 * k1[i] + d3 * k3[i] + d4 * k4[i] + d5 * k5[i] + d6 * k6[i]);
+      double ei = hh * (e1 * k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k7[i]);
       double scv = P.oatol + P.ortol * dmax(fabs(y[i]), fabs(yn[i]));
       err += (ei / scv) * (ei / scv);
     }
     err = sqrt(err / neq);
     if (!(err <= 1.0)) {
       if (!(err == err)) return false;
-      h = hh * dmax(0.2, 0.9 * pow(err, -0.25));
+      h = hh * dmax(0.2, 0.9 * pow(err, -0.2));
       continue;
     }
     for (int i = 0; i < neq; i++) y[i] = yn[i];

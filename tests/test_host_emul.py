@@ -71,10 +71,9 @@ def test_kernel_bodies_match_oracle(emul, cfg, over):
     got, npts = run_emul(emul, kw)
     ref = orc.run(_args=args_from_kwargs(**kw))
     relI, flux, quv, nanok = cases.image_errors(got, ref['ivals'])
-    lsoda = over.get('iname') == 'lsoda'
     assert nanok
-    assert relI < (2e-4 if lsoda else 1e-4), (relI, flux, quv)
-    assert flux < (2e-5 if lsoda else 1e-5), flux
+    assert relI < 1e-4, (relI, flux, quv)
+    assert flux < 1e-5, flux
     assert quv < 1e-3, quv
 
 
