@@ -15,10 +15,10 @@
 
 namespace grt {
 
-enum { FL_DUMMY = 0, FL_SPHACC = 1, FL_THINDISK = 2, FL_HARM = 12, FL_FFJET = 13, FL_HARM3D = 19 };
+enum { FL_DUMMY = 0, FL_SPHACC = 1, FL_THINDISK = 2, FL_HARM = 12, FL_FFJET = 13, FL_HARM3D = 19, FL_IHARM = 29 };
 
 struct Cell {  // 48 bytes, 16-byte aligned
-  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, pad0, pad1;
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela /* iharm electron entropy */, pad1;
 };
 
 struct FluidDev {
@@ -31,17 +31,21 @@ struct FluidDev {
   const float *axth;  // uniqth                                  [nx2]
   const float *ax3;   // uniqx3 / uniqph                         [nx3]
   const Cell *cells;  // [n] packed snapshot
+  // iharm grid (fluid_model_iharm.f90:13-24, real(8) module variables read from the header file)
+  double hslope, mks_smooth, poly_xt, poly_alpha, startx1;
+  int is_mmks, eheat;
+  float gam;
   // SPHACC tables
   const float *uvals, *vvals, *uv, *tvals;  // 498, 498, 461 (=1/rvals), 461
 };
 
 struct FluidSample {
-  float rho, p, bmag;
+  float rho, p, bmag, kela;
   double u[4], b[4];
 };
 
 struct Field10 {
-  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0;
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela;
 };
 
 GRT_HD Field10 load_cell(const Cell *cells, size_t idx) {
@@ -50,10 +54,11 @@ GRT_HD Field10 load_cell(const Cell *cells, size_t idx) {
   const float4 *q = reinterpret_cast<const float4 *>(cells + idx);
   float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
   f.rho = a.x; f.p = a.y; f.vrl = a.z; f.vtl = a.w; f.vpl = b.x; f.b0 = b.y; f.br = b.z; f.bth = b.w; f.bph = c.x; f.u0 = c.y;
+  f.kela = c.z;
 #else
   const Cell &c = cells[idx];
   f.rho = c.rho; f.p = c.p; f.vrl = c.vrl; f.vtl = c.vtl; f.vpl = c.vpl; f.b0 = c.b0; f.br = c.br; f.bth = c.bth;
-  f.bph = c.bph; f.u0 = c.u0;
+  f.bph = c.bph; f.u0 = c.u0; f.kela = c.kela;
 #endif
   return f;
 }
@@ -143,6 +148,83 @@ GRT_HD double harm_x2_of_theta(double theta, double h) {
   return b;
 }
 
+// ---- generic Brent root finder (math.f90:56-135 zbrent, scalar) ----------------------------------------
+template <class Fn>
+GRT_HD double zbrent_hd(const Fn &func, double x1, double x2, double tol) {
+  const double eps = 2.220446049250313e-16;
+  double a = x1, b = x2, c, d = 0, e = 0, fa = func(a), fb = func(b), fc, p, q, r, s, tol1, xm;
+  if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) return nan("");
+  c = b;
+  fc = fb;
+  for (int iter = 0; iter < 100; iter++) {
+    if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
+      c = a; fc = fa; d = b - a; e = d;
+    }
+    if (fabs(fc) < fabs(fb)) {
+      a = b; b = c; c = a; fa = fb; fb = fc; fc = fa;
+    }
+    tol1 = 2.0 * eps * fabs(b) + 0.5 * tol;
+    xm = 0.5 * (c - b);
+    if (fabs(xm) <= tol1 || fb == 0.0) return b;
+    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+      s = fb / fa;
+      if (a == c) {
+        p = 2.0 * xm * s;
+        q = 1.0 - s;
+      } else {
+        q = fa / fc;
+        r = fb / fc;
+        p = s * (2.0 * xm * q * (q - r) - (b - a) * (r - 1.0));
+        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      p = fabs(p);
+      if (2.0 * p < dmin(3.0 * xm * q - fabs(tol1 * q), fabs(e * q))) {
+        e = d;
+        d = p / q;
+      } else {
+        d = xm;
+        e = d;
+      }
+    } else {
+      d = xm;
+      e = d;
+    }
+    a = b;
+    fa = fb;
+    b = b + ((fabs(d) > tol1) ? d : (signbit(xm) ? -fabs(tol1) : fabs(tol1)));
+    fb = func(b);
+  }
+  return b;
+}
+
+// ---- iharm coordinate maps (fluid_model_iharm.f90:82-118) ------------------------------------------------
+// theta(x2) of the MKS grid (real(8)) and theta(x2, x1) of the MMKS / FMKS grid (a real(4) function whose
+// sub-expressions are promoted by the real(8) module variables pi, hslope, startx1 exactly as written)
+struct IharmGrid {
+  double hslope, mks_smooth, poly_xt, poly_alpha, startx1;
+};
+GRT_HD double iharm_th_mks(const IharmGrid &G, double x2) {
+  return GRT_PI * x2 + (1. - G.hslope) / 2. * sin(2. * GRT_PI * x2);
+}
+GRT_HD float iharm_th_mmks(const IharmGrid &G, float x2, float x1) {
+  float A = (float)G.mks_smooth, B = (float)G.poly_xt, C = (float)G.poly_alpha;
+  float D = (float)(GRT_PI / (double)(2.f + 2.f / (r4pow(B, C) * (1 + C))));
+  float thetag = (float)(GRT_PI * (double)x2 + (1. - G.hslope) / 2. * sin(2. * GRT_PI * (double)x2));
+  float thetaj = (float)((double)(D * (2.f * x2 - 1.f) * (1.f + r4pow((2.f * x2 - 1.f) / B, C) / (1.f + C))) + GRT_PI / 2.);
+  return (float)((double)thetag + exp(-(double)A * ((double)x1 - G.startx1)) * (double)(thetaj - thetag));
+}
+struct IharmThetaMmks {
+  IharmGrid G;
+  double x1, th;
+  GRT_HD double operator()(double x) const { return th - (double)iharm_th_mmks(G, (float)x, (float)x1); }
+};
+struct IharmThetaMks {
+  IharmGrid G;
+  double th;
+  GRT_HD double operator()(double x) const { return th - iharm_th_mks(G, x); }
+};
+
 // bracket search equivalent to NR hunt/locate for an in-range x (1-based result clamped to [1,n-1])
 GRT_HD int bracket(const float *xx /*0-based*/, int n, float x) {
   bool ascnd = xx[n - 1] >= xx[0];
@@ -185,7 +267,7 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
   const double pcG = 6.67e-8, pcc = 2.99792458e10, pcc2 = pcc * pcc, pcmsun = 1.998e33, pcmp = 1.67262158e-24,
                pcsigt = 6.6523e-25, pcsigb = 5.6704e-5;
   float a = (float)ad;
-  s.rho = s.p = s.bmag = 0.f;
+  s.rho = s.p = s.bmag = s.kela = 0.f;
   for (int i = 0; i < 4; i++) s.u[i] = s.b[i] = 0.0;
   switch (F.model) {
     case FL_THINDISK: {
@@ -353,6 +435,47 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       s.p = (float)((double)v.p * fac);
       finish_grid(s, v, in, 0.f, zr, (float)thh, a, fac);
     } break;
+    case FL_IHARM: {
+      // iharm_vals (fluid_model_iharm.f90:222-424): nearest-neighbour lookup -- rd = td = pd = 1 puts all the weight on
+      // the upper corner of the cell in r, theta and phi; time weight 0 (nt = 1)
+      const int nx1 = F.nx1, nx2 = F.nx2, nx3 = F.nx3;
+      float theta = (float)thh, zr = (float)rr, zpp = (float)phh;
+      double sq1 = sqrt(1. - (double)a * (double)a);
+      float zphi = (float)((double)zpp + (double)a / (2.0 * sq1) * log(((double)zr - 1. - sq1) / ((double)zr - 1. + sq1)));
+      zphi = (float)fmod((double)zphi, 2. * pi);
+      if (zphi < 0.f) zphi = (float)((double)zphi + 2. * pi);
+      float x1 = r4log(zr), x3 = zphi, x2;
+      IharmGrid G{F.hslope, F.mks_smooth, F.poly_xt, F.poly_alpha, F.startx1};
+      if (F.is_mmks == 1) {
+        IharmThetaMmks fn{G, (double)x1, (double)theta};
+        x2 = (float)zbrent_hd(fn, -1.0, 1.0, 1e-6);
+      } else {
+        IharmThetaMks fn{G, (double)theta};
+        x2 = (float)zbrent_hd(fn, 0.0, 1.0, 1e-6);
+      }
+      int lx1 = (int)floorf((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
+      int ux1 = lx1 + 1;
+      int lx2 = (int)floorf((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;
+      int ux2 = lx2 + 1;
+      int lx3 = (int)floorf((x3 - F.ax3[0]) / (F.ax3[nx3 - 1] - F.ax3[0]) * (float)(nx3 - 1)) + 1;
+      int ux3 = lx3 + 1;
+      lx2 = (lx2 >= 1) ? lx2 : 1;
+      lx2 = (lx2 <= nx2) ? lx2 : nx2;
+      ux2 = (ux2 >= 1) ? ux2 : 1;
+      ux2 = (ux2 <= nx2) ? ux2 : nx2;
+      if (ux3 > nx3) ux3 = 1;
+      if (lx3 < 1) lx3 = nx3;
+      // guards: the reference indexes uniqr(lx1) / the data arrays out of bounds outside the radial range
+      int lx1s = lx1 < 1 ? 1 : (lx1 > nx1 ? nx1 : lx1), ux1s = ux1 < 1 ? 1 : (ux1 > nx1 ? nx1 : ux1);
+      float rh = 1.f + sqrtf(1.f - a * a);
+      double fac = (F.axr[lx1s - 1] <= rh) ? 1e-3 : 1.0;
+      Field10 v = load_cell(F.cells, (size_t)(ux1s - 1) * nx2 * nx3 + (size_t)(ux2 - 1) * nx3 + (size_t)(ux3 - 1));
+      bool in = x1 > F.ax1[0];
+      s.rho = (float)((double)(in ? v.rho : 0.f) * fac);
+      s.p = (float)((double)(in ? v.p : 1.f) * fac);
+      s.kela = (F.eheat == 1) ? (float)((double)(in ? v.kela : 1.f) * fac) : 0.f;
+      finish_grid(s, v, in, 0.f, zr, (float)thh, a, 1.0);
+    } break;
     default:
       break;
   }
@@ -366,7 +489,7 @@ struct CgsVars {
   double ncgs, ncgsnth, bcgs, tcgs;
 };
 
-GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bmag, CgsVars &o) {
+GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bmag, float kela, float gam, CgsVars &o) {
   const double pi = GRT_PI;
   const double pcG = 6.67e-8, pcc = 2.99792458e10, pcmsun = 1.998e33, pcmp = 1.67262158e-24, pck = 1.38e-16;
   o.ncgs = o.ncgsnth = o.bcgs = o.tcgs = 0.0;
@@ -411,6 +534,40 @@ GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bma
           o.ncgs = 0.0;
           o.tcgs = 1e9;
         }
+      }
+    } break;
+    case FL_IHARM: {  // convert_fluidvars_iharm (fluid.f90:995-1026)
+      double mdot = pcG * sp.mbh * pcmsun / (pcc * pcc * pcc);
+      double lcgs = pcG * sp.mbh * pcmsun / (pcc * pcc), tcg = lcgs / pcc;
+      double rhocgs = sp.mdot / mdot / (lcgs * lcgs * lcgs) * tcg * (double)rho;
+      o.ncgs = rhocgs / pcmp;
+      double pcgs = (double)p * rhocgs / (double)rho * (pcc * pcc);
+      o.tcgs = pcgs / o.ncgs / pck;
+      o.bcgs = (double)bmag * sqrt(rhocgs / (double)rho) * pcc;
+      o.bcgs = o.bcgs * sqrt(4.0 * pi);
+      double rc2 = o.ncgs * pcmp;
+      if (sp.gminval >= 1.0) {  // monika_e with p = u (gamma-1) (f%p holds the internal energy)
+        float pg = p * (gam - 1.f);
+        double beta = (double)(pg / (bmag * bmag)) / 0.5;
+        double b2 = beta * beta;
+        double rlow = 1.0 / sp.muval - 1.0, rhigh = sp.gminval * (1.0 / sp.muval - 1.0);
+        double trat = ((double)bmag > 0.0) ? rhigh * b2 / (1.0 + b2) + rlow / (1.0 + b2) : rhigh;
+        o.tcgs = 2.0 * o.tcgs / 3.0 / (2.0 + trat);
+      } else if (sp.gminval < 0.0) {
+        if (sp.gminval == -1.0) {  // ressler_e: electron entropy -> T_e
+          const double pcm = 9.10938188e-28;
+          double thetae = pcmp / pcm * (double)kela * pow((double)rho, 4.0 / 3.0 - 1.);
+          o.tcgs = thetae * pcm * (pcc * pcc) / pck;
+        }
+      }
+      double bmagrho = sq((double)bmag) / (double)rho;
+      o.ncgsnth = (bmagrho > 1.0)
+                      ? sp.jetalphaval * sq(o.bcgs) / 8.0 / pi / sp.gminval * (sp.p1 - 2.0) / (sp.p1 - 1.0) / 8.2e-7
+                      : 0.0;
+      double sigmacgs = (o.bcgs * o.bcgs) / (rc2 * 8.988e20 * 4.0 * pi);
+      if (sigmacgs >= sp.sigcut) {
+        o.ncgs = 0.0;
+        o.tcgs = 1e9;
       }
     } break;
     default:

@@ -21,12 +21,14 @@ void build_camera(Camera &c, int standard, double mu0, double phi0, double a, do
 
 // ---- fluid snapshot on the host (reference module state of fluid_model_*.f90) --------------------------
 struct HostCell {
-  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, pad0, pad1;
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela, pad1;
 };
 struct FluidHost {
   int model = 0, nx1 = 0, nx2 = 0, nx3 = 1;
   float h = 0, asim = 0, gam = 0;
   float td_mbh = 0, td_mdot = 0, td_rin = 0, td_rout = 0;
+  double hslope = 0, mks_smooth = 0, poly_xt = 0, poly_alpha = 0, startx1 = 0;  // iharm header (fluid_model_iharm.f90:427-470)
+  int is_mmks = 0, eheat = 0;
   std::vector<float> ax1, axr, ax2, axth, ax3;
   std::vector<HostCell> cells;
   std::vector<float> uvals, vvals, uv, tvals;

@@ -15,6 +15,7 @@
 #include <map>
 #include <sstream>
 
+#include "grt_fluid.cuh"
 #include "grt_host.h"
 #include "grt_tables.h"
 
@@ -90,6 +91,7 @@ int fluid_model_id(const std::string &f) {
   if (f == "HARM") return 12;
   if (f == "FFJET") return 13;
   if (f == "HARM3D") return 19;
+  if (f == "IHARM") return 29;
   return -1;
 }
 int emis_type_id(const std::string &e, int *neq) {
@@ -171,7 +173,7 @@ void ingest_cell(FluidHost &f, size_t i, float r, float x2, float th, double rho
   c.vrl = vrl; c.vtl = vtl; c.vpl = vpl;
   c.b0 = (float)b[0]; c.br = (float)b[1]; c.bth = (float)b[2]; c.bph = (float)b[3];
   c.u0 = (float)u[0];
-  c.pad0 = c.pad1 = 0.f;
+  c.kela = c.pad1 = 0.f;
 }
 
 int load_ffjet(FluidHost &f, const std::string &path) {
@@ -212,7 +214,7 @@ int load_ffjet(FluidHost &f, const std::string &path) {
     HostCell &c = f.cells[i];
     c.rho = rho[i]; c.p = 0.f;  // p_arr is allocated but never filled/read by the reference
     c.vrl = vr[i]; c.vtl = vth[i]; c.vpl = vph[i];
-    c.b0 = b0[i]; c.br = br[i]; c.bth = bth[i]; c.bph = bph[i]; c.u0 = u0[i]; c.pad0 = c.pad1 = 0.f;
+    c.b0 = b0[i]; c.br = br[i]; c.bth = bth[i]; c.bph = bph[i]; c.u0 = u0[i]; c.kela = c.pad1 = 0.f;
   }
   return GRT_OK;
 }
@@ -303,6 +305,118 @@ int load_harm3d(FluidHost &f, const grt_args &a) {
   return GRT_OK;
 }
 
+
+// iharm: header text file (read_iharm_data_header, fluid_model_iharm.f90:427-470) + `<dfile><indf %03d>.bin`, a stream of
+// float32 data(13+eHEAT, n) = x1,x2,x3, rho, u, u^mu(4), b^mu(4) [, kel] per cell in (M)MKS components
+// (read_iharm_data_file :508-651; load_iharm_data :684-747).  nt = 1.
+int load_iharm(FluidHost &f, const grt_args &a) {
+  std::ifstream hf(a.fhfile);
+  if (!hf) return GRT_ERR_IO;
+  std::vector<double> header(200, -1e20);
+  for (int i = 0; i < 200; i++)
+    if (!(hf >> header[i])) break;
+  f.nx1 = (int)header[1]; f.nx2 = (int)header[2]; f.nx3 = (int)header[3];
+  f.asim = (float)header[4];
+  f.hslope = header[5];
+  f.gam = (float)header[6];
+  f.mks_smooth = header[7]; f.poly_xt = header[8]; f.poly_alpha = header[9]; f.startx1 = header[10];
+  f.is_mmks = (int)header[11];
+  f.eheat = (int)header[12];
+  if (f.nx1 < 2 || f.nx2 < 2 || f.nx3 < 2) return GRT_ERR_IO;
+  if (std::fabs(f.asim - (float)a.spin) > 1e-4f) {
+    fprintf(stderr, "grtrans_b200: ERROR -- Different simulation and grtrans spin values! %g %g\n", f.asim, a.spin);
+    return GRT_ERR_BAD_ARG;
+  }
+  if (a.fnt > 1) return GRT_ERR_BAD_ARG;  // time axis (nload / nt > 1) is outside the supported scope
+  char append[16];
+  snprintf(append, sizeof append, "%03d", a.findf);
+  std::string path = std::string(a.fdfile) + append + ".bin";
+  FILE *fp = fopen(path.c_str(), "rb");
+  if (!fp) return GRT_ERR_IO;
+  const size_t n = (size_t)f.nx1 * f.nx2 * f.nx3;
+  const int dlen = 13 + f.eheat;
+  std::vector<float> data((size_t)dlen * n);
+  bool ok = fread(data.data(), 4, data.size(), fp) == data.size();
+  fclose(fp);
+  if (!ok) return GRT_ERR_IO;
+  grt::IharmGrid G{f.hslope, f.mks_smooth, f.poly_xt, f.poly_alpha, f.startx1};
+  f.cells.resize(n);
+  f.ax1.resize(f.nx1); f.axr.resize(f.nx1); f.ax2.resize(f.nx2); f.axth.resize(f.nx2); f.ax3.resize(f.nx3);
+  for (size_t i = 0; i < n; i++) {
+    const float *d = data.data() + (size_t)dlen * i;
+    float x1 = d[0], x2 = d[1];
+    float r = std::exp(x1);
+    float th = (f.is_mmks == 1) ? grt::iharm_th_mmks(G, x2, x1) : (float)grt::iharm_th_mks(G, (double)x2);
+    double um[4] = {d[5], d[6], d[7], d[8]}, bm[4] = {d[9], d[10], d[11], d[12]};
+    double uks[4], bks[4];
+    if (f.is_mmks == 1) {  // ummks2uks :165-184: central differences of the real(4) theta function
+      double x1d = (double)x1, x2d = (double)x2;
+      double dx2 = 1e-6 * x2d, dx1 = 1e-4 * x1d;
+      double drdx1 = std::exp(x1d);
+      double dthdx1 = (double)(grt::iharm_th_mmks(G, (float)x2d, (float)(x1d + .5 * dx1)) -
+                               grt::iharm_th_mmks(G, (float)x2d, (float)(x1d - .5 * dx1))) / dx1;
+      double dthdx2 = (double)(grt::iharm_th_mmks(G, (float)(x2d + .5 * dx2), (float)x1d) -
+                               grt::iharm_th_mmks(G, (float)(x2d - .5 * dx2), (float)x1d)) / dx2;
+      for (int c = 0; c < 2; c++) {
+        const double *v = c ? bm : um;
+        double *o = c ? bks : uks;
+        o[0] = v[0];
+        o[1] = drdx1 * v[1];
+        o[2] = dthdx1 * v[1] + dthdx2 * v[2];
+        o[3] = v[3];
+      }
+    } else {  // umksh2uks :186-220
+      float dthdx2 = (float)(PI * (1. + (1. - f.hslope) * std::cos(2 * PI * (double)x2)));
+      for (int c = 0; c < 2; c++) {
+        const double *v = c ? bm : um;
+        double *o = c ? bks : uks;
+        o[0] = v[0];
+        o[1] = (double)r * v[1];
+        o[2] = v[2] * (double)dthdx2;
+        o[3] = v[3];
+      }
+    }
+    double rr = (double)r, as = (double)f.asim;
+    double delta = rr * rr - 2.0 * rr + as * as;
+    double u[4], b[4];
+    for (int c = 0; c < 2; c++) {  // uks2ubl (kerr.f90:131-144)
+      const double *v = c ? bks : uks;
+      double *o = c ? b : u;
+      o[0] = v[0] - 2.0 * rr / delta * v[1];
+      o[1] = v[1];
+      o[2] = v[2];
+      o[3] = v[3] - as / delta * v[1];
+    }
+    float vr = (float)(u[1] / u[0]), vt = (float)(u[2] / u[0]), om = (float)(u[3] / u[0]);
+    float aa = f.asim, mu = std::cos(th);  // lnrf_frame_real (kerr.f90:427-449)
+    float D = r * r - 2.f * r + aa * aa;
+    float AR = (r * r + aa * aa) * (r * r + aa * aa) - aa * aa * D * (1.f - mu * mu);
+    float RHO = r * r + aa * aa * mu * mu;
+    float ENU = std::sqrt(D * RHO / AR), EMU1 = std::sqrt(RHO / D), EMU2 = std::sqrt(RHO);
+    float EPSI = std::sqrt(1.f - mu * mu) * std::sqrt(AR / RHO), OM = 2.f * aa * r / AR;
+    float vrl = EMU1 / ENU * vr, vtl = EMU2 / ENU * vt, vpl = EPSI / ENU * (om - OM);
+    if (!((double)D > 0.0)) vrl = vtl = vpl = 0.f;
+    HostCell &c = f.cells[i];
+    c.rho = d[3];
+    c.p = d[4];  // internal energy u (the (gamma-1) factor is applied in the unit conversion, fluid.f90:1008)
+    c.vrl = vrl; c.vtl = vtl; c.vpl = vpl;
+    c.b0 = (float)b[0]; c.br = (float)b[1]; c.bth = (float)b[2]; c.bph = (float)b[3];
+    c.u0 = (float)u[0];
+    c.kela = (f.eheat == 1) ? d[13] : 0.f;
+    c.pad1 = 0.f;
+  }
+  for (int i = 0; i < f.nx3; i++) f.ax3[i] = data[(size_t)dlen * i + 2];
+  for (int i = 0; i < f.nx2; i++) {
+    f.ax2[i] = data[(size_t)dlen * ((size_t)i * f.nx3) + 1];
+    f.axth[i] = 0.f;  // (uniqth is only built for BL == 1, never set by the reader)
+  }
+  for (int i = 0; i < f.nx1; i++) {
+    f.ax1[i] = data[(size_t)dlen * ((size_t)i * f.nx3 * f.nx2)];
+    f.axr[i] = std::exp(f.ax1[i]);
+  }
+  return GRT_OK;
+}
+
 }  // namespace
 
 int load_fluid(FluidHost &f, const grt_args &a) {
@@ -327,6 +441,7 @@ int load_fluid(FluidHost &f, const grt_args &a) {
     case 12: return load_harm2d(f, a);
     case 13: return load_ffjet(f, a.fdfile);
     case 19: return load_harm3d(f, a);
+    case 29: return load_iharm(f, a);
     default: return GRT_ERR_BAD_ARG;
   }
 }

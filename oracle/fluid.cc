@@ -554,6 +554,180 @@ static void harm3d_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> 
   }
 }
 
+
+// ------------------------------------------------------------------ IHARM
+// fluid_model_iharm.f90.  theta(x2) of the MKS grid (calcthmksh :82-87, real(8)) and theta(x2,x1) of the MMKS/FMKS grid
+// (calcthmmks :107-118, a real(4) function whose sub-expressions are promoted by the real(8) module variables pi, hslope,
+// startx1 exactly as written).
+static double calcthmksh(const FluidData &fd, double x2) {
+  return pi * x2 + (1. - fd.hslope) / 2. * std::sin(2. * pi * x2);
+}
+static float calcthmmks(const FluidData &fd, float x2, float x1) {
+  float A = (float)fd.mks_smooth, B = (float)fd.poly_xt, C = (float)fd.poly_alpha;
+  float D = (float)(pi / (double)(2.f + 2.f / (std::pow(B, C) * (1 + C))));
+  float thetag = (float)(pi * (double)x2 + (1. - fd.hslope) / 2. * std::sin(2. * pi * (double)x2));
+  float thetaj = (float)((double)(D * (2.f * x2 - 1.f) * (1.f + std::pow((2.f * x2 - 1.f) / B, C) / (1.f + C))) + pi / 2.);
+  return (float)((double)thetag + std::exp(-(double)A * ((double)x1 - fd.startx1)) * (double)(thetaj - thetag));
+}
+
+// iharm_vals :222-424: nearest-neighbour lookup (rd = td = pd = 1 selects the upper corner of the cell in all three
+// directions, time weight 0).  nt = 1 only (tindx = 0).
+static void iharm_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) {
+  float a = (float)g.a;
+  int nx1 = fd.nx1, nx2 = fd.nx2, nx3 = fd.nx3;
+  std::vector<float> uniqx1(nx1 + 1), uniqr(nx1 + 1), uniqx2(nx2 + 1), uniqx3(nx3 + 1);
+  for (int i = 1; i <= nx3; i++) uniqx3[i] = fd.x3_arr[i - 1];
+  for (int i = 1; i <= nx2; i++) uniqx2[i] = fd.x2_arr[(size_t)(i - 1) * nx3];
+  for (int i = 1; i <= nx1; i++) {
+    uniqx1[i] = fd.x1_arr[(size_t)(i - 1) * nx3 * nx2];
+    uniqr[i] = std::exp(uniqx1[i]);
+  }
+  float rh = 1.f + std::sqrt(1.f - std::pow(a, 2.f));
+  for (int i = 0; i < g.npts; i++) {
+    float theta = (float)g.x[i].d[2];
+    float zr = (float)g.x[i].d[1];
+    float zpp = (float)g.x[i].d[3];
+    float zphi = (float)bl2ks_phi((double)zr, (double)zpp, (double)a);
+    zphi = (float)std::fmod((double)zphi, 2. * pi);
+    if (zphi < 0.f) zphi = (float)((double)zphi + 2. * pi);
+    float x1 = std::log(zr), x2, x3 = zphi;
+    if (fd.is_mmks == 1) {  // transformbl2mmks :132-146
+      double x1d = (double)x1, thd = (double)theta;
+      x2 = (float)zbrent([&](double x) { return thd - (double)calcthmmks(fd, (float)x, (float)x1d); }, -1.0, 1.0, 1e-6);
+    } else {  // transformbl2mksh :148-163
+      double thd = (double)theta;
+      x2 = (float)zbrent([&](double x) { return thd - calcthmksh(fd, x); }, 0.0, 1.0, 1e-6);
+    }
+    int lx1 = (int)std::floor((x1 - uniqx1[1]) / (uniqx1[nx1] - uniqx1[1]) * (float)(nx1 - 1)) + 1;
+    int ux1 = lx1 + 1;
+    int lx2 = (int)std::floor((x2 - uniqx2[1]) / (uniqx2[nx2] - uniqx2[1]) * (float)(nx2 - 1)) + 1;
+    int ux2 = lx2 + 1;
+    int lx3 = (int)std::floor((x3 - uniqx3[1]) / (uniqx3[nx3] - uniqx3[1]) * (float)(nx3 - 1)) + 1;
+    int ux3 = lx3 + 1;
+    lx2 = (lx2 >= 1) ? lx2 : 1;
+    lx2 = (lx2 <= nx2) ? lx2 : nx2;
+    ux2 = (ux2 >= 1) ? ux2 : 1;
+    ux2 = (ux2 <= nx2) ? ux2 : nx2;
+    if (ux3 > nx3) ux3 = 1;
+    if (lx3 < 1) lx3 = nx3;
+    // guards: the reference indexes uniqr(lx1) / the data arrays out of bounds outside the radial range
+    int lx1s = std::min(std::max(lx1, 1), nx1), ux1s = std::min(std::max(ux1, 1), nx1);
+    double pfac = 1.0, nfac = 1.0;
+    if (uniqr[lx1s] <= rh) {
+      pfac = 1e-3;
+      nfac = 1e-3;
+    }
+    size_t idx = (size_t)(ux1s - 1) * nx2 * nx3 + (size_t)(ux2 - 1) * nx3 + (size_t)(ux3 - 1);
+    bool in = x1 > uniqx1[1];
+    FluidPt &p = f[i];
+    p.rho = (float)((double)(in ? fd.rho_arr[idx] : 0.f) * nfac);
+    p.p = (float)((double)(in ? fd.p_arr[idx] : 1.f) * pfac);
+    if (fd.eheat == 1) p.kela = (float)((double)(in ? fd.kela_arr[idx] : 1.f) * pfac);
+    float vrl0 = in ? fd.vrl_arr[idx] : 0.f;
+    float vtl0 = in ? fd.vtl_arr[idx] : 0.f;
+    p.b[0] = in ? fd.b0_arr[idx] : 1.f;
+    p.b[1] = in ? fd.br_arr[idx] : 1.f;
+    p.b[2] = in ? fd.bth_arr[idx] : 1.f;
+    p.b[3] = in ? fd.bph_arr[idx] : 1.f;
+    p.u[0] = in ? (double)fd.u0_arr[idx] : 1.0;
+    float vpl0 = in ? fd.vpl_arr[idx] : 0.f;
+    finish_grid_point(p, zr, (float)g.x[i].d[2], a, vrl0, vtl0, vpl0, 1.0);
+  }
+}
+
+// read_iharm_data_header :427-470, read_iharm_data_file :508-651, load_iharm_data :684-747 (nt = 1)
+static bool load_iharm(FluidData &fd, const FluidArgs &fa, double a) {
+  std::ifstream hf(fa.hfile);
+  if (!hf) return false;
+  std::vector<double> header(200, -1e20);
+  for (int i = 0; i < 200; i++)
+    if (!(hf >> header[i])) break;
+  fd.nx1 = (int)header[1]; fd.nx2 = (int)header[2]; fd.nx3 = (int)header[3];
+  fd.asim = (float)header[4];
+  fd.hslope = header[5];
+  fd.gam = (float)header[6];  // (gam is real(8) in the module; f%gamma is real)
+  fd.mks_smooth = header[7]; fd.poly_xt = header[8]; fd.poly_alpha = header[9]; fd.startx1 = header[10];
+  fd.is_mmks = (int)header[11];
+  fd.eheat = (int)header[12];
+  if (std::fabs(fd.asim - (float)a) > 1e-4f) {
+    fprintf(stderr, "ERROR -- Different simulation and grtrans spin values!\n");
+    return false;
+  }
+  char append[16];
+  snprintf(append, sizeof append, "%03d", fa.indf);
+  FILE *fp = fopen((fa.dfile + append + ".bin").c_str(), "rb");
+  if (!fp) return false;
+  size_t n = (size_t)fd.nx1 * fd.nx2 * fd.nx3;
+  int dlen = 13 + fd.eheat;
+  std::vector<float> data((size_t)dlen * n);
+  bool ok = fread(data.data(), 4, data.size(), fp) == data.size();
+  fclose(fp);
+  if (!ok) return false;
+  fd.x1_arr.resize(n); fd.x2_arr.resize(n); fd.x3_arr.resize(n); fd.r_arr.resize(n); fd.th_arr.resize(n); fd.ph_arr.resize(n);
+  fd.rho_arr.resize(n); fd.p_arr.resize(n); fd.u0_arr.resize(n); fd.vrl_arr.resize(n); fd.vtl_arr.resize(n);
+  fd.vpl_arr.resize(n); fd.b0_arr.resize(n); fd.br_arr.resize(n); fd.bth_arr.resize(n); fd.bph_arr.resize(n);
+  if (fd.eheat == 1) fd.kela_arr.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    const float *d = data.data() + (size_t)dlen * i;  // data(1:dlen, i)
+    // grid=transpose(data(1:3,:)) is real(8); x?_arr are real
+    float x1 = d[0], x2 = d[1], x3 = d[2];
+    fd.x1_arr[i] = x1; fd.x2_arr[i] = x2; fd.x3_arr[i] = x3;
+    float r = std::exp(x1);
+    fd.r_arr[i] = r;
+    fd.ph_arr[i] = x3;
+    float th = (fd.is_mmks == 1) ? calcthmmks(fd, x2, x1) : (float)calcthmksh(fd, (double)x2);
+    fd.th_arr[i] = th;
+    double um[4] = {d[5], d[6], d[7], d[8]}, bm[4] = {d[9], d[10], d[11], d[12]};
+    double uks[4], bks[4];
+    if (fd.is_mmks == 1) {  // ummks2uks :165-184 (central differences of the real(4) theta function)
+      double x1d = (double)x1, x2d = (double)x2;
+      double dx2 = 1e-6 * x2d, dx1 = 1e-4 * x1d;
+      double drdx1 = std::exp(x1d);
+      double dthdx1 = (double)(calcthmmks(fd, (float)x2d, (float)(x1d + .5 * dx1)) - calcthmmks(fd, (float)x2d, (float)(x1d - .5 * dx1))) / dx1;
+      double dthdx2 = (double)(calcthmmks(fd, (float)(x2d + .5 * dx2), (float)x1d) - calcthmmks(fd, (float)(x2d - .5 * dx2), (float)x1d)) / dx2;
+      for (int c = 0; c < 2; c++) {
+        const double *v = c ? bm : um;
+        double *o = c ? bks : uks;
+        o[1] = drdx1 * v[1];
+        o[2] = dthdx1 * v[1] + dthdx2 * v[2];
+        o[3] = v[3];
+        o[0] = v[0];
+      }
+    } else {  // umksh2uks :186-220
+      float dthdx2 = (float)(pi * (1. + (1. - fd.hslope) * std::cos(2 * pi * (double)x2)));
+      for (int c = 0; c < 2; c++) {
+        const double *v = c ? bm : um;
+        double *o = c ? bks : uks;
+        o[0] = v[0];
+        o[1] = (double)r * v[1];
+        o[2] = v[2] * (double)dthdx2;
+        o[3] = v[3];
+      }
+    }
+    // uks2ubl (kerr.f90:131-144)
+    double rr = (double)r, asim = (double)fd.asim;
+    double delta = rr * rr - 2.0 * rr + asim * asim;
+    double u[4], b[4];
+    for (int c = 0; c < 2; c++) {
+      const double *v = c ? bks : uks;
+      double *o = c ? b : u;
+      o[0] = v[0] - 2.0 * rr / delta * v[1];
+      o[1] = v[1];
+      o[2] = v[2];
+      o[3] = v[3] - asim / delta * v[1];
+    }
+    float vrl, vtl, vpl;
+    lnrf_frame_real((float)(u[1] / u[0]), (float)(u[2] / u[0]), (float)(u[3] / u[0]), r, fd.asim, th, vrl, vtl, vpl);
+    fd.rho_arr[i] = (float)(double)d[3];
+    fd.p_arr[i] = (float)(double)d[4];  // (internal energy u: the (gamma-1) factor is applied in convert_fluidvars_iharm)
+    fd.b0_arr[i] = (float)b[0]; fd.br_arr[i] = (float)b[1]; fd.bth_arr[i] = (float)b[2]; fd.bph_arr[i] = (float)b[3];
+    fd.u0_arr[i] = (float)u[0];
+    fd.vrl_arr[i] = vrl; fd.vtl_arr[i] = vtl; fd.vpl_arr[i] = vpl;
+    if (fd.eheat == 1) fd.kela_arr[i] = (float)(double)d[13];
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------ HARM data ingestion
 // umksh2uks + uks2ubl + lnrf_frame (fluid_model_harm.f90:73-98,380-386,468-485; kerr.f90:131-144).
 // Inputs are per-cell MKS contravariant components as the dump stores them.  For the 3-D model
@@ -677,6 +851,9 @@ bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const F
   } else if (fname == "HARM3D") {
     fd.model = F_HARM3D;
     fd.ok = load_harm3d(fd, fa, a);
+  } else if (fname == "IHARM") {
+    fd.model = F_IHARM;
+    fd.ok = load_iharm(fd, fa, a);
   } else {
     fd.model = F_DUMMY;
   }
@@ -692,6 +869,7 @@ void get_fluid_vars(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) 
     case F_THINDISK: get_thindisk_fluidvars(fd, g, f); break;
     case F_HARM: harm_vals(fd, g, f); break;
     case F_HARM3D: harm3d_vals(fd, g, f); break;
+    case F_IHARM: iharm_vals(fd, g, f); break;
     default: break;
   }
 }
@@ -755,6 +933,32 @@ void convert_fluid_vars(const FluidData &fd, const std::vector<FluidPt> &f, cons
           ncgsnth[i] = 0.0;
         // andrew_sigcut (fluid.f90:792-810)
         double rhocgs = ncgs[i] * pc::mp;
+        double sigmacgs = (bcgs[i] * bcgs[i]) / (rhocgs * 8.988e20 * 4.0 * pi);
+        if (sigmacgs >= sp.sigcut) {
+          ncgs[i] = 0.0;
+          tcgs[i] = 1e9;
+        }
+      } break;
+      case F_IHARM: {  // convert_fluidvars_iharm (fluid.f90:995-1026)
+        double mdot = pc::G * sp.mbh * pc::msun / (pc::c * pc::c * pc::c);
+        scale_sim_units(sp.mbh, sp.mdot, mdot, p.rho, p.p, p.bmag, ncgs[i], bcgs[i], tcgs[i]);
+        double rhocgs = ncgs[i] * pc::mp;
+        if (sp.gminval >= 1.0) {
+          // f%p holds the internal energy u: monika_e gets p = u (gamma-1) (real(4) product)
+          double trat = monika_e(p.rho, p.p * (fd.gam - 1.f), p.bmag, 1.0 / sp.muval - 1.0, sp.gminval * (1.0 / sp.muval - 1.0));
+          tcgs[i] = 2.0 * tcgs[i] / 3.0 / (2.0 + trat);
+        } else if (sp.gminval < 0.0) {
+          if (sp.gminval == -1.0) {  // ressler_e (fluid.f90:894-903): electron entropy -> T_e
+            double gamma = 4.0 / 3.0;
+            double thetae = pc::mp / pc::m * (double)p.kela * std::pow((double)p.rho, gamma - 1.);
+            tcgs[i] = thetae * pc::m * pc::c2 / pc::k;
+          }
+        }
+        double bmagrho = std::pow((double)p.bmag, 2.0) / (double)p.rho;
+        if (bmagrho > 1.0)
+          ncgsnth[i] = sp.jetalphaval * std::pow(bcgs[i], 2.0) / 8.0 / pi / sp.gminval * (sp.p1 - 2.0) / (sp.p1 - 1.0) / 8.2e-7;
+        else
+          ncgsnth[i] = 0.0;
         double sigmacgs = (bcgs[i] * bcgs[i]) / (rhocgs * 8.988e20 * 4.0 * pi);
         if (sigmacgs >= sp.sigcut) {
           ncgs[i] = 0.0;

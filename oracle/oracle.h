@@ -90,7 +90,7 @@ void comoving_ortho(double r, double th, double a, double alpha, double beta, do
 
 // ---------------------------------------------------------------------------------------------
 // fluid models
-enum FluidModel { F_DUMMY = 0, F_SPHACC = 1, F_THINDISK = 2, F_HARM = 12, F_FFJET = 13, F_HARM3D = 19 };
+enum FluidModel { F_DUMMY = 0, F_SPHACC = 1, F_THINDISK = 2, F_HARM = 12, F_FFJET = 13, F_HARM3D = 19, F_IHARM = 29 };
 
 struct FluidArgs {  // subset of fluid.f90:fluid_args that the supported models read
   std::string dfile, hfile, gfile;
@@ -109,11 +109,15 @@ struct FluidData {  // module-level state of fluid_model_{thindisk,sphacc,ffjet,
   float h = 0, asim = 0, gam = 0;
   std::vector<float> x1_arr, x2_arr, x3_arr, r_arr, th_arr, ph_arr;
   std::vector<float> rho_arr, p_arr, u0_arr, vrl_arr, vpl_arr, vtl_arr, b0_arr, br_arr, bth_arr, bph_arr;
+  // iharm (fluid_model_iharm.f90:13-24): real(8) module variables + flags from the header file
+  std::vector<float> kela_arr;
+  double hslope = 0, mks_smooth = 0, poly_xt = 0, poly_alpha = 0, startx1 = 0;
+  int is_mmks = 0, eheat = 0;
   bool ok = true;
 };
 
 struct FluidPt {  // one entry of fluid.f90:type fluid
-  float rho = 0, p = 0, bmag = 0;
+  float rho = 0, p = 0, bmag = 0, kela = 0;
   double u[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
 };
 

@@ -61,6 +61,25 @@ def cfg_harm3d(n=40, nup=100, nfreq=4, iname='delo', **kw):
     return d
 
 
+def iharm_snapshots(mmks=1):
+    import make_snapshot as ms
+    os.makedirs(SNAPDIR, exist_ok=True)
+    prefix = os.path.join(SNAPDIR, "iharm_%s_" % ("mmks" if mmks else "mks"))
+    if not os.path.exists(prefix + "040.bin"):
+        ms.write_iharm(prefix, indf=40, eheat=1, mmks=mmks)
+    return prefix + "header.txt", prefix
+
+
+def cfg_iharm(n=40, nup=100, nfreq=4, iname='delo', mmks=1, **kw):
+    """gmin >= 1: R-beta (monika_e) electrons; gmin = -1: electron entropy (ressler_e)."""
+    hfile, prefix = iharm_snapshots(mmks)
+    d = dict(fname='IHARM', ename='POLSYNCHTH', nvals=4, iname=iname, spin=.9375, standard=1, nn=[n, n, nup], uout=.04,
+             mbh=4e6, mdotmin=1e20, mdotmax=1e20, nmu=1, mumin=.6428, mumax=.6428, gridvals=[-13., 13., -13., 13.],
+             nfreq=nfreq, fmin=1e10, fmax=1e13, muval=.25, gmin=1., fdfile=prefix, fhfile=hfile, findf=40, fnt=1)
+    d.update(kw)
+    return d
+
+
 def image_errors(got, ref):
     """got/ref: ivals[nvals,npix,ncams].  Returns (max rel dI over pixels with I > 1e-4 Imax per camera, flux error,
     max |dQUV|/Imax, nan masks equal)."""

@@ -132,6 +132,64 @@ def write_harm3d(path, **kw):
     return path
 
 
+def iharm_arrays(nx1=64, nx2=32, nx3=32, a=0.9375, hslope=0.3, mmks=1, mks_smooth=0.5, poly_xt=0.82, poly_alpha=14.0,
+                 rin=1.1, rout=40.0, seed=12345):
+    """(M)MKS grid of iharm3d / ebhlight: x1 = log r, theta(x2[, x1]) per fluid_model_iharm.f90:82-118, x3 = phi."""
+    dx1 = np.log(rout / rin) / nx1
+    startx1 = np.log(rin)
+    x1 = startx1 + (np.arange(nx1) + 0.5) * dx1
+    x2 = (np.arange(nx2) + 0.5) / nx2
+    x3 = (np.arange(nx3) + 0.5) * 2. * np.pi / nx3
+    X1, X2, X3 = np.meshgrid(x1, x2, x3, indexing='ij')  # x3 fastest, x1 slowest
+
+    def theta(x2v, x1v):
+        thg = np.pi * x2v + 0.5 * (1. - hslope) * np.sin(2. * np.pi * x2v)
+        if not mmks:
+            return thg
+        D = np.pi / (2. + 2. / (poly_xt ** poly_alpha * (1. + poly_alpha)))
+        y = 2. * x2v - 1.
+        thj = D * y * (1. + (y / poly_xt) ** poly_alpha / (1. + poly_alpha)) + np.pi / 2.
+        return thg + np.exp(-mks_smooth * (x1v - startx1)) * (thj - thg)
+
+    r = np.exp(X1); th = theta(X2, X1); ph = X3
+    rho, uu, u, b = _fluid(r, th, ph, a, seed, True)
+    e = 1e-5
+    dthdx2 = (theta(X2 + e, X1) - theta(X2 - e, X1)) / (2 * e)
+    dthdx1 = (theta(X2, X1 + e) - theta(X2, X1 - e)) / (2 * e)
+
+    def to_code(v):  # KS (t, r, theta, phi) components -> (t, x1, x2, x3) components
+        o = v.copy()
+        o[..., 1] = v[..., 1] / r
+        o[..., 2] = (v[..., 2] - dthdx1 * o[..., 1]) / dthdx2
+        return o
+    # electron entropy such that Theta_e = (m_p/m_e) kel rho^(1/3) ~ 3..30 in the torus
+    kel = 10. * (9.10938188e-28 / 1.67262158e-24) / np.maximum(rho, 1e-12) ** (1. / 3.) * (0.3 + np.exp(-((r - 8.) / 6.) ** 2))
+    return dict(nx1=nx1, nx2=nx2, nx3=nx3, a=a, hslope=hslope, mmks=int(bool(mmks)), mks_smooth=mks_smooth, poly_xt=poly_xt,
+                poly_alpha=poly_alpha, startx1=startx1, rin=rin, rout=rout, x1=X1, x2=X2, x3=X3, rho=rho, u=uu,
+                ucon=to_code(u), bcon=to_code(b), kel=kel, gam=4. / 3.)
+
+
+def write_iharm(prefix, indf=40, eheat=1, **kw):
+    """Writes `<prefix>%03d.bin` (float32 data(13+eHEAT, n) stream) and `<prefix>header.txt`
+    (fluid_model_iharm.f90:427-470, :508-651).  Returns (header path, data prefix)."""
+    d = iharm_arrays(**kw)
+    n = d['nx1'] * d['nx2'] * d['nx3']
+    dlen = 13 + (1 if eheat else 0)
+    data = np.zeros((n, dlen), np.float32)
+    data[:, 0] = d['x1'].ravel(); data[:, 1] = d['x2'].ravel(); data[:, 2] = d['x3'].ravel()
+    data[:, 3] = d['rho'].ravel(); data[:, 4] = d['u'].ravel()
+    data[:, 5:9] = d['ucon'].reshape(n, 4); data[:, 9:13] = d['bcon'].reshape(n, 4)
+    if eheat:
+        data[:, 13] = d['kel'].ravel()
+    data.tofile("%s%03d.bin" % (prefix, indf))
+    hdr = [0.0, d['nx1'], d['nx2'], d['nx3'], d['a'], d['hslope'], d['gam'], d['mks_smooth'], d['poly_xt'], d['poly_alpha'],
+           d['startx1'], d['mmks'], 1 if eheat else 0, 0, 8 + (2 if eheat else 0), d['rin'], d['rout']]
+    hpath = prefix + "header.txt"
+    with open(hpath, 'w') as f:
+        f.write(" ".join("%.17g" % v for v in hdr) + "\n")
+    return hpath, prefix
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) >= 3 and sys.argv[1] == "harm2d":

@@ -36,6 +36,8 @@ CONFIGS = [
      cases.cfg_ffjet(n=100, nup=100, nfreq=25, iname='lsoda'), None),
     ("cfg4 HARM(synthetic dump) POLSYNCHTH nn=[150,150,400] nfreq=1 nvals=4 delo",
      cases.cfg_harm(n=150, nup=400, nfreq=1, fmin=2.3e11, fmax=2.3e11, iname='delo'), (9001, 13500)),
+    ("next-row IHARM (synthetic FMKS dump, R-beta electrons) POLSYNCHTH nn=[128,128,400] nfreq=8 nvals=4 delo",
+     cases.cfg_iharm(n=128, nup=400, nfreq=8, mmks=1, fmin=1e11, fmax=1e13), (8001, 9280)),
 ]
 
 
