@@ -225,51 +225,104 @@ GRT_HD void polsynchth_eval(double nu, double n, double b, double t, double thet
 }
 
 // ---- power-law synchrotron ------------------------------------------------------------------------
-GRT_HD double pl_lookup(double lx, int p_iy, const double *xv, int nx, const double *yv) {
-  int ix = (int)((lx - xv[0]) / (xv[nx - 1] - xv[0]) * (nx));
-  ix = (ix < (nx - 1)) ? ((ix > 1) ? ix : 1) : (nx - 1);
-  int indx = p_iy * nx + ix;
-  double yix = yv[indx - 1], yix1 = yv[indx], xix1 = xv[ix], xix = xv[ix - 1];
-  return exp(yix + (yix1 - yix) / (xix1 - xix) * (lx - xix));
+// polsynchpl / synchpl (polsynchemis.f90:527-631, 633-698) with the tabulated G(x) integrals (:62-92, 107-525).  Like
+// the thermal model it is split into per-run constants (p, gmin, gmax), a per-point part (field, angle, density) and the
+// per-(point, frequency) part, which is 15 exp (12 of them the log-log table lookups) and ~80 multiply-adds:
+//   x**q with x = nu/(1.5 nu_B,perp)  ->  exp(q lr),  lr = log(nu_obs) - [log g + log(1.5 nu_B,perp)]
+// and the five 81-point tables share one index / weight computation per abscissa.
+struct PlConst {  // per run
+  double p, gmin, gmax, cA, l2gmin, l2gmax, hp, am, kq, kv;
+  int iy;
+};
+GRT_HD PlConst pl_const(double p, double gmin, double gmax) {
+  PlConst c;
+  c.p = p; c.gmin = gmin; c.gmax = gmax;
+  c.cA = (p - 1.0) / (pow(gmin, 1.0 - p) - pow(gmax, 1.0 - p));
+  c.l2gmin = 2.0 * log(gmin);
+  c.l2gmax = 2.0 * log(gmax);
+  c.iy = (p < 5.0) ? ((p > 3.2) ? 1 : 0) : 2;
+  const double alpha = (p - 1) / 2.0;
+  c.hp = (p - 1.0) / 2.0;
+  c.am = alpha - 1.0 / 2.0;
+  c.kq = pow(gmin, -2.0 * alpha + 1.0) * pow(alpha - 1.0 / 2.0, -1.0);
+  c.kv = 2.0 * (alpha + 3.0 / 2.0) / (alpha + 1) * log(gmin) * pow(gmin, -2 * (alpha + 1));
+  return c;
+}
+struct PlPoint {  // per geodesic point
+  double nnth, nubperp, L, itanth;  // L = log(g) + log(1.5 nu_B,perp);  itanth = 1/(tan(th) + sign(cos th) 1e-10)
+};
+template <bool POL>
+GRT_HD void pl_point(double nnth, double b, double th, double g, PlPoint &P) {
+  const double ec = pc::e, c = pc::c, m = pc::m, pi = GRT_PI;
+  double sinth = POL ? sin(th) + 1e-10 : sin(th);
+  P.nnth = nnth;
+  P.nubperp = ec * b / m / c / 2.0 / pi * sinth + 1e-10;
+  P.L = log(g) + log(1.5 * P.nubperp);
+  P.itanth = POL ? 1.0 / (tan(th) + (signbit(cos(th)) ? -1.0 : 1.0) * 1e-10) : 0.0;
 }
 
+struct PlAbscissa {  // position of one log-abscissa in a table
+  int ix;
+  double w;
+};
+GRT_HD PlAbscissa pl_locate(double lx, const double *xv, int nx) {
+  PlAbscissa a;
+  int ix = (int)((lx - xv[0]) / (xv[nx - 1] - xv[0]) * (nx));
+  ix = (ix < (nx - 1)) ? ((ix > 1) ? ix : 1) : (nx - 1);
+  a.ix = ix;
+  a.w = (lx - xv[ix - 1]) / (xv[ix] - xv[ix - 1]);
+  return a;
+}
+GRT_HD double pl_value(const PlAbscissa &a, int iy, int nx, const double *yv) {
+  const double y0 = yv[iy * nx + a.ix - 1], y1 = yv[iy * nx + a.ix];
+  return exp_fast(y0 + (y1 - y0) * a.w);
+}
+
+// comoving coefficients at frequency nu = nu_obs/g;  lnu_obs = log(nu_obs)
 template <bool POL>
-GRT_HD void synchpl_eval(const EmisTables &T, double nu, double nnth, double b, double th, double p, double gmin,
-                         double gmax, double *e) {
+GRT_HD void pl_eval(const EmisTables &T, const PlConst &C, const PlPoint &P, double nu, double lnu_obs, double *e) {
   const double ec = pc::e, c = pc::c, m = pc::m, pi = GRT_PI;
   for (int i = 0; i < 11; i++) e[i] = 0.0;
-  double sinth = POL ? sin(th) + 1e-10 : sin(th);
-  double nubperp = ec * b / m / c / 2.0 / pi * sinth + 1e-10;
-  double nucmin = 3.0 / 2.0 * nubperp * gmin * gmin, nucmax = 3.0 / 2.0 * nubperp * gmax * gmax;
-  double omega0 = nubperp * 2.0 * pi, omega = nu * 2.0 * pi;
-  double lxmin = log(nu / nucmin), lxmax = log(nu / nucmax);
-  double A = (p - 1.0) * nnth / (pow(gmin, 1.0 - p) - pow(gmax, 1.0 - p));
-  int iy = (p < 5.0) ? ((p > 3.2) ? 1 : 0) : 2;
-  double gxfac = pl_lookup(lxmax, iy, T.gx, 181, T.gy) - pl_lookup(lxmin, iy, T.gx, 181, T.gy);
-  double gafac = pl_lookup(lxmax, iy, T.xv, 81, T.ya) - pl_lookup(lxmin, iy, T.xv, 81, T.ya);
-  double s3 = POL ? sqrt(3.0) : (double)sqrtf(3.f);
-  double jfac = A * ec * ec / c * s3 / 4.0 * pow(3.0 * nubperp / 2.0 / nu, (p - 1.0) / 2.0) * nubperp;
-  double afac = pow(2.0 * pi, 3) * A * ec * ec * sqrt(3.0) * omega0 * (p + 2.0) / 32.0 / (pi * pi) / m / c / (omega * omega) *
-                pow(2.0 * omega / 3.0 / omega0, -p / 2.0);
+  const double lr = lnu_obs - P.L;  // log(nu / (1.5 nu_B,perp))
+  const double A = C.cA * P.nnth;
+  const PlAbscissa gmx = pl_locate(lr - C.l2gmax, T.gx, 181), gmn = pl_locate(lr - C.l2gmin, T.gx, 181);
+  const PlAbscissa xmx = pl_locate(lr - C.l2gmax, T.xv, 81), xmn = pl_locate(lr - C.l2gmin, T.xv, 81);
+  const double gxfac = pl_value(gmx, C.iy, 181, T.gy) - pl_value(gmn, C.iy, 181, T.gy);
+  const double gafac = pl_value(xmx, C.iy, 81, T.ya) - pl_value(xmn, C.iy, 81, T.ya);
+  const double E1 = exp_fast(-C.hp * lr);  // (3 nu_B,perp / 2 nu)^((p-1)/2)
+  const double E2 = exp_fast(-0.5 * lr);   // (3 nu_B,perp / 2 nu)^(1/2)
+  const double s3 = POL ? sqrt(3.0) : (double)sqrtf(3.f);
+  const double jfac = A * ec * ec / c * s3 / 4.0 * E1 * P.nubperp;
+  const double omega0 = P.nubperp * 2.0 * pi, omega = nu * 2.0 * pi;
+  const double afac = (2.0 * pi) * (2.0 * pi) * (2.0 * pi) * A * ec * ec * sqrt(3.0) * omega0 * (C.p + 2.0) / 32.0 / (pi * pi) / m / c /
+                      (omega * omega) * (E1 * E2);  // (2 omega / 3 omega0)^(-p/2)
   e[0] = jfac * gxfac;
   e[4] = afac * gafac;
   if (POL) {
-    double tanth = tan(th) + (signbit(cos(th)) ? -1.0 : 1.0) * 1e-10;
-    double gpfac = pl_lookup(lxmax, iy, T.xv, 81, T.yp) - pl_lookup(lxmin, iy, T.xv, 81, T.yp);
-    double gapfac = pl_lookup(lxmax, iy, T.xv, 81, T.yap) - pl_lookup(lxmin, iy, T.xv, 81, T.yap);
-    double gvfac = pl_lookup(lxmax, iy, T.xv, 81, T.yv) - pl_lookup(lxmin, iy, T.xv, 81, T.yv);
-    double gavfac = pl_lookup(lxmax, iy, T.xv, 81, T.yav) - pl_lookup(lxmin, iy, T.xv, 81, T.yav);
+    const double gpfac = pl_value(xmx, C.iy, 81, T.yp) - pl_value(xmn, C.iy, 81, T.yp);
+    const double gapfac = pl_value(xmx, C.iy, 81, T.yap) - pl_value(xmn, C.iy, 81, T.yap);
+    const double gvfac = pl_value(xmx, C.iy, 81, T.yv) - pl_value(xmn, C.iy, 81, T.yv);
+    const double gavfac = pl_value(xmx, C.iy, 81, T.yav) - pl_value(xmn, C.iy, 81, T.yav);
     e[1] = jfac * gpfac;
-    e[3] = jfac * 4.0 / 3.0 / tanth * sqrt(3.0 * nubperp / 2.0 / nu) * gvfac;
-    double alpha = (p - 1) / 2.0;
-    double kperp = A * ec * ec / m / c / nubperp;
-    double nui = gmin * gmin * nubperp;
-    e[8] = 1.0 * kperp * pow(nubperp / nu, 3.0) * pow(gmin, -2.0 * alpha + 1.0) * (1.0 - pow(nui / nu, alpha - 1.0 / 2.0)) *
-           pow(alpha - 1.0 / 2.0, -1.0);
-    e[10] = 2.0 * (alpha + 3.0 / 2.0) / (alpha + 1) * kperp * pow(nubperp / nu, 2.0) * log(gmin) * pow(gmin, -2 * (alpha + 1)) / tanth;
+    e[3] = jfac * 4.0 / 3.0 * P.itanth * E2 * gvfac;
+    const double kperp = A * ec * ec / m / c / P.nubperp;
+    const double rb = P.nubperp / nu;  // nu_B,perp / nu
+    // (nui/nu)^(alpha-1/2), nui = gmin^2 nu_B,perp:  log(nui/nu) = 2 log gmin - lr - log 1.5
+    const double En = exp_fast(C.am * (C.l2gmin - lr - 0.4054651081081644));
+    e[8] = 1.0 * kperp * (rb * rb * rb) * C.kq * (1.0 - En);
+    e[10] = C.kv * kperp * (rb * rb) * P.itanth;
     e[5] = afac * gapfac;
-    e[7] = afac * 4.0 / 3.0 / tanth * gavfac * pow(2.0 * omega / 3.0 / omega0, -1.0 / 2.0);
+    e[7] = afac * 4.0 / 3.0 * P.itanth * gavfac * E2;
   }
+}
+
+// plain comoving values (the polsynchemis f2py surface)
+template <bool POL>
+GRT_HD void synchpl_eval(const EmisTables &T, double nu, double nnth, double b, double th, double p, double gmin,
+                         double gmax, double *e) {
+  PlPoint P;
+  pl_point<POL>(nnth, b, th, 1.0, P);
+  pl_eval<POL>(T, pl_const(p, gmin, gmax), P, nu, log(nu), e);
 }
 
 // angle-averaged thermal synchrotron (Mahadevan et al. 1996)

@@ -128,23 +128,34 @@ GRT_HDN double rf(double x, double y, double z) {
 }
 
 // ---- Carlson R_C ------------------------------------------------------------------------------
+// The reference iterates the duplication theorem (geokerr_wrapper.f:3608, ERRTOL=.0012, ~5 iterations with two square
+// roots each).  R_C is elementary, R_C(x,y) = atan(t)/(t sqrt x) for y > x, atanh(t)/(t sqrt x) for 0 < y < x with
+// t = sqrt(|y-x|/x) (DLMF 19.2.17-18), and it is called ~27 times per geodesic point (once per R_J iteration), so the closed
+// form is used: same value to round-off (the series is truncated at ~1e-17), about half the instructions.
 GRT_HDN double rc(double x, double y) {
   double w = 1.0;
-  if (!(y > 0.0)) {
+  if (!(y > 0.0)) {  // Cauchy principal value for y < 0
     double xt = x - y;
     w = sqrt(x) / sqrt(xt);
     x = xt;
     y = -y;
   }
-  double ave, s;
-  do {
-    double lam = 2.0 * sqrt(x) * sqrt(y) + y;
-    x = 0.25 * (x + lam);
-    y = 0.25 * (y + lam);
-    ave = (1.0 / 3.0) * (x + y + y);
-    s = (y - ave) / ave;
-  } while (fabs(s) > 0.0012);
-  return w * (1.0 + s * s * (0.3 + s * ((1.0 / 7.0) + s * (0.375 + s * (9.0 / 22.0))))) / sqrt(ave);
+  const double d = y - x;
+  if (d == 0.0) return w / sqrt(x);
+  if (x == 0.0) return w * (0.5 * GRT_PI) / sqrt(y);
+  const double sx = sqrt(x);
+  const double t = sqrt(fabs(d)) / sx;
+  double f;
+  if (t < 0.03) {  // atan(t)/t, atanh(t)/t by their series: exact to < 1e-17 and free of cancellation
+    const double q = (d > 0.0) ? -t * t : t * t;
+    f = 1.0 + q * (1.0 / 3.0 + q * (0.2 + q * (1.0 / 7.0 + q * (1.0 / 9.0 + q * (1.0 / 11.0)))));
+  } else if (d > 0.0) {
+    f = atan(t) / t;
+  } else {  // atanh(t) = log((sqrt(x) + sqrt(x-y)) / sqrt(y)): no cancellation for y << x
+    const double sd = sqrt(-d);
+    return w * log((sx + sd) / sqrt(y)) / sd;
+  }
+  return w * f / sx;
 }
 
 // ---- Carlson R_D ------------------------------------------------------------------------------

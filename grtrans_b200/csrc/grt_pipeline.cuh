@@ -117,9 +117,14 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
         o[12] = T.Ax4; o[13] = T.RQ; o[14] = T.RV0; o[15] = T.RV1;
       } break;
       case EM_POLSYNCHPL:
-      case EM_SYNCHPL:
-        o[4] = cg.ncgsnth; o[5] = cg.bcgs; o[6] = oo.ang;
-        break;
+      case EM_SYNCHPL: {
+        PlPoint Q;
+        if (A.etype == EM_POLSYNCHPL)
+          pl_point<true>(cg.ncgsnth, cg.bcgs, oo.ang, oo.g, Q);
+        else
+          pl_point<false>(cg.ncgsnth, cg.bcgs, oo.ang, oo.g, Q);
+        o[4] = Q.nnth; o[5] = Q.nubperp; o[6] = Q.L; o[7] = Q.itanth;
+      } break;
       case EM_SYNCHTHAV:
         o[4] = cg.ncgs; o[5] = cg.bcgs; o[6] = cg.tcgs;
         break;

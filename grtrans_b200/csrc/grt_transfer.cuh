@@ -25,7 +25,7 @@ namespace grt {
 #define GRT_NREC 16  // doubles per point record (128 B)
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
 //   POLSYNCHTH        [4..15] ThermalPoint (xp13, AI, AV, hkT_g, Ax, Ax^1.035, Ax^1.2, Ax^1.503, Ax^-8/3, RQ, RV0, RV1)
-//   POLSYNCHPL/SYNCHPL [4] n_nth, [5] B, [6] angle
+//   POLSYNCHPL/SYNCHPL [4] n_nth, [5] nu_B,perp, [6] log(g) + log(1.5 nu_B,perp), [7] 1/tan(angle)  (PlPoint)
 //   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
 
 // integration modes (rad_trans.f90:30-38 iflag x neq)
@@ -62,8 +62,23 @@ GRT_HD void prefetch_record(const double *p) {
 // record -> invariant, LBH-scaled coefficients at observed frequency F.nu.  jI_raw returns the comoving un-boosted j_I used
 // for the driver's `fac` (grtrans_driver.f90:183-187).  Replaces calc_emissivity + the e%j/e%K copy (emis.f90:461-571),
 // rotate_emis (:797-829), invariant_emis (:831-838) and the K*LBH scaling (grtrans_driver.f90:217).
+struct RunConst {  // per-thread constants of the march (emissivity-model constants that do not depend on the point)
+  PlConst pl;
+  double lnu;  // log(nu_obs)
+};
 template <int ET>
-GRT_HD void node_coef(const TransferParams &P, const double *rec, const FreqConst &F, Coef &c, double &jI_raw) {
+GRT_HD RunConst run_const(const TransferParams &P, double nu_obs) {
+  RunConst R;
+  R.lnu = 0.0;
+  if (ET == EM_POLSYNCHPL || ET == EM_SYNCHPL) {
+    R.pl = pl_const(P.p, P.gmin, P.gmax);
+    R.lnu = log(nu_obs);
+  }
+  return R;
+}
+
+template <int ET>
+GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *rec, const FreqConst &F, Coef &c, double &jI_raw) {
   const double g = rec[1];
   double e[11];
   bool invariant = false;  // e already holds j g^2 and K LBH / g
@@ -75,10 +90,11 @@ GRT_HD void node_coef(const TransferParams &P, const double *rec, const FreqCons
     invariant = true;
   } else {
     const double nu = F.nu / g;
-    if (ET == EM_POLSYNCHPL)
-      synchpl_eval<true>(P.tab, nu, rec[4], rec[5], rec[6], P.p, P.gmin, P.gmax, e);
-    else if (ET == EM_SYNCHPL)
-      synchpl_eval<false>(P.tab, nu, rec[4], rec[5], rec[6], P.p, P.gmin, P.gmax, e);
+    if (ET == EM_POLSYNCHPL || ET == EM_SYNCHPL) {
+      PlPoint Q;
+      Q.nnth = rec[4]; Q.nubperp = rec[5]; Q.L = rec[6]; Q.itanth = rec[7];
+      pl_eval<ET == EM_POLSYNCHPL>(P.tab, R.pl, Q, nu, R.lnu, e);
+    }
     else if (ET == EM_SYNCHTHAV)
       synchemis_eval(nu, rec[4], rec[5], rec[6], e);
     else {
@@ -309,10 +325,11 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
   for (int i = 0; i < neq; i++) out[i] = 0.0;
   if (npts <= 0) return;
   const FreqConst F = freq_const(nu_obs);
+  const RunConst R = run_const<ET>(P, nu_obs);
   double jraw;
   if (npts == 1) {
     Coef c;
-    node_coef<ET>(P, rec, F, c, jraw);
+    node_coef<ET>(P, R, rec, F, c, jraw);
     double fac = jraw / 1.0;
     if (fac / 1e16 > 0.0)
       for (int i = 0; i < neq; i++) out[i] = c.j[i];
@@ -330,7 +347,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
       const double *rk = rec + (size_t)k * GRT_NREC;
       if (k > 0) prefetch_record(rk - GRT_NREC);
       const double lamk = rk[0];
-      node_coef<ET>(P, rk, F, c0, jraw);
+      node_coef<ET>(P, R, rk, F, c0, jraw);
       fac += jraw * (lam0 - lamk);
       if (k < npts - 1) {
         const double dx = lamk - lam1;
@@ -361,7 +378,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
 #pragma unroll 1
     for (int k = 0; k < npts; k++) {
       const double *rk = rec + (size_t)k * GRT_NREC;
-      node_coef<ET>(P, rk, F, c, jraw);
+      node_coef<ET>(P, R, rk, F, c, jraw);
       if (k > 0) {
         fac += jraw * (lam0 - rk[0]);
         double ds = rk[0] - lprev;
@@ -388,7 +405,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
 #pragma unroll 1
     for (int k = 0; k < npts; k++) {
       const double *rk = rec + (size_t)k * GRT_NREC;
-      node_coef<ET>(P, rk, F, c, jraw);
+      node_coef<ET>(P, R, rk, F, c, jraw);
       fac += jraw * (lam0 - rk[0]);
       if (k > 0) tau -= (rk[0] - lprev) * (kprev + fabs(c.K[0])) / 2.0;
       kprev = fabs(c.K[0]);
@@ -420,7 +437,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     for (int s_ = i2 + 1; s_ >= i1 + 1 && ok; s_--) {
       const int src = (s_ == i2 + 1) ? up : s_;
       cb = ca;
-      node_coef<ET>(P, rec + (size_t)(src - 1) * GRT_NREC, F, ca, jraw);
+      node_coef<ET>(P, R, rec + (size_t)(src - 1) * GRT_NREC, F, ca, jraw);
       for (int i = 0; i < 4; i++) ca.j[i] /= fac;
       if (s_ <= i2) {
         double la = rec[(size_t)(s_ - 1) * GRT_NREC], lb = rec[(size_t)(s_ - 2) * GRT_NREC];
