@@ -89,6 +89,7 @@ GRT_HD double planck_bnu(double T, double nu) {
 // frequency nu = nu_obs/g (for the unit-level surface g = LBH = 1 gives the plain comoving polsynchth values).
 struct ThermalPoint {  // 12 doubles, stored in the point record
   double xp13;         // (g nu_c')^(-1/3):  (nu/nu_c')^(1/3) = nu_obs^(1/3) xp13
+  double ixp13, xpm32; // 1/xp13 and xp13^(-3/2): (nu/nu_c')^(-1/3), (nu/nu_c')^(-1/2) without a reciprocal / square root
   double AI, AV;       // comoving j_{I,Q} = AI nu_obs {iix,iqx},  j_V = AV nu_obs ivx   (the 1/g of nu = nu_obs/g folded in)
   double hkT_g;        // h/(k T g): h nu/(k T) = hkT_g nu_obs
   double Ax;           // xarg = Ax nu_obs^(-1/2)
@@ -103,7 +104,7 @@ struct ThermalPoint {  // 12 doubles, stored in the point record
 // hot loop only multiplies them.
 struct FreqConst {
   double nu, inu2, inu3;
-  double n13;                   // nu^(1/3)
+  double n13, in13;             // nu^(1/3), nu^(-1/3)
   double nm12;                  // nu^(-1/2)
   double nq1, nq2, nq3, nq4;    // nu^(-1.035/2), nu^(-1.2/2), nu^(-1.50316886/2), nu^(+4/3)
 };
@@ -115,6 +116,7 @@ GRT_HD FreqConst freq_const(double nu_obs) {
   f.inu3 = f.inu2 * i;
   const double l = log(nu_obs);
   f.n13 = exp(l * (1.0 / 3.0));
+  f.in13 = exp(l * (-1.0 / 3.0));
   f.nm12 = exp(-0.5 * l);
   f.nq1 = exp((-0.5 * 1.035) * l);
   f.nq2 = exp((-0.5 * 1.2) * l);
@@ -129,7 +131,10 @@ GRT_HD void thermal_point(double n, double b, double t, double theta, double g, 
   double sinth = sin(theta), costh = cos(theta), tanth = tan(theta);
   double nucfac = 3.0 * pc::e * b * sinth / 4.0 / GRT_PI / pc::m / pc::c * thetae * thetae + 1.0;
   double th2 = thetae * thetae;
-  P.xp13 = exp((-log(g) - log(nucfac)) * (1.0 / 3.0));
+  const double lxp = -log(g) - log(nucfac);
+  P.xp13 = exp(lxp * (1.0 / 3.0));
+  P.ixp13 = exp(lxp * (-1.0 / 3.0));
+  P.xpm32 = exp(lxp * (-0.5));
   P.AI = ec * ec / c / sqrt(3.0) / 2.0 * n / th2 / g;
   P.AV = 4.0 * ec * ec / c / 3.0 / sqrt(3.0) / tanth * n / 2.0 / (th2 * thetae) / g;
   P.hkT_g = pc::h / pc::k / t / g;
@@ -170,11 +175,11 @@ GRT_HD void thermal_point(double n, double b, double t, double theta, double g, 
 // the 16 < xarg < 6552 window of the high-frequency correction) and ~110 multiply-adds.
 GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, double *e, double &jraw) {
   const double x13 = F.n13 * P.xp13;
-  const double i13 = 1.0 / x13, i23 = i13 * i13;
+  const double i13 = F.in13 * P.ixp13, i23 = i13 * i13;
   const double ex = exp_fast(-1.8899 * x13);
   const double iix = 2.5651 * (1.0 + 1.92 * i13 + .9977 * i23) * ex;
   const double iqx = 2.5651 * (1.0 + .93193 * i13 + .499873 * i23) * ex;
-  const double ivx = (1.81384 * (i23 * i13) + 3.42319 * i23 + 0.0292545 * (i13 * sqrt(i13)) + 2.03773 * i13) * ex;
+  const double ivx = (1.81384 * (i23 * i13) + 3.42319 * i23 + 0.0292545 * (F.nm12 * P.xpm32) + 2.03773 * i13) * ex;
   const double ji = P.AI * F.nu * iix, jq = P.AI * F.nu * iqx, jv = P.AV * F.nu * ivx;
   jraw = ji;
   // 1/B_nu (bnu, polsynchemis.f90:1014-1032): Rayleigh-Jeans below h nu/kT = 1e-6; B_nu == 0 is replaced by epsilon

@@ -22,9 +22,9 @@
 
 namespace grt {
 
-#define GRT_NREC 16  // doubles per point record (128 B)
+#define GRT_NREC 20  // doubles per point record (160 B)
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
-//   POLSYNCHTH        [4..15] ThermalPoint (xp13, AI, AV, hkT_g, Ax, Ax^1.035, Ax^1.2, Ax^1.503, Ax^-8/3, RQ, RV0, RV1)
+//   POLSYNCHTH        [4..17] ThermalPoint (xp13, AI, AV, hkT_g, Ax, Ax^1.035, Ax^1.2, Ax^1.503, Ax^-8/3, RQ, RV0, RV1, 1/xp13, xp13^-1.5)
 //   POLSYNCHPL/SYNCHPL [4] n_nth, [5] nu_B,perp, [6] log(g) + log(1.5 nu_B,perp), [7] 1/tan(angle)  (PlPoint)
 //   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
 
@@ -85,7 +85,8 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
   if (ET == EM_POLSYNCHTH) {
     ThermalPoint T;
     T.xp13 = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.Ax = rec[8]; T.Ax1 = rec[9]; T.Ax2 = rec[10];
-    T.Ax3 = rec[11]; T.Ax4 = rec[12]; T.RQ = rec[13]; T.RV0 = rec[14]; T.RV1 = rec[15]; T.g = g;
+    T.Ax3 = rec[11]; T.Ax4 = rec[12]; T.RQ = rec[13]; T.RV0 = rec[14]; T.RV1 = rec[15]; T.ixp13 = rec[16];
+    T.xpm32 = rec[17]; T.g = g;
     thermal_eval(T, F, pc::c2 * P.LBH / (2.0 * pc::h), e, jI_raw);
     invariant = true;
   } else {
@@ -172,8 +173,10 @@ GRT_HD void solve_delo(double c1, double c2, const double *K, const double *x, d
   const double s3 = d2 * a3 + d * (r1 * a2 - r2 * a1) + r3 * ra;
   const double dn = d * (d2 + rr);
   const double det = d2 * (d2 + rr - aa) - ra * ra;
-  const double x0 = (x[0] * dn - (a1 * p1 + a2 * p2 + a3 * p3)) / det;
-  const double q = 1.0 / dn;
+  // one reciprocal for both 1/det and 1/dn (det ~ d^4, dn ~ d^3 with d = O(1): the product cannot over/underflow)
+  const double inv = 1.0 / (det * dn);
+  const double x0 = (x[0] * dn - (a1 * p1 + a2 * p2 + a3 * p3)) * (inv * dn);
+  const double q = inv * det;
   y[0] = x0;
   y[1] = (p1 - x0 * s1) * q;
   y[2] = (p2 - x0 * s2) * q;

@@ -308,3 +308,39 @@ def test_session_pipelined_fetch_equals_fetch():
         s.close()
     finally:
         del os.environ["GRT_TILE"]
+
+
+def test_config5_full_size_against_oracle_sample_and_tiling():
+    """BASELINE config 5 at its full size (1024x1024 x 400 pts x 64 freqs, 288x128x128 snapshot): (i) blocks of rays spread
+    over the camera are compared with the oracle run on exactly those geodesic indices, (ii) the image does not depend on
+    the tile size the session uses (size-independent property)."""
+    sys_path_root = os.path.dirname(cases.HERE)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("grt_bench", os.path.join(sys_path_root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    kw = bench.workload(1024, 64, cases.SNAPDIR, (288, 128, 128))
+    s = _lib.Session(args_from_kwargs(**kw))
+    view, nbytes = s.launch_fetch()
+    s.sync()
+    img = np.array(view)                     # [64 cams, 1024*1024 rays, 4]
+    s.close()
+    assert img.shape == (64, 1024 * 1024, 4) and nbytes == img.nbytes
+    npix = 1024 * 1024
+    for frac in (0.31, 0.5, 0.77):
+        i1 = int(frac * npix) + 400
+        i2 = i1 + 23
+        ref = orc.run(_args=args_from_kwargs(i1=i1, i2=i2, **kw))['ivals'][:, i1 - 1:i2, :]      # [4, 24, 64]
+        got = img[:, i1 - 1:i2, :].transpose(2, 1, 0).astype(np.float64)
+        relI, flux, quv, nanok = cases.image_errors(got, ref)
+        assert nanok and relI < 1e-4 and flux < 1e-5 and quv < 1e-3, (frac, relI, flux, quv)
+    os.environ["GRT_TILE"] = "20000"
+    try:
+        kw2 = dict(kw)
+        s2 = _lib.Session(args_from_kwargs(i1=300001, i2=360000, **kw2))
+        v2, _ = s2.launch_fetch()
+        s2.sync()
+        assert np.array_equal(np.asarray(v2), img[:, 300000:360000, :], equal_nan=True)
+        s2.close()
+    finally:
+        del os.environ["GRT_TILE"]
