@@ -261,7 +261,65 @@ int load_harm2d(FluidHost &f, const grt_args &a) {
 }
 
 // synthetic 3-D container (see oracle/fluid.cc load_harm3d for the layout; written by tools/make_snapshot.py)
+void harm3d_axes(FluidHost &f, const std::vector<float> &x1, const std::vector<float> &x2, const std::vector<float> &x3) {
+  f.ax1.resize(f.nx1); f.axr.resize(f.nx1); f.ax2.resize(f.nx2); f.axth.resize(f.nx2); f.ax3.resize(f.nx3);
+  for (int i = 0; i < f.nx3; i++) f.ax3[i] = x3[i];
+  for (int i = 0; i < f.nx2; i++) {
+    f.ax2[i] = x2[(size_t)i * f.nx3];
+    f.axth[i] = (float)(PI * (double)f.ax2[i]);
+  }
+  for (int i = 0; i < f.nx1; i++) {
+    f.ax1[i] = x1[(size_t)i * f.nx3 * f.nx2];
+    f.axr[i] = std::exp(f.ax1[i]);
+  }
+}
+
+// the reference's own harm3d input: header file of 15 numbers (fluid_model_harm3d.f90:337-366) + `<dfile>%03d.bin` =
+// one text header line, then float32 data(35, n) (:516-584): x1,x2,x3 columns 4-6, rho 10, u 11, u^mu 19-22, b^mu 27-30
+int load_harm3d_native(FluidHost &f, const grt_args &a, FILE *fp) {
+  std::ifstream hf(a.fhfile);
+  double header[15];
+  bool ok = (bool)hf;
+  for (int i = 0; ok && i < 15; i++) ok = (bool)(hf >> header[i]);
+  if (!ok) {
+    fclose(fp);
+    return GRT_ERR_IO;
+  }
+  f.nx1 = (int)header[1]; f.nx2 = (int)header[2]; f.nx3 = (int)header[3];
+  f.asim = (float)header[10]; f.gam = (float)header[11]; f.h = (float)header[13];
+  if (std::fabs(f.asim - (float)a.spin) > 1e-4f) {
+    fclose(fp);
+    return GRT_ERR_BAD_ARG;
+  }
+  int ch;
+  while ((ch = fgetc(fp)) != EOF && ch != 10) {
+  }
+  const size_t n = (size_t)f.nx1 * f.nx2 * f.nx3;
+  std::vector<float> data(35 * n);
+  ok = fread(data.data(), 4, data.size(), fp) == data.size();
+  fclose(fp);
+  if (!ok) return GRT_ERR_IO;
+  std::vector<float> x1(n), x2(n), x3(n);
+  f.cells.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    const float *d = data.data() + 35 * i;
+    x1[i] = d[3]; x2[i] = d[4]; x3[i] = d[5];
+    double uc[4] = {d[18], d[19], d[20], d[21]}, bc[4] = {d[26], d[27], d[28], d[29]};
+    double pp = d[10];
+    ingest_cell(f, i, std::exp(x1[i]), x2[i], (float)((double)x2[i] * PI), (double)d[9], (pp > (double)1e-18f) ? pp : (double)1e-18f, uc, bc, true);
+  }
+  harm3d_axes(f, x1, x2, x3);
+  return GRT_OK;
+}
+
 int load_harm3d(FluidHost &f, const grt_args &a) {
+  if (a.fnt > 1) return GRT_ERR_BAD_ARG;
+  {  // the reference's format if `<dfile>%03d.bin` exists, else the synthetic container (tools/make_snapshot.py)
+    char append[16];
+    snprintf(append, sizeof append, "%03d", a.findf);
+    FILE *fn = fopen((std::string(a.fdfile) + append + ".bin").c_str(), "rb");
+    if (fn) return load_harm3d_native(f, a, fn);
+  }
   FILE *fp = fopen(a.fdfile, "rb");
   if (!fp) return GRT_ERR_IO;
   int dims[3];
@@ -292,19 +350,9 @@ int load_harm3d(FluidHost &f, const grt_args &a) {
   if (!ok) return GRT_ERR_IO;
   f.cells.resize(n);
   for (size_t i = 0; i < n; i++) ingest_cell(f, i, g[3][i], g[1][i], g[4][i], rho[i], uu[i], &uc[4 * i], &bc[4 * i], true);
-  f.ax1.resize(f.nx1); f.axr.resize(f.nx1); f.ax2.resize(f.nx2); f.axth.resize(f.nx2); f.ax3.resize(f.nx3);
-  for (int i = 0; i < f.nx3; i++) f.ax3[i] = g[2][i];
-  for (int i = 0; i < f.nx2; i++) {
-    f.ax2[i] = g[1][(size_t)i * f.nx3];
-    f.axth[i] = (float)(PI * (double)f.ax2[i]);
-  }
-  for (int i = 0; i < f.nx1; i++) {
-    f.ax1[i] = g[0][(size_t)i * f.nx3 * f.nx2];
-    f.axr[i] = std::exp(f.ax1[i]);
-  }
+  harm3d_axes(f, g[0], g[1], g[2]);
   return GRT_OK;
 }
-
 
 // iharm: header text file (read_iharm_data_header, fluid_model_iharm.f90:427-470) + `<dfile><indf %03d>.bin`, a stream of
 // float32 data(13+eHEAT, n) = x1,x2,x3, rho, u, u^mu(4), b^mu(4) [, kel] per cell in (M)MKS components

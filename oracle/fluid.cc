@@ -809,7 +809,52 @@ static bool load_harm(FluidData &fd, const FluidArgs &fa, double a) {
 // Synthetic 3-D snapshot container used by config 5 (binary, little endian):
 //   int32 nx1,nx2,nx3; float32 asim,gam,h; then float32[n] x1,x2,x3,r,th,ph; float64[n] rho,u;
 //   float64[4n] ucon, bcon (MKS components, index (ix1*nx2+ix2)*nx3+ix3).
+// The reference's own harm3d input (fluid_model_harm3d.f90:337-366 header file of 15 numbers; :516-584 data file
+// `<dfile>%03d.bin` = one text header line + float32 data(35, n): x1,x2,x3 = columns 4-6, rho 10, u 11, u^mu 19-22,
+// b^mu 27-30; p = max(u, 1e-18) (gam-1)).
+static bool load_harm3d_native(FluidData &fd, const FluidArgs &fa, double a, FILE *fp) {
+  std::ifstream hf(fa.hfile);
+  if (!hf) { fclose(fp); return false; }
+  double header[15];
+  for (int i = 0; i < 15; i++)
+    if (!(hf >> header[i])) { fclose(fp); return false; }
+  fd.nx1 = (int)header[1]; fd.nx2 = (int)header[2]; fd.nx3 = (int)header[3];
+  fd.asim = (float)header[10]; fd.gam = (float)header[11]; fd.h = (float)header[13];
+  if (std::fabs(fd.asim - (float)a) > 1e-4f) { fclose(fp); return false; }
+  int ch;
+  while ((ch = fgetc(fp)) != EOF && ch != 10) {}
+  size_t n = (size_t)fd.nx1 * fd.nx2 * fd.nx3;
+  std::vector<float> data(35 * n);
+  bool ok = fread(data.data(), 4, data.size(), fp) == data.size();
+  fclose(fp);
+  if (!ok) return false;
+  fd.x1_arr.resize(n); fd.x2_arr.resize(n); fd.x3_arr.resize(n); fd.r_arr.resize(n); fd.th_arr.resize(n); fd.ph_arr.resize(n);
+  std::vector<double> rho(n), uu(n), ucon(4 * n), bcon(4 * n);
+  for (size_t i = 0; i < n; i++) {
+    const float *d = data.data() + 35 * i;
+    fd.x1_arr[i] = d[3]; fd.x2_arr[i] = d[4]; fd.x3_arr[i] = d[5];
+    fd.r_arr[i] = std::exp(fd.x1_arr[i]);
+    fd.th_arr[i] = (float)((double)fd.x2_arr[i] * pi);
+    fd.ph_arr[i] = fd.x3_arr[i];
+    rho[i] = d[9];
+    double pp = d[10];
+    uu[i] = (pp > (double)1e-18f) ? pp : (double)1e-18f;  // p=merge(p,pmin,p.gt.pmin); pmin=1e-18 is a single-precision literal
+    for (int c = 0; c < 4; c++) {
+      ucon[4 * i + c] = d[18 + c];
+      bcon[4 * i + c] = d[26 + c];
+    }
+  }
+  harm_transform_and_store(fd, rho, uu, ucon, bcon);
+  return true;
+}
+
 static bool load_harm3d(FluidData &fd, const FluidArgs &fa, double a) {
+  {  // the reference's format if `<dfile>%03d.bin` exists, else the synthetic container below
+    char append[16];
+    snprintf(append, sizeof append, "%03d", fa.indf);
+    FILE *fn = fopen((fa.dfile + append + ".bin").c_str(), "rb");
+    if (fn) return load_harm3d_native(fd, fa, a, fn);
+  }
   FILE *fp = fopen(fa.dfile.c_str(), "rb");
   if (!fp) return false;
   int dims[3];

@@ -61,6 +61,18 @@ def cfg_harm3d(n=40, nup=100, nfreq=4, iname='delo', **kw):
     return d
 
 
+def cfg_harm3d_native(n=40, nup=100, nfreq=4, iname='delo', **kw):
+    """HARM3D read from the reference's own file format (header file + `<dfile>%03d.bin`)."""
+    import make_snapshot as ms
+    os.makedirs(SNAPDIR, exist_ok=True)
+    prefix = os.path.join(SNAPDIR, "h3dnative_")
+    if not os.path.exists(prefix + "040.bin"):
+        ms.write_harm3d_native(prefix, indf=40)
+    d = cfg_harm3d(n=n, nup=nup, nfreq=nfreq, iname=iname, **kw)
+    d.update(fdfile=prefix, fhfile=prefix + "header.txt", findf=40, fnt=1)
+    return d
+
+
 def iharm_snapshots(mmks=1):
     import make_snapshot as ms
     os.makedirs(SNAPDIR, exist_ok=True)

@@ -175,6 +175,7 @@ IMAGE_CASES = [
     ("harm", dict(n=50, nup=400, nfreq=1, iname='delo'), 1e-4),
     ("harm3d", dict(n=50, nup=200, nfreq=4, iname='delo'), 1e-4),
     ("harm3d", dict(n=40, nup=100, nfreq=2, iname='delo', nmdot=3, mdotmin=1e19, mdotmax=1e21), 1e-4),
+    ("harm3d_native", dict(n=40, nup=100, nfreq=3), 1e-4),                        # the reference's own harm3d file format
     ("iharm", dict(n=50, nup=200, nfreq=4, mmks=1), 1e-4),                        # FMKS grid, R-beta electrons
     ("iharm", dict(n=50, nup=200, nfreq=4, mmks=0, gmin=-1.), 1e-4),              # MKS grid, electron-entropy T_e
     # (fmin=1e11: at 1e10 Hz nu << nu_c, the polsynchth fits give |j_V| > j_I, the transfer matrix has a growing mode and the

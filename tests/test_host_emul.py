@@ -62,6 +62,7 @@ EMUL_CASES = [
     ("harm", dict(n=24, nup=200, nfreq=2, iname='delo')),
     ("harm3d", dict(n=24, nup=100, nfreq=4, iname='delo')),
     ("harm3d", dict(n=16, nup=100, nfreq=2, iname='delo', nmdot=2, mdotmin=1e19, mdotmax=1e21)),
+    ("harm3d_native", dict(n=20, nup=100, nfreq=3)),                   # the reference's own harm3d file format
     ("iharm", dict(n=24, nup=100, nfreq=3, mmks=1)),                   # FMKS grid, R-beta electrons (monika_e)
     ("iharm", dict(n=24, nup=100, nfreq=3, mmks=0, gmin=-1.)),         # MKS grid, electron-entropy T_e (ressler_e)
     ("iharm", dict(n=20, nup=100, nfreq=2, mmks=1, iname='formal', sigcut=0.5)),

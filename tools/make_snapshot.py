@@ -132,6 +132,29 @@ def write_harm3d(path, **kw):
     return path
 
 
+def write_harm3d_native(prefix, indf=40, **kw):
+    """The reference's own harm3d input: `<prefix>header.txt` (15 numbers, fluid_model_harm3d.f90:337-366) and
+    `<prefix>%03d.bin` = a text header line + float32 data(35, n) (:516-584).  Returns (header path, data prefix)."""
+    d = harm3d_arrays(**kw)
+    n = d['nx1'] * d['nx2'] * d['nx3']
+    data = np.zeros((n, 35), np.float32)
+    data[:, 3] = d['x1'].ravel(); data[:, 4] = d['x2'].ravel(); data[:, 5] = d['x3'].ravel()
+    data[:, 6] = d['r'].ravel(); data[:, 7] = d['th'].ravel(); data[:, 8] = d['ph'].ravel()
+    data[:, 9] = d['rho'].ravel(); data[:, 10] = d['u'].ravel()
+    data[:, 18:22] = d['ucon'].reshape(n, 4); data[:, 26:30] = d['bcon'].reshape(n, 4)
+    x1 = d['x1'][:, 0, 0]; x2 = d['x2'][0, :, 0]; x3 = d['x3'][0, 0, :]
+    hdr = [0.0, d['nx1'], d['nx2'], d['nx3'], x1[0] - 0.5 * (x1[1] - x1[0]), 0.0, 0.0, x1[1] - x1[0], x2[1] - x2[0], x3[1] - x3[0],
+           d['a'], d['gam'], 0.9, 1.0, 0.0]
+    line = " ".join("%.17g" % v for v in hdr) + "\n"
+    with open("%s%03d.bin" % (prefix, indf), 'wb') as f:
+        f.write(line.encode())
+        data.tofile(f)
+    hpath = prefix + "header.txt"
+    with open(hpath, 'w') as f:
+        f.write(line)
+    return hpath, prefix
+
+
 def iharm_arrays(nx1=64, nx2=32, nx3=32, a=0.9375, hslope=0.3, mmks=1, mks_smooth=0.5, poly_xt=0.82, poly_alpha=14.0,
                  rin=1.1, rout=40.0, seed=12345):
     """(M)MKS grid of iharm3d / ebhlight: x1 = log r, theta(x2[, x1]) per fluid_model_iharm.f90:82-118, x3 = phi."""
