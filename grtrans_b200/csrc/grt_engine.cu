@@ -223,6 +223,8 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   F.td_mbh = s->fh.td_mbh; F.td_mdot = s->fh.td_mdot; F.td_rin = s->fh.td_rin; F.td_rout = s->fh.td_rout;
   F.hslope = s->fh.hslope; F.mks_smooth = s->fh.mks_smooth; F.poly_xt = s->fh.poly_xt; F.poly_alpha = s->fh.poly_alpha;
   F.startx1 = s->fh.startx1; F.is_mmks = s->fh.is_mmks; F.eheat = s->fh.eheat; F.gam = s->fh.gam;
+  F.kh = s->fh.kh; F.kr0 = s->fh.kr0; F.kaa = s->fh.kaa; F.kbb = s->fh.kbb; F.kpp = s->fh.kpp; F.ktype = s->fh.ktype;
+  F.x2mintrust = s->fh.x2mintrust; F.x2maxtrust = s->fh.x2maxtrust;
   SCK(own_h2d(s, &F.ax1, s->fh.ax1)); SCK(own_h2d(s, &F.axr, s->fh.axr)); SCK(own_h2d(s, &F.ax2, s->fh.ax2));
   SCK(own_h2d(s, &F.axth, s->fh.axth)); SCK(own_h2d(s, &F.ax3, s->fh.ax3));
   SCK(own_h2d(s, &F.uvals, s->fh.uvals)); SCK(own_h2d(s, &F.vvals, s->fh.vvals)); SCK(own_h2d(s, &F.uv, s->fh.uv));

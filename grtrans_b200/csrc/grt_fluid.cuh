@@ -15,10 +15,10 @@
 
 namespace grt {
 
-enum { FL_DUMMY = 0, FL_SPHACC = 1, FL_THINDISK = 2, FL_HARM = 12, FL_FFJET = 13, FL_HARM3D = 19, FL_IHARM = 29 };
+enum { FL_DUMMY = 0, FL_SPHACC = 1, FL_THINDISK = 2, FL_HARM = 12, FL_FFJET = 13, FL_HARM3D = 19, FL_KORAL = 22, FL_KORAL3D = 25, FL_KORAL3D_DISK = 26, FL_IHARM = 29 };
 
 struct Cell {  // 48 bytes, 16-byte aligned
-  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela /* iharm electron entropy */, pad1;
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela /* iharm electron entropy */, be /* koral3d Bernoulli parameter */;
 };
 
 struct FluidDev {
@@ -35,17 +35,20 @@ struct FluidDev {
   double hslope, mks_smooth, poly_xt, poly_alpha, startx1;
   int is_mmks, eheat;
   float gam;
+  // koral / koral3d MKS3 grid (fluid_model_koral.f90:11-29) and trust region in x2 (minpolecell cells at each pole)
+  float kh, kr0, kaa, kbb, kpp, x2mintrust, x2maxtrust;
+  int ktype;
   // SPHACC tables
   const float *uvals, *vvals, *uv, *tvals;  // 498, 498, 461 (=1/rvals), 461
 };
 
 struct FluidSample {
-  float rho, p, bmag, kela;
+  float rho, p, bmag, kela, be;
   double u[4], b[4];
 };
 
 struct Field10 {
-  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela;
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela, be;
 };
 
 GRT_HD Field10 load_cell(const Cell *cells, size_t idx) {
@@ -54,16 +57,17 @@ GRT_HD Field10 load_cell(const Cell *cells, size_t idx) {
   const float4 *q = reinterpret_cast<const float4 *>(cells + idx);
   float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
   f.rho = a.x; f.p = a.y; f.vrl = a.z; f.vtl = a.w; f.vpl = b.x; f.b0 = b.y; f.br = b.z; f.bth = b.w; f.bph = c.x; f.u0 = c.y;
-  f.kela = c.z;
+  f.kela = c.z; f.be = c.w;
 #else
   const Cell &c = cells[idx];
   f.rho = c.rho; f.p = c.p; f.vrl = c.vrl; f.vtl = c.vtl; f.vpl = c.vpl; f.b0 = c.b0; f.br = c.br; f.bth = c.bth;
-  f.bph = c.bph; f.u0 = c.u0; f.kela = c.kela;
+  f.bph = c.bph; f.u0 = c.u0; f.kela = c.kela; f.be = c.be;
 #endif
   return f;
 }
 
 #define GRT_FOR_FIELDS(OP) OP(rho) OP(p) OP(vrl) OP(vtl) OP(vpl) OP(b0) OP(br) OP(bth) OP(bph) OP(u0)
+#define GRT_FOR_FIELDS_BE(OP) GRT_FOR_FIELDS(OP) OP(be)
 
 // bilinear blend of four corners (interpolate.f90:171-182), all float32
 GRT_HD Field10 blend4(const Field10 &c0, const Field10 &c1, const Field10 &c2, const Field10 &c3, float xd, float yd) {
@@ -225,6 +229,18 @@ struct IharmThetaMks {
   GRT_HD double operator()(double x) const { return th - iharm_th_mks(G, x); }
 };
 
+// ---- koral MKS3 coordinate maps (fluid_model_koral.f90:62-80; real(4) arguments promoted by the real(8) pi) -------
+GRT_HD float koral_x2_of_theta(float th, float r, float h, float a, float b, float p) {
+  float rp = r4pow(r, p);
+  double num = atan(tan((double)(0.5f * h) * GRT_PI) * (1. - (double)(2.f * th) / GRT_PI));
+  float den = (b - a) * r4pow(2.f, p) + (a - 0.5f) * rp;
+  return (float)(0.5 * (1. + ((double)rp / ((double)h * GRT_PI)) * (num / (double)den)));
+}
+GRT_HD float koral_theta_of_x2(float x2, float r, float h, float a, float b, float p) {
+  float inner = -0.5f + x2 + (1.f - 2.f * x2) * (a + r4pow(2.f, p) * (b - a) / r4pow(r, p));
+  return (float)(0.5 * GRT_PI * (1. + tan((double)h * GRT_PI * (double)inner) / tan((double)(0.5f * h) * GRT_PI)));
+}
+
 // bracket search equivalent to NR hunt/locate for an in-range x (1-based result clamped to [1,n-1])
 GRT_HD int bracket(const float *xx /*0-based*/, int n, float x) {
   bool ascnd = xx[n - 1] >= xx[0];
@@ -267,7 +283,7 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
   const double pcG = 6.67e-8, pcc = 2.99792458e10, pcc2 = pcc * pcc, pcmsun = 1.998e33, pcmp = 1.67262158e-24,
                pcsigt = 6.6523e-25, pcsigb = 5.6704e-5;
   float a = (float)ad;
-  s.rho = s.p = s.bmag = s.kela = 0.f;
+  s.rho = s.p = s.bmag = s.kela = s.be = 0.f;
   for (int i = 0; i < 4; i++) s.u[i] = s.b[i] = 0.0;
   switch (F.model) {
     case FL_THINDISK: {
@@ -435,6 +451,90 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       s.p = (float)((double)v.p * fac);
       finish_grid(s, v, in, 0.f, zr, (float)thh, a, fac);
     } break;
+    case FL_KORAL:
+    case FL_KORAL3D:
+    case FL_KORAL3D_DISK: {
+      // koral_vals (fluid_model_koral.f90:84-286) / koral3d_vals (fluid_model_koral3d.f90:83-346): x2 fastest, then x1, then
+      // x3; closed-form MKS3 maps; cells next to the poles (and, for KORAL3D_DISK, a polar cone) are not trusted
+      const bool d3 = F.model != FL_KORAL;
+      const int nx1 = F.nx1, nx2 = F.nx2, nx3 = d3 ? F.nx3 : 1;
+      float theta = (float)thh, zr = (float)rr;
+      float x1 = (float)log((double)zr - (double)F.kr0);
+      float x2 = koral_x2_of_theta(theta, zr, F.kh, F.kaa, F.kbb, F.kpp);
+      int lx1 = (int)floorf((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
+      int ux1 = lx1 + 1;
+      lx1 = (lx1 >= 1) ? lx1 : 1;
+      ux1 = (ux1 <= nx1) ? ux1 : nx1;
+      lx1 = lx1 > nx1 ? nx1 : lx1;  // guards (the reference reads out of bounds outside the radial range)
+      ux1 = ux1 < 1 ? 1 : ux1;
+      int lx2 = (int)floorf((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;
+      int ux2 = lx2 + 1;
+      lx2 = (lx2 >= 1) ? lx2 : 1;
+      ux2 = (ux2 <= nx2) ? ux2 : nx2;
+      lx2 = lx2 > nx2 ? nx2 : lx2;
+      ux2 = ux2 < 1 ? 1 : ux2;
+      float pd = 0.f;
+      int lx3 = 1, ux3 = 1;
+      if (d3) {
+        float zphi = (float)phh;
+        zphi = (float)fmod((double)zphi, 2. * pi);
+        if (zphi < 0.f) zphi = (float)((double)zphi + 2. * pi);
+        if ((double)zphi > pi) zphi = (float)((double)zphi - 2. * pi);
+        lx3 = (int)floorf((zphi - F.ax3[0]) / (F.ax3[nx3 - 1] - F.ax3[0]) * (float)(nx3 - 1)) + 1;
+        ux3 = lx3 + 1;
+        int lx3s = lx3 < 1 ? 1 : (lx3 > nx3 ? nx3 : lx3);
+        float minph = F.ax3[lx3s - 1];
+        ux3 = (ux3 <= nx3) ? ux3 : 1;
+        if (lx3 < 1) {
+          lx3 = nx3;
+          minph = (float)((double)F.ax3[lx3 - 1] - 2. * pi);
+        }
+        lx3 = lx3 > nx3 ? nx3 : lx3;
+        pd = (zphi - minph) / (F.ax3[1] - F.ax3[0]);
+      }
+      float rd = (zr - F.axr[lx1 - 1]) / (F.axr[ux1 - 1] - F.axr[lx1 - 1]);
+      float rh = 1.f + sqrtf(1.f - a * a);
+      double fac = 1.0;
+      if (F.axr[lx1 - 1] <= rh || lx1 == 1) {
+        rd = 1.f;
+        if (d3) fac = 1e-3;
+      }
+      float thl = koral_theta_of_x2(F.ax2[lx2 - 1], F.axr[lx1 - 1], F.kh, F.kaa, F.kbb, F.kpp);
+      float thu = koral_theta_of_x2(F.ax2[ux2 - 1], F.axr[lx1 - 1], F.kh, F.kaa, F.kbb, F.kpp);
+      float thone = koral_theta_of_x2(F.ax2[0], F.axr[lx1 - 1], F.kh, F.kaa, F.kbb, F.kpp);
+      float td = (ux2 != lx2) ? fabsf((theta - thl) / (thu - thl)) : fabsf((theta - thl) / thone);
+      size_t x2l = lx2 - 1, x2u = ux2 - 1, x1l = (size_t)(lx1 - 1) * nx2, x1u = (size_t)(ux1 - 1) * nx2;
+      size_t x3l = (size_t)(lx3 - 1) * nx2 * nx1, x3u = (size_t)(ux3 - 1) * nx2 * nx1;
+      Field10 v;
+      if (d3) {
+        Field10 c0 = load_cell(F.cells, x1l + x2l + x3l), c1 = load_cell(F.cells, x1l + x2u + x3l),
+                c2 = load_cell(F.cells, x1u + x2l + x3l), c3 = load_cell(F.cells, x1u + x2u + x3l),
+                c4 = load_cell(F.cells, x1l + x2l + x3u), c5 = load_cell(F.cells, x1l + x2u + x3u),
+                c6 = load_cell(F.cells, x1u + x2l + x3u), c7 = load_cell(F.cells, x1u + x2u + x3u);
+        // quadlininterp(vv, td=0, xd=pd, yd=rd, zd=td) (interpolate.f90:203-232): theta, then r, then phi, then time
+#define OP(f) { float i1 = c0.f * (1.f - td) + c1.f * td, i2 = c2.f * (1.f - td) + c3.f * td;                 float j1 = c4.f * (1.f - td) + c5.f * td, j2 = c6.f * (1.f - td) + c7.f * td;                 float m1 = i1 * (1.f - rd) + i2 * rd, m2 = j1 * (1.f - rd) + j2 * rd;                       float w1 = m1 * (1.f - pd) + m2 * pd; v.f = w1 * (1.f - 0.f) + w1 * 0.f; }
+        GRT_FOR_FIELDS_BE(OP)
+#undef OP
+      } else {
+        Field10 c0 = load_cell(F.cells, x1l + x2l), c1 = load_cell(F.cells, x1l + x2u), c2 = load_cell(F.cells, x1u + x2l),
+                c3 = load_cell(F.cells, x1u + x2u);
+#define OP(f) { float i1 = c0.f * (1.f - td) + c1.f * td, i2 = c2.f * (1.f - td) + c3.f * td;                 float w1 = i1 * (1.f - rd) + i2 * rd; v.f = w1 * (1.f - 0.f) + w1 * 0.f; }
+        GRT_FOR_FIELDS_BE(OP)
+#undef OP
+      }
+      bool in = x1 > F.ax1[0];
+      bool trust = (x2 > F.x2mintrust) && (x2 < F.x2maxtrust);
+      if (d3 && F.ktype == 1) trust = trust && (theta > 0.25f) && (theta < (float)(pi - 0.25));
+      bool ok = in && trust;
+      s.rho = (float)((double)(in ? v.rho : 0.f) * fac);
+      s.p = (float)((double)(in ? v.p : 1.f) * fac);
+      if (!trust) {
+        s.rho = 0.f;
+        s.p = 1.f;
+      }
+      s.be = (d3 && ok) ? v.be : 0.f;
+      finish_grid(s, v, ok, 1.f, zr, (float)thh, a, 1.0);
+    } break;
     case FL_IHARM: {
       // iharm_vals (fluid_model_iharm.f90:222-424): nearest-neighbour lookup -- rd = td = pd = 1 puts all the weight on
       // the upper corner of the cell in r, theta and phi; time weight 0 (nt = 1)
@@ -489,7 +589,8 @@ struct CgsVars {
   double ncgs, ncgsnth, bcgs, tcgs;
 };
 
-GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bmag, float kela, float gam, CgsVars &o) {
+GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bmag, float kela, float be, float gam,
+                   CgsVars &o) {
   const double pi = GRT_PI;
   const double pcG = 6.67e-8, pcc = 2.99792458e10, pcmsun = 1.998e33, pcmp = 1.67262158e-24, pck = 1.38e-16;
   o.ncgs = o.ncgsnth = o.bcgs = o.tcgs = 0.0;
@@ -535,6 +636,35 @@ GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bma
           o.tcgs = 1e9;
         }
       }
+    } break;
+    case FL_KORAL:
+    case FL_KORAL3D:
+    case FL_KORAL3D_DISK: {  // convert_fluidvars_koral (fluid.f90:1075-1162): koral quantities are already cgs
+      double rhocgs = (double)rho;
+      o.ncgs = rhocgs / pcmp;
+      o.bcgs = (double)bmag * sqrt(4 * pi);
+      o.bcgs = o.bcgs * sqrt(sp.nfac);
+      o.ncgs = o.ncgs * sp.nfac;
+      rhocgs = rhocgs * sp.nfac;
+      if (sp.gminval >= 1.0) {  // charles_e(rho, p+Be, 2p+Be, bmag, 1, 1, gmin) (fluid.f90:845-868): p = T_e, Be = T_p
+        float pp = p + be, uu = 2.f * p + be;
+        double beta = 2.0 * (double)rho * pck * (double)pp / pcmp / (double)(bmag * bmag);
+        double b2 = beta * beta;
+        double trat = ((double)bmag > 0.0) ? sp.gminval * b2 / (1.0 + b2) + 1.0 / (1.0 + b2) : sp.gminval;
+        o.tcgs = (double)uu / (2.0 + trat);
+      } else if (sp.gminval < 0.0) {
+        o.tcgs = (double)p;
+      }
+      double sigmacgs = (o.bcgs * o.bcgs) / (rhocgs * 8.988e20 * 4.0 * pi);
+      if (sigmacgs >= sp.sigcut) {
+        o.ncgs = 0.0;
+        o.tcgs = 1e9;
+      }
+      if (model == FL_KORAL3D_DISK && be >= 0.05f) {  // zero out the jet (Bernoulli cut)
+        o.tcgs = 10.;
+        o.bcgs = 0.;
+      }
+      o.ncgsnth = 0.;
     } break;
     case FL_IHARM: {  // convert_fluidvars_iharm (fluid.f90:995-1026)
       double mdot = pcG * sp.mbh * pcmsun / (pcc * pcc * pcc);

@@ -21,7 +21,7 @@ void build_camera(Camera &c, int standard, double mu0, double phi0, double a, do
 
 // ---- fluid snapshot on the host (reference module state of fluid_model_*.f90) --------------------------
 struct HostCell {
-  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela, pad1;
+  float rho, p, vrl, vtl, vpl, b0, br, bth, bph, u0, kela, be;
 };
 struct FluidHost {
   int model = 0, nx1 = 0, nx2 = 0, nx3 = 1;
@@ -29,6 +29,8 @@ struct FluidHost {
   float td_mbh = 0, td_mdot = 0, td_rin = 0, td_rout = 0;
   double hslope = 0, mks_smooth = 0, poly_xt = 0, poly_alpha = 0, startx1 = 0;  // iharm header (fluid_model_iharm.f90:427-470)
   int is_mmks = 0, eheat = 0;
+  float kh = 0, kr0 = 0, kaa = 0, kbb = 0, kpp = 0, x2mintrust = 0, x2maxtrust = 0;  // koral MKS3 grid (fluid_model_koral.f90)
+  int ktype = 0;
   std::vector<float> ax1, axr, ax2, axth, ax3;
   std::vector<HostCell> cells;
   std::vector<float> uvals, vvals, uv, tvals;

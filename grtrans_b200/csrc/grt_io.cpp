@@ -92,6 +92,9 @@ int fluid_model_id(const std::string &f) {
   if (f == "FFJET") return 13;
   if (f == "HARM3D") return 19;
   if (f == "IHARM") return 29;
+  if (f == "KORAL") return 22;
+  if (f == "KORAL3D") return 25;
+  if (f == "KORAL3D_DISK") return 26;
   return -1;
 }
 int emis_type_id(const std::string &e, int *neq) {
@@ -173,7 +176,7 @@ void ingest_cell(FluidHost &f, size_t i, float r, float x2, float th, double rho
   c.vrl = vrl; c.vtl = vtl; c.vpl = vpl;
   c.b0 = (float)b[0]; c.br = (float)b[1]; c.bth = (float)b[2]; c.bph = (float)b[3];
   c.u0 = (float)u[0];
-  c.kela = c.pad1 = 0.f;
+  c.kela = c.be = 0.f;
 }
 
 int load_ffjet(FluidHost &f, const std::string &path) {
@@ -214,7 +217,7 @@ int load_ffjet(FluidHost &f, const std::string &path) {
     HostCell &c = f.cells[i];
     c.rho = rho[i]; c.p = 0.f;  // p_arr is allocated but never filled/read by the reference
     c.vrl = vr[i]; c.vtl = vth[i]; c.vpl = vph[i];
-    c.b0 = b0[i]; c.br = br[i]; c.bth = bth[i]; c.bph = bph[i]; c.u0 = u0[i]; c.kela = c.pad1 = 0.f;
+    c.b0 = b0[i]; c.br = br[i]; c.bth = bth[i]; c.bph = bph[i]; c.u0 = u0[i]; c.kela = c.be = 0.f;
   }
   return GRT_OK;
 }
@@ -451,7 +454,7 @@ int load_iharm(FluidHost &f, const grt_args &a) {
     c.b0 = (float)b[0]; c.br = (float)b[1]; c.bth = (float)b[2]; c.bph = (float)b[3];
     c.u0 = (float)u[0];
     c.kela = (f.eheat == 1) ? d[13] : 0.f;
-    c.pad1 = 0.f;
+    c.be = 0.f;
   }
   for (int i = 0; i < f.nx3; i++) f.ax3[i] = data[(size_t)dlen * i + 2];
   for (int i = 0; i < f.nx2; i++) {
@@ -462,6 +465,82 @@ int load_iharm(FluidHost &f, const grt_args &a) {
     f.ax1[i] = data[(size_t)dlen * ((size_t)i * f.nx3 * f.nx2)];
     f.axr[i] = std::exp(f.ax1[i]);
   }
+  return GRT_OK;
+}
+
+// koral (2-D, fluid_model_koral.f90:296-488) and koral3d "shortfile" (fluid_model_koral3d.f90:359-632) inputs: a header
+// file of 10 / 11 numbers and an ASCII dump `<dfile>%03d` / `<dfile>%04d` (its own header line, then 38 / 23 columns per
+// cell, x2 fastest, then x1, then x3).  u^mu, b^mu are Boyer-Lindquist components already; rho, b are scaled by scalefac.
+int load_koral(FluidHost &f, const grt_args &a) {
+  const bool d3 = f.model != 22;
+  if (a.fnt > 1) return GRT_ERR_BAD_ARG;
+  std::ifstream hf(a.fhfile);
+  if (!hf) return GRT_ERR_IO;
+  const int nhead = d3 ? 11 : 10;
+  std::vector<double> header(nhead);
+  for (int i = 0; i < nhead; i++)
+    if (!(hf >> header[i])) return GRT_ERR_IO;
+  const int o = d3 ? 1 : 0;
+  f.nx1 = (int)header[1]; f.nx2 = (int)header[2]; f.nx3 = d3 ? (int)header[3] : 1;
+  f.asim = (float)header[3 + o];
+  f.kr0 = (float)header[5 + o]; f.kh = (float)header[6 + o]; f.kaa = (float)header[7 + o]; f.kbb = (float)header[8 + o];
+  f.kpp = (float)header[9 + o];
+  f.ktype = (f.model == 26) ? 1 : 0;
+  if (f.nx1 < 2 || f.nx2 < 8 || (d3 && f.nx3 < 2)) return GRT_ERR_IO;
+  if (std::fabs(f.asim - (float)a.spin) > 1e-4f) return GRT_ERR_BAD_ARG;
+  char append[16];
+  snprintf(append, sizeof append, d3 ? "%04d" : "%03d", a.findf);
+  std::ifstream df(std::string(a.fdfile) + append);
+  if (!df) return GRT_ERR_IO;
+  double tmp;
+  for (int i = 0; i < nhead; i++)
+    if (!(df >> tmp)) return GRT_ERR_IO;
+  const size_t n = (size_t)f.nx1 * f.nx2 * f.nx3;
+  const int dlen = d3 ? 23 : 38, rhopos = 10, vpos = 12, bpos = d3 ? 16 : 25, ppos = d3 ? 21 : 33, gridpos = 4, bepos = 22;
+  const double scalefac = a.fscalefac, sq = std::sqrt(scalefac);
+  std::vector<double> row(dlen);
+  std::vector<float> x1(n), x2(n), x3(n);
+  f.cells.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    for (int c = 0; c < dlen; c++)
+      if (!(df >> row[c])) return GRT_ERR_IO;
+    x1[i] = (float)row[gridpos - 1]; x2[i] = (float)row[gridpos];
+    float r, th;
+    if (d3) {
+      x3[i] = (float)row[gridpos + 1]; r = (float)row[gridpos + 2]; th = (float)row[gridpos + 3];
+    } else {
+      r = (float)row[gridpos + 1]; th = (float)row[gridpos + 2];
+    }
+    const double *u = &row[vpos - 1], *b = &row[bpos - 1];
+    float vr = (float)(u[1] / u[0]), vt = (float)(u[2] / u[0]), om = (float)(u[3] / u[0]);
+    float aa = f.asim, mu = std::cos(th);  // lnrf_frame_real (kerr.f90:427-449)
+    float D = r * r - 2.f * r + aa * aa;
+    float AR = (r * r + aa * aa) * (r * r + aa * aa) - aa * aa * D * (1.f - mu * mu);
+    float RHO = r * r + aa * aa * mu * mu;
+    float ENU = std::sqrt(D * RHO / AR), EMU1 = std::sqrt(RHO / D), EMU2 = std::sqrt(RHO);
+    float EPSI = std::sqrt(1.f - mu * mu) * std::sqrt(AR / RHO), OM = 2.f * aa * r / AR;
+    float vrl = EMU1 / ENU * vr, vtl = EMU2 / ENU * vt, vpl = EPSI / ENU * (om - OM);
+    if (!((double)D > 0.0)) vrl = vtl = vpl = 0.f;
+    HostCell &c = f.cells[i];
+    c.rho = (float)(row[rhopos - 1] * scalefac);
+    c.p = (float)row[ppos - 1];
+    c.be = d3 ? (float)row[bepos - 1] : 0.f;
+    c.b0 = (float)(b[0] * sq); c.br = (float)(b[1] * sq); c.bth = (float)(b[2] * sq); c.bph = (float)(b[3] * sq);
+    c.u0 = (float)u[0];
+    c.vrl = vrl; c.vtl = vtl; c.vpl = vpl;
+    c.kela = 0.f;
+  }
+  f.ax1.resize(f.nx1); f.axr.resize(f.nx1); f.ax2.resize(f.nx2); f.axth.assign(f.nx2, 0.f); f.ax3.assign(std::max(f.nx3, 2), 0.f);
+  for (int i = 0; i < f.nx2; i++) f.ax2[i] = x2[i];
+  for (int i = 0; i < f.nx1; i++) {
+    f.ax1[i] = x1[(size_t)i * f.nx2];
+    f.axr[i] = f.kr0 + std::exp(f.ax1[i]);
+  }
+  if (d3)
+    for (int i = 0; i < f.nx3; i++) f.ax3[i] = x3[(size_t)i * f.nx2 * f.nx1];
+  const int minpolecell = 4;
+  f.x2mintrust = f.ax2[minpolecell - 1];
+  f.x2maxtrust = f.ax2[f.nx2 - (minpolecell - 1) - 1];
   return GRT_OK;
 }
 
@@ -490,6 +569,9 @@ int load_fluid(FluidHost &f, const grt_args &a) {
     case 13: return load_ffjet(f, a.fdfile);
     case 19: return load_harm3d(f, a);
     case 29: return load_iharm(f, a);
+    case 22:
+    case 25:
+    case 26: return load_koral(f, a);
     default: return GRT_ERR_BAD_ARG;
   }
 }

@@ -104,7 +104,7 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
   size_t dst = (size_t)ray * maxpts + slot;
   for (int mm = 0; mm < A.nparams; mm++) {
     CgsVars cg;
-    to_cgs(A.F.model, A.sp[mm], fs.rho, fs.p, fs.bmag, fs.kela, A.F.gam, cg);
+    to_cgs(A.F.model, A.sp[mm], fs.rho, fs.p, fs.bmag, fs.kela, fs.be, A.F.gam, cg);
     double *q = rec + ((size_t)mm * nrays * maxpts + dst) * GRT_NREC;
     double o[GRT_NREC];
     for (int i = 0; i < GRT_NREC; i++) o[i] = 0.0;

@@ -24,7 +24,7 @@ static RunArgs to_run(const grt_args *a) {
   r.sigcut = a->sigcut; r.ftscl = a->ftscl; r.frscl = a->frscl;
   for (int i = 0; i < 7; i++) r.coefindx[i] = a->epcoefindx[i];
   r.fargs.dfile = a->fdfile; r.fargs.hfile = a->fhfile; r.fargs.gfile = a->fgfile; r.fargs.nt = a->fnt;
-  r.fargs.indf = a->findf; r.fargs.mdot = a->fmdot; r.fargs.mbh = a->mbh; r.fargs.rin = a->frin; r.fargs.rout = a->frout;
+  r.fargs.indf = a->findf; r.fargs.mdot = a->fmdot; r.fargs.mbh = a->mbh; r.fargs.rin = a->frin; r.fargs.rout = a->frout; r.fargs.scalefac = a->fscalefac;
   return r;
 }
 

@@ -728,6 +728,188 @@ static bool load_iharm(FluidData &fd, const FluidArgs &fa, double a) {
   return true;
 }
 
+
+// ------------------------------------------------------------------ KORAL (2-D) and KORAL3D
+// MKS3 coordinate maps (fluid_model_koral.f90:62-80; real(4) arguments, promoted by the real(8) pi as written)
+static float koral_x2_of_theta(float th, float r, float h, float a, float b, float p) {
+  float rp = std::pow(r, p);
+  double num = std::atan(std::tan((double)(0.5f * h) * pi) * (1. - (double)(2.f * th) / pi));
+  float den = (b - a) * std::pow(2.f, p) + (a - 0.5f) * rp;
+  return (float)(0.5 * (1. + ((double)rp / ((double)h * pi)) * (num / (double)den)));
+}
+static float koral_theta_of_x2(float x2, float r, float h, float a, float b, float p) {
+  float inner = -0.5f + x2 + (1.f - 2.f * x2) * (a + std::pow(2.f, p) * (b - a) / std::pow(r, p));
+  return (float)(0.5 * pi * (1. + std::tan((double)h * pi * (double)inner) / std::tan((double)(0.5f * h) * pi)));
+}
+
+// koral_vals (fluid_model_koral.f90:84-286) / koral3d_vals (fluid_model_koral3d.f90:83-346); nt = 1
+static void koral_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) {
+  const bool d3 = fd.model != F_KORAL;
+  float a = (float)g.a;
+  int nx1 = fd.nx1, nx2 = fd.nx2, nx3 = d3 ? fd.nx3 : 1;
+  std::vector<float> uniqx1(nx1 + 1), uniqr(nx1 + 1), uniqx2(nx2 + 1), uniqx3(nx3 + 1);
+  for (int i = 1; i <= nx2; i++) uniqx2[i] = fd.x2_arr[i - 1];
+  for (int i = 1; i <= nx1; i++) {
+    uniqx1[i] = fd.x1_arr[(size_t)(i - 1) * nx2];
+    uniqr[i] = fd.kr0 + std::exp(uniqx1[i]);
+  }
+  if (d3)
+    for (int i = 1; i <= nx3; i++) uniqx3[i] = fd.x3_arr[(size_t)(i - 1) * nx2 * nx1];
+  float rh = 1.f + std::sqrt(1.f - std::pow(a, 2.f));
+  float x2mintrust = uniqx2[fd.minpolecell], x2maxtrust = uniqx2[nx2 - (fd.minpolecell - 1)];
+  float thmintrust = 0.f, thmaxtrust = (float)pi;
+  if (fd.ktype == 1) {
+    thmintrust = 0.25f;
+    thmaxtrust = (float)(pi - 0.25);
+  }
+  for (int i = 0; i < g.npts; i++) {
+    float theta = (float)g.x[i].d[2];
+    float zr = (float)g.x[i].d[1];
+    float x1 = (float)std::log((double)zr - (double)fd.kr0);
+    float x2 = koral_x2_of_theta(theta, zr, fd.kh, fd.kaa, fd.kbb, fd.kpp);
+    int lx1 = (int)std::floor((x1 - uniqx1[1]) / (uniqx1[nx1] - uniqx1[1]) * (float)(nx1 - 1)) + 1;
+    int ux1 = lx1 + 1;
+    lx1 = (lx1 >= 1) ? lx1 : 1;
+    ux1 = (ux1 <= nx1) ? ux1 : nx1;
+    lx1 = std::min(lx1, nx1);  // guard (the reference reads uniqr(lx1) out of bounds beyond the outer edge)
+    ux1 = std::max(ux1, 1);
+    int lx2 = (int)std::floor((x2 - uniqx2[1]) / (uniqx2[nx2] - uniqx2[1]) * (float)(nx2 - 1)) + 1;
+    int ux2 = lx2 + 1;
+    lx2 = (lx2 >= 1) ? lx2 : 1;
+    ux2 = (ux2 <= nx2) ? ux2 : nx2;
+    lx2 = std::min(lx2, nx2);  // guard
+    ux2 = std::max(ux2, 1);
+    float pd = 0.f;
+    int lx3 = 1, ux3 = 1;
+    if (d3) {
+      float zphi = (float)g.x[i].d[3];
+      zphi = (float)std::fmod((double)zphi, 2. * pi);
+      if (zphi < 0.f) zphi = (float)((double)zphi + 2. * pi);
+      if ((double)zphi > pi) zphi = (float)((double)zphi - 2. * pi);
+      float x3 = zphi;
+      lx3 = (int)std::floor((x3 - uniqx3[1]) / (uniqx3[nx3] - uniqx3[1]) * (float)(nx3 - 1)) + 1;
+      ux3 = lx3 + 1;
+      int lx3s = std::min(std::max(lx3, 1), nx3);
+      float minph = uniqx3[lx3s];
+      ux3 = (ux3 <= nx3) ? ux3 : 1;
+      if (lx3 < 1) {
+        lx3 = nx3;
+        minph = (float)((double)uniqx3[lx3] - 2. * pi);
+      }
+      lx3 = std::min(lx3, nx3);  // guard
+      pd = (zphi - minph) / (uniqx3[2] - uniqx3[1]);
+    }
+    float rd = (zr - uniqr[lx1]) / (uniqr[ux1] - uniqr[lx1]);
+    double pfac = 1.0, nfac = 1.0;
+    if (uniqr[lx1] <= rh || lx1 == 1) {
+      rd = 1.f;
+      if (d3) {
+        pfac = 1e-3;
+        nfac = 1e-3;
+      }
+    }
+    float thl = koral_theta_of_x2(uniqx2[lx2], uniqr[lx1], fd.kh, fd.kaa, fd.kbb, fd.kpp);
+    float thu = koral_theta_of_x2(uniqx2[ux2], uniqr[lx1], fd.kh, fd.kaa, fd.kbb, fd.kpp);
+    float thone = koral_theta_of_x2(uniqx2[1], uniqr[lx1], fd.kh, fd.kaa, fd.kbb, fd.kpp);
+    float td = (ux2 != lx2) ? std::fabs((theta - thl) / (thu - thl)) : std::fabs((theta - thl) / thone);
+    // x2 fastest, then x1, then x3
+    size_t x2l = lx2 - 1, x2u = ux2 - 1, x1l = (size_t)(lx1 - 1) * nx2, x1u = (size_t)(ux1 - 1) * nx2;
+    size_t x3l = (size_t)(lx3 - 1) * nx2 * nx1, x3u = (size_t)(ux3 - 1) * nx2 * nx1;
+    size_t idx[16] = {x1l + x2l + x3l, x1l + x2u + x3l, x1u + x2l + x3l, x1u + x2u + x3l,
+                      x1l + x2l + x3u, x1l + x2u + x3u, x1u + x2l + x3u, x1u + x2u + x3u};
+    for (int q = 0; q < 8; q++) idx[8 + q] = idx[q];
+    auto gat = [&](const std::vector<float> &arr) {
+      float v[16];
+      if (d3) {
+        for (int q = 0; q < 16; q++) v[q] = arr[idx[q]];
+        return quadlin(v, 0.f, pd, rd, td);
+      }
+      for (int q = 0; q < 4; q++) v[q] = v[4 + q] = arr[idx[q]];
+      return trilin(v, 0.f, rd, td);
+    };
+    bool in = x1 > uniqx1[1];
+    bool trust = (x2 > x2mintrust) && (x2 < x2maxtrust);
+    if (d3 && fd.ktype == 1) trust = trust && (theta > thmintrust) && (theta < thmaxtrust);
+    bool ok = in && trust;
+    FluidPt &p = f[i];
+    // (the reference applies nfac/pfac between the two merges; a masked value is 0 (rho) or pfac (p) either way)
+    p.rho = (float)((double)(in ? gat(fd.rho_arr) : 0.f) * nfac);
+    p.p = (float)((double)(in ? gat(fd.p_arr) : 1.f) * pfac);
+    if (!trust) {
+      p.rho = 0.f;
+      p.p = 1.f;
+    }
+    p.be = (d3 && ok) ? gat(fd.be_arr) : 0.f;
+    float vrl0 = ok ? gat(fd.vrl_arr) : 0.f;
+    float vtl0 = ok ? gat(fd.vtl_arr) : 1.f;
+    p.b[0] = ok ? gat(fd.b0_arr) : 1.f;
+    p.b[1] = ok ? gat(fd.br_arr) : 1.f;
+    p.b[2] = ok ? gat(fd.bth_arr) : 1.f;
+    p.b[3] = ok ? gat(fd.bph_arr) : 1.f;
+    p.u[0] = ok ? (double)gat(fd.u0_arr) : 1.0;
+    float vpl0 = ok ? gat(fd.vpl_arr) : 0.f;
+    finish_grid_point(p, zr, (float)g.x[i].d[2], a, vrl0, vtl0, vpl0, 1.0);
+  }
+}
+
+// read_koral_data_header / read_koral_data_file / load_koral_data (fluid_model_koral.f90:296-488) and the koral3d
+// "shortfile" variants (fluid_model_koral3d.f90:359-632): ASCII, list-directed
+static bool load_koral(FluidData &fd, const FluidArgs &fa, double a) {
+  const bool d3 = fd.model != F_KORAL;
+  std::ifstream hf(fa.hfile);
+  if (!hf) return false;
+  int nhead = d3 ? 11 : 10;
+  std::vector<double> header(nhead);
+  for (int i = 0; i < nhead; i++)
+    if (!(hf >> header[i])) return false;
+  int o = d3 ? 1 : 0;
+  fd.nx1 = (int)header[1]; fd.nx2 = (int)header[2]; fd.nx3 = d3 ? (int)header[3] : 1;
+  fd.asim = (float)header[3 + o];
+  fd.kr0 = (float)header[5 + o]; fd.kh = (float)header[6 + o]; fd.kaa = (float)header[7 + o]; fd.kbb = (float)header[8 + o];
+  fd.kpp = (float)header[9 + o];
+  fd.scalefac = fa.scalefac;
+  if (std::fabs(fd.asim - (float)a) > 1e-4f) return false;
+  char append[16];
+  snprintf(append, sizeof append, d3 ? "%04d" : "%03d", fa.indf);
+  std::ifstream df(fa.dfile + append);
+  if (!df) return false;
+  double tmp;
+  for (int i = 0; i < nhead; i++)
+    if (!(df >> tmp)) return false;
+  size_t n = (size_t)fd.nx1 * fd.nx2 * fd.nx3;
+  int dlen = d3 ? 23 : 38;
+  int rhopos = 10, vpos = 12, bpos = d3 ? 16 : 25, ppos = d3 ? 21 : 33, gridpos = 4, bepos = 22;
+  fd.x1_arr.resize(n); fd.x2_arr.resize(n); fd.x3_arr.resize(n); fd.r_arr.resize(n); fd.th_arr.resize(n); fd.ph_arr.resize(n);
+  fd.rho_arr.resize(n); fd.p_arr.resize(n); fd.u0_arr.resize(n); fd.vrl_arr.resize(n); fd.vtl_arr.resize(n);
+  fd.vpl_arr.resize(n); fd.b0_arr.resize(n); fd.br_arr.resize(n); fd.bth_arr.resize(n); fd.bph_arr.resize(n);
+  fd.be_arr.assign(n, 0.f);
+  std::vector<double> row(dlen);
+  double sq = std::sqrt(fd.scalefac);
+  for (size_t i = 0; i < n; i++) {
+    for (int c = 0; c < dlen; c++)
+      if (!(df >> row[c])) return false;
+    fd.x1_arr[i] = (float)row[gridpos - 1]; fd.x2_arr[i] = (float)row[gridpos];
+    if (d3) {
+      fd.x3_arr[i] = (float)row[gridpos + 1]; fd.r_arr[i] = (float)row[gridpos + 2]; fd.th_arr[i] = (float)row[gridpos + 3];
+      fd.ph_arr[i] = (float)row[gridpos + 4];
+    } else {
+      fd.r_arr[i] = (float)row[gridpos + 1]; fd.th_arr[i] = (float)row[gridpos + 2];
+    }
+    const double *u = &row[vpos - 1], *b = &row[bpos - 1];
+    float vrl, vtl, vpl;
+    lnrf_frame_real((float)(u[1] / u[0]), (float)(u[2] / u[0]), (float)(u[3] / u[0]), fd.r_arr[i], fd.asim, fd.th_arr[i], vrl,
+                    vtl, vpl);
+    fd.rho_arr[i] = (float)(row[rhopos - 1] * fd.scalefac);
+    fd.p_arr[i] = (float)row[ppos - 1];  // (electron temperature straight from koral)
+    if (d3) fd.be_arr[i] = (float)row[bepos - 1];
+    fd.b0_arr[i] = (float)(b[0] * sq); fd.br_arr[i] = (float)(b[1] * sq); fd.bth_arr[i] = (float)(b[2] * sq);
+    fd.bph_arr[i] = (float)(b[3] * sq);
+    fd.u0_arr[i] = (float)u[0];
+    fd.vrl_arr[i] = vrl; fd.vtl_arr[i] = vtl; fd.vpl_arr[i] = vpl;
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------ HARM data ingestion
 // umksh2uks + uks2ubl + lnrf_frame (fluid_model_harm.f90:73-98,380-386,468-485; kerr.f90:131-144).
 // Inputs are per-cell MKS contravariant components as the dump stores them.  For the 3-D model
@@ -899,6 +1081,10 @@ bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const F
   } else if (fname == "IHARM") {
     fd.model = F_IHARM;
     fd.ok = load_iharm(fd, fa, a);
+  } else if (fname == "KORAL" || fname == "KORAL3D" || fname == "KORAL3D_DISK") {
+    fd.model = (fname == "KORAL") ? F_KORAL : (fname == "KORAL3D" ? F_KORAL3D : F_KORAL3D_DISK);
+    fd.ktype = (fname == "KORAL3D_DISK") ? 1 : 0;
+    fd.ok = load_koral(fd, fa, a);
   } else {
     fd.model = F_DUMMY;
   }
@@ -915,6 +1101,9 @@ void get_fluid_vars(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f) 
     case F_HARM: harm_vals(fd, g, f); break;
     case F_HARM3D: harm3d_vals(fd, g, f); break;
     case F_IHARM: iharm_vals(fd, g, f); break;
+    case F_KORAL:
+    case F_KORAL3D:
+    case F_KORAL3D_DISK: koral_vals(fd, g, f); break;
     default: break;
   }
 }
@@ -983,6 +1172,35 @@ void convert_fluid_vars(const FluidData &fd, const std::vector<FluidPt> &f, cons
           ncgs[i] = 0.0;
           tcgs[i] = 1e9;
         }
+      } break;
+      case F_KORAL:
+      case F_KORAL3D:
+      case F_KORAL3D_DISK: {  // convert_fluidvars_koral (fluid.f90:1075-1162); quantities are already cgs
+        double rhocgs = (double)p.rho;
+        ncgs[i] = rhocgs / pc::mp;
+        bcgs[i] = (double)p.bmag * std::sqrt(4 * pi);
+        bcgs[i] = bcgs[i] * std::sqrt(sp.nfac);
+        ncgs[i] = ncgs[i] * sp.nfac;
+        rhocgs = rhocgs * sp.nfac;
+        if (sp.gminval >= 1.0) {  // charles_e(rho, p+Be, 2p+Be, bmag, 1, 1, gmin): p = T_e, Be = T_p here (fluid.f90:845-868)
+          float pp = p.p + p.be, uu = 2.f * p.p + p.be;
+          double beta = 2.0 * (double)p.rho * pc::k * (double)pp / pc::mp / (double)(p.bmag * p.bmag);
+          double b2 = beta * beta;
+          double trat = ((double)p.bmag > 0.0) ? sp.gminval * b2 / (1.0 + b2) + 1.0 / (1.0 + b2) : sp.gminval;
+          tcgs[i] = (double)uu / (2.0 + trat);
+        } else if (sp.gminval < 0.0) {
+          tcgs[i] = (double)p.p;
+        }
+        double sigmacgs = (bcgs[i] * bcgs[i]) / (rhocgs * 8.988e20 * 4.0 * pi);
+        if (sigmacgs >= sp.sigcut) {
+          ncgs[i] = 0.0;
+          tcgs[i] = 1e9;
+        }
+        if (fd.ktype == 1 && p.be >= 0.05f) {  // zero out the jet (Bernoulli cut)
+          tcgs[i] = 10.;
+          bcgs[i] = 0.;
+        }
+        ncgsnth[i] = 0.;
       } break;
       case F_IHARM: {  // convert_fluidvars_iharm (fluid.f90:995-1026)
         double mdot = pc::G * sp.mbh * pc::msun / (pc::c * pc::c * pc::c);

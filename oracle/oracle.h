@@ -90,12 +90,12 @@ void comoving_ortho(double r, double th, double a, double alpha, double beta, do
 
 // ---------------------------------------------------------------------------------------------
 // fluid models
-enum FluidModel { F_DUMMY = 0, F_SPHACC = 1, F_THINDISK = 2, F_HARM = 12, F_FFJET = 13, F_HARM3D = 19, F_IHARM = 29 };
+enum FluidModel { F_DUMMY = 0, F_SPHACC = 1, F_THINDISK = 2, F_HARM = 12, F_FFJET = 13, F_HARM3D = 19, F_KORAL = 22, F_KORAL3D = 25, F_KORAL3D_DISK = 26, F_IHARM = 29 };
 
 struct FluidArgs {  // subset of fluid.f90:fluid_args that the supported models read
   std::string dfile, hfile, gfile;
   int nt = 1, indf = 0;
-  double mdot = 0.1, mbh = 10., rin = -1., rout = 1e8;
+  double mdot = 0.1, mbh = 10., rin = -1., rout = 1e8, scalefac = 1.0;
 };
 
 struct FluidData {  // module-level state of fluid_model_{thindisk,sphacc,ffjet,harm,harm3d}.f90
@@ -113,11 +113,16 @@ struct FluidData {  // module-level state of fluid_model_{thindisk,sphacc,ffjet,
   std::vector<float> kela_arr;
   double hslope = 0, mks_smooth = 0, poly_xt = 0, poly_alpha = 0, startx1 = 0;
   int is_mmks = 0, eheat = 0;
+  // koral / koral3d (fluid_model_koral.f90:11-29): MKS3 grid parameters, Bernoulli parameter, density scale factor
+  float kh = 0, kr0 = 0, kaa = 0, kbb = 0, kpp = 0;
+  double scalefac = 1.0;
+  int ktype = 0, minpolecell = 4;
+  std::vector<float> be_arr;
   bool ok = true;
 };
 
 struct FluidPt {  // one entry of fluid.f90:type fluid
-  float rho = 0, p = 0, bmag = 0, kela = 0;
+  float rho = 0, p = 0, bmag = 0, kela = 0, be = 0;
   double u[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
 };
 

@@ -92,6 +92,22 @@ def cfg_iharm(n=40, nup=100, nfreq=4, iname='delo', mmks=1, **kw):
     return d
 
 
+def cfg_koral(n=40, nup=100, nfreq=4, iname='delo', threed=True, fname=None, **kw):
+    """KORAL (2-D) / KORAL3D / KORAL3D_DISK on a synthetic MKS3 dump.  gmin < 0: T_e straight from the dump; gmin >= 1:
+    R-beta split of T_p + T_e (charles_e)."""
+    import make_snapshot as ms
+    os.makedirs(SNAPDIR, exist_ok=True)
+    prefix = os.path.join(SNAPDIR, "koral%s_" % ("3d" if threed else "2d"))
+    if not os.path.exists(prefix + ("0040" if threed else "040")):
+        ms.write_koral(prefix, indf=40, threed=threed)
+    d = dict(fname=fname or ('KORAL3D' if threed else 'KORAL'), ename='POLSYNCHTH', nvals=4, iname=iname, spin=.9375,
+             standard=1, nn=[n, n, nup], uout=.04, mbh=4e6, nmu=1, mumin=.6428, mumax=.6428,
+             gridvals=[-13., 13., -13., 13.], nfreq=nfreq, fmin=1e11, fmax=1e13, gmin=-1., ntscl=1., nrscl=1.,
+             fdfile=prefix, fhfile=prefix + "header.txt", findf=40, fnt=1, fscalefac=1.)
+    d.update(kw)
+    return d
+
+
 def image_errors(got, ref):
     """got/ref: ivals[nvals,npix,ncams].  Returns (max rel dI over pixels with I > 1e-4 Imax per camera, flux error,
     max |dQUV|/Imax, nan masks equal)."""

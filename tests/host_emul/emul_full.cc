@@ -28,6 +28,8 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
   F.td_mbh = fh.td_mbh; F.td_mdot = fh.td_mdot; F.td_rin = fh.td_rin; F.td_rout = fh.td_rout;
   F.hslope = fh.hslope; F.mks_smooth = fh.mks_smooth; F.poly_xt = fh.poly_xt; F.poly_alpha = fh.poly_alpha;
   F.startx1 = fh.startx1; F.is_mmks = fh.is_mmks; F.eheat = fh.eheat; F.gam = fh.gam;
+  F.kh = fh.kh; F.kr0 = fh.kr0; F.kaa = fh.kaa; F.kbb = fh.kbb; F.kpp = fh.kpp; F.ktype = fh.ktype;
+  F.x2mintrust = fh.x2mintrust; F.x2maxtrust = fh.x2maxtrust;
   F.ax1 = fh.ax1.data(); F.axr = fh.axr.data(); F.ax2 = fh.ax2.data(); F.axth = fh.axth.data(); F.ax3 = fh.ax3.data();
   F.cells = reinterpret_cast<const Cell *>(fh.cells.data());
   F.uvals = fh.uvals.data(); F.vvals = fh.vvals.data(); F.uv = fh.uv.data(); F.tvals = fh.tvals.data();

@@ -81,7 +81,7 @@ def test_camera_constants_bit_exact():
             assert np.array_equal(outs[0][4], outs[1][4])
 
 
-@pytest.mark.parametrize("cfg", ["sphacc", "ffjet", "harm", "harm3d", "thindisk", "iharm"])
+@pytest.mark.parametrize("cfg", ["sphacc", "ffjet", "harm", "harm3d", "thindisk", "iharm", "koral"])
 def test_fluid_and_frame_stage(cfg):
     kw = getattr(cases, "cfg_" + cfg)(n=30)
     a = args_from_kwargs(**kw)
@@ -108,11 +108,13 @@ def test_fluid_and_frame_stage(cfg):
     for k in ['ncgs', 'ncgsnth', 'bcgs', 'tcgs']:
         den = np.nanmax(np.abs(d[k])) + 1e-300
         assert np.nanmax(np.abs(g[k] - d[k])) / den < 5e-6, k
-    if cfg in ("harm", "harm3d", "ffjet", "iharm"):
+    if cfg in ("harm", "harm3d", "ffjet", "iharm", "koral"):
         # reference's fluid invariants (test_harm.f90:68-73, unit_tests_public.py:38-51): u.u = -1, u.b small
         import scipy  # noqa: F401
         r = g['r']; th = g['th']
         m = (np.arange(g['cap'])[None, :] < g['npts'][:, None]) & (r > 2.5)
+        if cfg == "koral":      # the cells next to the poles are replaced by fill values (not a normalised 4-velocity)
+            m &= (th > 0.9) & (th < np.pi - 0.9) & (r < 35.)
         aa = a.spin
         cth, sth = np.cos(th), np.sin(th)
         delta = r * r - 2 * r + aa * aa; rho2 = r * r + aa * aa * cth * cth
@@ -121,7 +123,7 @@ def test_fluid_and_frame_stage(cfg):
         grr = rho2 / delta; ghh = rho2; gpp = sigma / rho2 * sth * sth
         u = g['u']
         udotu = gtt * u[..., 0] ** 2 + 2 * gtp * u[..., 0] * u[..., 3] + grr * u[..., 1] ** 2 + ghh * u[..., 2] ** 2 + gpp * u[..., 3] ** 2
-        assert np.max(np.abs(udotu[m] + 1)) < (1e-1 if cfg in ("ffjet", "iharm") else 1e-2)
+        assert np.max(np.abs(udotu[m] + 1)) < (1e-1 if cfg in ("ffjet", "iharm", "koral") else 1e-2)
 
 
 def test_emissivity_surfaces():
@@ -176,6 +178,9 @@ IMAGE_CASES = [
     ("harm3d", dict(n=50, nup=200, nfreq=4, iname='delo'), 1e-4),
     ("harm3d", dict(n=40, nup=100, nfreq=2, iname='delo', nmdot=3, mdotmin=1e19, mdotmax=1e21), 1e-4),
     ("harm3d_native", dict(n=40, nup=100, nfreq=3), 1e-4),                        # the reference's own harm3d file format
+    ("koral", dict(n=50, nup=200, nfreq=4, threed=True), 1e-4),                   # KORAL3D, T_e straight from the dump
+    ("koral", dict(n=40, nup=100, nfreq=3, threed=False), 1e-4),                  # KORAL (2-D)
+    ("koral", dict(n=40, nup=100, nfreq=3, threed=True, fname='KORAL3D_DISK', gmin=10.), 1e-4),  # Bernoulli cut, R-beta
     ("iharm", dict(n=50, nup=200, nfreq=4, mmks=1), 1e-4),                        # FMKS grid, R-beta electrons
     ("iharm", dict(n=50, nup=200, nfreq=4, mmks=0, gmin=-1.), 1e-4),              # MKS grid, electron-entropy T_e
     # (fmin=1e11: at 1e10 Hz nu << nu_c, the polsynchth fits give |j_V| > j_I, the transfer matrix has a growing mode and the

@@ -66,6 +66,9 @@ EMUL_CASES = [
     ("iharm", dict(n=24, nup=100, nfreq=3, mmks=1)),                   # FMKS grid, R-beta electrons (monika_e)
     ("iharm", dict(n=24, nup=100, nfreq=3, mmks=0, gmin=-1.)),         # MKS grid, electron-entropy T_e (ressler_e)
     ("iharm", dict(n=20, nup=100, nfreq=2, mmks=1, iname='formal', sigcut=0.5)),
+    ("koral", dict(n=24, nup=100, nfreq=3, threed=True)),                                  # KORAL3D, T_e from the dump
+    ("koral", dict(n=24, nup=100, nfreq=3, threed=False)),                                 # KORAL (2-D)
+    ("koral", dict(n=20, nup=100, nfreq=2, threed=True, fname='KORAL3D_DISK', gmin=10.)),  # Bernoulli cut + R-beta electrons
 ]
 
 
@@ -83,7 +86,8 @@ def test_kernel_bodies_match_oracle(emul, cfg, over):
 
 @pytest.mark.parametrize("cfg,over", [("ffjet", dict(n=40, nup=100)), ("sphacc", dict(n=30, nup=100)),
                                       ("harm", dict(n=24, nup=400)), ("thindisk", dict(n=50)),
-                                      ("iharm", dict(n=24, nup=100, mmks=1)), ("iharm", dict(n=24, nup=100, mmks=0))])
+                                      ("iharm", dict(n=24, nup=100, mmks=1)), ("iharm", dict(n=24, nup=100, mmks=0)),
+                                      ("koral", dict(n=24, nup=100, threed=True)), ("koral", dict(n=24, nup=100, threed=False))])
 def test_geodesic_points_match_oracle(emul, cfg, over):
     """Per-point geodesic + frame quantities of the kernel bodies against the oracle (same checks as the GPU tests)."""
     kw = getattr(cases, "cfg_" + cfg)(**over)

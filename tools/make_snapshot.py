@@ -213,6 +213,66 @@ def write_iharm(prefix, indf=40, eheat=1, **kw):
     return hpath, prefix
 
 
+def koral_arrays(threed=True, nx1=48, nx2=40, nx3=16, a=0.9375, h=0.7, r0=0.0, aa=0.0, bb=0.05, pp=2.0, rin=1.1, rout=40.0,
+                 seed=12345):
+    """KORAL MKS3 grid (fluid_model_koral.f90:62-80): x1 = log(r - r0), theta(x2, r), x3 = phi in (-pi, pi); BL vectors."""
+    dx1 = (np.log(rout - r0) - np.log(rin - r0)) / nx1
+    x1 = np.log(rin - r0) + (np.arange(nx1) + 0.5) * dx1
+    x2 = (np.arange(nx2) + 0.5) / nx2
+    x3 = -np.pi + (np.arange(nx3) + 0.5) * 2. * np.pi / nx3 if threed else np.zeros(1)
+    X3, X1, X2 = np.meshgrid(x3, x1, x2, indexing='ij')   # x2 fastest, then x1, then x3
+    r = r0 + np.exp(X1)
+    w = aa + 2. ** pp * (bb - aa) / r ** pp
+    th = 0.5 * np.pi * (1. + np.tan(h * np.pi * (-0.5 + X2 + (1. - 2. * X2) * w)) / np.tan(0.5 * h * np.pi))
+    rho, uu, u, b = _fluid(r, th, X3, a, seed, threed)
+
+    def ks2bl(v):
+        delta = r ** 2 - 2. * r + a ** 2
+        o = v.copy()
+        o[..., 0] = v[..., 0] - 2. * r / delta * v[..., 1]
+        o[..., 3] = v[..., 3] - a / delta * v[..., 1]
+        return o
+    te = 4e10 * (0.5 + np.exp(-((r - 8.) / 6.) ** 2)) * (1. + 0.3 * np.cos(th) ** 2)
+    be = -0.05 + 0.3 * np.cos(th) ** 4 * (1. - np.exp(-r / 10.))
+    return dict(nx1=nx1, nx2=nx2, nx3=(nx3 if threed else 1), a=a, h=h, r0=r0, aa=aa, bb=bb, pp=pp, x1=X1, x2=X2, x3=X3, r=r, th=th,
+                rho=1e-16 * rho, te=te, be=be, ucon=ks2bl(u), bcon=600. * ks2bl(b))
+
+
+def write_koral(prefix, indf=40, threed=True, **kw):
+    """ASCII dumps read by fluid_model_koral.f90:318-402 (38 columns) / fluid_model_koral3d.f90:397-514 ("shortfile", 23
+    columns): `<prefix>%03d` / `<prefix>%04d` and the header file `<prefix>header.txt`.  Returns (header path, prefix)."""
+    d = koral_arrays(threed=threed, **kw)
+    n = d['nx1'] * d['nx2'] * d['nx3']
+    dlen = 23 if threed else 38
+    rows = np.zeros((n, dlen))
+    rows[:, 3] = d['x1'].ravel(); rows[:, 4] = d['x2'].ravel()
+    if threed:
+        rows[:, 5] = d['x3'].ravel(); rows[:, 6] = d['r'].ravel(); rows[:, 7] = d['th'].ravel(); rows[:, 8] = d['x3'].ravel()
+        bpos, ppos = 15, 20
+        rows[:, 21] = d['be'].ravel()
+    else:
+        rows[:, 5] = d['r'].ravel(); rows[:, 6] = d['th'].ravel()
+        bpos, ppos = 24, 32
+    rows[:, 9] = d['rho'].ravel()
+    rows[:, 11:15] = d['ucon'].reshape(n, 4)
+    rows[:, bpos:bpos + 4] = d['bcon'].reshape(n, 4)
+    rows[:, ppos] = d['te'].ravel()
+    if threed:
+        hdr = [0.0, d['nx1'], d['nx2'], d['nx3'], d['a'], 0.0, d['r0'], d['h'], d['aa'], d['bb'], d['pp']]
+        path = "%s%04d" % (prefix, indf)
+    else:
+        hdr = [0.0, d['nx1'], d['nx2'], d['a'], 0.0, d['r0'], d['h'], d['aa'], d['bb'], d['pp']]
+        path = "%s%03d" % (prefix, indf)
+    line = " ".join("%.17g" % v for v in hdr) + "\n"
+    with open(path, 'w') as f:
+        f.write(line)
+        np.savetxt(f, rows, fmt="%.9e")
+    hpath = prefix + "header.txt"
+    with open(hpath, 'w') as f:
+        f.write(line)
+    return hpath, prefix
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) >= 3 and sys.argv[1] == "harm2d":

@@ -38,6 +38,8 @@ CONFIGS = [
      cases.cfg_harm(n=150, nup=400, nfreq=1, fmin=2.3e11, fmax=2.3e11, iname='delo'), (9001, 13500)),
     ("next-row IHARM (synthetic FMKS dump, R-beta electrons) POLSYNCHTH nn=[128,128,400] nfreq=8 nvals=4 delo",
      cases.cfg_iharm(n=128, nup=400, nfreq=8, mmks=1, fmin=1e11, fmax=1e13), (8001, 9280)),
+    ("next-row KORAL3D (synthetic MKS3 dump, T_e from the dump) POLSYNCHTH nn=[128,128,400] nfreq=8 nvals=4 delo",
+     cases.cfg_koral(n=128, nup=400, nfreq=8, threed=True), (8001, 9280)),
 ]
 
 
