@@ -43,7 +43,17 @@ def workload(nx, nfreq, snapdir, grid):
     n1, n2, n3 = grid
     path = os.path.join(snapdir, "h3d_%dx%dx%d.bin" % (n1, n2, n3))
     if not os.path.exists(path):
-        ms.write_harm3d(path, nx1=n1, nx2=n2, nx3=n3, rin=1.1, rout=50.0)
+        # one writer per node (local rank 0) writes to a private name and renames atomically; the other ranks wait
+        if int(os.environ.get("LOCAL_RANK", 0)) == 0:
+            tmp = "%s.tmp.%d" % (path, os.getpid())
+            ms.write_harm3d(tmp, nx1=n1, nx2=n2, nx3=n3, rin=1.1, rout=50.0)
+            os.replace(tmp, path)
+        else:
+            t0 = time.time()
+            while not os.path.exists(path):
+                if time.time() - t0 > 900:
+                    raise RuntimeError("timed out waiting for %s" % path)
+                time.sleep(0.5)
     kw = dict(fname='HARM3D', ename='POLSYNCHTH', nvals=4, iname='delo', spin=.9375, standard=1, nn=[nx, nx, 400], uout=.04,
               mbh=4e6, mdotmin=1e20, mdotmax=1e20, nmu=1, mumin=.6428, mumax=.6428, gridvals=[-13., 13., -13., 13.],
               nfreq=nfreq, fmin=1e10, fmax=1e13, muval=.25, gmin=1., fdfile=path)
@@ -176,6 +186,9 @@ def main():
     from grtrans_b200 import _lib, args_from_kwargs
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line: the box exports NCCL_DEBUG=VERSION, which prints a banner to stdout
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
