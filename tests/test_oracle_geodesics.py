@@ -122,3 +122,60 @@ def test_reference_invariants_along_rays():
         assert np.max(np.abs(kk[sel]) / scale[sel]) < 1e-6
         pol = d['s2xi'] ** 2 + d['c2xi'] ** 2
         assert np.nanmax(np.abs(pol[sel] - 1)) < 1e-6
+
+
+def _metric(r, th, a):
+    cth, sth = np.cos(th), np.sin(th)
+    delta = r * r - 2 * r + a * a; rho2 = r * r + a * a * cth * cth
+    sigma = (r * r + a * a) ** 2 - a * a * delta * sth * sth
+    return (-(delta - a * a * sth * sth) / rho2, -2 * a * r * sth * sth / rho2, rho2 / delta, rho2, sigma / rho2 * sth * sth)
+
+
+def _dot(g, x, y):
+    gtt, gtp, grr, ghh, gpp = g
+    return (gtt * x[..., 0] * y[..., 0] + gtp * (x[..., 0] * y[..., 3] + x[..., 3] * y[..., 0]) + grr * x[..., 1] * y[..., 1] +
+            ghh * x[..., 2] * y[..., 2] + gpp * x[..., 3] * y[..., 3])
+
+
+@pytest.mark.parametrize("cfg", ["harm3d", "ffjet", "sphacc"])
+def test_comoving_frame_redshift_and_angle(cfg):
+    """comoving_ortho (kerr.f90:586-730) builds an explicit tetrad; the same two scalars follow covariantly from the dumped
+    vectors: g = 1/(-k.u) and cos(angle) = k.b / ((-k.u) |b|), clamped to +-0.99 like the reference."""
+    kw = getattr(cases, "cfg_" + cfg)(n=20)
+    a_ = args_from_kwargs(**kw)
+    npix = a_.nn[0] * a_.nn[1]
+    d = orc.ray_dump(1, npix, _args=args_from_kwargs(**kw))
+    a = a_.spin
+    m = (np.arange(d['cap'])[None, :] < d['npts'][:, None]) & (d['status'][:, None] == 1) & (d['r'] > 1.2 * (1 + np.sqrt(1 - a * a)))
+    g = _metric(d['r'], d['th'], a)
+    k = np.stack([d['kt'], d['kr'], d['kth'], d['kph']], -1)
+    ku = _dot(g, k, d['u']); kb = _dot(g, k, d['b']); bb = _dot(g, d['b'], d['b']); uu = _dot(g, d['u'], d['u'])
+    sel = m & (np.abs(uu + 1) < 1e-3) & (bb > 0)          # points where the interpolated float32 u is a unit vector
+    assert sel.sum() > 1000
+    # float32 fluid vectors: agreement to the accuracy u.u = -1 holds
+    assert np.max(np.abs(d['rshift'][sel] * (-ku[sel]) - 1)) < 2e-3
+    # the projection into the fluid frame also involves u.b (zero only to float32 accuracy)
+    cosang = np.clip(kb[sel] / ((-ku[sel]) * np.sqrt(bb[sel])), -0.99, 0.99)
+    assert np.percentile(np.abs(np.cos(d['ang'][sel]) - cosang), 99) < 5e-3
+
+
+def test_thindisk_blackbody_image_closed_form():
+    """BASELINE config 1 (THINDISK, BB, npts = 1): I_nu = B_nu(T, nu/g) g^3 (grtrans_driver.f90:293-297) from the dumped disk
+    temperature and redshift, evaluated here in numpy with the reference's constants."""
+    kw = cases.cfg_thindisk(n=50, nfreq=6)
+    a_ = args_from_kwargs(**kw)
+    npix = a_.nn[0] * a_.nn[1]
+    out = orc.run(_args=args_from_kwargs(**kw))
+    d = orc.ray_dump(1, npix, _args=args_from_kwargs(**kw))
+    h, kb, c = 6.626e-27, 1.38e-16, 2.99792458e10
+    ok = (d['status'] == 1) & (d['npts'] == 1)
+    T = d['tcgs'][:, 0]; g = d['rshift'][:, 0]
+    for f, nu in enumerate(out['freqs']):
+        nuc = nu / g
+        with np.errstate(over='ignore', invalid='ignore', divide='ignore'):
+            B = 2 * h * nuc / c ** 2 * nuc * nuc / (np.exp(h * nuc / kb / T) - 1.0)
+        B = np.where(B == 0, np.finfo(float).eps, B)
+        I = np.where(ok, B * g ** 3, 0.0)
+        ref = out['ivals'][0, :, f]
+        w = ref > 1e-6 * ref.max()
+        assert np.max(np.abs(I[w] / ref[w] - 1)) < 2e-6       # float32 image
