@@ -57,3 +57,25 @@ def test_planck_limits():
     T, nu = 1e7, 1e18
     assert abs(L.orc_bnu(T, nu) / (2 * h * nu ** 3 / c2 / np.expm1(h * nu / k / T)) - 1) < 1e-12
     assert L.orc_bnu(1.0, 1e20) == np.finfo(float).eps   # underflow replaced by epsilon()
+
+
+def test_thermal_synchrotron_against_independent_fit():
+    """polsynchth (Dexter 2016 fits, polsynchemis.f90:700-863) against the independent fitting formula of Leung, Gammie &
+    Noble (2011, eq. 72) for the same quantity j_I(nu, n, B, Theta_e, theta): two different approximations of the exact
+    thermal synchrotron emissivity, so agreement is at the few-per-cent level -- a check of units, constants and
+    functional form that shares nothing with the reference's code.  Also: 0.55 < j_Q/j_I < 0.9."""
+    from scipy.special import kv
+    e, m, c, k = 4.8032e-10, 9.10938188e-28, 2.99792458e10, 1.38e-16
+    rng = np.random.RandomState(1)
+    n = 2000
+    thetae = 10 ** rng.uniform(0.5, 1.5, n); T = thetae * m * c * c / k
+    B = 10 ** rng.uniform(0, 2, n); th = rng.uniform(0.3, np.pi - 0.3, n); ne = 1e5 * np.ones(n)
+    nus = (2. / 9.) * e * B / (2 * np.pi * m * c) * thetae ** 2 * np.sin(th)
+    X = 10 ** rng.uniform(0, 3.5, n); nu = X * nus
+    j_leung = ne * np.sqrt(2) * np.pi * e * e * nus / (3 * kv(2, 1 / thetae) * c) * (X ** 0.5 + 2 ** (11. / 12.) * X ** (1. / 6.)) ** 2 * \
+        np.exp(-X ** (1. / 3.))
+    E = orc.polsynchth(nu, ne, B, T, th)
+    r = E[:, 0] / j_leung
+    assert 0.94 < r.min() and r.max() < 1.01, (r.min(), r.max())
+    frac = E[:, 1] / E[:, 0]
+    assert frac.min() > 0.5 and frac.max() < 0.92
