@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -463,8 +464,11 @@ extern "C" int grt_session_fetch(grt_session *s, float *image, int *ray_index) {
 namespace {
 struct ModuleData {
   bool allocated = false;
-  std::vector<double> ivals, ab, freqs;
-  std::vector<float> pixvals, pixloc;  // [ncams][npix][nv], [npix][2]
+  // ivals / pixvals are large (2 GB + 1 GB for 1024^2 x 64 cameras): plain uninitialised arrays filled by all host threads
+  std::unique_ptr<double[]> ivals;
+  std::unique_ptr<float[]> pixvals;  // [ncams][npix][nv]
+  std::vector<double> ab, freqs;
+  std::vector<float> pixloc;  // [npix][2]
   int nv = 0, npix = 0, ncams = 0, nx = 0, ny = 0;
   grt_args args;
 } g_mod;
@@ -481,38 +485,44 @@ extern "C" int grt_main(const grt_args *a) {
   grt_session *s = nullptr;
   int rc = grt_session_create(a, 0, 0, 1, &s);
   if (rc != GRT_OK) return rc;
-  rc = grt_session_launch(s);
+  // the image streams back tile by tile into pinned host memory while later tiles are computed
+  const float *img = nullptr;
+  rc = grt_session_launch_fetch(s, &img, nullptr);
   if (rc == GRT_OK) rc = grt_session_sync(s);
   if (rc != GRT_OK) {
     grt_session_destroy(s);
     return rc;
   }
   const int nv = s->nvals, npix = s->npix, ncams = s->ncams;
-  std::vector<float> img((size_t)ncams * s->nlocal * nv);
-  rc = grt_session_fetch(s, img.data(), nullptr);
-  if (rc != GRT_OK) {
-    grt_session_destroy(s);
-    return rc;
-  }
+  const long long nlocal = s->nlocal;
   ModuleData &M = g_mod;
   M.nv = nv; M.npix = npix; M.ncams = ncams; M.nx = a->nn[0]; M.ny = a->nn[1];
   M.args = *a;
-  M.pixvals.assign((size_t)ncams * npix * nv, 0.f);
+  const size_t total = (size_t)ncams * npix * nv;
+  M.pixvals.reset(new float[std::max<size_t>(total, 1)]);
+  M.ivals.reset(new double[std::max<size_t>(total, 1)]);
   M.pixloc.assign((size_t)npix * 2, 0.f);
-  for (int c = 0; c < ncams; c++)
-    for (long long q = 0; q < s->nlocal; q++) {
-      int pix = s->ray_index[q] - 1;
-      for (int k = 0; k < nv; k++) M.pixvals[((size_t)c * npix + pix) * nv + k] = img[((size_t)c * s->nlocal + q) * nv + k];
+  // one rank, one contiguous range i1..i2: local ray q is pixel first + q.  Pixels outside the range stay 0 like the
+  // reference's camera arrays; module array ivals(nv, npix, ncams) column-major == [cam][pix][nv] in C order
+  const long long first = nlocal ? (long long)s->ray_index[0] - 1 : 0;
+  float *pv = M.pixvals.get();
+  double *iv = M.ivals.get();
+#pragma omp parallel for schedule(static)
+  for (long long cp = 0; cp < (long long)ncams * npix; cp++) {
+    const long long c = cp / npix, pix = cp % npix, q = pix - first;
+    const bool in = q >= 0 && q < nlocal;
+    for (int k = 0; k < nv; k++) {
+      float v = in ? img[((size_t)c * nlocal + q) * nv + k] : 0.f;
+      pv[(size_t)cp * nv + k] = v;
+      iv[(size_t)cp * nv + k] = (double)v;
     }
+  }
   // ab(:,:) = dble(c(1)%pixloc): only pixels i1..i2 are ever saved (camera.f90:28-39)
-  for (long long q = 0; q < s->nlocal; q++) {
+  for (long long q = 0; q < nlocal; q++) {
     int pix = s->ray_index[q] - 1;
     M.pixloc[(size_t)pix * 2] = (float)s->cams[0].alpha[pix];
     M.pixloc[(size_t)pix * 2 + 1] = (float)s->cams[0].beta[pix];
   }
-  // module arrays: ivals(nv, npix, ncams) column-major == [cam][pix][nv] in C order
-  M.ivals.resize(M.pixvals.size());
-  for (size_t i = 0; i < M.pixvals.size(); i++) M.ivals[i] = (double)M.pixvals[i];
   M.ab.resize(M.pixloc.size());
   for (size_t i = 0; i < M.pixloc.size(); i++) M.ab[i] = (double)M.pixloc[i];
   M.freqs = s->freqs;
@@ -524,7 +534,7 @@ extern "C" int grt_main(const grt_args *a) {
 
 extern "C" int grt_get_ivals(const double **ivals, int dims[3]) {
   if (!g_mod.allocated) return GRT_ERR_STATE;
-  *ivals = g_mod.ivals.data();
+  *ivals = g_mod.ivals.get();
   dims[0] = g_mod.nv; dims[1] = g_mod.npix; dims[2] = g_mod.ncams;
   return GRT_OK;
 }
@@ -544,7 +554,7 @@ extern "C" int grt_get_freqs(const double **freqs, int *nfreq) {
 extern "C" int grt_write_output(const grt_args *a, const char *outfile) {
   if (!g_mod.allocated) return GRT_ERR_STATE;
   return grt_host::write_output(*a, outfile, g_mod.nx, g_mod.ny, g_mod.nv, g_mod.ncams, g_mod.pixloc.data(),
-                                g_mod.pixvals.data(), g_mod.freqs);
+                                g_mod.pixvals.get(), g_mod.freqs);
 }
 
 extern "C" int grt_read_inputs(const char *ifile, grt_args *a) { return grt_host::read_inputs_file(ifile, a); }

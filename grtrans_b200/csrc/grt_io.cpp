@@ -352,7 +352,9 @@ int load_harm3d(FluidHost &f, const grt_args &a) {
   fclose(fp);
   if (!ok) return GRT_ERR_IO;
   f.cells.resize(n);
-  for (size_t i = 0; i < n; i++) ingest_cell(f, i, g[3][i], g[1][i], g[4][i], rho[i], uu[i], &uc[4 * i], &bc[4 * i], true);
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; i++)
+    ingest_cell(f, (size_t)i, g[3][i], g[1][i], g[4][i], rho[i], uu[i], &uc[4 * i], &bc[4 * i], true);
   harm3d_axes(f, g[0], g[1], g[2]);
   return GRT_OK;
 }
