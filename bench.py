@@ -33,8 +33,11 @@ W_RT = 9.4e2    # per (pixel, point, freq): POLSYNCHTH emissivity + rotate/scale
 B_GATHER = 320  # bytes per (pixel, point): 8 corners x 10 fields x 4 B (3-D)
 B_RECORD = 160  # bytes per (pixel, point) read by the transfer kernel (one point record)
 # from the ncu --set full capture of one k_transfer launch at this configuration (profiles/r1_ncu_summary.md):
-NCU_TRANSFER = {"dram_bytes_per_launch": 3.824378e9 + 0.110865e9, "fp64_pipe_busy_pct": 66.3, "issue_active_pct": 65.9,
-                "launch": "65536-ray tile (32768 blocks x 128 threads)", "source": "profiles/r1_ncu_summary.md"}
+NCU_TRANSFER = {"dram_bytes_per_launch": 4.802363e9 + 0.223055e9, "fp64_pipe_busy_pct": 66.3, "issue_active_pct": 66.0,
+                "launch": "65536-ray tile (32768 blocks x 128 threads), 57.6 ms under ncu",
+                "other_kernels": {"k_geo_points": {"fp64_pipe_busy_pct": 49.2, "ms": 16.5},
+                                  "k_fluid_ortho": {"fp64_pipe_busy_pct": 32.8, "ms": 9.2, "dram_write_gb": 4.83}},
+                "source": "profiles/r1_ncu_summary.md"}
 
 
 def workload(nx, nfreq, snapdir, grid):
