@@ -10,7 +10,8 @@
 
 namespace grt {
 
-enum { EM_POLSYNCHTH = 2, EM_SYNCHPL = 3, EM_POLSYNCHPL = 4, EM_BB = 8, EM_BBPOL = 9, EM_SYNCHTHAV = 13 };
+enum { EM_POLSYNCHTH = 2, EM_SYNCHPL = 3, EM_POLSYNCHPL = 4, EM_BB = 8, EM_BBPOL = 9, EM_SYNCHTHAV = 13,
+       EM_HYBRIDTHPL = 20, EM_HYBRIDTH = 21, EM_HYBRIDPL = 22 };
 
 namespace pc {
 constexpr double h = 6.626e-27, k = 1.38e-16, c = 2.99792458e10, e = 4.8032e-10, G = 6.67e-8, m = 9.10938188e-28,

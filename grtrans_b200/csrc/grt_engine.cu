@@ -165,7 +165,7 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   const char *te = getenv("GRT_TILE");
   long long tile = te ? atoll(te) : 65536;
   // bound the per-tile record buffer to ~24 GB
-  long long per_ray = (long long)s->maxpts * (GRT_NREC * 8LL * s->nparams + 5 * 8 + 2);
+  long long per_ray = (long long)s->maxpts * (record_doubles(etype) * 8LL * s->nparams + 5 * 8 + 2);
   while (tile > 1024 && tile * per_ray > (24LL << 30)) tile /= 2;
   s->tile = (int)std::max<long long>(1, std::min<long long>(tile, std::max<long long>(s->nlocal, 1)));
   if (cudaStreamCreate(&s->stream) != cudaSuccess) {
@@ -202,7 +202,7 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   SCK(own(s, &s->d_meta, T));
   SCK(own(s, &s->pa.u, TP)); SCK(own(s, &s->pa.mu, TP)); SCK(own(s, &s->pa.dt, TP)); SCK(own(s, &s->pa.dphi, TP));
   SCK(own(s, &s->pa.lam, TP)); SCK(own(s, &s->pa.tpm, TP)); SCK(own(s, &s->pa.tpr, TP));
-  SCK(own(s, &s->d_rec, TP * GRT_NREC * s->nparams));
+  SCK(own(s, &s->d_rec, TP * record_doubles(etype) * s->nparams));
   SCK(own(s, &s->d_image, (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nvals));
   SCK(cudaMemset(s->d_image, 0, (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nvals * sizeof(float)));
   {

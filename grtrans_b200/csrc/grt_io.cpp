@@ -101,7 +101,8 @@ int emis_type_id(const std::string &e, int *neq) {
   struct {
     const char *n;
     int t, q;
-  } tab[] = {{"POLSYNCHTH", 2, 4}, {"SYNCHPL", 3, 1}, {"POLSYNCHPL", 4, 4}, {"BB", 8, 1}, {"BBPOL", 9, 4}, {"SYNCHTHAV", 13, 1}};
+  } tab[] = {{"POLSYNCHTH", 2, 4}, {"SYNCHPL", 3, 1}, {"POLSYNCHPL", 4, 4}, {"BB", 8, 1}, {"BBPOL", 9, 4}, {"SYNCHTHAV", 13, 1},
+             {"HYBRIDTHPL", 20, 4}, {"HYBRIDTH", 21, 4}, {"HYBRIDPL", 22, 4}};
   for (auto &x : tab)
     if (e == x.n) {
       *neq = x.q;

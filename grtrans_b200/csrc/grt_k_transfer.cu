@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(128, 4) k_transfer(const RayMeta *__restrict__
   double out[4] = {0, 0, 0, 0};
   if (m.status == 1 && m.npts > 0) {
     P.LBH = lbh_m[mm];
-    const double *rr = rec + ((size_t)mm * nrays * maxpts + (size_t)ray * maxpts) * GRT_NREC;
+    const double *rr = rec + ((size_t)mm * nrays * maxpts + (size_t)ray * maxpts) * record_doubles(ET);
     ray_transfer_t<ET, MODE>(P, rr, m.npts, freqs[f], out);
   }
   int cam = cam0 + mm * nfreq + f;

@@ -105,11 +105,19 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
   for (int mm = 0; mm < A.nparams; mm++) {
     CgsVars cg;
     to_cgs(A.F.model, A.sp[mm], fs.rho, fs.p, fs.bmag, fs.kela, fs.be, A.F.gam, cg);
-    double *q = rec + ((size_t)mm * nrays * maxpts + dst) * GRT_NREC;
-    double o[GRT_NREC];
-    for (int i = 0; i < GRT_NREC; i++) o[i] = 0.0;
+    const int nrec = record_doubles(A.etype);
+    double *q = rec + ((size_t)mm * nrays * maxpts + dst) * nrec;
+    double o[GRT_NREC_MAX];
+    for (int i = 0; i < GRT_NREC_MAX; i++) o[i] = 0.0;
     o[0] = lam; o[1] = oo.g; o[2] = oo.s2xi; o[3] = oo.c2xi;
     switch (A.etype) {
+      case EM_HYBRIDTHPL:
+      case EM_HYBRIDTH:
+      case EM_HYBRIDPL: {  // thermal data as below + the power-law population's point data
+        PlPoint Q;
+        pl_point<true>(cg.ncgsnth, cg.bcgs, oo.ang, oo.g, Q);
+        o[18] = Q.nnth; o[19] = Q.nubperp; o[20] = Q.L; o[21] = Q.itanth;
+      }  // fall through
       case EM_POLSYNCHTH: {
         ThermalPoint T;
         thermal_point(cg.ncgs, cg.bcgs, cg.tcgs, oo.ang, oo.g, pc::G * A.sp[mm].mbh * pc::msun / pc::c2, T);
@@ -140,9 +148,10 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
 #if defined(__CUDA_ARCH__)
     double2 *q2 = reinterpret_cast<double2 *>(q);
 #pragma unroll
-    for (int i = 0; i < GRT_NREC / 2; i++) q2[i] = make_double2(o[2 * i], o[2 * i + 1]);
+    for (int i = 0; i < GRT_NREC_MAX / 2; i++)
+      if (2 * i < nrec) q2[i] = make_double2(o[2 * i], o[2 * i + 1]);
 #else
-    for (int i = 0; i < GRT_NREC; i++) q[i] = o[i];
+    for (int i = 0; i < nrec; i++) q[i] = o[i];
 #endif
     if (mm == 0 && sd.ncgs) {
       sd.ncgs[dst] = cg.ncgs; sd.ncgsnth[dst] = cg.ncgsnth; sd.bcgs[dst] = cg.bcgs; sd.tcgs[dst] = cg.tcgs;

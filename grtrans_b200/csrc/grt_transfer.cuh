@@ -22,10 +22,14 @@
 
 namespace grt {
 
-#define GRT_NREC 20  // doubles per point record (160 B)
+#define GRT_NREC 20      // doubles per point record (160 B) ...
+#define GRT_NREC_MAX 24  // ... 24 for the hybrid thermal + power-law emissivities (thermal and power-law point data)
+GRT_HD constexpr bool em_is_hybrid(int et) { return et == EM_HYBRIDTHPL || et == EM_HYBRIDTH || et == EM_HYBRIDPL; }
+GRT_HD constexpr int record_doubles(int etype) { return em_is_hybrid(etype) ? GRT_NREC_MAX : GRT_NREC; }
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
 //   POLSYNCHTH        [4..17] ThermalPoint (xp13, AI, AV, hkT_g, Ax, Ax^1.035, Ax^1.2, Ax^1.503, Ax^-8/3, RQ, RV0, RV1, 1/xp13, xp13^-1.5)
 //   POLSYNCHPL/SYNCHPL [4] n_nth, [5] nu_B,perp, [6] log(g) + log(1.5 nu_B,perp), [7] 1/tan(angle)  (PlPoint)
+//   HYBRIDTHPL/TH/PL  [4..17] ThermalPoint, [18..21] PlPoint (24-double record)
 //   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
 
 // integration modes (rad_trans.f90:30-38 iflag x neq)
@@ -70,7 +74,7 @@ template <int ET>
 GRT_HD RunConst run_const(const TransferParams &P, double nu_obs) {
   RunConst R;
   R.lnu = 0.0;
-  if (ET == EM_POLSYNCHPL || ET == EM_SYNCHPL) {
+  if (ET == EM_POLSYNCHPL || ET == EM_SYNCHPL || em_is_hybrid(ET)) {
     R.pl = pl_const(P.p, P.gmin, P.gmax);
     R.lnu = log(nu_obs);
   }
@@ -82,13 +86,28 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
   const double g = rec[1];
   double e[11];
   bool invariant = false;  // e already holds j g^2 and K LBH / g
-  if (ET == EM_POLSYNCHTH) {
+  if (ET == EM_POLSYNCHTH || em_is_hybrid(ET)) {
     ThermalPoint T;
     T.xp13 = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.Ax = rec[8]; T.Ax1 = rec[9]; T.Ax2 = rec[10];
     T.Ax3 = rec[11]; T.Ax4 = rec[12]; T.RQ = rec[13]; T.RV0 = rec[14]; T.RV1 = rec[15]; T.ixp13 = rec[16];
     T.xpm32 = rec[17]; T.g = g;
     thermal_eval(T, F, pc::c2 * P.LBH / (2.0 * pc::h), e, jI_raw);
     invariant = true;
+    if (em_is_hybrid(ET)) {  // emis.f90:469-485: add the power-law population (brought to the same invariant form)
+      PlPoint Q;
+      Q.nnth = rec[18]; Q.nubperp = rec[19]; Q.L = rec[20]; Q.itanth = rec[21];
+      double ep[11];
+      pl_eval<true>(P.tab, R.pl, Q, F.nu / g, R.lnu, ep);
+      const double g2 = g * g, kg = P.LBH / g;
+      if (ET == EM_HYBRIDTHPL) {
+        jI_raw += ep[0];
+        for (int i = 0; i < 4; i++) e[i] += ep[i] * g2;
+      } else if (ET == EM_HYBRIDPL) {
+        jI_raw = ep[0];
+        for (int i = 0; i < 4; i++) e[i] = ep[i] * g2;
+      }
+      for (int i = 4; i < 11; i++) e[i] += ep[i] * kg;
+    }
   } else {
     const double nu = F.nu / g;
     if (ET == EM_POLSYNCHPL || ET == EM_SYNCHPL) {
@@ -112,7 +131,8 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
   }
   for (int i = 0; i < 4; i++) c.j[i] = 0.0;
   for (int i = 0; i < 7; i++) c.K[i] = 0.0;
-  constexpr bool POL = (ET == EM_POLSYNCHTH || ET == EM_POLSYNCHPL || ET == EM_BBPOL);
+  constexpr bool POL = (ET == EM_POLSYNCHTH || ET == EM_POLSYNCHPL || ET == EM_BBPOL || ET == EM_HYBRIDTHPL ||
+                        ET == EM_HYBRIDTH || ET == EM_HYBRIDPL);
   if (POL) {
     for (int i = 0; i < 4; i++) c.j[i] = e[i];
     for (int i = 0; i < 7; i++)
@@ -325,6 +345,7 @@ GRT_HD bool ck_interval(int neq, const Coef &ca, const Coef &cb, double la, doub
 template <int ET, int MODE>
 GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
   constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
+  constexpr int NREC = em_is_hybrid(ET) ? GRT_NREC_MAX : GRT_NREC;  // record stride of this emissivity model
   for (int i = 0; i < neq; i++) out[i] = 0.0;
   if (npts <= 0) return;
   const FreqConst F = freq_const(nu_obs);
@@ -347,8 +368,8 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     double lam1 = 0.0;
 #pragma unroll 1
     for (int k = npts - 1; k >= 0; k--) {
-      const double *rk = rec + (size_t)k * GRT_NREC;
-      if (k > 0) prefetch_record(rk - GRT_NREC);
+      const double *rk = rec + (size_t)k * NREC;
+      if (k > 0) prefetch_record(rk - NREC);
       const double lamk = rk[0];
       node_coef<ET>(P, R, rk, F, c0, jraw);
       fac += jraw * (lam0 - lamk);
@@ -380,7 +401,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     double tau = 0.0, acc = 0.0, yprev = 0.0, kprev = 0.0, lprev = 0.0;
 #pragma unroll 1
     for (int k = 0; k < npts; k++) {
-      const double *rk = rec + (size_t)k * GRT_NREC;
+      const double *rk = rec + (size_t)k * NREC;
       node_coef<ET>(P, R, rk, F, c, jraw);
       if (k > 0) {
         fac += jraw * (lam0 - rk[0]);
@@ -407,7 +428,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     bool cut = false;
 #pragma unroll 1
     for (int k = 0; k < npts; k++) {
-      const double *rk = rec + (size_t)k * GRT_NREC;
+      const double *rk = rec + (size_t)k * NREC;
       node_coef<ET>(P, R, rk, F, c, jraw);
       fac += jraw * (lam0 - rk[0]);
       if (k > 0) tau -= (rk[0] - lprev) * (kprev + fabs(c.K[0])) / 2.0;
@@ -440,10 +461,10 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     for (int s_ = i2 + 1; s_ >= i1 + 1 && ok; s_--) {
       const int src = (s_ == i2 + 1) ? up : s_;
       cb = ca;
-      node_coef<ET>(P, R, rec + (size_t)(src - 1) * GRT_NREC, F, ca, jraw);
+      node_coef<ET>(P, R, rec + (size_t)(src - 1) * NREC, F, ca, jraw);
       for (int i = 0; i < 4; i++) ca.j[i] /= fac;
       if (s_ <= i2) {
-        double la = rec[(size_t)(s_ - 1) * GRT_NREC], lb = rec[(size_t)(s_ - 2) * GRT_NREC];
+        double la = rec[(size_t)(s_ - 1) * NREC], lb = rec[(size_t)(s_ - 2) * NREC];
         if (lb > la) ok = ck_interval(neq, ca, cb, la, lb, y, h, P);
       }
     }
@@ -453,7 +474,8 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
 }
 
 // runtime dispatcher (host emulator / generic callers); the CUDA kernels are instantiated per (ET, MODE) directly
-#define GRT_FOR_ETYPES(OP) OP(EM_POLSYNCHTH) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL)
+#define GRT_FOR_ETYPES(OP) \
+  OP(EM_POLSYNCHTH) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_HYBRIDPL)
 template <int ET>
 GRT_HD void ray_transfer_e(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
   switch (transfer_mode(P)) {

@@ -133,6 +133,18 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
         switch (etype) {
           case E_POLSYNCHTH: polsynchth(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], K11); break;
           case E_POLSYNCHPL: polsynchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, K11); break;
+          case E_HYBRIDTHPL:
+          case E_HYBRIDTH:
+          case E_HYBRIDPL: {  // emis.f90:469-485: thermal + power-law populations
+            double Kth[11], Kpl[11];
+            polsynchth(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], Kth);
+            polsynchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, Kpl);
+            for (int c = 0; c < 11; c++) {
+              if (etype == E_HYBRIDTHPL) K11[c] = Kth[c] + Kpl[c];
+              else if (c < 4) K11[c] = (etype == E_HYBRIDTH) ? Kth[c] : Kpl[c];   // emission of one population ...
+              else K11[c] = Kth[c] + Kpl[c];                                       // ... absorbed by both
+            }
+          } break;
           case E_SYNCHPL: synchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, K11); break;
           case E_SYNCHTHAV: synchemis(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], K11); break;
           case E_BB: K11[0] = bnu(w.tcgs[p], nu); break;

@@ -323,6 +323,9 @@ int emis_type_from_name(const std::string &ename, int &neq) {
   if (ename == "SYNCHPL") { neq = 1; return E_SYNCHPL; }
   if (ename == "BB") { neq = 1; return E_BB; }
   if (ename == "BBPOL") { neq = 4; return E_BBPOL; }
+  if (ename == "HYBRIDTHPL") { neq = 4; return E_HYBRIDTHPL; }
+  if (ename == "HYBRIDTH") { neq = 4; return E_HYBRIDTH; }
+  if (ename == "HYBRIDPL") { neq = 4; return E_HYBRIDPL; }
   neq = 1;
   return -1;
 }

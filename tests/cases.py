@@ -52,8 +52,13 @@ def cfg_harm(n=40, nup=100, nfreq=2, iname='delo', **kw):
     return d
 
 
-def cfg_harm3d(n=40, nup=100, nfreq=4, iname='delo', **kw):
+def cfg_harm3d(n=40, nup=100, nfreq=4, iname='delo', magnetized=False, **kw):
     _, _, p3 = snapshots()
+    if magnetized:      # b^2/rho > 1 in part of the flow: the non-thermal population of nonthermale_b2 is switched on
+        import make_snapshot as ms
+        p3 = os.path.join(SNAPDIR, "h3d_small_magnetized.bin")
+        if not os.path.exists(p3):
+            ms.write_harm3d(p3, bfac=40.)
     d = dict(fname='HARM3D', ename='POLSYNCHTH', nvals=4, iname=iname, spin=.9375, standard=1, nn=[n, n, nup], uout=.04,
              mbh=4e6, mdotmin=1e20, mdotmax=1e20, nmu=1, mumin=.6428, mumax=.6428, gridvals=[-13., 13., -13., 13.],
              nfreq=nfreq, fmin=1e10, fmax=1e13, muval=.25, gmin=1., fdfile=p3)

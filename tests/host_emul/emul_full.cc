@@ -69,7 +69,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
       r.phi0 = c.phi0; r.t0 = 0; r.tpm = c.tpm[ix]; r.tpr = c.tpr[ix];
       RayInv inv;
       geo_setup(r, fl, inv);
-      std::vector<double> bu(mp), bmu(mp), bdt(mp), bdp(mp), bl(mp), rec((size_t)nparams * mp * GRT_NREC, 0.0);
+      std::vector<double> bu(mp), bmu(mp), bdt(mp), bdp(mp), bl(mp), rec((size_t)nparams * mp * GRT_NREC_MAX, 0.0);
       std::vector<signed char> btm(mp), btr(mp);
       PointArrays pa{bu.data(), bmu.data(), bdt.data(), bdp.data(), bl.data(), btm.data(), btr.data()};
       for (int s = 0; s < mp; s++) point_store(inv, fl.nup, s, (size_t)s, pa);
@@ -99,7 +99,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
       for (int mm = 0; mm < nparams; mm++)
         for (int f = 0; f < nfreq; f++) {
           double out[4] = {0, 0, 0, 0};
-          if (m.status == 1 && m.npts > 0) ray_transfer(P, rec.data() + (size_t)mm * mp * GRT_NREC, m.npts, freqs[f], out);
+          if (m.status == 1 && m.npts > 0) ray_transfer(P, rec.data() + (size_t)mm * mp * record_doubles(etype), m.npts, freqs[f], out);
           int cam = jm * nparams * nfreq + mm * nfreq + f;
           for (int k = 0; k < nv; k++) image[((size_t)cam * n + q) * nv + k] = (float)out[k];
         }

@@ -178,6 +178,10 @@ IMAGE_CASES = [
     ("harm3d", dict(n=50, nup=200, nfreq=4, iname='delo'), 1e-4),
     ("harm3d", dict(n=40, nup=100, nfreq=2, iname='delo', nmdot=3, mdotmin=1e19, mdotmax=1e21), 1e-4),
     ("harm3d_native", dict(n=40, nup=100, nfreq=3), 1e-4),                        # the reference's own harm3d file format
+    # thermal + power-law electron populations (emis.f90:469-485) on a magnetised snapshot
+    ("harm3d", dict(n=50, nup=200, nfreq=4, ename='HYBRIDTHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True), 1e-4),
+    ("harm3d", dict(n=40, nup=100, nfreq=3, ename='HYBRIDTH', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True), 1e-4),
+    ("harm3d", dict(n=40, nup=100, nfreq=3, ename='HYBRIDPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True, iname='formal'), 1e-4),
     ("koral", dict(n=50, nup=200, nfreq=4, threed=True), 1e-4),                   # KORAL3D, T_e straight from the dump
     ("koral", dict(n=40, nup=100, nfreq=3, threed=False), 1e-4),                  # KORAL (2-D)
     ("koral", dict(n=40, nup=100, nfreq=3, threed=True, fname='KORAL3D_DISK', gmin=10.), 1e-4),  # Bernoulli cut, R-beta

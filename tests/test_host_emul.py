@@ -66,6 +66,10 @@ EMUL_CASES = [
     ("iharm", dict(n=24, nup=100, nfreq=3, mmks=1)),                   # FMKS grid, R-beta electrons (monika_e)
     ("iharm", dict(n=24, nup=100, nfreq=3, mmks=0, gmin=-1.)),         # MKS grid, electron-entropy T_e (ressler_e)
     ("iharm", dict(n=20, nup=100, nfreq=2, mmks=1, iname='formal', sigcut=0.5)),
+    # thermal + power-law electrons (nonthermale_b2 switches the power law on where b^2/rho > 1)
+    ("harm3d", dict(n=20, nup=100, nfreq=3, ename='HYBRIDTHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True)),
+    ("harm3d", dict(n=16, nup=100, nfreq=2, ename='HYBRIDTH', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True)),
+    ("harm3d", dict(n=16, nup=100, nfreq=2, ename='HYBRIDPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True, iname='formal')),
     ("koral", dict(n=24, nup=100, nfreq=3, threed=True)),                                  # KORAL3D, T_e from the dump
     ("koral", dict(n=24, nup=100, nfreq=3, threed=False)),                                 # KORAL (2-D)
     ("koral", dict(n=20, nup=100, nfreq=2, threed=True, fname='KORAL3D_DISK', gmin=10.)),  # Bernoulli cut + R-beta electrons

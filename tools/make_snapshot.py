@@ -29,7 +29,7 @@ def _ks_metric(r, th, a):
     return g
 
 
-def _fluid(r, th, ph, a, seed, threed):
+def _fluid(r, th, ph, a, seed, threed, bfac=1.0):
     rng = np.random.RandomState(seed)
     amp1, amp2, ph1, ph2 = 0.3 * rng.rand() + 0.2, 0.2 * rng.rand() + 0.1, 2 * np.pi * rng.rand(), 2 * np.pi * rng.rand()
     g = _ks_metric(r, th, a)
@@ -52,7 +52,7 @@ def _fluid(r, th, ph, a, seed, threed):
         rho = rho * (1. + amp1 * np.cos(ph - ph1) + amp2 * np.cos(2. * ph - ph2))
     uu = rho * 0.02 * (r / r0) ** -1.0           # internal energy density (code units)
     # magnetic field: toroidal + radial pieces, b^t from u.b = 0
-    b0 = 0.05 * np.sqrt(rho)
+    b0 = 0.05 * bfac * np.sqrt(rho)
     br = 0.3 * b0 / r
     bp = b0 / r * (1. + (0.2 * np.sin(ph) if threed else 0.))
     bth = 0.1 * b0 / r * np.cos(th)
@@ -105,14 +105,14 @@ def write_harm2d(prefix, indf=40, **kw):
     return path
 
 
-def harm3d_arrays(nx1=64, nx2=32, nx3=32, a=0.9375, rin=1.1, rout=40.0, seed=12345):
+def harm3d_arrays(nx1=64, nx2=32, nx3=32, a=0.9375, rin=1.1, rout=40.0, seed=12345, bfac=1.0):
     dx1 = np.log(rout / rin) / nx1
     x1 = np.log(rin) + (np.arange(nx1) + 0.5) * dx1
     x2 = (np.arange(nx2) + 0.5) / nx2
     x3 = (np.arange(nx3) + 0.5) * 2. * np.pi / nx3
     X1, X2, X3 = np.meshgrid(x1, x2, x3, indexing='ij')  # phi fastest
     r = np.exp(X1); th = np.pi * X2; ph = X3
-    rho, uu, u, b = _fluid(r, th, ph, a, seed, True)
+    rho, uu, u, b = _fluid(r, th, ph, a, seed, True, bfac)
     dth = np.pi * np.ones_like(r)
     return dict(nx1=nx1, nx2=nx2, nx3=nx3, a=a, x1=X1, x2=X2, x3=X3, r=r, th=th, ph=ph, rho=rho, u=uu,
                 ucon=_to_mks(u, r, dth), bcon=_to_mks(b, r, dth), gam=4. / 3.)
