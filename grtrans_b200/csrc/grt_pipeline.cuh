@@ -11,8 +11,8 @@ struct PointArrays {  // raw geokerr outputs, [ray][maxpts]
   signed char *tpm, *tpr;
 };
 
-struct RayMeta {  // per ray after finalize
-  int i1, npts, status;
+struct RayMeta {  // per ray after finalize (explicit padding: the struct is copied to the host as raw bytes)
+  int i1, npts, status, pad;
   double lamN, dt1;
 };
 
@@ -63,6 +63,7 @@ GRT_HD void ray_finalize(int npts, size_t i, int maxpts, int usegeor, PointArray
   double sumr = 0.0;
   for (int k = 0; k < npts; k++) sumr += 1.0 / u[i1 - 1 + k];
   m.i1 = i1;
+  m.pad = 0;
   m.npts = npts;
   m.status = (sumr < 0.0) ? -1 : 1;
   // (sic) LAMBDAI(g%npts): the trimmed COUNT indexes the untrimmed array
