@@ -58,6 +58,8 @@ struct grt_session {
   std::vector<void *> registered;      // host buffers pinned in place with cudaHostRegister
   std::vector<double> freqs, mdots, mu0;
   int nmu = 1, nparams = 1, nfreq = 1, nvals = 1, ncams = 1, maxpts = 1, npix = 0;
+  int nt = 1;                // observer-time frames per mu0 (pgrtrans.f90:195-212)
+  bool fluid_moved = false;  // the resident dumps were advanced by a previous pass over the nt frames
   std::vector<grt_host::Camera> cams;  // one per mu0
   std::vector<int> ray_index;          // 1-based geodesic indices owned by this rank
   long long nlocal = 0;
@@ -121,6 +123,59 @@ extern "C" int grt_device_count(void) {
 
 extern "C" const char *grt_version(void) { return "grtrans_b200 0.1 (sm_100a)"; }
 
+// nload > 1 (pgrtrans.f90:172-194): one-point geodesics (nup = 1, no extra points) of ALL pixels i1..i2 give the coordinate
+// time DTI(1) at which each ray reaches its single point; t0 = that time shifted so that the earliest pixel is 0
+// (`where(t0>0) t0=t0-maxval(t0) elsewhere t0=0`; `t0=t0-minval(t0)`), subtracted from every point's t afterwards
+// (geodesics.f90:345).  Every rank computes the full table (1/nup of the geodesic work): no collective needed.
+static int arrival_time_offsets(grt_session *s, int i1, int i2) {
+  const long long nall = (long long)i2 - i1 + 1;
+  if (nall <= 0) return GRT_OK;
+  const int chunk = s->tile;
+  RayConst *d_tmp = nullptr;
+  if (dalloc(&d_tmp, (size_t)chunk) != cudaSuccess) return GRT_ERR_CUDA;
+  std::vector<RayConst> rc(chunk);
+  std::vector<RayMeta> hm(chunk);
+  int rcode = GRT_OK;
+  for (int j = 0; j < s->nmu && rcode == GRT_OK; j++) {
+    const grt_host::Camera &c = s->cams[j];
+    GeoFlags f1{1, 0, 0, 0, c.usegeor, 1};
+    std::vector<double> t0((size_t)s->npix, 0.0);
+    for (long long off = 0; off < nall && rcode == GRT_OK; off += chunk) {
+      int n = (int)std::min<long long>(chunk, nall - off);
+      for (int q = 0; q < n; q++) {
+        int ix = i1 - 1 + (int)off + q;
+        RayConst &r = rc[q];
+        r.a = c.a; r.mu0 = c.mu0; r.u0 = c.u0; r.uout = c.uout; r.alpha = c.alpha[ix]; r.beta = c.beta[ix];
+        r.q2 = c.q2[ix]; r.l = c.l[ix]; r.su = c.su[ix]; r.sm = c.sm[ix]; r.uf = c.uf[ix]; r.muf = c.muf[ix];
+        r.offset = c.offset; r.phi0 = c.phi0; r.t0 = 0.0; r.tpm = c.tpm[ix]; r.tpr = c.tpr[ix];
+      }
+      bool ok = cudaMemcpyAsync(d_tmp, rc.data(), (size_t)n * sizeof(RayConst), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+      launch_ray_setup(d_tmp, f1, s->d_inv, n, s->stream);
+      launch_geo_points(s->d_inv, 1, 1, n, s->pa, s->stream);
+      launch_ray_finalize(s->d_inv, 1, c.usegeor, n, s->pa, s->d_meta, s->stream);
+      ok = ok && cudaMemcpyAsync(hm.data(), s->d_meta, (size_t)n * sizeof(RayMeta), cudaMemcpyDeviceToHost, s->stream) == cudaSuccess;
+      ok = ok && cudaStreamSynchronize(s->stream) == cudaSuccess;
+      if (!ok) {
+        rcode = GRT_ERR_CUDA;
+        break;
+      }
+      for (int q = 0; q < n; q++) t0[i1 - 1 + off + q] = (hm[q].npts == 0) ? 0.0 : hm[q].dt1;
+    }
+    if (rcode != GRT_OK) break;
+    double mx = -1e300, mn = 1e300;
+    for (double v : t0) mx = std::max(mx, v);
+    for (double &v : t0) v = (v > 0.) ? v - mx : 0.;
+    for (double v : t0) mn = std::min(mn, v);
+    for (double &v : t0) v -= mn;
+    for (long long q = 0; q < s->nlocal; q++) s->h_rc[j][q].t0 = t0[s->ray_index[q] - 1];
+    if (s->nlocal &&
+        cudaMemcpy(s->d_rc[j], s->h_rc[j].data(), (size_t)s->nlocal * sizeof(RayConst), cudaMemcpyHostToDevice) != cudaSuccess)
+      rcode = GRT_ERR_CUDA;
+  }
+  cudaFree(d_tmp);
+  return rcode;
+}
+
 extern "C" int grt_session_create(const grt_args *a, int device, int rank, int nranks, grt_session **out) {
   *out = nullptr;
   if (grt_device_count() <= 0) return GRT_ERR_NO_DEVICE;
@@ -133,13 +188,14 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
     fprintf(stderr, "grtrans_b200: unsupported fname/ename/iname '%s'/'%s'/'%s'\n", a->fname, a->ename, a->iname);
     return GRT_ERR_BAD_ARG;
   }
-  if (a->nmdot > 8 || a->nt != 1 || (a->nvals != 1 && a->nvals != 4) || a->extra != 0) return GRT_ERR_BAD_ARG;
+  if (a->nmdot > 8 || a->nt < 1 || (a->nvals != 1 && a->nvals != 4) || a->extra != 0) return GRT_ERR_BAD_ARG;
   if (std::string(a->stype) != "const") return GRT_ERR_BAD_ARG;
   grt_session *s = new grt_session();
   s->args = *a;
   s->device = device; s->rank = rank; s->nranks = nranks < 1 ? 1 : nranks;
   grt_host::make_grids(*a, s->freqs, s->mdots, s->mu0);
   s->nmu = a->nmu; s->nparams = a->nmdot; s->nfreq = a->nfreq; s->nvals = a->nvals;
+  s->nt = a->nt;
   s->ncams = a->nmdot * a->nfreq * a->nmu * a->nt;
   s->npix = a->nn[0] * a->nn[1];
   int rcio = grt_host::load_fluid(s->fh, *a);
@@ -152,6 +208,10 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   for (int j = 0; j < s->nmu; j++)
     grt_host::build_camera(s->cams[j], a->standard, s->mu0[j], a->phi0, a->spin, a->uout, a->rcut, a->nrotype, a->gridvals,
                            a->nn[0], a->nn[1], a->nn[2]);
+  if (a->nload > 1)
+    // (sic) the t0 pre-pass of an nload > 1 run (initialize_geo_tabs, geodesics.f90:113-128) zeroes kext / next / mufill in
+    // the shared geokerr_args and only nup is restored (pgrtrans.f90:176-189): the main pass has no mu-fill points
+    for (auto &c : s->cams) c.kext = c.next = c.mufill = 0;
   s->maxpts = s->cams[0].maxpts();
   s->fl = GeoFlags{a->nn[2], s->cams[0].kext, s->cams[0].next, s->cams[0].mufill, s->cams[0].usegeor, 1};
   // shard i1..i2 in interleaved tiles of 256 rays
@@ -221,6 +281,7 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   FluidDev &F = s->fk.F;
   memset(&F, 0, sizeof(F));
   F.model = s->fh.model; F.nx1 = s->fh.nx1; F.nx2 = s->fh.nx2; F.nx3 = s->fh.nx3; F.h = s->fh.h;
+  F.nslots = s->fh.nslots; F.ncell = s->fh.ncell; F.tstep = s->fh.tstep;
   F.td_mbh = s->fh.td_mbh; F.td_mdot = s->fh.td_mdot; F.td_rin = s->fh.td_rin; F.td_rout = s->fh.td_rout;
   F.hslope = s->fh.hslope; F.mks_smooth = s->fh.mks_smooth; F.poly_xt = s->fh.poly_xt; F.poly_alpha = s->fh.poly_alpha;
   F.startx1 = s->fh.startx1; F.is_mmks = s->fh.is_mmks; F.eheat = s->fh.eheat; F.gam = s->fh.gam;
@@ -267,13 +328,20 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   };
   for (auto &v : s->h_rc) pin(v.data(), v.size() * sizeof(RayConst));
   pin(s->fh.cells.data(), s->fh.cells.size() * sizeof(grt_host::HostCell));
+  if (a->nload > 1) {
+    int rc = arrival_time_offsets(s, i1, i2);
+    if (rc != GRT_OK) {
+      session_free(s);
+      return rc;
+    }
+  }
   *out = s;
   return GRT_OK;
 }
 
 extern "C" void grt_session_destroy(grt_session *s) { session_free(s); }
 
-static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump sd, bool time_stages) {
+static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump sd, bool time_stages, int frame = 0) {
   long long total = (long long)n * s->maxpts;
   if (time_stages) cudaEventRecord(s->ev[0], s->stream);
   launch_ray_setup(s->d_rc[jmu] + off, s->fl, s->d_inv, n, s->stream);
@@ -284,9 +352,33 @@ static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump 
   launch_fluid_ortho(s->d_rc[jmu] + off, s->d_inv, s->d_meta, s->fk, total, n, s->pa, s->d_rec, sd, s->stream);
   if (time_stages) cudaEventRecord(s->ev[3], s->stream);
   launch_transfer(s->d_meta, s->tp, s->d_lbh, s->d_freqs, s->nfreq, s->nparams, n, s->maxpts, s->d_rec, s->d_image, off,
-                  s->nlocal, jmu * s->nparams * s->nfreq, s->stream);
+                  s->nlocal, (jmu * s->nt + frame) * s->nparams * s->nfreq, s->stream);
   if (time_stages) cudaEventRecord(s->ev[4], s->stream);
   return (cudaGetLastError() == cudaSuccess) ? GRT_OK : GRT_ERR_CUDA;
+}
+
+// Move the resident dumps on by the observer time dt (advance_fluid_timestep, fluid.f90:245-281), or back to the initial
+// dump set, and refresh the device copy.  The frames already queued must have finished reading the old cells first.
+static int reload_dumps(grt_session *s, bool restart, double dt) {
+  if (s->fh.cells.empty()) return GRT_OK;
+  CK(cudaStreamSynchronize(s->stream));
+  int rc;
+  if (restart) {
+    grt_host::FluidHost fresh;
+    rc = grt_host::load_fluid(fresh, s->args);
+    if (rc != GRT_OK) return rc;
+    if (fresh.cells.size() != s->fh.cells.size()) return GRT_ERR_IO;
+    std::copy(fresh.cells.begin(), fresh.cells.end(), s->fh.cells.begin());  // (the pinned mirror stays where it is)
+    s->fh.indf = fresh.indf; s->fh.tdump = fresh.tdump; s->fh.tstep = fresh.tstep; s->fh.toffset = fresh.toffset;
+    s->fh.tstep_d = fresh.tstep_d; s->fh.toffset_d = fresh.toffset_d;
+  } else {
+    rc = grt_host::advance_fluid(s->fh, s->args, dt);
+    if (rc != GRT_OK) return rc;
+  }
+  s->fk.F.tstep = s->fh.tstep;
+  CK(cudaMemcpyAsync(const_cast<Cell *>(s->fk.F.cells), s->fh.cells.data(), s->fh.cells.size() * sizeof(Cell),
+                     cudaMemcpyHostToDevice, s->stream));
+  return GRT_OK;
 }
 
 static int launch_all(grt_session *s, bool fetch) {
@@ -296,20 +388,33 @@ static int launch_all(grt_session *s, bool fetch) {
   memset(&sd, 0, sizeof(sd));
   s->launches = 0;
   const size_t rowb = (size_t)s->nvals * sizeof(float);
+  if (s->fluid_moved) {  // a previous pass advanced the dumps through the nt frames: start again from dump `findf`
+    int rc = reload_dumps(s, true, 0.0);
+    if (rc != GRT_OK) return rc;
+    s->fluid_moved = false;
+  }
   for (int j = 0; j < s->nmu; j++)
-    for (long long off = 0; off < s->nlocal; off += s->tile) {
-      int n = (int)std::min<long long>(s->tile, s->nlocal - off);
-      int rc = launch_tile(s, j, off, n, sd, false);
-      if (rc != GRT_OK) return rc;
-      s->launches += 5;
-      if (fetch) {
-        // this tile's pixels of the nparams*nfreq cameras of mu0 index j: a 2-D block of the [cam][ray][nvals] image
-        CK(cudaEventRecord(s->tile_done, s->stream));
-        CK(cudaStreamWaitEvent(s->copy_stream, s->tile_done, 0));
-        size_t cam0 = (size_t)j * s->nparams * s->nfreq;
-        size_t o = (cam0 * s->nlocal + off) * s->nvals;
-        CK(cudaMemcpy2DAsync(s->h_image + o, (size_t)s->nlocal * rowb, s->d_image + o, (size_t)s->nlocal * rowb, (size_t)n * rowb,
-                             (size_t)s->nparams * s->nfreq, cudaMemcpyDeviceToHost, s->copy_stream));
+    for (int l = 0; l < s->nt; l++) {
+      for (long long off = 0; off < s->nlocal; off += s->tile) {
+        int n = (int)std::min<long long>(s->tile, s->nlocal - off);
+        int rc = launch_tile(s, j, off, n, sd, false, l);
+        if (rc != GRT_OK) return rc;
+        s->launches += 5;
+        if (fetch) {
+          // this tile's pixels of the nparams*nfreq cameras of (mu0 index j, frame l): a 2-D block of the
+          // [cam][ray][nvals] image
+          CK(cudaEventRecord(s->tile_done, s->stream));
+          CK(cudaStreamWaitEvent(s->copy_stream, s->tile_done, 0));
+          size_t cam0 = ((size_t)j * s->nt + l) * s->nparams * s->nfreq;
+          size_t o = (cam0 * s->nlocal + off) * s->nvals;
+          CK(cudaMemcpy2DAsync(s->h_image + o, (size_t)s->nlocal * rowb, s->d_image + o, (size_t)s->nlocal * rowb,
+                               (size_t)n * rowb, (size_t)s->nparams * s->nfreq, cudaMemcpyDeviceToHost, s->copy_stream));
+        }
+      }
+      if (l < s->nt - 1) {  // pgrtrans.f90:211 (the dumps keep moving on across the mu0 loop; no advance after the last frame)
+        int rc = reload_dumps(s, false, s->args.dt);
+        if (rc != GRT_OK) return rc;
+        s->fluid_moved = true;
       }
     }
   return GRT_OK;
@@ -385,7 +490,7 @@ extern "C" int grt_session_sync(grt_session *s) {
 extern "C" int grt_session_launch_count(const grt_session *s) {
   if (!s) return 0;
   long long tiles = (s->nlocal + s->tile - 1) / std::max(1, s->tile);
-  return (int)(5 * tiles * s->nmu);
+  return (int)(5 * tiles * s->nmu * s->nt);
 }
 
 extern "C" int grt_session_time(grt_session *s, float *total_ms, float stage_ms[4]) {

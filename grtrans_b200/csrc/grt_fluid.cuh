@@ -30,7 +30,10 @@ struct FluidDev {
   const float *ax2;   // uniqx2                                  [nx2]
   const float *axth;  // uniqth                                  [nx2]
   const float *ax3;   // uniqx3 / uniqph                         [nx3]
-  const Cell *cells;  // [n] packed snapshot
+  const Cell *cells;  // [nslots][ncell] packed snapshot(s): slot k = dump file indf-k (load_harm_data, fluid_model_harm.f90:459-486)
+  int nslots;                  // nt of the fluid module (dumps resident for slow light)
+  unsigned long long ncell;    // cells per dump
+  float tstep;                 // dump spacing, real(4) module variable (t(1)-t(2), default 20.)
   // iharm grid (fluid_model_iharm.f90:13-24, real(8) module variables read from the header file)
   double hslope, mks_smooth, poly_xt, poly_alpha, startx1;
   int is_mmks, eheat;
@@ -276,8 +279,26 @@ GRT_HD float krolik_c(float r, float a) {
 }
 
 // ---- the sampler ---------------------------------------------------------------------------------
-GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, double phh, const double *k4,
-                          FluidSample &s) {
+// Dump slot of a geodesic point (fluid_model_harm.f90:133-183; same lines in the harm3d / koral / koral3d modules): tt = KS
+// look-back time of the point relative to the first point of the ray, real(4); tindx = floor(tt/tstep), at most nt-1.  The
+// time weight is zero (rttd=0.), so the sample is slot tindx alone.  harm and koral add 1d-8 to tt before the floor.
+GRT_HD double bl2ks_time(double r, double x, double a) {  // kerr.f90:147-154
+  double sq1 = sqrt(1. - a * a);
+  return x + log(r * r - 2 * r + a * a) + 1. / (2.0 * sq1) * log((r - 1. - sq1) / (r - 1 + sq1));
+}
+GRT_HD const Cell *slot_cells(const FluidDev &F, float a, double rr, double tpt, double r1) {
+  if (F.nslots <= 1) return F.cells;
+  float zr = (float)rr, zt = (float)tpt, zr1 = (float)r1;
+  float tt = (float)(bl2ks_time((double)zr, (double)zt, (double)a) - bl2ks_time((double)zr1, 0.0, (double)a));
+  tt = (F.model == FL_HARM3D) ? -tt : (float)((double)(-tt) + 1e-8);
+  float q = floorf(tt / F.tstep);
+  int tindx = (q <= (float)(F.nslots - 2)) ? (int)q : F.nslots - 1;
+  if (tindx < 0) tindx = 0;  // guard
+  return F.cells + F.ncell * (unsigned long long)tindx;
+}
+
+GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, double phh, double tpt, double r1,
+                          const double *k4, FluidSample &s) {
   const double pi = GRT_PI;
   // reference constants (phys_constants.f90)
   const double pcG = 6.67e-8, pcc = 2.99792458e10, pcc2 = pcc * pcc, pcmsun = 1.998e33, pcmp = 1.67262158e-24,
@@ -285,6 +306,7 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
   float a = (float)ad;
   s.rho = s.p = s.bmag = s.kela = s.be = 0.f;
   for (int i = 0; i < 4; i++) s.u[i] = s.b[i] = 0.0;
+  const Cell *const cells = slot_cells(F, a, rr, tpt, r1);
   switch (F.model) {
     case FL_THINDISK: {
       float r = (float)rr, th = (float)thh;
@@ -361,8 +383,8 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       float td = (theta - F.axth[lx2 - 1]) / (F.axth[ux2 - 1] - F.axth[lx2 - 1]);
       float rd = (zr - F.axr[lx1 - 1]) / (F.axr[ux1 - 1] - F.axr[lx1 - 1]);
       int x1l = lx1 - 1, x1u = ux1 - 1, x2l = (lx2 - 1) * nx1, x2u = (ux2 - 1) * nx1;  // r fastest
-      Field10 v = blend4(load_cell(F.cells, x1l + x2l), load_cell(F.cells, x1l + x2u), load_cell(F.cells, x1u + x2l),
-                         load_cell(F.cells, x1u + x2u), rd, td);
+      Field10 v = blend4(load_cell(cells, x1l + x2l), load_cell(cells, x1l + x2u), load_cell(cells, x1u + x2l),
+                         load_cell(cells, x1u + x2u), rd, td);
       bool in = x1 > F.ax1[0];
       s.rho = in ? v.rho : 0.f;
       s.p = in ? v.p : 1.f;
@@ -387,8 +409,8 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       if (F.axr[lx1 - 1] <= rh) rd = 1.f;
       int x2l = lx2 - 1, x2u = ux2 - 1, x1l = (lx1 - 1) * nx2, x1u = (ux1 - 1) * nx2;  // theta fastest
       // trilinear with time weight 0 (rttd=0.) reduces to the first time slice: y=w1*(1-0)+w2*0
-      Field10 v = blend4(load_cell(F.cells, x1l + x2l), load_cell(F.cells, x1l + x2u), load_cell(F.cells, x1u + x2l),
-                         load_cell(F.cells, x1u + x2u), rd, td);
+      Field10 v = blend4(load_cell(cells, x1l + x2l), load_cell(cells, x1l + x2u), load_cell(cells, x1u + x2l),
+                         load_cell(cells, x1u + x2u), rd, td);
 #define OP(f) v.f = v.f * (1.f - 0.f) + v.f * 0.f;
       GRT_FOR_FIELDS(OP)
 #undef OP
@@ -438,10 +460,10 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       size_t x3l = lx3 - 1, x3u = ux3 - 1, x2l = (size_t)(lx2 - 1) * nx3, x2u = (size_t)(ux2 - 1) * nx3;
       size_t x1l = (size_t)(lx1 - 1) * nx2 * nx3, x1u = (size_t)(ux1 - 1) * nx2 * nx3;
       // quadlininterp(vv, td=0, xd=pd, yd=rd, zd=td): theta, then r, then phi
-      Field10 lo = blend4(load_cell(F.cells, x1l + x2l + x3l), load_cell(F.cells, x1l + x2u + x3l),
-                          load_cell(F.cells, x1u + x2l + x3l), load_cell(F.cells, x1u + x2u + x3l), rd, td);
-      Field10 hi = blend4(load_cell(F.cells, x1l + x2l + x3u), load_cell(F.cells, x1l + x2u + x3u),
-                          load_cell(F.cells, x1u + x2l + x3u), load_cell(F.cells, x1u + x2u + x3u), rd, td);
+      Field10 lo = blend4(load_cell(cells, x1l + x2l + x3l), load_cell(cells, x1l + x2u + x3l),
+                          load_cell(cells, x1u + x2l + x3l), load_cell(cells, x1u + x2u + x3l), rd, td);
+      Field10 hi = blend4(load_cell(cells, x1l + x2l + x3u), load_cell(cells, x1l + x2u + x3u),
+                          load_cell(cells, x1u + x2l + x3u), load_cell(cells, x1u + x2u + x3u), rd, td);
       Field10 v;
 #define OP(f) { float w1 = lo.f * (1.f - pd) + hi.f * pd; v.f = w1 * (1.f - 0.f) + w1 * 0.f; }
       GRT_FOR_FIELDS(OP)
@@ -507,17 +529,17 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       size_t x3l = (size_t)(lx3 - 1) * nx2 * nx1, x3u = (size_t)(ux3 - 1) * nx2 * nx1;
       Field10 v;
       if (d3) {
-        Field10 c0 = load_cell(F.cells, x1l + x2l + x3l), c1 = load_cell(F.cells, x1l + x2u + x3l),
-                c2 = load_cell(F.cells, x1u + x2l + x3l), c3 = load_cell(F.cells, x1u + x2u + x3l),
-                c4 = load_cell(F.cells, x1l + x2l + x3u), c5 = load_cell(F.cells, x1l + x2u + x3u),
-                c6 = load_cell(F.cells, x1u + x2l + x3u), c7 = load_cell(F.cells, x1u + x2u + x3u);
+        Field10 c0 = load_cell(cells, x1l + x2l + x3l), c1 = load_cell(cells, x1l + x2u + x3l),
+                c2 = load_cell(cells, x1u + x2l + x3l), c3 = load_cell(cells, x1u + x2u + x3l),
+                c4 = load_cell(cells, x1l + x2l + x3u), c5 = load_cell(cells, x1l + x2u + x3u),
+                c6 = load_cell(cells, x1u + x2l + x3u), c7 = load_cell(cells, x1u + x2u + x3u);
         // quadlininterp(vv, td=0, xd=pd, yd=rd, zd=td) (interpolate.f90:203-232): theta, then r, then phi, then time
 #define OP(f) { float i1 = c0.f * (1.f - td) + c1.f * td, i2 = c2.f * (1.f - td) + c3.f * td;                 float j1 = c4.f * (1.f - td) + c5.f * td, j2 = c6.f * (1.f - td) + c7.f * td;                 float m1 = i1 * (1.f - rd) + i2 * rd, m2 = j1 * (1.f - rd) + j2 * rd;                       float w1 = m1 * (1.f - pd) + m2 * pd; v.f = w1 * (1.f - 0.f) + w1 * 0.f; }
         GRT_FOR_FIELDS_BE(OP)
 #undef OP
       } else {
-        Field10 c0 = load_cell(F.cells, x1l + x2l), c1 = load_cell(F.cells, x1l + x2u), c2 = load_cell(F.cells, x1u + x2l),
-                c3 = load_cell(F.cells, x1u + x2u);
+        Field10 c0 = load_cell(cells, x1l + x2l), c1 = load_cell(cells, x1l + x2u), c2 = load_cell(cells, x1u + x2l),
+                c3 = load_cell(cells, x1u + x2u);
 #define OP(f) { float i1 = c0.f * (1.f - td) + c1.f * td, i2 = c2.f * (1.f - td) + c3.f * td;                 float w1 = i1 * (1.f - rd) + i2 * rd; v.f = w1 * (1.f - 0.f) + w1 * 0.f; }
         GRT_FOR_FIELDS_BE(OP)
 #undef OP
@@ -569,7 +591,7 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
       int lx1s = lx1 < 1 ? 1 : (lx1 > nx1 ? nx1 : lx1), ux1s = ux1 < 1 ? 1 : (ux1 > nx1 ? nx1 : ux1);
       float rh = 1.f + sqrtf(1.f - a * a);
       double fac = (F.axr[lx1s - 1] <= rh) ? 1e-3 : 1.0;
-      Field10 v = load_cell(F.cells, (size_t)(ux1s - 1) * nx2 * nx3 + (size_t)(ux2 - 1) * nx3 + (size_t)(ux3 - 1));
+      Field10 v = load_cell(cells, (size_t)(ux1s - 1) * nx2 * nx3 + (size_t)(ux2 - 1) * nx3 + (size_t)(ux3 - 1));
       bool in = x1 > F.ax1[0];
       s.rho = (float)((double)(in ? v.rho : 0.f) * fac);
       s.p = (float)((double)(in ? v.p : 1.f) * fac);

@@ -32,11 +32,21 @@ struct FluidHost {
   float kh = 0, kr0 = 0, kaa = 0, kbb = 0, kpp = 0, x2mintrust = 0, x2maxtrust = 0;  // koral MKS3 grid (fluid_model_koral.f90)
   int ktype = 0;
   std::vector<float> ax1, axr, ax2, axth, ax3;
-  std::vector<HostCell> cells;
+  std::vector<HostCell> cells;  // [nslots][ncell]
   std::vector<float> uvals, vvals, uv, tvals;
+  // time axis of the gridded models (fluid_model_harm.f90:13-16, 446-546 and its copies in the harm3d / iharm / koral
+  // modules): nslots = fnt dumps resident, slot k = dump file indf-k; tstep / toffset are real(4) there (real(8) in iharm)
+  int nslots = 1, indf = 0;
+  size_t ncell = 0;
+  double tcur = 0;            // time stamp of the dump read last (NaN: the format carries none)
+  std::vector<double> tdump;  // t(1:nt)
+  float tstep = 20.f, toffset = 0.f;
+  double tstep_d = 20., toffset_d = 0.;
 };
 // returns GRT_OK / GRT_ERR_IO / GRT_ERR_BAD_ARG
 int load_fluid(FluidHost &f, const grt_args &a);
+// advance_fluid_timestep (fluid.f90:245-281): moves the resident dumps on by the observer time dt (no-op for analytic models)
+int advance_fluid(FluidHost &f, const grt_args &a, double dt);
 
 // emissivity tables (log of the tabulated G(x) integrals; Chandrasekhar table)
 struct EmisTablesHost {

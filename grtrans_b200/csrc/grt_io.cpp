@@ -241,6 +241,7 @@ int load_harm2d(FluidHost &f, const grt_args &a) {
   if (!df) return GRT_ERR_IO;
   for (double &v : hd)
     if (!(df >> v)) return GRT_ERR_IO;
+  f.tcur = hd[0];  // fluid_model_harm.f90:328
   const size_t n = (size_t)f.nx1 * f.nx2;
   f.cells.resize(n);
   std::vector<float> x1(n), x2(n);
@@ -295,9 +296,12 @@ int load_harm3d_native(FluidHost &f, const grt_args &a, FILE *fp) {
     fclose(fp);
     return GRT_ERR_BAD_ARG;
   }
+  // dump time = first number of the text header line (what the reference's ASCII branch reads, :407; its binary branch
+  // leaves tcur unassigned, so tstep is undefined there when nt > 1)
   int ch;
-  while ((ch = fgetc(fp)) != EOF && ch != 10) {
-  }
+  std::string line;
+  while ((ch = fgetc(fp)) != EOF && ch != 10) line.push_back((char)ch);
+  f.tcur = atof(line.c_str());
   const size_t n = (size_t)f.nx1 * f.nx2 * f.nx3;
   std::vector<float> data(35 * n);
   ok = fread(data.data(), 4, data.size(), fp) == data.size();
@@ -317,7 +321,6 @@ int load_harm3d_native(FluidHost &f, const grt_args &a, FILE *fp) {
 }
 
 int load_harm3d(FluidHost &f, const grt_args &a) {
-  if (a.fnt > 1) return GRT_ERR_BAD_ARG;
   {  // the reference's format if `<dfile>%03d.bin` exists, else the synthetic container (tools/make_snapshot.py)
     char append[16];
     snprintf(append, sizeof append, "%03d", a.findf);
@@ -334,6 +337,7 @@ int load_harm3d(FluidHost &f, const grt_args &a) {
   }
   f.nx1 = dims[0]; f.nx2 = dims[1]; f.nx3 = dims[2];
   f.asim = par[0]; f.gam = par[1]; f.h = par[2];
+  f.tcur = std::nan("");  // the container is a single dump without a time stamp
   if (std::fabs(f.asim - (float)a.spin) > 1e-4f) {
     fclose(fp);
     return GRT_ERR_BAD_ARG;
@@ -381,7 +385,7 @@ int load_iharm(FluidHost &f, const grt_args &a) {
     fprintf(stderr, "grtrans_b200: ERROR -- Different simulation and grtrans spin values! %g %g\n", f.asim, a.spin);
     return GRT_ERR_BAD_ARG;
   }
-  if (a.fnt > 1) return GRT_ERR_BAD_ARG;  // time axis (nload / nt > 1) is outside the supported scope
+  f.tcur = header[0];  // :441 (the only assignment of tcur: every dump slot would carry the header file's time)
   char append[16];
   snprintf(append, sizeof append, "%03d", a.findf);
   std::string path = std::string(a.fdfile) + append + ".bin";
@@ -476,7 +480,6 @@ int load_iharm(FluidHost &f, const grt_args &a) {
 // cell, x2 fastest, then x1, then x3).  u^mu, b^mu are Boyer-Lindquist components already; rho, b are scaled by scalefac.
 int load_koral(FluidHost &f, const grt_args &a) {
   const bool d3 = f.model != 22;
-  if (a.fnt > 1) return GRT_ERR_BAD_ARG;
   std::ifstream hf(a.fhfile);
   if (!hf) return GRT_ERR_IO;
   const int nhead = d3 ? 11 : 10;
@@ -496,8 +499,10 @@ int load_koral(FluidHost &f, const grt_args &a) {
   std::ifstream df(std::string(a.fdfile) + append);
   if (!df) return GRT_ERR_IO;
   double tmp;
-  for (int i = 0; i < nhead; i++)
+  for (int i = 0; i < nhead; i++) {
     if (!(df >> tmp)) return GRT_ERR_IO;
+    if (i == 0) f.tcur = tmp;  // tcur=header(1)
+  }
   const size_t n = (size_t)f.nx1 * f.nx2 * f.nx3;
   const int dlen = d3 ? 23 : 38, rhopos = 10, vpos = 12, bpos = d3 ? 16 : 25, ppos = d3 ? 21 : 33, gridpos = 4, bepos = 22;
   const double scalefac = a.fscalefac, sq = std::sqrt(scalefac);
@@ -549,7 +554,80 @@ int load_koral(FluidHost &f, const grt_args &a) {
 
 }  // namespace
 
+namespace {
+int load_one_dump(FluidHost &f, const grt_args &a);
+
+bool has_time_axis(int model) { return model == 12 || model == 19 || model == 22 || model == 25 || model == 26 || model == 29; }
+
+// load_*_data(count): dump files indf, indf-1, ... into slots 0..count-1; tstep = t(1)-t(2) when more than one is read
+int read_dump_slots(FluidHost &f, const grt_args &a, int count) {
+  for (int k = 0; k < count; k++) {
+    grt_args b = a;
+    b.findf = f.indf - k;
+    FluidHost one;
+    int rc = load_one_dump(one, b);
+    if (rc != GRT_OK) return rc;
+    if (one.cells.size() != f.ncell) return GRT_ERR_IO;
+    if (f.nslots > 1 && std::isnan(one.tcur)) return GRT_ERR_BAD_ARG;
+    std::copy(one.cells.begin(), one.cells.end(), f.cells.begin() + (size_t)k * f.ncell);
+    f.tdump[k] = one.tcur;
+  }
+  if (count > 1) {
+    f.tstep_d = f.tdump[0] - f.tdump[1];
+    f.tstep = (float)f.tstep_d;
+  }
+  return GRT_OK;
+}
+}  // namespace
+
 int load_fluid(FluidHost &f, const grt_args &a) {
+  int rc = load_one_dump(f, a);
+  if (rc != GRT_OK) return rc;
+  f.indf = a.findf;
+  f.ncell = f.cells.size();
+  f.nslots = 1;
+  f.tdump.assign(1, f.tcur);
+  if (has_time_axis(f.model) && a.fnt > 1) {
+    // iharm: t(k) is the header file's time for every slot, so tstep = 0 and the slot index is undefined in the reference
+    if (f.model == 29) return GRT_ERR_BAD_ARG;
+    f.nslots = a.fnt;
+    f.tdump.assign(a.fnt, 0.0);
+    f.cells.resize(f.ncell * (size_t)a.fnt);
+    rc = read_dump_slots(f, a, a.fnt);
+  }
+  return rc;
+}
+
+// advance_*_timestep + update_*_data (fluid_model_harm.f90:511-546; the same code in the harm3d, iharm, koral3d modules).
+// Mixed real(4)/real(8) arithmetic as declared there.  (sic) the reference shifts every field of the older slots except
+// u0_arr, so after an update by 0 < nupdate <= nt dumps those slots keep the u^t they held before.
+int advance_fluid(FluidHost &f, const grt_args &a, double dtobs) {
+  if (!has_time_axis(f.model)) return GRT_OK;
+  int nupdate;
+  if (f.model == 29) {
+    nupdate = (int)std::floor(dtobs / f.tstep_d);
+    f.toffset_d = f.toffset_d + dtobs - f.tstep_d * nupdate;
+    nupdate += (int)std::floor(f.toffset_d / f.tstep_d);
+    f.toffset_d -= std::floor(f.toffset_d / f.tstep_d) * f.tstep_d;
+  } else {
+    nupdate = (int)std::floor(dtobs / (double)f.tstep);
+    f.toffset = (float)((double)f.toffset + dtobs - (double)(f.tstep * (float)nupdate));
+    nupdate += (int)std::floor(f.toffset / f.tstep);
+    f.toffset = f.toffset - (float)(int)std::floor(f.toffset / f.tstep) * f.tstep;
+  }
+  f.indf += nupdate;
+  if (nupdate > f.nslots) return read_dump_slots(f, a, f.nslots);
+  if (nupdate <= 0) return GRT_OK;
+  const size_t keep = (size_t)(f.nslots - nupdate) * f.ncell, sh = (size_t)nupdate * f.ncell;
+  std::vector<float> u0(keep);
+  for (size_t i = 0; i < keep; i++) u0[i] = f.cells[sh + i].u0;
+  std::copy_backward(f.cells.begin(), f.cells.begin() + keep, f.cells.end());
+  for (size_t i = 0; i < keep; i++) f.cells[sh + i].u0 = u0[i];
+  return read_dump_slots(f, a, nupdate);
+}
+
+namespace {
+int load_one_dump(FluidHost &f, const grt_args &a) {
   f = FluidHost();
   f.model = fluid_model_id(a.fname);
   switch (f.model) {
@@ -578,6 +656,7 @@ int load_fluid(FluidHost &f, const grt_args &a) {
     default: return GRT_ERR_BAD_ARG;
   }
 }
+}  // namespace
 
 // ------------------------------------------------------------------------------------------ namelists
 namespace {

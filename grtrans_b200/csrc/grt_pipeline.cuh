@@ -99,7 +99,9 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
   double k4[4];
   null_momentum(r0.q2, r0.l, r0.a, r, cos(th), r0.su * pm1(tpr), r0.sm * pm1(tpm), k4);
   FluidSample fs;
-  fluid_sample(A.F, r0.a, r, th, ph, k4, fs);
+  // radius of the ray's first point: reference of the look-back time that picks the dump slot (nslots > 1)
+  const double r1 = (A.F.nslots > 1) ? 1.0 / pa.u[(size_t)ray * maxpts + (m.i1 - 1)] : r;
+  fluid_sample(A.F, r0.a, r, th, ph, t, r1, k4, fs);
   OrthoOut oo;
   comoving_ortho(r, th, r0.a, r0.alpha, r0.beta, r0.mu0, fs.u, fs.b, k4, oo);
   size_t dst = (size_t)ray * maxpts + slot;

@@ -13,7 +13,7 @@ using namespace orc;
 static RunArgs to_run(const grt_args *a) {
   RunArgs r;
   r.standard = a->standard; r.nmu = a->nmu; r.nrotype = a->nrotype; r.nvals = a->nvals; r.nfreq = a->nfreq;
-  r.nmdot = a->nmdot; r.nt = a->nt; r.nload = a->nload; r.extra = a->extra; r.i1 = a->i1; r.i2 = a->i2;
+  r.nmdot = a->nmdot; r.nt = a->nt; r.nload = a->nload; r.extra = a->extra; r.i1 = a->i1; r.i2 = a->i2; r.dt = a->dt;
   r.mumin = a->mumin; r.mumax = a->mumax; r.phi0 = a->phi0; r.spin = a->spin; r.uout = a->uout; r.uin = a->uin;
   r.rcut = a->rcut;
   for (int i = 0; i < 4; i++) r.gridvals[i] = a->gridvals[i];
@@ -138,6 +138,32 @@ int orc_ray_dump(const grt_args *a, int i1, int i2, int cap, int *npts, int *sta
     if (stokes)
       for (int z = 0; z < nfreq * ra.nvals; z++)
         stokes[q * nfreq * ra.nvals + z] = (z < (int)d.stokes.size()) ? d.stokes[z] : 0.0;
+  }
+  return 0;
+}
+
+// host logic of the time axis: load the dump slots, advance nsteps times by dt; out[step*5..] = indf, toffset, tstep,
+// slot-weighted sums of rho_arr and u0_arr
+int orc_fluid_series(const grt_args *a, int nsteps, double dt, double *out) {
+  RunArgs r = to_run(a);
+  FluidData fd;
+  FluidArgs fa = r.fargs;
+  fa.mbh = r.mbh;
+  if (!load_fluid_model(fd, r.fname, r.spin, fa)) return 1;
+  for (int st = 0; st <= nsteps; st++) {
+    if (st > 0) {
+      advance_fluid_timestep(fd, r.fname, r.spin, fa, dt);
+      if (!fd.ok) return 1;
+    }
+    double sr = 0, su = 0;
+    for (int k = 0; k < fd.nt; k++)
+      for (size_t i = 0; i < fd.ncell; i++) {
+        sr += (k + 1) * (double)fd.rho_arr[(size_t)k * fd.ncell + i];
+        su += (k + 1) * (double)fd.u0_arr[(size_t)k * fd.ncell + i];
+      }
+    double *o = out + 5 * st;
+    o[0] = fd.indf; o[1] = (fd.model == F_IHARM) ? fd.toffset_d : (double)fd.toffset;
+    o[2] = (fd.model == F_IHARM) ? fd.tstep_d : (double)fd.tstep; o[3] = sr; o[4] = su;
   }
   return 0;
 }

@@ -262,6 +262,26 @@ void grtrans_main(const RunArgs &A, RunResult &res) {
     GeokerrArgs gargs;
     initialize_pixels(gargs, A.standard, mu0[jm], A.phi0, A.spin, A.uout, A.uin, A.rcut, A.nrotype, A.gridvals[0],
                       A.gridvals[1], A.gridvals[2], A.gridvals[3], nro, nphi, nup);
+    if (A.nload > 1) {
+      // pgrtrans.f90:172-191: one-point geodesics give each pixel's arrival-time offset t0.  (sic) initialize_geo_tabs
+      // (geodesics.f90:113-128) zeroes kext / next / mufill in the shared gargs and only nup is restored afterwards, so the
+      // main pass of an nload > 1 run has no mu-fill points.
+      gargs.nup = 1;
+      gargs.kext = 0; gargs.next = 0; gargs.mufill = 0;
+#pragma omp parallel for num_threads(nth) schedule(static, 1)
+      for (int i = i1; i <= i2; i++) {
+        Geo g;
+        int status;
+        initialize_geodesic(g, gargs, i, status);
+        gargs.t0[i - 1] = (g.npts == 0) ? 0.0 : g.x[0].d[0];
+      }
+      double mx = -1e300, mn = 1e300;
+      for (double v : gargs.t0) mx = std::max(mx, v);
+      for (double &v : gargs.t0) v = (v > 0.) ? v - mx : 0.;
+      for (double v : gargs.t0) mn = std::min(mn, v);
+      for (double &v : gargs.t0) v -= mn;
+      gargs.nup = nup;
+    }
     auto t0 = std::chrono::steady_clock::now();
     long long npoints = 0;
     for (int lt = 0; lt < A.nt; lt++) {
@@ -284,6 +304,7 @@ void grtrans_main(const RunArgs &A, RunResult &res) {
           }
         }
       }
+      if (lt < A.nt - 1) advance_fluid_timestep(fd, A.fname, A.spin, fa, A.dt);  // pgrtrans.f90:211
     }
     res.loop_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     res.npoints += npoints;

@@ -151,6 +151,22 @@ static double bl2ks_phi(double r, double x, double a) {
   return x + a / (2.0 * std::sqrt(1. - a * a)) * std::log((r - 1. - std::sqrt(1. - a * a)) / (r - 1. + std::sqrt(1. - a * a)));
 }
 
+// Dump slot of one geodesic point (fluid_model_harm.f90:133-183; the same lines in the harm3d :147-234, iharm :258-327,
+// koral :118-190 and koral3d :123-218 modules): tt = KS look-back time of the point relative to the ray's first point
+// (real(4)); tindx = floor(tt/tstep) limited to nt-1.  `eps`: harm / koral add 1d-8 before flooring.  The time weight is
+// forced to zero (rttd=0.), so the sample is slot tindx alone; slot tindx+1 only enters multiplied by zero.
+static size_t time_slot_offset(const FluidData &fd, const Geo &g, int i, float a, bool eps) {
+  if (fd.nt <= 1) return 0;  // (nt=1: tindx=maxtindx+1=0 whenever tt>=0)
+  float zr = (float)g.x[i].d[1], zt = (float)g.x[i].d[0], zr1 = (float)g.x[0].d[1];
+  float tt = (float)(bl2ks_time((double)zr, (double)zt, (double)a) - bl2ks_time((double)zr1, 0.0, (double)a));
+  tt = eps ? (float)((double)(-tt) + 1e-8) : -tt;
+  int maxtindx = fd.nt - 2;
+  double q = (fd.model == F_IHARM) ? std::floor((double)tt / fd.tstep_d) : (double)std::floor(tt / fd.tstep);
+  int tindx = (q <= (double)maxtindx) ? (int)q : maxtindx + 1;
+  if (tindx < 0) tindx = 0;  // guard (the reference would index before the arrays)
+  return fd.ncell * (size_t)tindx;
+}
+
 // ------------------------------------------------------------------ THINDISK
 // kerr.f90:102-129 krolikc (real(4) variables, mixed-mode arithmetic as written)
 static float krolikc(float r, float a) {
@@ -445,8 +461,10 @@ static void harm_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f
     float rd = (zr - uniqr[lx1s]) / (uniqr[ux1s] - uniqr[lx1s]);
     if (uniqr[lx1s] <= rh) rd = 1.f;
     int x2l = lx2 - 1, x2u = ux2 - 1, x1l = (lx1s - 1) * nx2, x1u = (ux1s - 1) * nx2;
-    // nt=1: tindx=0 and the "second time slice" wraps onto the first (indx-n), rttd=0
-    int idx[8] = {x1l + x2l, x1l + x2u, x1u + x2l, x1u + x2u, x1l + x2l, x1l + x2u, x1u + x2l, x1u + x2u};
+    // rttd=0: the "second time slice" enters with weight zero (and wraps onto the last slot, indx-n)
+    size_t ts = time_slot_offset(fd, g, i, a, true);
+    size_t idx[8] = {ts + x1l + x2l, ts + x1l + x2u, ts + x1u + x2l, ts + x1u + x2u, ts + x1l + x2l, ts + x1l + x2u,
+                     ts + x1u + x2l, ts + x1u + x2u};
     auto gat = [&](const std::vector<float> &arr) {
       float v[8];
       for (int q = 0; q < 8; q++) v[q] = arr[idx[q]];
@@ -532,7 +550,11 @@ static void harm3d_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> 
     size_t x1l = (size_t)(lx1s - 1) * nx2 * nx3, x1u = (size_t)(ux1s - 1) * nx2 * nx3;
     size_t idx[16] = {x1l + x2l + x3l, x1l + x2u + x3l, x1u + x2l + x3l, x1u + x2u + x3l,
                       x1l + x2l + x3u, x1l + x2u + x3u, x1u + x2l + x3u, x1u + x2u + x3u};
-    for (int q = 0; q < 8; q++) idx[8 + q] = idx[q];  // nt=1: second slice wraps to the first
+    {
+      size_t ts = time_slot_offset(fd, g, i, a, false);
+      for (int q = 0; q < 8; q++) idx[q] += ts;
+    }
+    for (int q = 0; q < 8; q++) idx[8 + q] = idx[q];  // second slice: weight zero (rttd=0.)
     auto gat = [&](const std::vector<float> &arr) {
       float v[16];
       for (int q = 0; q < 16; q++) v[q] = arr[idx[q]];
@@ -618,6 +640,7 @@ static void iharm_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &
       nfac = 1e-3;
     }
     size_t idx = (size_t)(ux1s - 1) * nx2 * nx3 + (size_t)(ux2 - 1) * nx3 + (size_t)(ux3 - 1);
+    idx += time_slot_offset(fd, g, i, a, false);
     bool in = x1 > uniqx1[1];
     FluidPt &p = f[i];
     p.rho = (float)((double)(in ? fd.rho_arr[idx] : 0.f) * nfac);
@@ -642,6 +665,7 @@ static bool load_iharm(FluidData &fd, const FluidArgs &fa, double a) {
   std::vector<double> header(200, -1e20);
   for (int i = 0; i < 200; i++)
     if (!(hf >> header[i])) break;
+  fd.tcur = header[0];  // (the only place tcur is set: every dump slot gets the header file's time, :441,745)
   fd.nx1 = (int)header[1]; fd.nx2 = (int)header[2]; fd.nx3 = (int)header[3];
   fd.asim = (float)header[4];
   fd.hslope = header[5];
@@ -817,7 +841,11 @@ static void koral_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &
     size_t x3l = (size_t)(lx3 - 1) * nx2 * nx1, x3u = (size_t)(ux3 - 1) * nx2 * nx1;
     size_t idx[16] = {x1l + x2l + x3l, x1l + x2u + x3l, x1u + x2l + x3l, x1u + x2u + x3l,
                       x1l + x2l + x3u, x1l + x2u + x3u, x1u + x2l + x3u, x1u + x2u + x3u};
-    for (int q = 0; q < 8; q++) idx[8 + q] = idx[q];
+    {
+      size_t ts = time_slot_offset(fd, g, i, a, true);
+      for (int q = 0; q < 8; q++) idx[q] += ts;
+    }
+    for (int q = 0; q < 8; q++) idx[8 + q] = idx[q];  // second slice: weight zero (rttd=0.)
     auto gat = [&](const std::vector<float> &arr) {
       float v[16];
       if (d3) {
@@ -874,8 +902,10 @@ static bool load_koral(FluidData &fd, const FluidArgs &fa, double a) {
   std::ifstream df(fa.dfile + append);
   if (!df) return false;
   double tmp;
-  for (int i = 0; i < nhead; i++)
+  for (int i = 0; i < nhead; i++) {
     if (!(df >> tmp)) return false;
+    if (i == 0) fd.tcur = tmp;  // tcur=header(1)
+  }
   size_t n = (size_t)fd.nx1 * fd.nx2 * fd.nx3;
   int dlen = d3 ? 23 : 38;
   int rhopos = 10, vpos = 12, bpos = d3 ? 16 : 25, ppos = d3 ? 21 : 33, gridpos = 4, bepos = 22;
@@ -969,6 +999,7 @@ static bool load_harm(FluidData &fd, const FluidArgs &fa, double a) {
   if (!df) return false;
   for (int i = 0; i < 26; i++)
     if (!(df >> header[i])) return false;
+  fd.tcur = header[0];  // :328
   size_t n = (size_t)fd.nx1 * fd.nx2;
   fd.x1_arr.resize(n); fd.x2_arr.resize(n); fd.r_arr.resize(n); fd.th_arr.resize(n);
   std::vector<double> rho(n), uu(n), ucon(4 * n), bcon(4 * n);
@@ -1003,8 +1034,13 @@ static bool load_harm3d_native(FluidData &fd, const FluidArgs &fa, double a, FIL
   fd.nx1 = (int)header[1]; fd.nx2 = (int)header[2]; fd.nx3 = (int)header[3];
   fd.asim = (float)header[10]; fd.gam = (float)header[11]; fd.h = (float)header[13];
   if (std::fabs(fd.asim - (float)a) > 1e-4f) { fclose(fp); return false; }
+  // The binary branch of read_harm3d_data_file never assigns tcur (:441-446; only the ASCII branch does, :407), so t(k)
+  // and tstep are undefined in the reference when nt > 1.  Here the time is the first number of the text header line,
+  // which is what the ASCII branch reads (header(1)).
   int ch;
-  while ((ch = fgetc(fp)) != EOF && ch != 10) {}
+  std::string line;
+  while ((ch = fgetc(fp)) != EOF && ch != 10) line.push_back((char)ch);
+  fd.tcur = atof(line.c_str());
   size_t n = (size_t)fd.nx1 * fd.nx2 * fd.nx3;
   std::vector<float> data(35 * n);
   bool ok = fread(data.data(), 4, data.size(), fp) == data.size();
@@ -1060,8 +1096,8 @@ static bool load_harm3d(FluidData &fd, const FluidArgs &fa, double a) {
   return true;
 }
 
-// fluid.f90:163-243
-bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa) {
+// fluid.f90:163-243 with one dump slot
+static bool load_fluid_single(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa) {
   fd = FluidData();
   if (fname == "SPHACC") {
     fd.model = F_SPHACC;
@@ -1089,6 +1125,86 @@ bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const F
     fd.model = F_DUMMY;
   }
   return fd.ok;
+}
+
+static bool has_time_axis(int model) {
+  return model == F_HARM || model == F_HARM3D || model == F_IHARM || model == F_KORAL || model == F_KORAL3D ||
+         model == F_KORAL3D_DISK;
+}
+static std::vector<float> *slot_fields(FluidData &fd, int q) {
+  std::vector<float> *f[12] = {&fd.rho_arr, &fd.p_arr, &fd.vrl_arr, &fd.vtl_arr, &fd.vpl_arr, &fd.b0_arr, &fd.br_arr,
+                               &fd.bth_arr, &fd.bph_arr, &fd.kela_arr, &fd.be_arr, &fd.u0_arr};
+  return f[q];
+}
+
+// load_*_data(nload) (fluid_model_harm.f90:446-509 and its copies): dump files indf, indf-1, ... fill slots 0..nload-1 of
+// the nt-slot arrays; with more than one file read, tstep = t(1)-t(2).
+static bool load_slots(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa, int nload) {
+  for (int k = 0; k < nload; k++) {
+    FluidData one;
+    FluidArgs fb = fa;
+    fb.indf = fd.indf - k;
+    fb.nt = 1;
+    if (!load_fluid_single(one, fname, a, fb)) return false;
+    for (int q = 0; q < 12; q++) {
+      std::vector<float> &dst = *slot_fields(fd, q), &src = *slot_fields(one, q);
+      if (src.empty()) continue;
+      if (dst.size() < fd.ncell * (size_t)fd.nt) dst.resize(fd.ncell * (size_t)fd.nt, 0.f);
+      std::copy(src.begin(), src.end(), dst.begin() + (size_t)k * fd.ncell);
+    }
+    fd.tdump[k] = one.tcur;
+  }
+  if (nload > 1) {
+    fd.tstep_d = fd.tdump[0] - fd.tdump[1];
+    fd.tstep = (float)fd.tstep_d;
+  }
+  return true;
+}
+
+// fluid.f90:163-243
+bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa) {
+  if (!load_fluid_single(fd, fname, a, fa)) return false;
+  fd.indf = fa.indf;
+  fd.nt = 1;
+  fd.ncell = fd.rho_arr.size();
+  fd.tdump.assign(1, fd.tcur);
+  if (has_time_axis(fd.model) && fa.nt > 1) {
+    fd.nt = fa.nt;
+    fd.tdump.assign(fa.nt, 0.0);
+    fd.ok = load_slots(fd, fname, a, fa, fa.nt);
+  }
+  return fd.ok;
+}
+
+// advance_*_timestep + update_*_data (fluid_model_harm.f90:511-546; identical code in the harm3d :689-723, iharm :799-841,
+// koral3d :635-669 modules).  tstep/toffset are real(4) (real(8) in iharm); mixed-mode arithmetic as written.  (sic) the shift
+// of the slots leaves u0_arr where it was: after an update by 0 < nupdate <= nt slots the older slots keep the u^t of the
+// dump that occupied them before.
+void advance_fluid_timestep(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa, double dtobs) {
+  if (!has_time_axis(fd.model)) return;
+  int nupdate;
+  if (fd.model == F_IHARM) {
+    nupdate = (int)std::floor(dtobs / fd.tstep_d);
+    fd.toffset_d = fd.toffset_d + dtobs - fd.tstep_d * nupdate;
+    nupdate = nupdate + (int)std::floor(fd.toffset_d / fd.tstep_d);
+    fd.toffset_d = fd.toffset_d - std::floor(fd.toffset_d / fd.tstep_d) * fd.tstep_d;
+  } else {
+    nupdate = (int)std::floor(dtobs / (double)fd.tstep);
+    fd.toffset = (float)((double)fd.toffset + dtobs - (double)(fd.tstep * (float)nupdate));
+    nupdate = nupdate + (int)std::floor(fd.toffset / fd.tstep);
+    fd.toffset = fd.toffset - (float)(int)std::floor(fd.toffset / fd.tstep) * fd.tstep;
+  }
+  fd.indf += nupdate;
+  if (nupdate > fd.nt) {
+    fd.ok = load_slots(fd, fname, a, fa, fd.nt);
+  } else if (nupdate > 0) {
+    size_t sh = fd.ncell * (size_t)nupdate, tot = fd.ncell * (size_t)fd.nt;
+    for (int q = 0; q < 11; q++) {  // every field but u0_arr
+      std::vector<float> &v = *slot_fields(fd, q);
+      if (v.size() == tot && sh < tot) std::copy_backward(v.begin(), v.begin() + (tot - sh), v.end());
+    }
+    fd.ok = load_slots(fd, fname, a, fa, nupdate);
+  }
 }
 
 // fluid.f90:473-526

@@ -118,6 +118,14 @@ struct FluidData {  // module-level state of fluid_model_{thindisk,sphacc,ffjet,
   double scalefac = 1.0;
   int ktype = 0, minpolecell = 4;
   std::vector<float> be_arr;
+  // time axis (fluid_model_harm.f90:13-16,446-546 and the same code in the harm3d / iharm / koral modules): `nt` dump slots of
+  // `ncell` cells each, slot k (0-based) = dump file indf-k; tstep / toffset are real(4) module variables (real(8) in iharm)
+  size_t ncell = 0;
+  int indf = 0;
+  double tcur = 0;              // time stamp of the dump file read last
+  std::vector<double> tdump;    // t(1:nt)
+  float tstep = 20.f, toffset = 0.f;
+  double tstep_d = 20., toffset_d = 0.;
   bool ok = true;
 };
 
@@ -133,6 +141,7 @@ struct SourceParams {  // fluid.f90:69-75
 };
 
 bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa);
+void advance_fluid_timestep(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa, double dtobs);
 void get_fluid_vars(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f);
 void convert_fluid_vars(const FluidData &fd, const std::vector<FluidPt> &f, const SourceParams &sp,
                         std::vector<double> &ncgs, std::vector<double> &ncgsnth, std::vector<double> &bcgs,
@@ -174,6 +183,7 @@ void tsum(int n, const double *x, const double *y, double *out);
 struct RunArgs {
   int standard = 1, nmu = 1, nrotype = 2, nvals = 1, nfreq = 1, nmdot = 1, nt = 1, nload = 1, extra = 0, i1 = 1,
       i2 = -1;
+  double dt = 5.;  // observer-time spacing of the nt frames (pgrtrans.f90:211 advance_fluid_timestep(fname,dt))
   double mumin = 0, mumax = 0, phi0 = -0.5, spin = 0, uout = 0.04, uin = 1, rcut = 1;
   double gridvals[4] = {-25, 25, -25, 25};
   int nn[3] = {100, 100, 1};

@@ -113,6 +113,30 @@ def cfg_koral(n=40, nup=100, nfreq=4, iname='delo', threed=True, fname=None, **k
     return d
 
 
+def cfg_series(kind='harm2d', n=24, nup=100, nfreq=2, fnt=3, nload=1, nt=1, dt=10., **kw):
+    """Time axis of the gridded models: dumps 36..46 of a synthetic series (time 10 per dump, the torus moves from dump to
+    dump), fnt dumps resident (slow light: each point samples the dump of its own look-back time), nload > 1 = per-pixel
+    arrival-time offsets t0, nt frames dt apart (advance_fluid_timestep)."""
+    import make_snapshot as ms
+    os.makedirs(SNAPDIR, exist_ok=True)
+    prefix = os.path.join(SNAPDIR, "series_%s_" % kind)
+    probe = prefix + ("0046" if kind == 'koral3d' else ("046.bin" if kind == 'harm3d' else "046"))
+    if not os.path.exists(probe):
+        small = dict(harm2d=dict(nx1=64, nx2=48), harm3d=dict(nx1=40, nx2=24, nx3=16), koral3d=dict(nx1=32, nx2=32, nx3=8),
+                     koral=dict(nx1=40, nx2=40))[kind]
+        ms.write_series(kind, prefix, **small)
+    if kind == 'harm2d':
+        d = cfg_harm(n=n, nup=nup, nfreq=nfreq, fdfile=prefix, fhfile=prefix + "040", findf=40)
+    elif kind == 'harm3d':
+        d = cfg_harm3d(n=n, nup=nup, nfreq=nfreq, fdfile=prefix, fhfile=prefix + "header.txt", findf=40)
+    else:
+        d = cfg_koral(n=n, nup=nup, nfreq=nfreq, threed=(kind == 'koral3d'))
+        d.update(fdfile=prefix, fhfile=prefix + "header.txt", findf=40)
+    d.update(fnt=fnt, nload=nload, nt=nt, dt=dt)
+    d.update(kw)
+    return d
+
+
 def image_errors(got, ref):
     """got/ref: ivals[nvals,npix,ncams].  Returns (max rel dI over pixels with I > 1e-4 Imax per camera, flux error,
     max |dQUV|/Imax, nan masks equal)."""

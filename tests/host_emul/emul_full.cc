@@ -32,6 +32,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
   F.x2mintrust = fh.x2mintrust; F.x2maxtrust = fh.x2maxtrust;
   F.ax1 = fh.ax1.data(); F.axr = fh.axr.data(); F.ax2 = fh.ax2.data(); F.axth = fh.axth.data(); F.ax3 = fh.ax3.data();
   F.cells = reinterpret_cast<const Cell *>(fh.cells.data());
+  F.nslots = fh.nslots; F.ncell = fh.ncell; F.tstep = fh.tstep;
   F.uvals = fh.uvals.data(); F.vvals = fh.vvals.data(); F.uv = fh.uv.data(); F.tvals = fh.tvals.data();
   TransferParams P;
   memset(&P, 0, sizeof(P));
@@ -104,6 +105,31 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
           for (int k = 0; k < nv; k++) image[((size_t)cam * n + q) * nv + k] = (float)out[k];
         }
     }
+  }
+  return 0;
+}
+
+// Host logic of the time axis: load the dump slots, then advance `nsteps` times by dt.  out[(step)*5 + ..] = indf, toffset,
+// tstep, sum_k (k+1) sum_cells rho, sum_k (k+1) sum_cells u0 (slot-weighted, so a slot shift is visible).
+extern "C" int emul_fluid_series(const grt_args *a, int nsteps, double dt, double *out) {
+  grt_host::FluidHost fh;
+  int rc = grt_host::load_fluid(fh, *a);
+  if (rc) return rc;
+  for (int st = 0; st <= nsteps; st++) {
+    if (st > 0) {
+      rc = grt_host::advance_fluid(fh, *a, dt);
+      if (rc) return rc;
+    }
+    double sr = 0, su = 0;
+    for (int k = 0; k < fh.nslots; k++)
+      for (size_t i = 0; i < fh.ncell; i++) {
+        const grt_host::HostCell &c = fh.cells[(size_t)k * fh.ncell + i];
+        sr += (k + 1) * (double)c.rho;
+        su += (k + 1) * (double)c.u0;
+      }
+    double *o = out + 5 * st;
+    o[0] = fh.indf; o[1] = (fh.model == 29) ? fh.toffset_d : (double)fh.toffset;
+    o[2] = (fh.model == 29) ? fh.tstep_d : (double)fh.tstep; o[3] = sr; o[4] = su;
   }
   return 0;
 }

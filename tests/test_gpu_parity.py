@@ -172,6 +172,9 @@ IMAGE_CASES = [
     ("sphacc", dict(n=50, nfreq=8, iname='delo'), 1e-4),
     ("sphacc", dict(n=50, nfreq=8, iname='formal'), 1e-4),
     ("sphacc", dict(n=40, nfreq=4, iname='delo', nvals=1), 1e-4),      # A21: Stokes-I only with a polarised model
+    # nrotype=1: circular camera grid, log-spaced radii a1..rcut (geokerr_wrapper.f:139-149,186-195)
+    ("sphacc", dict(n=40, nfreq=3, nrotype=1, gridvals=[1., 0., 0., 0.], rcut=15.), 1e-4),
+    ("harm", dict(n=32, nup=200, nfreq=1, nrotype=1, gridvals=[.5, 0., 0., 0.], rcut=13.), 1e-4),
     ("ffjet", dict(n=50, nfreq=4, iname='delo'), 1e-4),
     ("ffjet", dict(n=50, nfreq=4, iname='formal'), 1e-4),
     ("harm", dict(n=50, nup=400, nfreq=1, iname='delo'), 1e-4),

@@ -57,6 +57,7 @@ EMUL_CASES = [
     ("sphacc", dict(n=24, nfreq=6, iname='formal')),
     ("sphacc", dict(n=20, nfreq=4, iname='delo', nvals=1)),
     ("sphacc", dict(n=16, nfreq=3, iname='lsoda')),
+    ("sphacc", dict(n=24, nfreq=3, nrotype=1, gridvals=[1., 0., 0., 0.], rcut=15.)),   # circular camera grid
     ("ffjet", dict(n=24, nfreq=4, iname='delo')),
     ("ffjet", dict(n=20, nfreq=3, iname='formal')),
     ("harm", dict(n=24, nup=200, nfreq=2, iname='delo')),
@@ -74,6 +75,27 @@ EMUL_CASES = [
     ("koral", dict(n=24, nup=100, nfreq=3, threed=False)),                                 # KORAL (2-D)
     ("koral", dict(n=20, nup=100, nfreq=2, threed=True, fname='KORAL3D_DISK', gmin=10.)),  # Bernoulli cut + R-beta electrons
 ]
+
+
+# several dumps resident (slow light): each point samples the dump slot of its own look-back time
+EMUL_CASES += [("series", dict(kind=k, fnt=f)) for k, f in (("harm2d", 3), ("harm3d", 3), ("koral3d", 2), ("koral", 2))]
+
+
+@pytest.mark.parametrize("kind,fnt,nsteps,dt", [("harm2d", 1, 4, 25.), ("harm2d", 3, 3, 10.), ("harm2d", 2, 2, 30.),
+                                                 ("harm3d", 2, 2, 20.), ("koral3d", 2, 2, 10.), ("koral", 3, 2, 7.)])
+def test_dump_slots_and_advance_match_oracle(emul, kind, fnt, nsteps, dt):
+    """Host logic of the time axis (load_*_data / advance_*_timestep / update_*_data): dump index, accumulated offset,
+    dump spacing and the slot contents (slot-weighted sums of rho and of the unshifted (sic) u0) after each advance."""
+    a = args_from_kwargs(**cases.cfg_series(kind, fnt=fnt))
+    got = np.zeros((nsteps + 1, 5)); ref = np.zeros((nsteps + 1, 5))
+    assert emul.emul_fluid_series(C.byref(a), C.c_int(nsteps), C.c_double(dt), got.ctypes.data_as(C.c_void_p)) == 0
+    assert orc.lib().orc_fluid_series(C.byref(a), C.c_int(nsteps), C.c_double(dt), ref.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(got[:, 0], ref[:, 0])                     # dump index
+    assert np.array_equal(got[:, 1:3], ref[:, 1:3])                 # toffset, tstep (real(4) arithmetic)
+    assert np.allclose(got[:, 3:], ref[:, 3:], rtol=1e-9)
+    assert got[0, 0] == 40 and got[-1, 0] > 40                      # the series really moved on
+    if fnt > 1:
+        assert got[0, 2] == 10.                                     # tstep = t(1) - t(2) from the dump headers
 
 
 @pytest.mark.parametrize("cfg,over", EMUL_CASES)

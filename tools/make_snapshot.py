@@ -29,7 +29,7 @@ def _ks_metric(r, th, a):
     return g
 
 
-def _fluid(r, th, ph, a, seed, threed, bfac=1.0):
+def _fluid(r, th, ph, a, seed, threed, bfac=1.0, phase=0.0):
     rng = np.random.RandomState(seed)
     amp1, amp2, ph1, ph2 = 0.3 * rng.rand() + 0.2, 0.2 * rng.rand() + 0.1, 2 * np.pi * rng.rand(), 2 * np.pi * rng.rand()
     g = _ks_metric(r, th, a)
@@ -46,7 +46,9 @@ def _fluid(r, th, ph, a, seed, threed, bfac=1.0):
     ut = 1. / np.sqrt(-norm)
     u = np.stack([ut, ut * vr, np.zeros_like(r), ut * om], -1)
     # density: Gaussian torus + floor, azimuthal m=1,2 modes
-    r0, w, hh = 8.0, 5.0, 0.45
+    # `phase` moves the torus and rotates the azimuthal pattern: consecutive dumps of a time series differ
+    r0, w, hh = 8.0 + 4.0 * phase, 5.0, 0.45 * (1. + 0.5 * phase)
+    ph = ph + 2.0 * phase
     rho = np.exp(-((r - r0) / w) ** 2) * np.exp(-(np.cos(th) / hh) ** 2) + 1e-4 * (r / r0) ** -1.5
     if threed:
         rho = rho * (1. + amp1 * np.cos(ph - ph1) + amp2 * np.cos(2. * ph - ph2))
@@ -72,7 +74,7 @@ def _to_mks(v, r, dthdx2):
     return o
 
 
-def harm2d_arrays(nx1=96, nx2=64, a=0.9375, hslope=0.3, rin=1.1, rout=40.0, seed=12345):
+def harm2d_arrays(nx1=96, nx2=64, a=0.9375, hslope=0.3, rin=1.1, rout=40.0, seed=12345, phase=0.0):
     dx1 = np.log(rout / rin) / nx1
     x1 = np.log(rin) + (np.arange(nx1) + 0.5) * dx1
     x2 = (np.arange(nx2) + 0.5) / nx2
@@ -80,17 +82,17 @@ def harm2d_arrays(nx1=96, nx2=64, a=0.9375, hslope=0.3, rin=1.1, rout=40.0, seed
     r = np.exp(X1)
     th = np.pi * X2 + 0.5 * (1. - hslope) * np.sin(2. * np.pi * X2)
     dthdx2 = np.pi * (1. + (1. - hslope) * np.cos(2. * np.pi * X2))
-    rho, uu, u, b = _fluid(r, th, np.zeros_like(r), a, seed, False)
+    rho, uu, u, b = _fluid(r, th, np.zeros_like(r), a, seed, False, phase=phase)
     return dict(nx1=nx1, nx2=nx2, a=a, h=hslope, dx1=dx1, dx2=1. / nx2, startx1=np.log(rin), startx2=0., x1=X1, x2=X2,
                 r=r, th=th, rho=rho, u=uu, ucon=_to_mks(u, r, dthdx2), bcon=_to_mks(b, r, dthdx2), gam=4. / 3.)
 
 
-def write_harm2d(prefix, indf=40, **kw):
+def write_harm2d(prefix, indf=40, time=0.0, **kw):
     """Writes `<prefix>%03d` (dump, also usable as the header file).  Returns the path."""
     d = harm2d_arrays(**kw)
     path = "%s%03d" % (prefix, indf)
     hdr = np.zeros(26)
-    hdr[0] = 0.0; hdr[1] = d['nx1']; hdr[2] = d['nx2']; hdr[3] = d['startx1']; hdr[4] = d['startx2']; hdr[5] = d['dx1']
+    hdr[0] = time; hdr[1] = d['nx1']; hdr[2] = d['nx2']; hdr[3] = d['startx1']; hdr[4] = d['startx2']; hdr[5] = d['dx1']
     hdr[6] = d['dx2']; hdr[9] = d['a']; hdr[10] = d['gam']; hdr[24] = d['h']
     n = d['nx1'] * d['nx2']
     rows = np.zeros((n, 34))
@@ -105,14 +107,14 @@ def write_harm2d(prefix, indf=40, **kw):
     return path
 
 
-def harm3d_arrays(nx1=64, nx2=32, nx3=32, a=0.9375, rin=1.1, rout=40.0, seed=12345, bfac=1.0):
+def harm3d_arrays(nx1=64, nx2=32, nx3=32, a=0.9375, rin=1.1, rout=40.0, seed=12345, bfac=1.0, phase=0.0):
     dx1 = np.log(rout / rin) / nx1
     x1 = np.log(rin) + (np.arange(nx1) + 0.5) * dx1
     x2 = (np.arange(nx2) + 0.5) / nx2
     x3 = (np.arange(nx3) + 0.5) * 2. * np.pi / nx3
     X1, X2, X3 = np.meshgrid(x1, x2, x3, indexing='ij')  # phi fastest
     r = np.exp(X1); th = np.pi * X2; ph = X3
-    rho, uu, u, b = _fluid(r, th, ph, a, seed, True, bfac)
+    rho, uu, u, b = _fluid(r, th, ph, a, seed, True, bfac, phase=phase)
     dth = np.pi * np.ones_like(r)
     return dict(nx1=nx1, nx2=nx2, nx3=nx3, a=a, x1=X1, x2=X2, x3=X3, r=r, th=th, ph=ph, rho=rho, u=uu,
                 ucon=_to_mks(u, r, dth), bcon=_to_mks(b, r, dth), gam=4. / 3.)
@@ -132,7 +134,7 @@ def write_harm3d(path, **kw):
     return path
 
 
-def write_harm3d_native(prefix, indf=40, **kw):
+def write_harm3d_native(prefix, indf=40, time=0.0, **kw):
     """The reference's own harm3d input: `<prefix>header.txt` (15 numbers, fluid_model_harm3d.f90:337-366) and
     `<prefix>%03d.bin` = a text header line + float32 data(35, n) (:516-584).  Returns (header path, data prefix)."""
     d = harm3d_arrays(**kw)
@@ -143,7 +145,7 @@ def write_harm3d_native(prefix, indf=40, **kw):
     data[:, 9] = d['rho'].ravel(); data[:, 10] = d['u'].ravel()
     data[:, 18:22] = d['ucon'].reshape(n, 4); data[:, 26:30] = d['bcon'].reshape(n, 4)
     x1 = d['x1'][:, 0, 0]; x2 = d['x2'][0, :, 0]; x3 = d['x3'][0, 0, :]
-    hdr = [0.0, d['nx1'], d['nx2'], d['nx3'], x1[0] - 0.5 * (x1[1] - x1[0]), 0.0, 0.0, x1[1] - x1[0], x2[1] - x2[0], x3[1] - x3[0],
+    hdr = [time, d['nx1'], d['nx2'], d['nx3'], x1[0] - 0.5 * (x1[1] - x1[0]), 0.0, 0.0, x1[1] - x1[0], x2[1] - x2[0], x3[1] - x3[0],
            d['a'], d['gam'], 0.9, 1.0, 0.0]
     line = " ".join("%.17g" % v for v in hdr) + "\n"
     with open("%s%03d.bin" % (prefix, indf), 'wb') as f:
@@ -214,7 +216,7 @@ def write_iharm(prefix, indf=40, eheat=1, **kw):
 
 
 def koral_arrays(threed=True, nx1=48, nx2=40, nx3=16, a=0.9375, h=0.7, r0=0.0, aa=0.0, bb=0.05, pp=2.0, rin=1.1, rout=40.0,
-                 seed=12345):
+                 seed=12345, phase=0.0):
     """KORAL MKS3 grid (fluid_model_koral.f90:62-80): x1 = log(r - r0), theta(x2, r), x3 = phi in (-pi, pi); BL vectors."""
     dx1 = (np.log(rout - r0) - np.log(rin - r0)) / nx1
     x1 = np.log(rin - r0) + (np.arange(nx1) + 0.5) * dx1
@@ -224,7 +226,7 @@ def koral_arrays(threed=True, nx1=48, nx2=40, nx3=16, a=0.9375, h=0.7, r0=0.0, a
     r = r0 + np.exp(X1)
     w = aa + 2. ** pp * (bb - aa) / r ** pp
     th = 0.5 * np.pi * (1. + np.tan(h * np.pi * (-0.5 + X2 + (1. - 2. * X2) * w)) / np.tan(0.5 * h * np.pi))
-    rho, uu, u, b = _fluid(r, th, X3, a, seed, threed)
+    rho, uu, u, b = _fluid(r, th, X3, a, seed, threed, phase=phase)
 
     def ks2bl(v):
         delta = r ** 2 - 2. * r + a ** 2
@@ -238,7 +240,7 @@ def koral_arrays(threed=True, nx1=48, nx2=40, nx3=16, a=0.9375, h=0.7, r0=0.0, a
                 rho=1e-16 * rho, te=te, be=be, ucon=ks2bl(u), bcon=600. * ks2bl(b))
 
 
-def write_koral(prefix, indf=40, threed=True, **kw):
+def write_koral(prefix, indf=40, threed=True, time=0.0, **kw):
     """ASCII dumps read by fluid_model_koral.f90:318-402 (38 columns) / fluid_model_koral3d.f90:397-514 ("shortfile", 23
     columns): `<prefix>%03d` / `<prefix>%04d` and the header file `<prefix>header.txt`.  Returns (header path, prefix)."""
     d = koral_arrays(threed=threed, **kw)
@@ -258,10 +260,10 @@ def write_koral(prefix, indf=40, threed=True, **kw):
     rows[:, bpos:bpos + 4] = d['bcon'].reshape(n, 4)
     rows[:, ppos] = d['te'].ravel()
     if threed:
-        hdr = [0.0, d['nx1'], d['nx2'], d['nx3'], d['a'], 0.0, d['r0'], d['h'], d['aa'], d['bb'], d['pp']]
+        hdr = [time, d['nx1'], d['nx2'], d['nx3'], d['a'], 0.0, d['r0'], d['h'], d['aa'], d['bb'], d['pp']]
         path = "%s%04d" % (prefix, indf)
     else:
-        hdr = [0.0, d['nx1'], d['nx2'], d['a'], 0.0, d['r0'], d['h'], d['aa'], d['bb'], d['pp']]
+        hdr = [time, d['nx1'], d['nx2'], d['a'], 0.0, d['r0'], d['h'], d['aa'], d['bb'], d['pp']]
         path = "%s%03d" % (prefix, indf)
     line = " ".join("%.17g" % v for v in hdr) + "\n"
     with open(path, 'w') as f:
@@ -271,6 +273,24 @@ def write_koral(prefix, indf=40, threed=True, **kw):
     with open(hpath, 'w') as f:
         f.write(line)
     return hpath, prefix
+
+
+def write_series(kind, prefix, first=36, last=46, tstep=10.0, **kw):
+    """A time series of dumps `first..last` (dump k: time k*tstep, torus displaced by phase 0.04*(k-40)) for the slow-light /
+    movie paths (fnt > 1, nt > 1).  kind: 'harm2d' | 'harm3d' | 'koral3d' | 'koral'.  Returns what the single writer returns."""
+    out = None
+    for k in range(first, last + 1):
+        a = dict(indf=k, time=k * tstep, phase=0.04 * (k - 40))
+        a.update(kw)
+        if kind == 'harm2d':
+            out = write_harm2d(prefix, **a)
+        elif kind == 'harm3d':
+            out = write_harm3d_native(prefix, **a)
+        elif kind == 'koral3d':
+            out = write_koral(prefix, threed=True, **a)
+        else:
+            out = write_koral(prefix, threed=False, **a)
+    return out
 
 
 if __name__ == "__main__":
