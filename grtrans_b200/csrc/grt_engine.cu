@@ -213,7 +213,10 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
     // the shared geokerr_args and only nup is restored (pgrtrans.f90:176-189): the main pass has no mu-fill points
     for (auto &c : s->cams) c.kext = c.next = c.mufill = 0;
   s->maxpts = s->cams[0].maxpts();
-  s->fl = GeoFlags{a->nn[2], s->cams[0].kext, s->cams[0].next, s->cams[0].mufill, s->cams[0].usegeor, 1};
+  s->fl = GeoFlags{a->nn[2], s->cams[0].kext, s->cams[0].next, s->cams[0].mufill, s->cams[0].usegeor, 1, 0};
+  // the coordinate time along the ray only selects the dump slot of a point: with one dump resident its radial integral
+  // (one R_J + R_C per point) is left out
+  s->fl.skip_t = (s->fh.nslots <= 1) ? 1 : 0;
   // shard i1..i2 in interleaved tiles of 256 rays
   int i1 = a->i1 < 1 ? 1 : a->i1, i2 = (a->i2 < 1 || a->i2 > s->npix) ? s->npix : a->i2;
   const int shard = 256;

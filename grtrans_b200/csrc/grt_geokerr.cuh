@@ -30,6 +30,9 @@ struct RayConst {  // one pixel of the camera (geodesics.f90:12-21 geokerr_args,
 
 struct GeoFlags {
   int nup, kext, next, mufill, usegeor, phit;
+  // 1: leave out the p4 = -2 radial integral that only the coordinate time t_u needs (one R_J + R_C per point).  The images do
+  // not depend on t unless several dumps are resident (slow light) or t0 offsets are computed; dt is then meaningless.
+  int skip_t;
 };
 
 struct RayInv {
@@ -48,6 +51,7 @@ struct RayInv {
   // layout (GEOKERR)
   double ub, du, ufleg, offset, uout;
   int tpr, kmax, nkeep, npts, nfill, kext, usegeor, equatorial;
+  int skip_t;  // GeoFlags::skip_t
   // mu-fill
   double fmu0, fmuf, fmuminus, fmuplus;
   int ftpm0, ftpmf;
@@ -99,9 +103,9 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
       const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
-      double t[3];
+      double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll 1
-      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      for (int q = c.skip_t; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
       o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   } else if (kind == 3) {
@@ -113,9 +117,9 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
       const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
-      double t[3];
+      double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll 1
-      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      for (int q = c.skip_t; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
       o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   } else if (kind == 5) {
@@ -126,9 +130,9 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
       const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
-      double t[3];
+      double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll 1
-      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      for (int q = c.skip_t; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
       o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   } else if (kind == 6) {
@@ -140,9 +144,9 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
       const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
-      double t[3];
+      double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll 1
-      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      for (int q = c.skip_t; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
       o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   } else {
@@ -156,9 +160,9 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
     if (PHIT) {
       o.t1 = sgnv * F.m4(0.0, 1.0, r);
       const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
-      double t[3];
+      double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll 1
-      for (int q = 0; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
+      for (int q = c.skip_t; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], r);  // one copy of m2 (code size, see header)
       o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
     }
   }
@@ -742,7 +746,7 @@ GRT_HDN void geo_setup(const RayConst &rc, const GeoFlags &fl, RayInv &c) {
   c.umi = 1.0 - sqrt(1.0 - c.a * c.a);
   c.ur = -1.0 / (2.0 * sqrt(1.0 - c.a * c.a));
   c.qs = sgn(c.q2);
-  c.offset = rc.offset; c.uout = rc.uout; c.kext = fl.kext; c.usegeor = fl.usegeor;
+  c.offset = rc.offset; c.uout = rc.uout; c.kext = fl.kext; c.usegeor = fl.usegeor; c.skip_t = fl.skip_t;
   c.iu0 = c.tu0c = c.phiu0c = c.tu01 = 0.0;
   c.i1mu = c.i3mu = c.rffmu1 = c.rffmu3 = c.rdc = c.rjc = c.tmu1 = c.tmu3 = c.phimu1 = c.phimu3 = 0.0;
   c.f5 = c.g5 = c.iut = c.c1j = c.c2j = c.c3j = c.c4j = c.c5j = c.m1j = c.nj = 0.0;

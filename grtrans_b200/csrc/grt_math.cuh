@@ -117,10 +117,11 @@ GRT_HDN double rf(double x, double y, double z) {
     ave = (1.0 / 3.0) * (x + y + z);
     if (ave == 0.0) {
       dx = dy = dz = 0.0;
-    } else {
-      dx = (ave - x) / ave;
-      dy = (ave - y) / ave;
-      dz = (ave - z) / ave;
+    } else {  // one reciprocal instead of three divisions (the deviations only feed the 1e-3-sized series correction)
+      const double iave = 1.0 / ave;
+      dx = (ave - x) * iave;
+      dy = (ave - y) * iave;
+      dz = (ave - z) * iave;
     }
   } while (dmax(dmax(fabs(dx), fabs(dy)), fabs(dz)) > 0.0025);
   double e2 = dx * dy - dz * dz, e3 = dx * dy * dz;
@@ -132,7 +133,22 @@ GRT_HDN double rf(double x, double y, double z) {
 // roots each).  R_C is elementary, R_C(x,y) = atan(t)/(t sqrt x) for y > x, atanh(t)/(t sqrt x) for 0 < y < x with
 // t = sqrt(|y-x|/x) (DLMF 19.2.17-18), and it is called ~27 times per geodesic point (once per R_J iteration), so the closed
 // form is used: same value to round-off (the series is truncated at ~1e-17), about half the instructions.
-GRT_HDN double rc(double x, double y) {
+// R_C(x, y) for y > 0 with sx = sqrt(x) supplied by the caller (R_J knows it without a square root), scaled by w
+GRT_HDN double rc_pos(double x, double sx, double y, double w = 1.0) {
+  const double d = y - x;
+  if (d == 0.0) return w / sx;
+  if (x == 0.0) return w * (0.5 * GRT_PI) / sqrt(y);
+  const double sd = sqrt(fabs(d));
+  const double t = sd / sx;
+  if (t < 0.03) {  // atan(t)/t, atanh(t)/t by their series: exact to < 1e-17 and free of cancellation
+    const double q = (d > 0.0) ? -t * t : t * t;
+    const double f = 1.0 + q * (1.0 / 3.0 + q * (0.2 + q * (1.0 / 7.0 + q * (1.0 / 9.0 + q * (1.0 / 11.0)))));
+    return w * f / sx;
+  }
+  if (d > 0.0) return w * atan(t) / sd;            // atan(t) / (t sqrt x)
+  return w * log((sx + sd) / sqrt(y)) / sd;        // atanh(t) = log((sqrt x + sqrt(x-y)) / sqrt y): no cancellation for y << x
+}
+GRT_HD double rc(double x, double y) {
   double w = 1.0;
   if (!(y > 0.0)) {  // Cauchy principal value for y < 0
     double xt = x - y;
@@ -140,22 +156,7 @@ GRT_HDN double rc(double x, double y) {
     x = xt;
     y = -y;
   }
-  const double d = y - x;
-  if (d == 0.0) return w / sqrt(x);
-  if (x == 0.0) return w * (0.5 * GRT_PI) / sqrt(y);
-  const double sx = sqrt(x);
-  const double t = sqrt(fabs(d)) / sx;
-  double f;
-  if (t < 0.03) {  // atan(t)/t, atanh(t)/t by their series: exact to < 1e-17 and free of cancellation
-    const double q = (d > 0.0) ? -t * t : t * t;
-    f = 1.0 + q * (1.0 / 3.0 + q * (0.2 + q * (1.0 / 7.0 + q * (1.0 / 9.0 + q * (1.0 / 11.0)))));
-  } else if (d > 0.0) {
-    f = atan(t) / t;
-  } else {  // atanh(t) = log((sqrt(x) + sqrt(x-y)) / sqrt(y)): no cancellation for y << x
-    const double sd = sqrt(-d);
-    return w * log((sx + sd) / sqrt(y)) / sd;
-  }
-  return w * f / sx;
+  return rc_pos(x, sqrt(x), y, w);
 }
 
 // ---- Carlson R_D ------------------------------------------------------------------------------
@@ -171,9 +172,10 @@ GRT_HDN double rd(double x, double y, double z) {
     y = 0.25 * (y + lam);
     z = 0.25 * (z + lam);
     ave = 0.2 * (x + y + 3.0 * z);
-    dx = (ave - x) / ave;
-    dy = (ave - y) / ave;
-    dz = (ave - z) / ave;
+    const double iave = 1.0 / ave;
+    dx = (ave - x) * iave;
+    dy = (ave - y) * iave;
+    dz = (ave - z) * iave;
   } while (dmax(dmax(fabs(dx), fabs(dy)), fabs(dz)) > 0.0015);
   double ea = dx * dy, eb = dz * dz, ec = ea - eb, ed = ea - 6.0 * eb, ee = ed + ec + ec;
   return 3.0 * sum +
@@ -203,19 +205,20 @@ GRT_HDN double rj(double x, double y, double z, double p) {
   do {
     double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
     double lam = sx * (sy + sz) + sy * sz;
-    double al = sq(p * (sx + sy + sz) + sx * sy * sz);
+    double sal = p * (sx + sy + sz) + sx * sy * sz;  // alpha = sal^2: its square root is known (sal > 0 since p > 0)
     double be = p * sq(p + lam);
-    sum += fac * rc(al, be);
+    sum += fac * rc_pos(sal * sal, sal, be);
     fac *= 0.25;
     x = 0.25 * (x + lam);
     y = 0.25 * (y + lam);
     z = 0.25 * (z + lam);
     p = 0.25 * (p + lam);
     ave = 0.2 * (x + y + z + p + p);
-    dx = (ave - x) / ave;
-    dy = (ave - y) / ave;
-    dz = (ave - z) / ave;
-    dp = (ave - p) / ave;
+    const double iave = 1.0 / ave;
+    dx = (ave - x) * iave;
+    dy = (ave - y) * iave;
+    dz = (ave - z) * iave;
+    dp = (ave - p) * iave;
   } while (dmax(dmax(fabs(dx), fabs(dy)), dmax(fabs(dz), fabs(dp))) > 0.0015);
   double ea = dx * (dy + dz) + dy * dz, eb = dx * dy * dz, ec = dp * dp, ed = ea - 3.0 * ec,
          ee = eb + 2.0 * dp * (ea - ec);

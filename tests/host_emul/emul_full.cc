@@ -60,7 +60,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
                            a->nn[1], a->nn[2]);
     int mp = c.maxpts();
     fk.maxpts = mp;
-    GeoFlags fl{a->nn[2], c.kext, c.next, c.mufill, c.usegeor, 1};
+    GeoFlags fl{a->nn[2], c.kext, c.next, c.mufill, c.usegeor, 1, (fh.nslots <= 1) ? 1 : 0};  // as grt_session_create
 #pragma omp parallel for schedule(dynamic, 4)
     for (int q = 0; q < n; q++) {
       int ix = i1 - 1 + q;
