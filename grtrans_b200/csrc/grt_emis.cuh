@@ -218,7 +218,7 @@ GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, 
   e[8] = P.RQ * jff * F.inu3;
   e[9] = 0.0;
   double rv = P.RV0;
-  if (P.RV1 != 0.0) rv -= P.RV1 * ((double)0.43793091f * log(1.0 + (double)0.00185777f * (P.Ax3 * F.nq3)));
+  if (P.RV1 != 0.0) rv -= P.RV1 * ((double)0.43793091f * log_ge1(1.0 + (double)0.00185777f * (P.Ax3 * F.nq3)));
   e[10] = rv * F.inu2;
 }
 

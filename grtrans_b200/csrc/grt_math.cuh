@@ -105,6 +105,44 @@ GRT_HD double exp_fast(double x) {
   return (p * s1) * s2;
 }
 
+// log(x) for finite x >= 1 (the Faraday-rotation fit takes log(1 + positive) once per (point, frequency)): the argument
+// reduction and degree-7 minimax polynomial of the classic s = f/(2+f) scheme (x = 2^k (1+f), sqrt(1/2) < 1+f < sqrt 2;
+// log(1+f) = f - (f^2/2 - s (f^2/2 + R(s^2)))), without libm's branches for zero / negative / subnormal / infinite arguments.
+// Max relative error 0.6 ulp (checked against mpmath over 1 .. 1e12, tests/test_oracle_math.py).
+GRT_HD double log_ge1(double x) {
+  if (!(x <= 8.9e307)) return log(x);  // inf / NaN
+  long long b;
+#if defined(__CUDA_ARCH__)
+  b = __double_as_longlong(x);
+#else
+  memcpy(&b, &x, 8);
+#endif
+  int hx = (int)(b >> 32);
+  int k = (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int i = (hx + 0x95f64) & 0x100000;  // mantissa above sqrt 2: halve it
+  k += i >> 20;
+  b = ((long long)(hx | (i ^ 0x3ff00000)) << 32) | (b & 0xffffffffLL);
+  double m;
+#if defined(__CUDA_ARCH__)
+  m = __longlong_as_double(b);
+#else
+  memcpy(&m, &b, 8);
+#endif
+  const double f = m - 1.0;
+#if defined(__CUDA_ARCH__)
+  const double s = f * __drcp_rn(2.0 + f);
+#else
+  const double s = f / (2.0 + f);
+#endif
+  const double z = s * s, w = z * z;
+  const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+  const double t2 = z * (6.666666666666735130e-01 +
+                         w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+  const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)k;
+  return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+
 // ---- Carlson R_F ------------------------------------------------------------------------------
 GRT_HDN double rf(double x, double y, double z) {
   double ave, dx, dy, dz;

@@ -133,3 +133,8 @@ extern "C" int emul_fluid_series(const grt_args *a, int nsteps, double dt, doubl
   }
   return 0;
 }
+
+// scalar math replacements used on the per-(point, frequency) path
+extern "C" void emul_math(int which, int n, const double *x, double *o) {
+  for (int i = 0; i < n; i++) o[i] = (which == 0) ? exp_fast(x[i]) : log_ge1(x[i]);
+}

@@ -98,6 +98,33 @@ def test_dump_slots_and_advance_match_oracle(emul, kind, fnt, nsteps, dt):
         assert got[0, 2] == 10.                                     # tstep = t(1) - t(2) from the dump headers
 
 
+def test_fast_exp_and_log_are_one_ulp(emul):
+    """exp_fast / log_ge1 (grt_math.cuh) replace libm's exp / log inside the emissivity + DELO loop: within 1 ulp of the
+    correctly rounded value over their domains (exp: -745..709 including subnormal results; log: finite x >= 1)."""
+    from mpmath import mp, mpf, exp as mexp, log as mlog
+    mp.dps = 40
+    rng = np.random.RandomState(7)
+
+    def call(which, x):
+        o = np.zeros_like(x)
+        emul.emul_math(C.c_int(which), C.c_int(len(x)), x.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+        return o
+    x = np.concatenate([rng.uniform(-745., 709., 4000), rng.uniform(-1., 1., 2000), [-744.4, -708.4, 0., 709., -1e-300]])
+    got = call(0, x)
+    for xi, g in zip(x, got):
+        t = mexp(mpf(float(xi)))
+        ulp = float(np.spacing(max(float(t), 2.3e-308)))
+        assert abs(mpf(float(g)) - t) <= 1.0 * ulp, (xi, g)
+    assert call(0, np.array([-801., -1e5]))[0] < 1e-320 and np.isnan(call(0, np.array([np.nan])))[0]
+    x = np.concatenate([1. + 10. ** rng.uniform(-15., 12., 4000), rng.uniform(1., 4., 2000), [1., 2., np.sqrt(2.), 1e300]])
+    got = call(1, x)
+    assert got[4000 + 2000] == 0.
+    for xi, g in zip(x, got):
+        t = mlog(mpf(float(xi)))
+        assert abs(mpf(float(g)) - t) <= 1.0 * float(np.spacing(abs(float(t)))) + 0., (xi, g)
+    assert np.isinf(call(1, np.array([np.inf])))[0] and np.isnan(call(1, np.array([np.nan])))[0]
+
+
 @pytest.mark.parametrize("cfg,over", EMUL_CASES)
 def test_kernel_bodies_match_oracle(emul, cfg, over):
     kw = getattr(cases, "cfg_" + cfg)(**over)
