@@ -11,7 +11,14 @@
 namespace grt {
 
 enum { EM_POLSYNCHTH = 2, EM_SYNCHPL = 3, EM_POLSYNCHPL = 4, EM_BB = 8, EM_BBPOL = 9, EM_SYNCHTHAV = 13,
-       EM_HYBRIDTHPL = 20, EM_HYBRIDTH = 21, EM_HYBRIDPL = 22 };
+       EM_HYBRIDTHPL = 20, EM_HYBRIDTH = 21, EM_HYBRIDPL = 22,
+       // unpolarised thermal models sharing SYNCHTHAV's point record (n, B, T) and kernel slot (em_slot)
+       EM_BREMS = 5, EM_SYNCHTHAVNOABS = 14, EM_SYNCHTHBREMS = 27 };
+// kernel / record slot of an emissivity type: the (n, B, T) scalar models run in the SYNCHTHAV instantiations and pick
+// their formula from TransferParams::etype at run time (a thread-uniform switch)
+GRT_HD constexpr int em_slot(int et) {
+  return (et == EM_BREMS || et == EM_SYNCHTHAVNOABS || et == EM_SYNCHTHBREMS) ? EM_SYNCHTHAV : et;
+}
 
 namespace pc {
 constexpr double h = 6.626e-27, k = 1.38e-16, c = 2.99792458e10, e = 4.8032e-10, G = 6.67e-8, m = 9.10938188e-28,
@@ -342,6 +349,34 @@ GRT_HD void synchemis_eval(double nu, double n, double B, double T, double *e) {
   double jnu = 4.43e-30 / 2.0 * nu * n * ipx / (thetae * thetae);
   e[0] = jnu;
   e[4] = (fabs(jnu) > 0.) ? jnu / planck_bnu(T, nu) : 0.0;
+}
+
+// free-free emission / absorption (brememisHEROIC, emis.f90:188-238); literals without d0 are single precision there
+GRT_HD void brems_eval(double nu, double ne, double T, double *e) {
+  for (int i = 0; i < 11; i++) e[i] = 0.0;
+  const double rho = ne * (double)1.67219e-24f;
+  const double sqrtt = sqrt(T);
+  const double thetae = pc::k * T / pc::m / pc::c2;
+  const double sqrtthetae = sqrt(thetae);
+  const double r10 = 1e5 / T, r2 = r10 * r10, r4 = r2 * r2, r8 = r4 * r4;
+  const double tempfactor = 1. / (sqrtt + r8 * r2) + 1e-32;
+  const double arg = pc::h * nu / (pc::k * T);
+  double fei, fee;
+  if (thetae < 1.) {
+    fei = (double)1.016f * sqrtthetae * (1 + (double)1.781f * pow(thetae, (double)1.34f));
+    fee = thetae * sqrtthetae * (1 + (double)1.1f * thetae + thetae * thetae * (1 - 1.25 * sqrtthetae));
+  } else {
+    fei = (double)1.432f * thetae * (log((double)1.123f * thetae + (double)0.48f) + 1.5);
+    fee = (double)1.328f * thetae * (log((double)1.123f * thetae) + (double)1.28f);
+  }
+  double anu = 0.0;
+  if (!(arg > 100.)) {
+    const double x = (arg < (double)1.e-8f) ? arg : 1 - exp(-arg);
+    anu = (1.10e61 / sqrtt) * rho * rho * fei * x * tempfactor / (nu * nu * nu);
+    anu = anu + (1.14e51 / sqrtt / T) * rho * rho * fee * x * tempfactor / (nu * nu);
+  }
+  e[0] = anu * planck_bnu(T, nu);
+  e[4] = anu;
 }
 
 // Chandrasekhar (1960) Table XXIV limb darkening / polarisation degree, float32 linear interpolation

@@ -182,7 +182,7 @@ void launch_transfer(const RayMeta *meta, const TransferParams &P, const double 
   long long tt = (long long)nrays * nparams * nfreq;
   unsigned grid = (unsigned)((tt + B - 1) / B);
   const int mode = transfer_mode(P);
-  switch (P.etype) {
+  switch (em_slot(P.etype)) {
 #define OP(E) \
   case E: launch_transfer_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0); break;
     GRT_FOR_ETYPES(OP)

@@ -113,7 +113,7 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
     double o[GRT_NREC_MAX];
     for (int i = 0; i < GRT_NREC_MAX; i++) o[i] = 0.0;
     o[0] = lam; o[1] = oo.g; o[2] = oo.s2xi; o[3] = oo.c2xi;
-    switch (A.etype) {
+    switch (em_slot(A.etype)) {
       case EM_HYBRIDTHPL:
       case EM_HYBRIDTH:
       case EM_HYBRIDPL: {  // thermal data as below + the power-law population's point data

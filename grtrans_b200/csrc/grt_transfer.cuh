@@ -25,7 +25,7 @@ namespace grt {
 #define GRT_NREC 20      // doubles per point record (160 B) ...
 #define GRT_NREC_MAX 24  // ... 24 for the hybrid thermal + power-law emissivities (thermal and power-law point data)
 GRT_HD constexpr bool em_is_hybrid(int et) { return et == EM_HYBRIDTHPL || et == EM_HYBRIDTH || et == EM_HYBRIDPL; }
-GRT_HD constexpr int record_doubles(int etype) { return em_is_hybrid(etype) ? GRT_NREC_MAX : GRT_NREC; }
+GRT_HD constexpr int record_doubles(int etype) { return em_is_hybrid(etype) ? GRT_NREC_MAX : GRT_NREC; }  // (same for every em_slot member)
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
 //   POLSYNCHTH        [4..17] ThermalPoint (xp13, AI, AV, hkT_g, Ax, Ax^1.035, Ax^1.2, Ax^1.503, Ax^-8/3, RQ, RV0, RV1, 1/xp13, xp13^-1.5)
 //   POLSYNCHPL/SYNCHPL [4] n_nth, [5] nu_B,perp, [6] log(g) + log(1.5 nu_B,perp), [7] 1/tan(angle)  (PlPoint)
@@ -115,8 +115,20 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
       Q.nnth = rec[4]; Q.nubperp = rec[5]; Q.L = rec[6]; Q.itanth = rec[7];
       pl_eval<ET == EM_POLSYNCHPL>(P.tab, R.pl, Q, nu, R.lnu, e);
     }
-    else if (ET == EM_SYNCHTHAV)
-      synchemis_eval(nu, rec[4], rec[5], rec[6], e);
+    else if (ET == EM_SYNCHTHAV) {  // the (n, B, T) scalar models: emis.f90:525-540
+      if (P.etype == EM_BREMS) {
+        brems_eval(nu, rec[4], rec[6], e);
+      } else {
+        synchemis_eval(nu, rec[4], rec[5], rec[6], e);
+        if (P.etype == EM_SYNCHTHAVNOABS) e[4] = 0.0;
+        if (P.etype == EM_SYNCHTHBREMS) {
+          double eb[11];
+          brems_eval(nu, rec[4], rec[6], eb);
+          e[0] += eb[0];
+          e[4] += eb[4];
+        }
+      }
+    }
     else {
       for (int i = 0; i < 11; i++) e[i] = 0.0;
       if (ET == EM_BB) e[0] = planck_bnu(rec[6], nu);
@@ -487,7 +499,7 @@ GRT_HD void ray_transfer_e(const TransferParams &P, const double *rec, int npts,
   }
 }
 GRT_HDN void ray_transfer(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
-  switch (P.etype) {
+  switch (em_slot(P.etype)) {
 #define OP(E) case E: ray_transfer_e<E>(P, rec, npts, nu_obs, out); break;
     GRT_FOR_ETYPES(OP)
 #undef OP

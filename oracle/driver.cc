@@ -147,6 +147,17 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
           } break;
           case E_SYNCHPL: synchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, K11); break;
           case E_SYNCHTHAV: synchemis(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], K11); break;
+          case E_SYNCHTHAVNOABS:  // polsynchemis.f90:906-913: synchemis with the absorption columns zeroed
+            synchemis(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], K11);
+            for (int c = 4; c < 11; c++) K11[c] = 0.0;
+            break;
+          case E_BREMS: brememis(nu, w.ncgs[p], w.tcgs[p], K11); break;
+          case E_SYNCHTHBREMS: {  // emis.f90:531-534
+            double Kbr[11];
+            synchemis(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], K11);
+            brememis(nu, w.ncgs[p], w.tcgs[p], Kbr);
+            for (int c = 0; c < 11; c++) K11[c] += Kbr[c];
+          } break;
           case E_BB: K11[0] = bnu(w.tcgs[p], nu); break;
           case E_BBPOL: {
             double fcol = 1.8;

@@ -281,6 +281,41 @@ void synchemis(double nu, double n, double B, double T, double *e) {
   e[4] = anu;
 }
 
+// emis.f90:188-238 brememisHEROIC (free-free, unpolarised).  The literals without a d0 exponent are single precision in
+// the reference (1.016, 1.781, 1.34, 1.1, 1.432, 1.123, 0.48, 1.328, 1.28, 1.67219e-24, 1.e-8) and are promoted as such.
+void brememis(double nu, double ne, double T, double *e) {
+  using namespace pc;
+  const double epsilon = 1e-32;
+  for (int i = 0; i < 11; i++) e[i] = 0.0;
+  double temp = T;
+  double rho = ne * (double)1.67219e-24f;
+  double sqrtt = std::sqrt(temp);
+  double thetae = k * temp / m / c2;
+  double sqrtthetae = std::sqrt(thetae);
+  double tempfactor = 1. / (sqrtt + std::pow(1e5 / temp, 10)) + epsilon;
+  double arg = h * nu / (k * temp);
+  double fei, fee;
+  if (thetae < 1.) {
+    fei = (double)1.016f * sqrtthetae * (1 + (double)1.781f * std::pow(thetae, (double)1.34f));
+    fee = thetae * sqrtthetae * (1 + (double)1.1f * thetae + thetae * thetae * (1 - 1.25 * sqrtthetae));
+  } else {
+    fei = (double)1.432f * thetae * (std::log((double)1.123f * thetae + (double)0.48f) + 1.5);
+    fee = (double)1.328f * thetae * (std::log((double)1.123f * thetae) + (double)1.28f);
+  }
+  double anu;
+  if (arg > 100.) {
+    anu = 0.0;
+  } else if (arg < (double)1.e-8f) {
+    anu = (1.10e61 / sqrtt) * rho * rho * fei * arg * tempfactor / (nu * nu * nu);
+    anu = anu + (1.14e51 / sqrtt / temp) * rho * rho * fee * arg * tempfactor / (nu * nu);
+  } else {
+    anu = (1.10e61 / sqrtt) * rho * rho * fei * (1 - std::exp(-arg)) * tempfactor / (nu * nu * nu);
+    anu = anu + (1.14e51 / sqrtt / temp) * rho * rho * fee * (1 - std::exp(-arg)) * tempfactor / (nu * nu);
+  }
+  e[0] = anu * bnu(temp, nu);
+  e[4] = anu;
+}
+
 // ------------------------------------------------------------------ chandra_tab24.f90:29-38
 void interp_chandra_tab24(float mu, float &I, float &del) {
   static float ch_mu[22], ch_I[22], ch_delta[22];
@@ -326,6 +361,9 @@ int emis_type_from_name(const std::string &ename, int &neq) {
   if (ename == "HYBRIDTHPL") { neq = 4; return E_HYBRIDTHPL; }
   if (ename == "HYBRIDTH") { neq = 4; return E_HYBRIDTH; }
   if (ename == "HYBRIDPL") { neq = 4; return E_HYBRIDPL; }
+  if (ename == "BREMS") { neq = 1; return E_BREMS; }
+  if (ename == "SYNCHTHBREMS") { neq = 1; return E_SYNCHTHBREMS; }
+  if (ename == "SYNCHTHAVNOABS") { neq = 1; return E_SYNCHTHAVNOABS; }
   neq = 1;
   return -1;
 }

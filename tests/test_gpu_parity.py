@@ -181,6 +181,11 @@ IMAGE_CASES = [
     ("harm3d", dict(n=50, nup=200, nfreq=4, iname='delo'), 1e-4),
     ("harm3d", dict(n=40, nup=100, nfreq=2, iname='delo', nmdot=3, mdotmin=1e19, mdotmax=1e21), 1e-4),
     ("harm3d_native", dict(n=40, nup=100, nfreq=3), 1e-4),                        # the reference's own harm3d file format
+    # unpolarised (n, B, T) models: free-free, synchrotron + free-free, synchrotron without absorption (emis.f90:525-540)
+    ("harm3d", dict(n=32, nup=100, nfreq=4, ename='BREMS', nvals=1, fmin=1e12, fmax=1e18), 1e-4),
+    ("harm3d", dict(n=32, nup=100, nfreq=4, ename='SYNCHTHBREMS', nvals=1, fmin=1e11, fmax=1e17), 1e-4),
+    ("harm3d", dict(n=32, nup=100, nfreq=3, ename='SYNCHTHAVNOABS', nvals=1, iname='lsoda'), 1e-4),
+    ("sphacc", dict(n=32, nfreq=4, ename='SYNCHTHBREMS', nvals=1), 1e-4),
     # thermal + power-law electron populations (emis.f90:469-485) on a magnetised snapshot
     ("harm3d", dict(n=50, nup=200, nfreq=4, ename='HYBRIDTHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True), 1e-4),
     ("harm3d", dict(n=40, nup=100, nfreq=3, ename='HYBRIDTH', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True), 1e-4),

@@ -71,6 +71,10 @@ EMUL_CASES = [
     ("harm3d", dict(n=20, nup=100, nfreq=3, ename='HYBRIDTHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True)),
     ("harm3d", dict(n=16, nup=100, nfreq=2, ename='HYBRIDTH', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True)),
     ("harm3d", dict(n=16, nup=100, nfreq=2, ename='HYBRIDPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True, iname='formal')),
+    # unpolarised (n, B, T) models: free-free, synchrotron + free-free, synchrotron without absorption (emis.f90:525-540)
+    ("harm3d", dict(n=16, nup=100, nfreq=3, ename='BREMS', nvals=1, fmin=1e12, fmax=1e18)),
+    ("harm3d", dict(n=16, nup=100, nfreq=3, ename='SYNCHTHBREMS', nvals=1, fmin=1e11, fmax=1e17)),
+    ("harm3d", dict(n=16, nup=100, nfreq=3, ename='SYNCHTHAVNOABS', nvals=1, iname='lsoda')),
     ("koral", dict(n=24, nup=100, nfreq=3, threed=True)),                                  # KORAL3D, T_e from the dump
     ("koral", dict(n=24, nup=100, nfreq=3, threed=False)),                                 # KORAL (2-D)
     ("koral", dict(n=20, nup=100, nfreq=2, threed=True, fname='KORAL3D_DISK', gmin=10.)),  # Bernoulli cut + R-beta electrons
