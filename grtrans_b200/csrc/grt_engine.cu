@@ -189,7 +189,8 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
     return GRT_ERR_BAD_ARG;
   }
   if (a->nmdot > 8 || a->nt < 1 || (a->nvals != 1 && a->nvals != 4) || a->extra != 0) return GRT_ERR_BAD_ARG;
-  if (std::string(a->stype) != "const") return GRT_ERR_BAD_ARG;
+  const std::string stype(a->stype);
+  if (stype != "const" && stype != "tail") return GRT_ERR_BAD_ARG;
   grt_session *s = new grt_session();
   s->args = *a;
   s->device = device; s->rank = rank; s->nranks = nranks < 1 ? 1 : nranks;
@@ -316,8 +317,10 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
     SourceDev &sp = s->fk.sp[m];
     sp.mdot = s->mdots[m]; sp.mbh = a->mbh; sp.nfac = a->ftscl; sp.bfac = a->frscl; sp.jetalphaval = a->jetalpha;
     sp.gminval = a->gmin; sp.muval = a->muval; sp.gmax = a->gmax; sp.p1 = a->p1; sp.p2 = a->p2; sp.sigcut = a->sigcut;
+    sp.stail = (stype == "tail") ? 1 : 0; sp.pad = 0;
   }
   TransferParams &P = s->tp;
+  P.stail = (stype == "tail") ? 1 : 0;
   P.etype = etype; P.eneq = eneq; P.rneq = a->nvals; P.iflag = iflag; P.model = model;
   P.npts_is_one = (a->nn[2] == 1) ? 1 : 0;
   for (int i = 0; i < 7; i++) P.coefindx[i] = a->epcoefindx[i];

@@ -606,16 +606,51 @@ GRT_HDN void fluid_sample(const FluidDev &F, double ad, double rr, double thh, d
 // ---- code units -> cgs (convert_fluid_vars_arr and the per-model converters) -----------------------
 struct SourceDev {
   double nfac, bfac, mbh, mdot, p1, p2, gmax, gminval, jetalphaval, muval, sigcut;
+  int stail, pad;  // stype = 'tail' (assign_source_params_type, fluid.f90:1614-1624)
 };
 struct CgsVars {
-  double ncgs, ncgsnth, bcgs, tcgs;
+  double ncgs, ncgsnth, bcgs, tcgs, gmin;  // gmin: minimum Lorentz factor of the power law at this point (sp%gmin)
 };
+
+// calcgmin.f90:6-78: minimum Lorentz factor and non-thermal fraction of a power-law tail matched to a thermal distribution
+// of dimensionless temperature theta, carrying the fraction eta of its energy.  The fit constants are default-real literals
+// in the reference (single precision promoted to double).  (sic) its p = 3.5 branch assigns gmin_lin_sin_* twice and never
+// assigns gmin_inv_sin_*: uninitialised there, 0 here.
+GRT_HD void tail_gmin(double p, double theta, double eta, double &gmin, double &nfrac) {
+  const double azero = 3.0 / sqrt(2.0), astwo = log(sqrt(2.0));
+  double linc, invc;
+  if (p == 3.5) {
+    linc = (double)16.0797900684f + (double)-13.5593749125f * pow(eta, (double)0.276589155355f) +
+           (double)0.121815691108f * sin(eta * (double)0.121815691108f + (double)0.121815691108f);
+    invc = (double)0.722506578136f + (double)151.597731214f * pow(eta, (double)6.53997654139f);
+  } else {
+    linc = (double)21.38307186f + (double)-16.7811712f * pow(eta, (double)0.15128533f);
+    invc = (double)0.74798712f + (double)0.62609462f * pow(eta, (double)0.81567379f) +
+           (double).00638946501f * sin(eta * (double)-16.8034428f + (double)3.72208398f);
+  }
+  const double raw = theta * linc + invc;
+  gmin = (raw >= 1.0) ? raw : 1.0;
+  const double atheta = theta * azero * exp(astwo * tanh((double)0.52624783f * log(theta / (double)0.5668090982352612f)));
+  nfrac = eta * atheta * ((p - 2.) / (p - 1.)) * pow(gmin, p - 2.);
+}
+// assign_source_params (fluid.f90:1640-1677), applied after every model's unit conversion (fluid.f90:582)
+GRT_HD void source_params(const SourceDev &sp, CgsVars &o) {
+  o.gmin = sp.gminval;
+  if (!sp.stail) return;
+  const double pcc = 2.99792458e10, pck = 1.38e-16, pcm = 9.10938188e-28;
+  double g, x;
+  tail_gmin(sp.p2, sp.muval * pck * o.tcgs / pcm / pcc / pcc, sp.jetalphaval, g, x);
+  const bool in = g <= sp.gmax;
+  o.gmin = in ? g : sp.gmax / 2.0;
+  const double factor = in ? 1.0 : pow(sp.gmax / 2.0 / g, sp.p2 - 2.);
+  o.ncgsnth = factor * ((x > 0.0) ? x * o.ncgs * pow(o.gmin, 1. - sp.p2) : 0.0);
+}
 
 GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bmag, float kela, float be, float gam,
                    CgsVars &o) {
   const double pi = GRT_PI;
   const double pcG = 6.67e-8, pcc = 2.99792458e10, pcmsun = 1.998e33, pcmp = 1.67262158e-24, pck = 1.38e-16;
-  o.ncgs = o.ncgsnth = o.bcgs = o.tcgs = 0.0;
+  o.ncgs = o.ncgsnth = o.bcgs = o.tcgs = o.gmin = 0.0;
   switch (model) {
     case FL_SPHACC:
       o.ncgs = rho; o.bcgs = bmag; o.tcgs = p;
@@ -725,6 +760,7 @@ GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bma
     default:
       break;
   }
+  source_params(sp, o);
 }
 
 }  // namespace grt

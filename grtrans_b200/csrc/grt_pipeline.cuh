@@ -120,6 +120,10 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
         PlPoint Q;
         pl_point<true>(cg.ncgsnth, cg.bcgs, oo.ang, oo.g, Q);
         o[18] = Q.nnth; o[19] = Q.nubperp; o[20] = Q.L; o[21] = Q.itanth;
+        if (A.sp[mm].stail) {  // gmin varies from point to point: its share of pl_const travels with the record
+          const PlConst C = pl_const((double)(float)A.sp[mm].p1, (double)(float)cg.gmin, (double)(float)A.sp[mm].gmax);
+          o[22] = C.l2gmin; o[23] = C.kq; o[24] = C.kv; o[25] = C.cA;
+        }
       }  // fall through
       case EM_POLSYNCHTH: {
         ThermalPoint T;
@@ -135,6 +139,10 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
         else
           pl_point<false>(cg.ncgsnth, cg.bcgs, oo.ang, oo.g, Q);
         o[4] = Q.nnth; o[5] = Q.nubperp; o[6] = Q.L; o[7] = Q.itanth;
+        if (A.sp[mm].stail) {
+          const PlConst C = pl_const((double)(float)A.sp[mm].p1, (double)(float)cg.gmin, (double)(float)A.sp[mm].gmax);
+          o[8] = C.l2gmin; o[9] = C.kq; o[10] = C.kv; o[11] = C.cA;
+        }
       } break;
       case EM_SYNCHTHAV:
         o[4] = cg.ncgs; o[5] = cg.bcgs; o[6] = cg.tcgs;

@@ -23,7 +23,7 @@
 namespace grt {
 
 #define GRT_NREC 20      // doubles per point record (160 B) ...
-#define GRT_NREC_MAX 24  // ... 24 for the hybrid thermal + power-law emissivities (thermal and power-law point data)
+#define GRT_NREC_MAX 28  // ... 28 for the hybrid thermal + power-law emissivities (thermal and power-law point data)
 GRT_HD constexpr bool em_is_hybrid(int et) { return et == EM_HYBRIDTHPL || et == EM_HYBRIDTH || et == EM_HYBRIDPL; }
 GRT_HD constexpr int record_doubles(int etype) { return em_is_hybrid(etype) ? GRT_NREC_MAX : GRT_NREC; }  // (same for every em_slot member)
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
@@ -41,6 +41,7 @@ struct TransferParams {
   double LBH, gmin, gmax, p;  // emis_params pass through float32 in the reference
   double max_tau, hmax, ortol, oatol, thin;
   int maxsteps;
+  int stail;  // stype = 'tail': the power law's gmin-dependent constants come from the point record
   EmisTables tab;
 };
 
@@ -97,7 +98,13 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
       PlPoint Q;
       Q.nnth = rec[18]; Q.nubperp = rec[19]; Q.L = rec[20]; Q.itanth = rec[21];
       double ep[11];
-      pl_eval<true>(P.tab, R.pl, Q, F.nu / g, R.lnu, ep);
+      if (P.stail) {
+        PlConst C = R.pl;
+        C.l2gmin = rec[22]; C.kq = rec[23]; C.kv = rec[24]; C.cA = rec[25];
+        pl_eval<true>(P.tab, C, Q, F.nu / g, R.lnu, ep);
+      } else {
+        pl_eval<true>(P.tab, R.pl, Q, F.nu / g, R.lnu, ep);
+      }
       const double g2 = g * g, kg = P.LBH / g;
       if (ET == EM_HYBRIDTHPL) {
         jI_raw += ep[0];
@@ -113,7 +120,13 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
     if (ET == EM_POLSYNCHPL || ET == EM_SYNCHPL) {
       PlPoint Q;
       Q.nnth = rec[4]; Q.nubperp = rec[5]; Q.L = rec[6]; Q.itanth = rec[7];
-      pl_eval<ET == EM_POLSYNCHPL>(P.tab, R.pl, Q, nu, R.lnu, e);
+      if (P.stail) {  // per-point gmin (assign_source_params, fluid.f90:1656-1667)
+        PlConst C = R.pl;
+        C.l2gmin = rec[8]; C.kq = rec[9]; C.kv = rec[10]; C.cA = rec[11];
+        pl_eval<ET == EM_POLSYNCHPL>(P.tab, C, Q, nu, R.lnu, e);
+      } else {
+        pl_eval<ET == EM_POLSYNCHPL>(P.tab, R.pl, Q, nu, R.lnu, e);
+      }
     }
     else if (ET == EM_SYNCHTHAV) {  // the (n, B, T) scalar models: emis.f90:525-540
       if (P.etype == EM_BREMS) {

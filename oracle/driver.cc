@@ -49,7 +49,7 @@ namespace {
 struct RayWork {
   Geo g;
   std::vector<FluidPt> f;
-  std::vector<double> s2xi, c2xi, ang, rshift, cosne, ncgs, ncgsnth, bcgs, tcgs;
+  std::vector<double> s2xi, c2xi, ang, rshift, cosne, ncgs, ncgsnth, bcgs, tcgs, gmin;
   std::vector<double> ej, eK, j, K, tau, intensity, absK;
 };
 }  // namespace
@@ -118,9 +118,11 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
     sp.gminval = A.gmin; sp.muval = A.muval; sp.gmax = A.gmax; sp.p1 = A.p1; sp.p2 = A.p2; sp.sigcut = A.sigcut;
     double MBH = sp.mbh;
     double LBH = pc::G * MBH * pc::msun / pc::c2;
+    sp.type = (A.stype == "tail") ? 1 : 0;  // assign_source_params_type (fluid.f90:1614-1624)
     convert_fluid_vars(fd, w.f, sp, w.ncgs, w.ncgsnth, w.bcgs, w.tcgs);
+    assign_source_params(sp, w.ncgs, w.tcgs, w.ncgsnth, w.gmin);  // fluid.f90:582
     // emis_params are single precision in the reference (emis.f90:32-40): gmin, gmax, p1 pass through real(4)
-    double e_gmin = (double)(float)sp.gminval, e_gmax = (double)(float)A.gmax, e_p = (double)(float)A.p1;
+    double e_gmax = (double)(float)A.gmax, e_p = (double)(float)A.p1;
     if (dump && m == 0) {
       dump->ncgs = w.ncgs; dump->ncgsnth = w.ncgsnth; dump->bcgs = w.bcgs; dump->tcgs = w.tcgs;
     }
@@ -130,6 +132,7 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
       for (int p = 0; p < npts; p++) {
         double nu = freqs[k] / w.rshift[p];
         double K11[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const double e_gmin = (double)(float)w.gmin[p];  // ep%gmin=sp%gmin (grtrans_driver.f90:149), real(4)
         switch (etype) {
           case E_POLSYNCHTH: polsynchth(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], K11); break;
           case E_POLSYNCHPL: polsynchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, K11); break;

@@ -143,6 +143,8 @@ struct SourceParams {  // fluid.f90:69-75
 bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa);
 void advance_fluid_timestep(FluidData &fd, const std::string &fname, double a, const FluidArgs &fa, double dtobs);
 void get_fluid_vars(const FluidData &fd, const Geo &g, std::vector<FluidPt> &f);
+void assign_source_params(const SourceParams &sp, const std::vector<double> &ncgs, const std::vector<double> &tcgs,
+                          std::vector<double> &ncgsnth, std::vector<double> &gmin);
 void convert_fluid_vars(const FluidData &fd, const std::vector<FluidPt> &f, const SourceParams &sp,
                         std::vector<double> &ncgs, std::vector<double> &ncgsnth, std::vector<double> &bcgs,
                         std::vector<double> &tcgs);

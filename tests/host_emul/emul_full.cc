@@ -2,6 +2,7 @@
 // CPU, with the product's own host layer (grt_io.cpp), to compare kernel logic with the oracle without a
 // GPU.  NOT part of the product; never loaded by grtrans_b200.  Built by tests/test_host_emul.py.
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../grtrans_b200/csrc/grt_host.h"
@@ -47,7 +48,9 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
     SourceDev &sp = fk.sp[m];
     sp.mdot = mdots[m]; sp.mbh = a->mbh; sp.nfac = a->ftscl; sp.bfac = a->frscl; sp.jetalphaval = a->jetalpha;
     sp.gminval = a->gmin; sp.muval = a->muval; sp.gmax = a->gmax; sp.p1 = a->p1; sp.p2 = a->p2; sp.sigcut = a->sigcut;
+    sp.stail = (std::string(a->stype) == "tail") ? 1 : 0; sp.pad = 0;
   }
+  P.stail = (std::string(a->stype) == "tail") ? 1 : 0;
   P.etype = etype; P.eneq = eneq; P.rneq = nv; P.iflag = iflag; P.model = fh.model; P.npts_is_one = (a->nn[2] == 1);
   for (int i = 0; i < 7; i++) P.coefindx[i] = a->epcoefindx[i];
   P.LBH = pc::G * a->mbh * pc::msun / pc::c2;

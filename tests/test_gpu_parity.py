@@ -186,6 +186,13 @@ IMAGE_CASES = [
     ("harm3d", dict(n=32, nup=100, nfreq=4, ename='SYNCHTHBREMS', nvals=1, fmin=1e11, fmax=1e17), 1e-4),
     ("harm3d", dict(n=32, nup=100, nfreq=3, ename='SYNCHTHAVNOABS', nvals=1, iname='lsoda'), 1e-4),
     ("sphacc", dict(n=32, nfreq=4, ename='SYNCHTHBREMS', nvals=1), 1e-4),
+    # stype='tail': power law matched to the thermal distribution point by point (calcgmin.f90; fluid.f90:1656-1667)
+    ("harm3d", dict(n=32, nup=100, nfreq=3, ename='POLSYNCHPL', stype='tail', p1=3., p2=3., jetalpha=.1, fmin=1e11, fmax=1e14), 1e-4),
+    ("harm3d", dict(n=32, nup=100, nfreq=3, ename='HYBRIDTHPL', stype='tail', p1=3.5, p2=3.5, jetalpha=.05, fmin=1e11,
+                    fmax=1e14, iname='formal'), 1e-4),
+    ("harm", dict(n=32, nup=200, nfreq=2, ename='HYBRIDPL', stype='tail', p1=3., p2=3., jetalpha=.1, fmin=1e11, fmax=1e13), 1e-4),
+    ("harm3d", dict(n=32, nup=100, nfreq=2, ename='SYNCHPL', nvals=1, stype='tail', p1=3., p2=3., jetalpha=.1, gmax=20.,
+                    fmin=1e11, fmax=1e13), 1e-4),
     # thermal + power-law electron populations (emis.f90:469-485) on a magnetised snapshot
     ("harm3d", dict(n=50, nup=200, nfreq=4, ename='HYBRIDTHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True), 1e-4),
     ("harm3d", dict(n=40, nup=100, nfreq=3, ename='HYBRIDTH', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True), 1e-4),

@@ -75,6 +75,12 @@ EMUL_CASES = [
     ("harm3d", dict(n=16, nup=100, nfreq=3, ename='BREMS', nvals=1, fmin=1e12, fmax=1e18)),
     ("harm3d", dict(n=16, nup=100, nfreq=3, ename='SYNCHTHBREMS', nvals=1, fmin=1e11, fmax=1e17)),
     ("harm3d", dict(n=16, nup=100, nfreq=3, ename='SYNCHTHAVNOABS', nvals=1, iname='lsoda')),
+    # stype='tail': power law matched to the thermal distribution point by point (calcgmin.f90; fluid.f90:1656-1667)
+    ("harm3d", dict(n=16, nup=100, nfreq=3, ename='POLSYNCHPL', stype='tail', p1=3., p2=3., jetalpha=.1, fmin=1e11, fmax=1e14)),
+    ("harm3d", dict(n=16, nup=100, nfreq=3, ename='HYBRIDTHPL', stype='tail', p1=3.5, p2=3.5, jetalpha=.05, fmin=1e11,
+                    fmax=1e14, iname='formal')),
+    ("harm3d", dict(n=16, nup=100, nfreq=2, ename='SYNCHPL', nvals=1, stype='tail', p1=3., p2=3., jetalpha=.1, gmax=20.,
+                    fmin=1e11, fmax=1e13)),                                                # gmin capped at gmax/2
     ("koral", dict(n=24, nup=100, nfreq=3, threed=True)),                                  # KORAL3D, T_e from the dump
     ("koral", dict(n=24, nup=100, nfreq=3, threed=False)),                                 # KORAL (2-D)
     ("koral", dict(n=20, nup=100, nfreq=2, threed=True, fname='KORAL3D_DISK', gmin=10.)),  # Bernoulli cut + R-beta electrons
