@@ -23,7 +23,7 @@ SYMBOLS = ["grt_args_defaults", "grt_main", "grt_get_ivals", "grt_get_ab", "grt_
            "grt_geokerr_rays", "grt_ray_stage_dump", "grt_polsynchth", "grt_polsynchpl", "grt_synchemis",
            "grt_rt_integrate", "grt_session_create", "grt_session_destroy", "grt_session_launch", "grt_session_sync", "grt_session_launch_fetch", "grt_session_upload", "grt_session_run_timed",
            "grt_session_time", "grt_session_launch_count", "grt_session_counts", "grt_session_device_image",
-           "grt_session_fetch", "grt_session_ncams", "grt_version", "grt_device_count", "grt_dfma_peak"]
+           "grt_session_fetch", "grt_session_ncams", "grt_session_nvals", "grt_version", "grt_device_count", "grt_dfma_peak"]
 
 
 class GrtError(RuntimeError):
@@ -182,7 +182,7 @@ class Session(object):
         check(lib().grt_session_create(C.byref(a), C.c_int(device), C.c_int(rank), C.c_int(nranks), C.byref(self._h)),
               "grt_session_create")
         self.ncams = lib().grt_session_ncams(self._h)
-        self.nvals = a.nvals
+        self.nvals = lib().grt_session_nvals(self._h)   # values per pixel (nvals, + 19 diagnostics when extra = 1)
 
     def launch(self):
         check(lib().grt_session_launch(self._h), "grt_session_launch")

@@ -58,6 +58,8 @@ struct grt_session {
   std::vector<void *> registered;      // host buffers pinned in place with cudaHostRegister
   std::vector<double> freqs, mdots, mu0;
   int nmu = 1, nparams = 1, nfreq = 1, nvals = 1, ncams = 1, maxpts = 1, npix = 0;
+  int nextra = 0, nv = 1;    // extra = 1: 19 diagnostics follow the nvals Stokes values of every pixel (nv = nvals + nextra)
+  double *d_xrec = nullptr, *d_hist = nullptr;
   int nt = 1;                // observer-time frames per mu0 (pgrtrans.f90:195-212)
   bool fluid_moved = false;  // the resident dumps were advanced by a previous pass over the nt frames
   std::vector<grt_host::Camera> cams;  // one per mu0
@@ -188,7 +190,9 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
     fprintf(stderr, "grtrans_b200: unsupported fname/ename/iname '%s'/'%s'/'%s'\n", a->fname, a->ename, a->iname);
     return GRT_ERR_BAD_ARG;
   }
-  if (a->nmdot > 8 || a->nt < 1 || (a->nvals != 1 && a->nvals != 4) || a->extra != 0) return GRT_ERR_BAD_ARG;
+  if (a->nmdot > 8 || a->nt < 1 || (a->nvals != 1 && a->nvals != 4) || (a->extra != 0 && a->extra != 1)) return GRT_ERR_BAD_ARG;
+  // extra = 1 with one point per ray (7 quantities of the thin-disk polarisation geometry, calc_polar_psi) is not covered
+  if (a->extra == 1 && a->nn[2] == 1) return GRT_ERR_BAD_ARG;
   const std::string stype(a->stype);
   if (stype != "const" && stype != "tail") return GRT_ERR_BAD_ARG;
   grt_session *s = new grt_session();
@@ -197,6 +201,8 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   grt_host::make_grids(*a, s->freqs, s->mdots, s->mu0);
   s->nmu = a->nmu; s->nparams = a->nmdot; s->nfreq = a->nfreq; s->nvals = a->nvals;
   s->nt = a->nt;
+  s->nextra = (a->extra == 1) ? 19 : 0;  // pgrtrans.f90:107-113
+  s->nv = a->nvals + s->nextra;
   s->ncams = a->nmdot * a->nfreq * a->nmu * a->nt;
   s->npix = a->nn[0] * a->nn[1];
   int rcio = grt_host::load_fluid(s->fh, *a);
@@ -230,6 +236,8 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   long long tile = te ? atoll(te) : 65536;
   // bound the per-tile record buffer to ~24 GB
   long long per_ray = (long long)s->maxpts * (record_doubles(etype) * 8LL * s->nparams + 5 * 8 + 2);
+  if (s->nextra)  // + the per-point averaging inputs and the intensity history of every (ray, mdot, frequency) thread
+    per_ray += (long long)s->maxpts * 8LL * (8 * s->nparams + (long long)s->nparams * s->nfreq);
   while (tile > 1024 && tile * per_ray > (24LL << 30)) tile /= 2;
   s->tile = (int)std::max<long long>(1, std::min<long long>(tile, std::max<long long>(s->nlocal, 1)));
   if (cudaStreamCreate(&s->stream) != cudaSuccess) {
@@ -267,8 +275,12 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   SCK(own(s, &s->pa.u, TP)); SCK(own(s, &s->pa.mu, TP)); SCK(own(s, &s->pa.dt, TP)); SCK(own(s, &s->pa.dphi, TP));
   SCK(own(s, &s->pa.lam, TP)); SCK(own(s, &s->pa.tpm, TP)); SCK(own(s, &s->pa.tpr, TP));
   SCK(own(s, &s->d_rec, TP * record_doubles(etype) * s->nparams));
-  SCK(own(s, &s->d_image, (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nvals));
-  SCK(cudaMemset(s->d_image, 0, (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nvals * sizeof(float)));
+  SCK(own(s, &s->d_image, (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nv));
+  SCK(cudaMemset(s->d_image, 0, (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nv * sizeof(float)));
+  if (s->nextra) {
+    SCK(own(s, &s->d_xrec, TP * 8 * s->nparams));
+    SCK(own(s, &s->d_hist, TP * s->nparams * s->nfreq));
+  }
   {
     const double *p = nullptr;
     SCK(own_h2d(s, &p, s->freqs));
@@ -312,7 +324,7 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   SCK(own_h2d(s, &tb.yap, th.yap)); SCK(own_h2d(s, &tb.yav, th.yav));
   SCK(own_h2d(s, &tb.ch_mu, th.ch_mu)); SCK(own_h2d(s, &tb.ch_I, th.ch_I)); SCK(own_h2d(s, &tb.ch_del, th.ch_del));
   s->fk.tab = tb;
-  s->fk.nparams = s->nparams; s->fk.etype = etype; s->fk.maxpts = s->maxpts;
+  s->fk.nparams = s->nparams; s->fk.etype = etype; s->fk.maxpts = s->maxpts; s->fk.xrec = s->d_xrec;
   for (int m = 0; m < s->nparams; m++) {
     SourceDev &sp = s->fk.sp[m];
     sp.mdot = s->mdots[m]; sp.mbh = a->mbh; sp.nfac = a->ftscl; sp.bfac = a->frscl; sp.jetalphaval = a->jetalpha;
@@ -357,8 +369,12 @@ static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump 
   if (time_stages) cudaEventRecord(s->ev[2], s->stream);
   launch_fluid_ortho(s->d_rc[jmu] + off, s->d_inv, s->d_meta, s->fk, total, n, s->pa, s->d_rec, sd, s->stream);
   if (time_stages) cudaEventRecord(s->ev[3], s->stream);
-  launch_transfer(s->d_meta, s->tp, s->d_lbh, s->d_freqs, s->nfreq, s->nparams, n, s->maxpts, s->d_rec, s->d_image, off,
-                  s->nlocal, (jmu * s->nt + frame) * s->nparams * s->nfreq, s->stream);
+  if (s->nextra)
+    launch_transfer_extra(s->d_meta, s->tp, s->d_lbh, s->d_freqs, s->nfreq, s->nparams, n, s->maxpts, s->d_rec, s->d_xrec,
+                          s->d_hist, s->d_image, off, s->nlocal, (jmu * s->nt + frame) * s->nparams * s->nfreq, s->stream);
+  else
+    launch_transfer(s->d_meta, s->tp, s->d_lbh, s->d_freqs, s->nfreq, s->nparams, n, s->maxpts, s->d_rec, s->d_image, off,
+                    s->nlocal, (jmu * s->nt + frame) * s->nparams * s->nfreq, s->stream);
   if (time_stages) cudaEventRecord(s->ev[4], s->stream);
   return (cudaGetLastError() == cudaSuccess) ? GRT_OK : GRT_ERR_CUDA;
 }
@@ -393,7 +409,7 @@ static int launch_all(grt_session *s, bool fetch) {
   StageDump sd;
   memset(&sd, 0, sizeof(sd));
   s->launches = 0;
-  const size_t rowb = (size_t)s->nvals * sizeof(float);
+  const size_t rowb = (size_t)s->nv * sizeof(float);
   if (s->fluid_moved) {  // a previous pass advanced the dumps through the nt frames: start again from dump `findf`
     int rc = reload_dumps(s, true, 0.0);
     if (rc != GRT_OK) return rc;
@@ -412,7 +428,7 @@ static int launch_all(grt_session *s, bool fetch) {
           CK(cudaEventRecord(s->tile_done, s->stream));
           CK(cudaStreamWaitEvent(s->copy_stream, s->tile_done, 0));
           size_t cam0 = ((size_t)j * s->nt + l) * s->nparams * s->nfreq;
-          size_t o = (cam0 * s->nlocal + off) * s->nvals;
+          size_t o = (cam0 * s->nlocal + off) * s->nv;
           CK(cudaMemcpy2DAsync(s->h_image + o, (size_t)s->nlocal * rowb, s->d_image + o, (size_t)s->nlocal * rowb,
                                (size_t)n * rowb, (size_t)s->nparams * s->nfreq, cudaMemcpyDeviceToHost, s->copy_stream));
         }
@@ -434,12 +450,12 @@ extern "C" int grt_session_launch(grt_session *s) { return launch_all(s, false);
 extern "C" int grt_session_launch_fetch(grt_session *s, const float **host_image, long long *bytes) {
   if (!s) return GRT_ERR_BAD_ARG;
   if (cudaSetDevice(s->device) != cudaSuccess) return GRT_ERR_NO_DEVICE;
-  size_t nel = (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nvals;
+  size_t nel = (size_t)s->ncams * std::max<long long>(s->nlocal, 1) * s->nv;
   if (!s->h_image) CK(cudaHostAlloc((void **)&s->h_image, nel * sizeof(float), cudaHostAllocDefault));
   if (!s->copy_stream) CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
   if (!s->tile_done) CK(cudaEventCreateWithFlags(&s->tile_done, cudaEventDisableTiming));
   if (host_image) *host_image = s->h_image;
-  if (bytes) *bytes = (long long)((size_t)s->ncams * s->nlocal * s->nvals * sizeof(float));
+  if (bytes) *bytes = (long long)((size_t)s->ncams * s->nlocal * s->nv * sizeof(float));
   return launch_all(s, true);
 }
 
@@ -552,20 +568,21 @@ extern "C" int grt_session_counts(grt_session *s, long long *nrays_local, long l
 extern "C" int grt_session_device_image(grt_session *s, void **d_image, long long *nelem, void **d_ray_index, long long *nrays) {
   if (!s) return GRT_ERR_BAD_ARG;
   if (d_image) *d_image = s->d_image;
-  if (nelem) *nelem = (long long)s->ncams * s->nlocal * s->nvals;
+  if (nelem) *nelem = (long long)s->ncams * s->nlocal * s->nv;
   if (d_ray_index) *d_ray_index = s->d_ray_index;
   if (nrays) *nrays = s->nlocal;
   return GRT_OK;
 }
 
 extern "C" int grt_session_ncams(const grt_session *s) { return s ? s->ncams : 0; }
+extern "C" int grt_session_nvals(const grt_session *s) { return s ? s->nv : 0; }
 
 extern "C" int grt_session_fetch(grt_session *s, float *image, int *ray_index) {
   if (!s) return GRT_ERR_BAD_ARG;
   cudaSetDevice(s->device);
   CK(cudaStreamSynchronize(s->stream));
   if (image && s->nlocal)
-    CK(cudaMemcpy(image, s->d_image, (size_t)s->ncams * s->nlocal * s->nvals * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(image, s->d_image, (size_t)s->ncams * s->nlocal * s->nv * sizeof(float), cudaMemcpyDeviceToHost));
   if (ray_index)
     for (long long i = 0; i < s->nlocal; i++) ray_index[i] = s->ray_index[i];
   return GRT_OK;
@@ -604,7 +621,7 @@ extern "C" int grt_main(const grt_args *a) {
     grt_session_destroy(s);
     return rc;
   }
-  const int nv = s->nvals, npix = s->npix, ncams = s->ncams;
+  const int nv = s->nv, npix = s->npix, ncams = s->ncams;
   const long long nlocal = s->nlocal;
   ModuleData &M = g_mod;
   M.nv = nv; M.npix = npix; M.ncams = ncams; M.nx = a->nn[0]; M.ny = a->nn[1];

@@ -1,0 +1,72 @@
+// grtrans_b200 -- extra = 1: Stokes values plus the 19 per-pixel diagnostics of grtrans_driver.f90:230-292.
+//   k_extra   thread / (ray, mdot, nu)   the march of k_transfer with its intensity history kept in a scratch array, then
+//                                        one forward pass over the ray for the depth / average integrals
+// A diagnostic mode: its own translation unit so that the hot kernels of grt_k_transfer.cu are untouched.
+#include "grt_kernels.h"
+
+namespace grt {
+
+// image layout: [cam][ray_local][nvals + 19] float32
+template <int ET, int MODE>
+__global__ void __launch_bounds__(128) k_extra(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
+                                               const double *__restrict__ freqs, int nfreq, int nparams, int nrays, int maxpts,
+                                               const double *__restrict__ rec, const double *__restrict__ xrec,
+                                               double *__restrict__ hist, float *__restrict__ image, long long ray_off,
+                                               long long nlocal, int cam0) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)nrays * nparams * nfreq;
+  if (idx >= total) return;
+  int f = (int)(idx % nfreq);
+  int mm = (int)((idx / nfreq) % nparams);
+  int ray = (int)(idx / ((long long)nfreq * nparams));
+  RayMeta m = meta[ray];
+  constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
+  double out[4] = {0, 0, 0, 0}, xt[19];
+  for (int q = 0; q < 19; q++) xt[q] = 0.0;
+  if (m.status == 1 && m.npts > 0) {
+    P.LBH = lbh_m[mm];
+    const size_t base = (size_t)mm * nrays * maxpts + (size_t)ray * maxpts;
+    // history of this thread: hist[col * total + idx] (coalesced across the warp's frequencies)
+    ray_extra_t<ET, MODE>(P, rec + base * record_doubles(ET), xrec + base * 8, m.npts, freqs[f], out, xt, hist + idx, (size_t)total);
+  }
+  int cam = cam0 + mm * nfreq + f;
+  float *dst = image + ((size_t)cam * nlocal + (ray_off + ray)) * (neq + 19);
+  for (int i = 0; i < neq; i++) dst[i] = (float)out[i];
+  for (int q = 0; q < 19; q++) dst[neq + q] = (float)xt[q];
+}
+
+template <int ET>
+static void launch_extra_e(int mode, unsigned grid, cudaStream_t st, const RayMeta *meta, const TransferParams &P,
+                           const double *lbh_m, const double *freqs, int nfreq, int nparams, int nrays, int maxpts,
+                           const double *rec, const double *xrec, double *hist, float *image, long long ray_off, long long nlocal,
+                           int cam0) {
+  const int B = 128;
+#define GRT_LAUNCH(M) \
+  k_extra<ET, M><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0)
+  switch (mode) {
+    case MODE_DELO: GRT_LAUNCH(MODE_DELO); break;
+    case MODE_FORMAL: GRT_LAUNCH(MODE_FORMAL); break;
+    case MODE_QUAD: GRT_LAUNCH(MODE_QUAD); break;
+    case MODE_RK4: GRT_LAUNCH(MODE_RK4); break;
+    default: GRT_LAUNCH(MODE_RK1); break;
+  }
+#undef GRT_LAUNCH
+}
+
+void launch_transfer_extra(const RayMeta *meta, const TransferParams &P, const double *lbh_m, const double *freqs, int nfreq,
+                           int nparams, int nrays, int maxpts, const double *rec, const double *xrec, double *hist, float *image,
+                           long long ray_off, long long nlocal, int cam0, cudaStream_t st) {
+  const int B = 128;
+  long long tt = (long long)nrays * nparams * nfreq;
+  unsigned grid = (unsigned)((tt + B - 1) / B);
+  const int mode = transfer_mode(P);
+  switch (em_slot(P.etype)) {
+#define OP(E) \
+  case E: launch_extra_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0); break;
+    GRT_FOR_ETYPES(OP)
+#undef OP
+    default: break;
+  }
+}
+
+}  // namespace grt

@@ -27,6 +27,7 @@ struct FluidKernelArgs {
   SourceDev sp[8];
   int nparams, etype, maxpts;
   EmisTables tab;
+  double *xrec;  // extra = 1: [nparams][nrays][maxpts][8] = r, theta, phi, n, T, B, plasma beta, unused (else nullptr)
 };
 
 // in_range = false for the padding threads of the last block (they only take part in the phase barriers)
@@ -164,6 +165,12 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
 #else
     for (int i = 0; i < nrec; i++) q[i] = o[i];
 #endif
+    if (A.xrec) {  // quantities averaged along the ray by the extra = 1 diagnostics (grtrans_driver.f90:262-283)
+      double *x = A.xrec + ((size_t)mm * nrays * maxpts + dst) * 8;
+      x[0] = r; x[1] = th; x[2] = ph; x[3] = cg.ncgs; x[4] = cg.tcgs; x[5] = cg.bcgs;
+      x[6] = (double)(fs.p * 2.f / (fs.bmag * fs.bmag));  // f%p*2./f%bmag**2. in real(4)
+      x[7] = 0.0;
+    }
     if (mm == 0 && sd.ncgs) {
       sd.ncgs[dst] = cg.ncgs; sd.ncgsnth[dst] = cg.ncgsnth; sd.bcgs[dst] = cg.bcgs; sd.tcgs[dst] = cg.tcgs;
     }

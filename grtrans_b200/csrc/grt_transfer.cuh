@@ -83,7 +83,8 @@ GRT_HD RunConst run_const(const TransferParams &P, double nu_obs) {
 }
 
 template <int ET>
-GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *rec, const FreqConst &F, Coef &c, double &jI_raw) {
+GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *rec, const FreqConst &F, Coef &c, double &jI_raw,
+                      const bool emis_width = false) {  // emis_width: keep all columns of e%K (the extra = 1 depth integrals)
   const double g = rec[1];
   double e[11];
   bool invariant = false;  // e already holds j g^2 and K LBH / g
@@ -183,7 +184,7 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
     double s = invariant ? g : g * g * g;
     for (int i = 0; i < 4; i++) c.j[i] = c.j[i] * s;
   }
-  if (P.rneq == 1) {  // Stokes-I-only transfer of a polarised model (A21): keep j_I, alpha_I
+  if (P.rneq == 1 && !emis_width) {  // Stokes-I-only transfer of a polarised model (A21): keep j_I, alpha_I
     c.j[1] = c.j[2] = c.j[3] = 0.0;
     for (int i = 1; i < 7; i++) c.K[i] = 0.0;
   }
@@ -367,9 +368,20 @@ GRT_HD bool ck_interval(int neq, const Coef &ca, const Coef &cb, double la, doub
 // ---- the per-(ray, frequency) march ------------------------------------------------------------------
 // rec: [npts][GRT_NREC] records of this ray.  out: nvals Stokes values in cgs.  One instance per (emissivity, mode) so that
 // the hot loop of each kernel is a few thousand instructions (it has to live in the 32 KB L1.5 instruction cache).
-template <int ET, int MODE>
-GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
+// HIST (extra = 1 only): the march also records sqrt(I^2 + Q^2) of every output column of the reference's intensity array
+// (hist[col * hs], col 0-based; the caller zero-fills it), the number of columns r%npts and the emission scale fac.
+struct MarchInfo {
+  int rnpts;
+  double fac;
+};
+template <int ET, int MODE, bool HIST = false>
+GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out,
+                           double *hist = nullptr, size_t hs = 0, MarchInfo *info = nullptr) {
   constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
+  if (HIST) {
+    info->rnpts = npts;
+    info->fac = 0.0;
+  }
   constexpr int NREC = em_is_hybrid(ET) ? GRT_NREC_MAX : GRT_NREC;  // record stride of this emissivity model
   for (int i = 0; i < neq; i++) out[i] = 0.0;
   if (npts <= 0) return;
@@ -412,10 +424,12 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
         if (In[0] != In[0] && I[0] == I[0]) printf("NaN at k=%d dx=%g j0=%g K0=%g j1=%g K1=%g I=%g rq=%g rv=%g aq=%g\n", k, dx, c0.j[0], c0.K[0], c1.j[0], c1.K[0], I[0], c0.K[4], c0.K[6], c0.K[1]);
 #endif
         for (int i = 0; i < 4; i++) I[i] = In[i];
+        if (HIST) hist[(size_t)(npts - k - 1) * hs] = sqrt(In[0] * In[0] + In[1] * In[1]);  // intensity(:, npts-k) (1-based)
       }
       c1 = c0;
       lam1 = lamk;
     }
+    if (HIST) info->fac = fac;
     if (fac / 1e16 > 0.0)
       for (int i = 0; i < 4; i++) out[i] = I[i] * P.LBH;
     return;
@@ -441,6 +455,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
       kprev = fabs(c.K[0]);
       lprev = rk[0];
     }
+    if (HIST) info->fac = fac;
     if (fac / 1e16 > 0.0) out[0] = -acc * P.LBH;
     return;
   }
@@ -471,6 +486,10 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     i1 = (firstnz > 1) ? firstnz : 1;
     i2 = lastnz_cut;  // equals lamdex when j(lamdex) != 0
   }
+  if (HIST) {
+    info->fac = fac;
+    info->rnpts = i2;
+  }
   if (!(fac / 1e16 > 0.0) || i2 <= i1) return;
   {
     double y[4] = {0, 0, 0, 0};
@@ -491,11 +510,98 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
       if (s_ <= i2) {
         double la = rec[(size_t)(s_ - 1) * NREC], lb = rec[(size_t)(s_ - 2) * NREC];
         if (lb > la) ok = ck_interval(neq, ca, cb, la, lb, y, h, P);
+        // intensity(:, i1 + m), m = i2 - s_ + 1 (1-based column)
+        if (HIST && neq == 4 && ok) hist[(size_t)(i1 + i2 - s_) * hs] = sqrt(y[0] * y[0] + y[1] * y[1]);
       }
     }
     if (ok)
       for (int i = 0; i < neq; i++) out[i] = y[i] * fac * P.LBH;
+    else if (HIST)
+      for (int c = 0; c < npts; c++) hist[(size_t)c * hs] = 0.0;  // the failed integration returns zeros (odepack.f90:91-96)
   }
+}
+
+// ---- extra = 1: the 19 diagnostics of grtrans_driver.f90:230-292 (rays with more than one point) ------------------------
+// xrec: [npts][8] = r, theta, phi, n, T, B (cgs), plasma beta, unused.  xt[0..18] = r%tau(1:19):
+//   0-5   optical / Faraday depths int |alpha_I,Q,U,V|, |rho_Q|, |rho_V| ds at the photosphere index
+//   6-13  emission-weighted (j_I e^-tau) ray averages of r, theta, phi, n, T, B, beta, sign(cos theta)
+//   14-18 averages of r, theta, the two Faraday depths and sign(cos theta) weighted with the increments of sqrt(I^2+Q^2)
+// (sic) the photosphere index is npts whenever min(tau) < 1, i.e. always (tau(1) = 0); (sic) I and Q, not Q and U.
+template <int ET, int MODE>
+GRT_HD void ray_extra_t(const TransferParams &P, const double *rec, const double *xrec, int npts, double nu_obs, double *out,
+                        double *xt, double *hist, size_t hs) {
+  constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
+  constexpr int NREC = em_is_hybrid(ET) ? GRT_NREC_MAX : GRT_NREC;
+  for (int q = 0; q < 19; q++) xt[q] = 0.0;
+  for (int c = 0; c < npts; c++) hist[(size_t)c * hs] = 0.0;
+  MarchInfo mi;
+  ray_transfer_t<ET, MODE, true>(P, rec, npts, nu_obs, out, hist, hs, &mi);
+  if (npts <= 1 || !(mi.fac / 1e16 > 0.0)) return;  // r%tau(:) = 0
+  const int rnpts = mi.rnpts;
+  const FreqConst F = freq_const(nu_obs);
+  const RunConst R = run_const<ET>(P, nu_obs);
+  const int inds[6] = {0, 1, 2, 3, 4, 6};
+  const double lam0 = rec[0];
+  double ta[6] = {0, 0, 0, 0, 0, 0}, kprev[6] = {0, 0, 0, 0, 0, 0}, tau = 0.0;
+  double D = 0.0, X[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xprev[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dprev = 0.0, lprev = 0.0, sprev = 0.0;
+  double Sd = 0.0, Sr = 0.0, Sth = 0.0, S5 = 0.0, S6 = 0.0, Ssg = 0.0;
+  double best = 0.0, mintau = 0.0, snap[15];
+  int taudex = 1;
+  for (int q = 0; q < 15; q++) snap[q] = 0.0;
+  Coef c;
+  double jraw;
+#pragma unroll 1
+  for (int p = 0; p < npts; p++) {
+    const double *rk = rec + (size_t)p * NREC, *xr = xrec + (size_t)p * 8;
+    node_coef<ET>(P, R, rk, F, c, jraw, true);
+    const double lam = rk[0], sp_ = lam0 - lam;
+    double kabs[6];
+    for (int ii = 0; ii < 6; ii++) kabs[ii] = fabs(c.K[inds[ii]]);
+    if (p > 0) {
+      const double ds = sp_ - sprev;
+      for (int ii = 0; ii < 6; ii++) ta[ii] += ds * ((kprev[ii] + kabs[ii]) / 2.0);
+      tau -= (lam - lprev) * ((kprev[0] + kabs[0]) / 2.0);
+    }
+    const double d = c.j[0] * exp(-tau);
+    double x[8];
+    for (int q = 0; q < 7; q++) x[q] = xr[q];
+    x[7] = (cos(xr[1]) >= 0.0) ? 1.0 : -1.0;
+    if (p > 0) {
+      const double dl = lam - lprev;
+      D += dl * ((dprev + d) / 2.0);
+      for (int q = 0; q < 8; q++) X[q] += dl * ((dprev * xprev[q] + d * x[q]) / 2.0);
+    }
+    const double dist = fabs(tau - 1.0);
+    if (p == 0) {
+      best = dist;
+      mintau = tau;
+    }
+    if ((p > 0 && dist < best) || p == 1) {  // candidate photosphere index (index 1 is moved to 2)
+      if (dist < best || taudex == 1) {
+        if (dist < best) best = dist;
+        taudex = p + 1;
+        for (int ii = 0; ii < 6; ii++) snap[ii] = ta[ii];
+        snap[6] = D;
+        for (int q = 0; q < 8; q++) snap[7 + q] = X[q];
+      }
+    }
+    if (tau < mintau) mintau = tau;
+    if (neq == 4 && p + 1 <= rnpts - 1) {
+      const double dlp = hist[(size_t)(rnpts - p - 1) * hs] - hist[(size_t)(rnpts - p - 2) * hs];
+      Sd += dlp; Sr += dlp * x[0]; Sth += dlp * x[1]; S5 += dlp * ta[4]; S6 += dlp * ta[5]; Ssg += dlp * x[7];
+    }
+    for (int ii = 0; ii < 6; ii++) kprev[ii] = kabs[ii];
+    for (int q = 0; q < 8; q++) xprev[q] = x[q];
+    dprev = d; lprev = lam; sprev = sp_;
+  }
+  if (mintau < 1.0) {  // taudex = npts
+    for (int ii = 0; ii < 6; ii++) snap[ii] = ta[ii];
+    snap[6] = D;
+    for (int q = 0; q < 8; q++) snap[7 + q] = X[q];
+  }
+  for (int ii = 0; ii < 6; ii++) xt[ii] = snap[ii];
+  for (int q = 0; q < 8; q++) xt[6 + q] = 1.0 / snap[6] * snap[7 + q];
+  xt[14] = Sr / Sd; xt[15] = Sth / Sd; xt[16] = S5 / Sd; xt[17] = S6 / Sd; xt[18] = Ssg / Sd;
 }
 
 // runtime dispatcher (host emulator / generic callers); the CUDA kernels are instantiated per (ET, MODE) directly
@@ -511,6 +617,29 @@ GRT_HD void ray_transfer_e(const TransferParams &P, const double *rec, int npts,
     default: ray_transfer_t<ET, MODE_RK1>(P, rec, npts, nu_obs, out); break;
   }
 }
+template <int ET>
+GRT_HD void ray_extra_e(const TransferParams &P, const double *rec, const double *xrec, int npts, double nu_obs, double *out,
+                        double *xt, double *hist, size_t hs) {
+  switch (transfer_mode(P)) {
+    case MODE_DELO: ray_extra_t<ET, MODE_DELO>(P, rec, xrec, npts, nu_obs, out, xt, hist, hs); break;
+    case MODE_FORMAL: ray_extra_t<ET, MODE_FORMAL>(P, rec, xrec, npts, nu_obs, out, xt, hist, hs); break;
+    case MODE_QUAD: ray_extra_t<ET, MODE_QUAD>(P, rec, xrec, npts, nu_obs, out, xt, hist, hs); break;
+    case MODE_RK4: ray_extra_t<ET, MODE_RK4>(P, rec, xrec, npts, nu_obs, out, xt, hist, hs); break;
+    default: ray_extra_t<ET, MODE_RK1>(P, rec, xrec, npts, nu_obs, out, xt, hist, hs); break;
+  }
+}
+#if !defined(__CUDA_ARCH__)
+// host emulator only (the CUDA kernels are instantiated per (ET, MODE) in grt_k_extra.cu)
+inline void ray_extra(const TransferParams &P, const double *rec, const double *xrec, int npts, double nu_obs, double *out,
+                      double *xt, double *hist, size_t hs) {
+  switch (em_slot(P.etype)) {
+#define OP(E) case E: ray_extra_e<E>(P, rec, xrec, npts, nu_obs, out, xt, hist, hs); break;
+    GRT_FOR_ETYPES(OP)
+#undef OP
+    default: break;
+  }
+}
+#endif
 GRT_HDN void ray_transfer(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
   switch (em_slot(P.etype)) {
 #define OP(E) case E: ray_transfer_e<E>(P, rec, npts, nu_obs, out); break;

@@ -154,6 +154,8 @@ int grt_session_device_image(grt_session *s, void **d_image, long long *nelem, v
 /* copy the local image to host (float32 [ncams][nrays_local][nvals]) and the ray indices */
 int grt_session_fetch(grt_session *s, float *image, int *ray_index);
 int grt_session_ncams(const grt_session *s);
+/* values per pixel of the image: nvals, or nvals + 19 when extra = 1 (pgrtrans.f90:107-113, ivals(nvals+nextra,:,:) :221) */
+int grt_session_nvals(const grt_session *s);
 
 /* misc */
 const char *grt_version(void);

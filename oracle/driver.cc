@@ -54,12 +54,80 @@ struct RayWork {
 };
 }  // namespace
 
+// pgrtrans.f90:107-113: 19 extra quantities per pixel for rays with more than one point, 7 for nup = 1 (the latter need
+// calc_polar_psi and are not restated: extra is ignored for nup = 1)
+static int extra_count(const RunArgs &A) { return (A.extra == 1 && A.nn[2] > 1) ? 19 : 0; }
+
+// grtrans_driver.f90:230-292 (EXTRA_QUANTS == 1, npts > 1).  w.ej / w.eK hold the rotated, invariant, scaled coefficients,
+// w.tau the optical depth from the camera, w.intensity the integrator's output columns 1..rnpts.  rt[0..18] = r%tau(1:19).
+static void extra_quantities(const RayWork &w, int rneq, int rnpts, double iscale, double *rt) {
+  const Geo &g = w.g;
+  const int npts = g.npts;
+  for (int q = 0; q < 19; q++) rt[q] = 0.0;
+  std::vector<double> s(npts), y(npts), acc(npts), dummy(npts), norm(npts);
+  std::vector<std::vector<double>> tau_arr(6, std::vector<double>(npts));
+  const int inds[6] = {0, 1, 2, 3, 4, 6};  // K columns 1,2,3,4,5,7: alpha_I,Q,U,V, rho_Q, rho_V
+  for (int p = 0; p < npts; p++) s[p] = g.lambda[0] - g.lambda[p];
+  for (int ii = 0; ii < 6; ii++) {
+    for (int p = 0; p < npts; p++) y[p] = std::fabs(w.eK[(size_t)p * 7 + inds[ii]]);
+    tsum(npts, s.data(), y.data(), tau_arr[ii].data());
+  }
+  // photosphere index: minloc(|tau-1|); (sic) "if(minval(tau).lt.1d0) taudex=g%npts" -- tau(1) = 0, so this always holds
+  int taudex = 1;
+  double best = std::fabs(w.tau[0] - 1.0), mintau = w.tau[0];
+  for (int p = 1; p < npts; p++) {
+    double d = std::fabs(w.tau[p] - 1.0);
+    if (d < best) { best = d; taudex = p + 1; }
+    if (w.tau[p] < mintau) mintau = w.tau[p];
+  }
+  if (mintau < 1.0) taudex = npts;
+  if (taudex == 1) taudex = 2;
+  for (int ii = 0; ii < 6; ii++) rt[ii] = tau_arr[ii][taudex - 1];
+  for (int p = 0; p < npts; p++) dummy[p] = w.ej[(size_t)p * 4] * std::exp(-w.tau[p]);
+  tsum(npts, g.lambda.data(), dummy.data(), norm.data());
+  auto weighted = [&](auto val) {
+    for (int p = 0; p < npts; p++) y[p] = dummy[p] * val(p);
+    tsum(npts, g.lambda.data(), y.data(), acc.data());
+    return 1.0 / norm[taudex - 1] * acc[taudex - 1];
+  };
+  rt[6] = weighted([&](int p) { return g.x[p].d[1]; });
+  rt[7] = weighted([&](int p) { return g.x[p].d[2]; });
+  rt[8] = weighted([&](int p) { return g.x[p].d[3]; });
+  rt[9] = weighted([&](int p) { return w.ncgs[p]; });
+  rt[10] = weighted([&](int p) { return w.tcgs[p]; });
+  rt[11] = weighted([&](int p) { return w.bcgs[p]; });
+  rt[12] = weighted([&](int p) { return (double)(w.f[p].p * 2.f / (w.f[p].bmag * w.f[p].bmag)); });  // plasma beta, real(4)
+  rt[13] = weighted([&](int p) { return std::cos(g.x[p].d[2]) >= 0.0 ? 1.0 : -1.0; });
+  // (sic) "LP" increments use Stokes I and Q: sqrt(I(1,:)**2 + I(2,:)**2), reversed against the point arrays
+  {
+    std::vector<double> dlp(std::max(rnpts - 1, 0), 0.0);  // (rnpts < 2: empty sums, 0/0)
+    if (rneq == 4) {
+      auto P = [&](int col) {  // 1-based column
+        double a = w.intensity[(size_t)(col - 1) * 4] * iscale, b = w.intensity[(size_t)(col - 1) * 4 + 1] * iscale;
+        return std::sqrt(a * a + b * b);
+      };
+      for (int kk = 1; kk <= rnpts - 1; kk++) dlp[kk - 1] = P(rnpts + 1 - kk) - P(rnpts - kk);
+    }
+    double sd = 0, sr = 0, sth = 0, s5 = 0, s6 = 0, ssg = 0;
+    for (int kk = 0; kk < rnpts - 1; kk++) {
+      sd += dlp[kk];
+      sr += dlp[kk] * g.x[kk].d[1];
+      sth += dlp[kk] * g.x[kk].d[2];
+      s5 += dlp[kk] * tau_arr[4][kk];
+      s6 += dlp[kk] * tau_arr[5][kk];
+      ssg += dlp[kk] * (std::cos(g.x[kk].d[2]) >= 0.0 ? 1.0 : -1.0);
+    }
+    rt[14] = sr / sd; rt[15] = sth / sd; rt[16] = s5 / sd; rt[17] = s6 / sd; rt[18] = ssg / sd;
+  }
+}
+
 // Process one geodesic index for all (mdot, freq).  out[(m*nfreq+k)*nvals + s] in cgs (double).
 static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &gargs, int i,
                       const std::vector<double> &freqs, const std::vector<double> &mdots, double *out,
                       long long *npoints, RayDump *dump) {
   const int nfreq = (int)freqs.size(), nparams = (int)mdots.size(), nvals = A.nvals;
-  for (int q = 0; q < nparams * nfreq * nvals; q++) out[q] = 0.0;
+  const int nextra = extra_count(A), nout = nvals + nextra;  // pixel record: Stokes values, then the extra quantities
+  for (int q = 0; q < nparams * nfreq * nout; q++) out[q] = 0.0;
   RayWork w;
   Geo &g = w.g;
   int status;
@@ -188,7 +256,7 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
       } else {
         for (int p = 0; p < npts; p++) fac += w.ej[(size_t)p * 4] / npts;
       }
-      double *o = out + ((size_t)m * nfreq + k) * nvals;
+      double *o = out + ((size_t)m * nfreq + k) * nout;
       if (fac / 1e16 > 0.0) {
         if (eneq == 4) {  // rotate_emis emis.f90:797-829
           for (int p = 0; p < npts; p++) {
@@ -224,6 +292,7 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
                                w.intensity.data(), opt);
           if (rnpts >= 1)
             for (int c = 0; c < rneq; c++) o[c] = w.intensity[(size_t)(rnpts - 1) * rneq + c] * fac * LBH;
+          if (nextra == 19) extra_quantities(w, rneq, rnpts, fac * LBH, o + nvals);
         } else {
           // invariant_intensity(e,rshift,3); grtrans_compute_intensity
           double g3 = std::pow(w.rshift[0], 3);
@@ -245,7 +314,7 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
 void grtrans_ray_dump(const RunArgs &args, const FluidData &fd, const GeokerrArgs &gargs, int i,
                       const std::vector<double> &freqs, RayDump &d) {
   std::vector<double> mdots(1, args.mdotmin);
-  std::vector<double> out((size_t)freqs.size() * args.nvals);
+  std::vector<double> out((size_t)freqs.size() * (args.nvals + extra_count(args)));
   d = RayDump();
   drive_ray(args, fd, gargs, i, freqs, mdots, out.data(), nullptr, &d);
 }
@@ -258,11 +327,12 @@ void grtrans_main(const RunArgs &A, RunResult &res) {
   int npix = nro * nphi;
   int nparams = A.nmdot, nfreq = A.nfreq;
   int ncams = A.nmdot * A.nfreq * A.nmu * A.nt;
-  res.nvals = A.nvals;
+  res.nvals = A.nvals + extra_count(A);
   res.npix = npix;
   res.ncams = ncams;
   res.freqs = freqs;
-  res.pixvals.assign((size_t)ncams * npix * A.nvals, 0.f);
+  const int nout = A.nvals + extra_count(A);
+  res.pixvals.assign((size_t)ncams * npix * nout, 0.f);
   res.pixloc.assign((size_t)npix * 2, 0.f);
   res.loop_seconds = 0;
   res.npoints = 0;
@@ -302,15 +372,15 @@ void grtrans_main(const RunArgs &A, RunResult &res) {
       int l = jm * A.nt + lt;  // 0-based (j-1)*nt+l-1
 #pragma omp parallel num_threads(nth) reduction(+ : npoints)
       {
-        std::vector<double> out((size_t)nparams * nfreq * A.nvals);
+        std::vector<double> out((size_t)nparams * nfreq * nout);
 #pragma omp for schedule(static, 1)
         for (int i = i1; i <= i2; i++) {
           drive_ray(A, fd, gargs, i, freqs, mdots, out.data(), &npoints, nullptr);
           for (int m = 0; m < nparams; m++)
             for (int k = 0; k < nfreq; k++) {
               size_t cam = (size_t)l * nfreq * nparams + (size_t)m * nfreq + k;
-              for (int c = 0; c < A.nvals; c++)
-                res.pixvals[(cam * npix + (i - 1)) * A.nvals + c] = (float)out[((size_t)m * nfreq + k) * A.nvals + c];
+              for (int c = 0; c < nout; c++)
+                res.pixvals[(cam * npix + (i - 1)) * nout + c] = (float)out[((size_t)m * nfreq + k) * nout + c];
             }
           if (l == 0) {
             res.pixloc[(size_t)(i - 1) * 2] = (float)gargs.alpha[i - 1];

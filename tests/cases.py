@@ -137,6 +137,19 @@ def cfg_series(kind='harm2d', n=24, nup=100, nfreq=2, fnt=3, nload=1, nt=1, dt=1
     return d
 
 
+def extra_errors(got, ref, nvals):
+    """extra=1 images [nvals+19, npix, ncams]: the Stokes block by image_errors, the 19 diagnostics by their worst error relative
+    to the per-(quantity, camera) scale (depths, averages of r, theta, n, T, B ...).  Returns (image_errors tuple, worst extra error,
+    NaN masks of the extras equal)."""
+    import numpy as np
+    st = image_errors(got[:nvals], ref[:nvals])
+    g, r = got[nvals:], ref[nvals:]
+    nanok = np.array_equal(np.isnan(g), np.isnan(r))
+    g = np.nan_to_num(g); r = np.nan_to_num(r)
+    scale = np.maximum(np.abs(r).max(axis=1, keepdims=True), 1e-300)
+    return st, float((np.abs(g - r) / scale).max()), nanok
+
+
 def image_errors(got, ref):
     """got/ref: ivals[nvals,npix,ncams].  Returns (max rel dI over pixels with I > 1e-4 Imax per camera, flux error,
     max |dQUV|/Imax, nan masks equal)."""

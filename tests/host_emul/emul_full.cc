@@ -43,6 +43,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
   tb.ch_mu = th.ch_mu.data(); tb.ch_I = th.ch_I.data(); tb.ch_del = th.ch_del.data();
   fk.tab = tb;
   int nparams = a->nmdot, nfreq = a->nfreq, nv = a->nvals;
+  const int nextra = (a->extra == 1 && a->nn[2] > 1) ? 19 : 0, nout = nv + nextra;  // image: [cam][ray][nvals + nextra]
   fk.nparams = nparams; fk.etype = etype;
   for (int m = 0; m < nparams; m++) {
     SourceDev &sp = fk.sp[m];
@@ -74,6 +75,9 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
       RayInv inv;
       geo_setup(r, fl, inv);
       std::vector<double> bu(mp), bmu(mp), bdt(mp), bdp(mp), bl(mp), rec((size_t)nparams * mp * GRT_NREC_MAX, 0.0);
+      std::vector<double> xrec(nextra ? (size_t)nparams * mp * 8 : 0, 0.0), hist(nextra ? mp : 0, 0.0);
+      FluidKernelArgs fkr = fk;  // (per-thread copy: the extra-quantity record of this ray)
+      fkr.xrec = nextra ? xrec.data() : nullptr;
       std::vector<signed char> btm(mp), btr(mp);
       PointArrays pa{bu.data(), bmu.data(), bdt.data(), bdp.data(), bl.data(), btm.data(), btr.data()};
       for (int s = 0; s < mp; s++) point_store(inv, fl.nup, s, (size_t)s, pa);
@@ -91,7 +95,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
         sd.ncgs = n1.data(); sd.ncgsnth = n2.data(); sd.bcgs = n3.data(); sd.tcgs = n4.data();
         sd.rho = fr.data(); sd.p = fp.data(); sd.bmag = fb.data();
       }
-      for (int s = 0; s < mp; s++) point_record(r, m, fk, 0, s, 1, pa, rec.data(), sd);
+      for (int s = 0; s < mp; s++) point_record(r, m, fkr, 0, s, 1, pa, rec.data(), sd);
       if (jm == 0) npts_out[q] = (m.status == 1) ? m.npts : 0;
       if (stage && jm == 0)
         for (int s = 0; s < mp; s++) {
@@ -102,10 +106,18 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
         }
       for (int mm = 0; mm < nparams; mm++)
         for (int f = 0; f < nfreq; f++) {
-          double out[4] = {0, 0, 0, 0};
-          if (m.status == 1 && m.npts > 0) ray_transfer(P, rec.data() + (size_t)mm * mp * record_doubles(etype), m.npts, freqs[f], out);
+          double out[4] = {0, 0, 0, 0}, xt[19];
+          for (int k = 0; k < 19; k++) xt[k] = 0.0;
+          const double *rr = rec.data() + (size_t)mm * mp * record_doubles(etype);
+          if (m.status == 1 && m.npts > 0) {
+            if (nextra)
+              ray_extra(P, rr, xrec.data() + (size_t)mm * mp * 8, m.npts, freqs[f], out, xt, hist.data(), 1);
+            else
+              ray_transfer(P, rr, m.npts, freqs[f], out);
+          }
           int cam = jm * nparams * nfreq + mm * nfreq + f;
-          for (int k = 0; k < nv; k++) image[((size_t)cam * n + q) * nv + k] = (float)out[k];
+          for (int k = 0; k < nv; k++) image[((size_t)cam * n + q) * nout + k] = (float)out[k];
+          for (int k = 0; k < nextra; k++) image[((size_t)cam * n + q) * nout + nv + k] = (float)xt[k];
         }
     }
   }

@@ -208,6 +208,35 @@ IMAGE_CASES = [
 ]
 
 
+EXTRA_CASES = [("harm3d", dict(n=40, nup=100, nfreq=3, fmin=2e11, fmax=2e12)),
+               ("harm3d", dict(n=32, nup=200, nfreq=2, fmin=2e11, fmax=1e12, iname='formal', nmdot=2, mdotmin=1e19, mdotmax=1e20)),
+               ("harm3d", dict(n=32, nup=100, nfreq=2, fmin=2e11, fmax=1e12, iname='lsoda')),
+               ("harm3d", dict(n=32, nup=100, nfreq=2, fmin=2e11, fmax=1e12, nvals=1)),       # dlp = 0: NaN in 15-19
+               ("harm", dict(n=32, nup=200, nfreq=1)),
+               ("sphacc", dict(n=32, nfreq=3)),
+               ("ffjet", dict(n=32, nfreq=2, iname='formal')),
+               ("iharm", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12))]
+
+
+@pytest.mark.parametrize("cfg,over", EXTRA_CASES)
+def test_extra_quantities(cfg, over):
+    """extra=1 (grtrans_driver.f90:230-292): 19 diagnostics per pixel after the Stokes values -- optical / Faraday depths,
+    emission-weighted averages of r, theta, phi, n, T, B, beta along the ray, polarisation-weighted averages."""
+    kw = getattr(cases, "cfg_" + cfg)(extra=1, **over)
+    got = _lib.main(args_from_kwargs(**kw))['ivals']
+    ref = orc.run(_args=args_from_kwargs(**kw))['ivals']
+    nv = kw['nvals']
+    assert got.shape == ref.shape and got.shape[0] == nv + 19
+    (relI, flux, quv, nanok), xerr, xnan = cases.extra_errors(got, ref, nv)
+    assert nanok and relI < 1e-4 and flux < 1e-5 and quv < 1e-3, (relI, flux, quv)
+    assert xnan
+    assert xerr < 1e-4, xerr
+    # the Stokes block is the extra=0 image
+    kw0 = dict(kw); kw0['extra'] = 0
+    plain = _lib.main(args_from_kwargs(**kw0))['ivals']
+    assert np.array_equal(got[:nv], plain, equal_nan=True)
+
+
 @pytest.mark.parametrize("cfg,over,tol", IMAGE_CASES)
 def test_images_delo_formal_quadrature(cfg, over, tol):
     kw = getattr(cases, "cfg_" + cfg)(**over)
@@ -288,6 +317,30 @@ def test_file_interface_roundtrip(tmp_path):
         y.run_grtrans()
         y.read_grtrans_output(bin=1)
         assert np.array_equal(np.asarray(y.ivals).reshape(3, 400, 4)[0], x.ivals[:, :, 0])
+    finally:
+        os.chdir(cwd)
+
+
+def test_file_interface_with_extra_quantities(tmp_path):
+    """extra=1 through the file interface: the FITS / unformatted images carry nvals + 19 values per pixel
+    (camera.f90:105-133) and read back the way grtrans_batch.read_grtrans_output does."""
+    from grtrans_b200 import batch
+    kw = cases.cfg_sphacc(n=16, nfreq=2, extra=1)
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        x = batch.grtrans()
+        x.write_grtrans_inputs('inputs.in', oname='out.fits', **kw)
+        x.run_grtrans()
+        x.read_grtrans_output()
+        ref = _lib.main(args_from_kwargs(**kw))
+        assert x.ivals.shape == (256, 23, 2)
+        assert np.array_equal(x.ivals, ref['ivals'].transpose(1, 0, 2).astype(np.float32).astype(np.float64), equal_nan=True)
+        y = batch.grtrans()
+        y.write_grtrans_inputs('inputs2.in', oname='out.bin', cflag=0, **kw)
+        y.run_grtrans()
+        y.read_grtrans_output(bin=1)
+        assert np.array_equal(np.asarray(y.ivals).reshape(2, 256, 23)[0], x.ivals[:, :, 0], equal_nan=True)
     finally:
         os.chdir(cwd)
 

@@ -42,7 +42,8 @@ def run_emul(lib, kw, i1=None, i2=None):
     i2 = i2 or npix
     n = i2 - i1 + 1
     ncams = a.nmdot * a.nfreq * a.nmu
-    img = np.zeros((ncams, n, a.nvals), np.float32)
+    nv = a.nvals + (19 if (a.extra == 1 and a.nn[2] > 1) else 0)
+    img = np.zeros((ncams, n, nv), np.float32)
     npts = np.zeros(n, np.int32)
     rc = lib.emul_full(C.byref(a), C.c_int(i1), C.c_int(i2), img.ctypes.data_as(C.c_void_p), npts.ctypes.data_as(C.c_void_p),
                        None)
@@ -106,6 +107,29 @@ def test_dump_slots_and_advance_match_oracle(emul, kind, fnt, nsteps, dt):
     assert got[0, 0] == 40 and got[-1, 0] > 40                      # the series really moved on
     if fnt > 1:
         assert got[0, 2] == 10.                                     # tstep = t(1) - t(2) from the dump headers
+
+
+EXTRA_CASES = [("harm3d", dict(n=14, nup=100, nfreq=2, fmin=2e11, fmax=1e12)),
+               ("harm3d", dict(n=12, nup=100, nfreq=2, fmin=2e11, fmax=1e12, iname='formal')),
+               ("harm3d", dict(n=12, nup=100, nfreq=2, fmin=2e11, fmax=1e12, iname='lsoda')),
+               ("harm3d", dict(n=12, nup=100, nfreq=2, fmin=2e11, fmax=1e12, nvals=1)),       # dlp = 0: NaN in 15-19
+               ("sphacc", dict(n=14, nfreq=3)),
+               ("ffjet", dict(n=14, nfreq=2, iname='formal'))]
+
+
+@pytest.mark.parametrize("cfg,over", EXTRA_CASES)
+def test_extra_quantities_match_oracle(emul, cfg, over):
+    """extra=1 (grtrans_driver.f90:230-292): 19 diagnostics per pixel after the Stokes values."""
+    kw = getattr(cases, "cfg_" + cfg)(extra=1, **over)
+    got, npts = run_emul(emul, kw)
+    ref = orc.run(_args=args_from_kwargs(**kw))['ivals']
+    assert got.shape == ref.shape and got.shape[0] == kw['nvals'] + 19
+    (relI, flux, quv, nanok), xerr, xnan = cases.extra_errors(got, ref, kw['nvals'])
+    assert nanok and relI < 1e-4 and flux < 1e-5 and quv < 1e-3, (relI, flux, quv)
+    assert xnan
+    assert xerr < 1e-4, xerr
+    lit = np.nan_to_num(ref[0]) > 0
+    assert np.abs(np.nan_to_num(ref[kw['nvals']:kw['nvals'] + 14][:, lit])).max() > 0      # the diagnostics are not trivially zero
 
 
 def test_fast_exp_and_log_are_one_ulp(emul):
