@@ -53,6 +53,40 @@ static void launch_extra_e(int mode, unsigned grid, cudaStream_t st, const RayMe
 #undef GRT_LAUNCH
 }
 
+// The 45 instantiations are split over three objects (-DGRT_EXTRA_PART=0/1/2) so that the build compiles them in parallel.
+#ifndef GRT_EXTRA_PART
+#error "compile with -DGRT_EXTRA_PART=0, 1 or 2"
+#endif
+#if GRT_EXTRA_PART == 0
+#define GRT_PART_ETYPES(OP) OP(EM_POLSYNCHTH) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL)
+#define GRT_PART_NAME launch_extra_part0
+#elif GRT_EXTRA_PART == 1
+#define GRT_PART_ETYPES(OP) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_HYBRIDPL)
+#define GRT_PART_NAME launch_extra_part1
+#else
+#define GRT_PART_ETYPES(OP) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH)
+#define GRT_PART_NAME launch_extra_part2
+#endif
+
+#define GRT_EXTRA_ARGS                                                                                                     \
+  int mode, unsigned grid, cudaStream_t st, const RayMeta *meta, const TransferParams &P, const double *lbh_m,             \
+      const double *freqs, int nfreq, int nparams, int nrays, int maxpts, const double *rec, const double *xrec, double *hist, \
+      float *image, long long ray_off, long long nlocal, int cam0
+bool launch_extra_part0(GRT_EXTRA_ARGS);
+bool launch_extra_part1(GRT_EXTRA_ARGS);
+bool launch_extra_part2(GRT_EXTRA_ARGS);
+
+bool GRT_PART_NAME(GRT_EXTRA_ARGS) {
+  switch (em_slot(P.etype)) {
+#define OP(E) \
+  case E: launch_extra_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0); return true;
+    GRT_PART_ETYPES(OP)
+#undef OP
+    default: return false;
+  }
+}
+
+#if GRT_EXTRA_PART == 0
 void launch_transfer_extra(const RayMeta *meta, const TransferParams &P, const double *lbh_m, const double *freqs, int nfreq,
                            int nparams, int nrays, int maxpts, const double *rec, const double *xrec, double *hist, float *image,
                            long long ray_off, long long nlocal, int cam0, cudaStream_t st) {
@@ -60,13 +94,10 @@ void launch_transfer_extra(const RayMeta *meta, const TransferParams &P, const d
   long long tt = (long long)nrays * nparams * nfreq;
   unsigned grid = (unsigned)((tt + B - 1) / B);
   const int mode = transfer_mode(P);
-  switch (em_slot(P.etype)) {
-#define OP(E) \
-  case E: launch_extra_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0); break;
-    GRT_FOR_ETYPES(OP)
-#undef OP
-    default: break;
-  }
+#define GRT_TRY(F) F(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0)
+  if (!GRT_TRY(launch_extra_part0) && !GRT_TRY(launch_extra_part1)) (void)GRT_TRY(launch_extra_part2);
+#undef GRT_TRY
 }
+#endif
 
 }  // namespace grt

@@ -18,7 +18,13 @@ RUNS = [("thindisk", dict(n=12, nfreq=2)), ("thindisk", dict(n=10, nfreq=2, enam
         ("harm", dict(n=10, nup=100, nfreq=1)), ("harm3d", dict(n=10, nup=100, nfreq=2, nmdot=2, mdotmin=1e19, mdotmax=1e21)),
         ("harm3d", dict(n=8, nup=100, nfreq=2, ename='HYBRIDTHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True)),
         ("iharm", dict(n=10, nup=100, nfreq=2, mmks=1)), ("iharm", dict(n=8, nup=100, nfreq=2, mmks=0, gmin=-1.)),
-        ("koral", dict(n=10, nup=100, nfreq=2, threed=True)), ("koral", dict(n=8, nup=100, nfreq=2, threed=False))]
+        ("koral", dict(n=10, nup=100, nfreq=2, threed=True)), ("koral", dict(n=8, nup=100, nfreq=2, threed=False)),
+        # time axis: dump slots, arrival-time offsets, movie frames
+        ("series", dict(kind='harm2d', n=8, fnt=3, nload=3, nt=2, dt=10.)), ("series", dict(kind='harm3d', n=8, fnt=2, nt=2, dt=20.)),
+        # extra = 1 (history scratch + forward pass), the BREMS family, stype = 'tail'
+        ("harm3d", dict(n=8, nup=100, nfreq=2, extra=1)), ("harm3d", dict(n=8, nup=100, nfreq=2, extra=1, iname='lsoda')),
+        ("sphacc", dict(n=8, nfreq=2, extra=1, nvals=1)), ("harm3d", dict(n=8, nup=100, nfreq=2, ename='SYNCHTHBREMS', nvals=1)),
+        ("harm3d", dict(n=8, nup=100, nfreq=2, ename='POLSYNCHPL', stype='tail', p1=3., p2=3., jetalpha=.1))]
 os.environ["GRT_TILE"] = "64"   # several tiles per run
 for cfg, over in RUNS:
     kw = getattr(cases, "cfg_" + cfg)(**over)
