@@ -33,11 +33,11 @@ W_RT = 9.4e2    # per (pixel, point, freq): POLSYNCHTH emissivity + rotate/scale
 B_GATHER = 320  # bytes per (pixel, point): 8 corners x 10 fields x 4 B (3-D)
 B_RECORD = 160  # bytes per (pixel, point) read by the transfer kernel (one point record)
 # from the ncu --set full capture of one k_transfer launch at this configuration (profiles/r1_ncu_summary.md):
-NCU_TRANSFER = {"dram_bytes_per_launch": 4.802363e9 + 0.223055e9, "fp64_pipe_busy_pct": 66.3, "issue_active_pct": 66.0,
-                "launch": "65536-ray tile (32768 blocks x 128 threads), 57.6 ms under ncu",
-                "other_kernels": {"k_geo_points": {"fp64_pipe_busy_pct": 49.2, "ms": 16.5},
-                                  "k_fluid_ortho": {"fp64_pipe_busy_pct": 32.8, "ms": 9.2, "dram_write_gb": 4.83}},
-                "source": "profiles/r1_ncu_summary.md"}
+NCU_TRANSFER = {"dram_bytes_per_launch": 4.803515e9 + 0.225904e9, "fp64_pipe_busy_pct": 65.9, "issue_active_pct": 64.9,
+                "launch": "65536-ray tile (32768 blocks x 128 threads), 57.4 ms under ncu",
+                "other_kernels": {"k_geo_points": {"fp64_pipe_busy_pct": 46.8, "ms": 12.5},
+                                  "k_fluid_ortho": {"fp64_pipe_busy_pct": 34.3, "ms": 8.8, "dram_write_gb": 4.86}},
+                "source": "profiles/r1_ncu_summary.md (capture r1_v9)"}
 
 
 def workload(nx, nfreq, snapdir, grid):
@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--nx", type=int, default=int(os.environ.get("GRT_BENCH_NX", 1024)))
     ap.add_argument("--nfreq", type=int, default=64)
     ap.add_argument("--grid", default=os.environ.get("GRT_BENCH_GRID", "288x128x128"))
-    ap.add_argument("--cpu-rays", type=int, default=int(os.environ.get("GRT_BENCH_CPU_RAYS", 2048)))
+    ap.add_argument("--cpu-rays", type=int, default=int(os.environ.get("GRT_BENCH_CPU_RAYS", 16384)))
     ap.add_argument("--snapdir", default=os.environ.get("GRT_SNAPDIR", "/tmp/grt_snap"))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
