@@ -138,7 +138,18 @@ def cpu_reference_sample(kw, nthreads, target_rays):
     return rays, pts, secs
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout whenever
+    NCCL_DEBUG is VERSION or WARN, which the GPU boxes export), so file descriptor 1 is pointed at stderr for the whole run
+    and the JSON line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -182,7 +193,8 @@ def main():
                 "cpu_baseline": {"value": value, "unit": "rays*freq/s", "cores": ncores, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "rays*freq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "C++ restatement of the reference's OpenMP pixel loop (the Fortran cannot be compiled in this image)"}
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -324,7 +336,8 @@ def main():
                 "e2e": {"value": npix * args.nfreq / e2e_s, "unit": "rays*freq/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
                 "gpu_launches": int(sess.launch_count() * args.steps), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     sess.close()
     if world > 1:
         dist.destroy_process_group()
