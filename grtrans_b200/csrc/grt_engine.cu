@@ -191,8 +191,6 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
     return GRT_ERR_BAD_ARG;
   }
   if (a->nmdot > 8 || a->nt < 1 || (a->nvals != 1 && a->nvals != 4) || (a->extra != 0 && a->extra != 1)) return GRT_ERR_BAD_ARG;
-  // extra = 1 with one point per ray (7 quantities of the thin-disk polarisation geometry, calc_polar_psi) is not covered
-  if (a->extra == 1 && a->nn[2] == 1) return GRT_ERR_BAD_ARG;
   const std::string stype(a->stype);
   if (stype != "const" && stype != "tail") return GRT_ERR_BAD_ARG;
   grt_session *s = new grt_session();
@@ -201,7 +199,7 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   grt_host::make_grids(*a, s->freqs, s->mdots, s->mu0);
   s->nmu = a->nmu; s->nparams = a->nmdot; s->nfreq = a->nfreq; s->nvals = a->nvals;
   s->nt = a->nt;
-  s->nextra = (a->extra == 1) ? 19 : 0;  // pgrtrans.f90:107-113
+  s->nextra = (a->extra == 1) ? (a->nn[2] > 1 ? 19 : 7) : 0;  // pgrtrans.f90:107-113
   s->nv = a->nvals + s->nextra;
   s->ncams = a->nmdot * a->nfreq * a->nmu * a->nt;
   s->npix = a->nn[0] * a->nn[1];
@@ -371,7 +369,8 @@ static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump 
   if (time_stages) cudaEventRecord(s->ev[3], s->stream);
   if (s->nextra)
     launch_transfer_extra(s->d_meta, s->tp, s->d_lbh, s->d_freqs, s->nfreq, s->nparams, n, s->maxpts, s->d_rec, s->d_xrec,
-                          s->d_hist, s->d_image, off, s->nlocal, (jmu * s->nt + frame) * s->nparams * s->nfreq, s->stream);
+                          s->d_hist, s->d_image, off, s->nlocal, (jmu * s->nt + frame) * s->nparams * s->nfreq, s->nextra,
+                          s->stream);
   else
     launch_transfer(s->d_meta, s->tp, s->d_lbh, s->d_freqs, s->nfreq, s->nparams, n, s->maxpts, s->d_rec, s->d_image, off,
                     s->nlocal, (jmu * s->nt + frame) * s->nparams * s->nfreq, s->stream);

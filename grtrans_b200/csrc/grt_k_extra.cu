@@ -6,13 +6,13 @@
 
 namespace grt {
 
-// image layout: [cam][ray_local][nvals + 19] float32
+// image layout: [cam][ray_local][nvals + nextra] float32, nextra = 19 (rays of several points) or 7 (nup = 1)
 template <int ET, int MODE>
 __global__ void __launch_bounds__(128) k_extra(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
                                                const double *__restrict__ freqs, int nfreq, int nparams, int nrays, int maxpts,
                                                const double *__restrict__ rec, const double *__restrict__ xrec,
                                                double *__restrict__ hist, float *__restrict__ image, long long ray_off,
-                                               long long nlocal, int cam0) {
+                                               long long nlocal, int cam0, int nextra) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)nrays * nparams * nfreq;
   if (idx >= total) return;
@@ -30,19 +30,19 @@ __global__ void __launch_bounds__(128) k_extra(const RayMeta *__restrict__ meta,
     ray_extra_t<ET, MODE>(P, rec + base * record_doubles(ET), xrec + base * 8, m.npts, freqs[f], out, xt, hist + idx, (size_t)total);
   }
   int cam = cam0 + mm * nfreq + f;
-  float *dst = image + ((size_t)cam * nlocal + (ray_off + ray)) * (neq + 19);
+  float *dst = image + ((size_t)cam * nlocal + (ray_off + ray)) * (neq + nextra);
   for (int i = 0; i < neq; i++) dst[i] = (float)out[i];
-  for (int q = 0; q < 19; q++) dst[neq + q] = (float)xt[q];
+  for (int q = 0; q < nextra; q++) dst[neq + q] = (float)xt[q];
 }
 
 template <int ET>
 static void launch_extra_e(int mode, unsigned grid, cudaStream_t st, const RayMeta *meta, const TransferParams &P,
                            const double *lbh_m, const double *freqs, int nfreq, int nparams, int nrays, int maxpts,
                            const double *rec, const double *xrec, double *hist, float *image, long long ray_off, long long nlocal,
-                           int cam0) {
+                           int cam0, int nextra) {
   const int B = 128;
 #define GRT_LAUNCH(M) \
-  k_extra<ET, M><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0)
+  k_extra<ET, M><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0, nextra)
   switch (mode) {
     case MODE_DELO: GRT_LAUNCH(MODE_DELO); break;
     case MODE_FORMAL: GRT_LAUNCH(MODE_FORMAL); break;
@@ -71,7 +71,7 @@ static void launch_extra_e(int mode, unsigned grid, cudaStream_t st, const RayMe
 #define GRT_EXTRA_ARGS                                                                                                     \
   int mode, unsigned grid, cudaStream_t st, const RayMeta *meta, const TransferParams &P, const double *lbh_m,             \
       const double *freqs, int nfreq, int nparams, int nrays, int maxpts, const double *rec, const double *xrec, double *hist, \
-      float *image, long long ray_off, long long nlocal, int cam0
+      float *image, long long ray_off, long long nlocal, int cam0, int nextra
 bool launch_extra_part0(GRT_EXTRA_ARGS);
 bool launch_extra_part1(GRT_EXTRA_ARGS);
 bool launch_extra_part2(GRT_EXTRA_ARGS);
@@ -79,7 +79,7 @@ bool launch_extra_part2(GRT_EXTRA_ARGS);
 bool GRT_PART_NAME(GRT_EXTRA_ARGS) {
   switch (em_slot(P.etype)) {
 #define OP(E) \
-  case E: launch_extra_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0); return true;
+  case E: launch_extra_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0, nextra); return true;
     GRT_PART_ETYPES(OP)
 #undef OP
     default: return false;
@@ -89,12 +89,12 @@ bool GRT_PART_NAME(GRT_EXTRA_ARGS) {
 #if GRT_EXTRA_PART == 0
 void launch_transfer_extra(const RayMeta *meta, const TransferParams &P, const double *lbh_m, const double *freqs, int nfreq,
                            int nparams, int nrays, int maxpts, const double *rec, const double *xrec, double *hist, float *image,
-                           long long ray_off, long long nlocal, int cam0, cudaStream_t st) {
+                           long long ray_off, long long nlocal, int cam0, int nextra, cudaStream_t st) {
   const int B = 128;
   long long tt = (long long)nrays * nparams * nfreq;
   unsigned grid = (unsigned)((tt + B - 1) / B);
   const int mode = transfer_mode(P);
-#define GRT_TRY(F) F(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0)
+#define GRT_TRY(F) F(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, xrec, hist, image, ray_off, nlocal, cam0, nextra)
   if (!GRT_TRY(launch_extra_part0) && !GRT_TRY(launch_extra_part1)) (void)GRT_TRY(launch_extra_part2);
 #undef GRT_TRY
 }

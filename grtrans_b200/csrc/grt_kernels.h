@@ -23,10 +23,10 @@ void launch_transfer(const RayMeta *meta, const TransferParams &P, const double 
                      int nparams, int nrays, int maxpts, const double *rec, float *image, long long ray_off, long long nlocal,
                      int cam0, cudaStream_t st);
 
-// extra = 1: image layout [cam][ray_local][nvals + 19]; xrec [nparams][nrays][maxpts][8]; hist scratch [maxpts][nrays*nparams*nfreq]
+// extra = 1: image layout [cam][ray_local][nvals + nextra] (nextra = 19, or 7 for nup = 1); xrec [nparams][nrays][maxpts][8]; hist scratch [maxpts][nrays*nparams*nfreq]
 void launch_transfer_extra(const RayMeta *meta, const TransferParams &P, const double *lbh_m, const double *freqs, int nfreq,
                            int nparams, int nrays, int maxpts, const double *rec, const double *xrec, double *hist, float *image,
-                           long long ray_off, long long nlocal, int cam0, cudaStream_t st);
+                           long long ray_off, long long nlocal, int cam0, int nextra, cudaStream_t st);
 
 // unit-level surfaces
 void launch_polsynchth(int n, const double *nu, const double *nc, const double *b, const double *t, const double *th, double *e);

@@ -142,6 +142,29 @@ GRT_HD void disk_polvec(double r, double mu, const double *p, double a, double p
   for (int i = 0; i < 4; i++) f[i] = f[i] / s;
 }
 
+// calc_polar_psi (kerr.f90:954-996) + calc_kappapw (:1047-1063): polarisation angle at infinity of a photon emitted with the
+// thin-disk polarisation vector (psi = 0) through the Penrose-Walker constant, which is a single-precision complex there
+GRT_HD void polar_psi(double r, double muf, double q2, double a, double alpha, double beta, double rshift, double mus,
+                      const double *p, double &c2psi, double &s2psi, double &cosne) {
+  double f[4];
+  disk_polvec(r, muf, p, a, 0.0, f);
+  const double sm2 = 1.0 - muf * muf;
+  const double al = (p[0] * f[1] - p[1] * f[0]) + a * sm2 * (p[1] * f[3] - p[3] * f[1]);
+  const double be = (r * r + a * a) * sqrt(sm2) * (p[3] * f[2] - p[2] * f[3]) - a * sqrt(sm2) * (p[0] * f[2] - p[2] * f[0]);
+  const float x1 = (float)al, y1 = (float)(-be), x2 = (float)r, y2 = (float)(-a * muf);
+#if defined(__CUDA_ARCH__)
+  const float re = __fsub_rn(__fmul_rn(x1, x2), __fmul_rn(y1, y2)), im = __fadd_rn(__fmul_rn(x1, y2), __fmul_rn(y1, x2));
+#else
+  const float re = x1 * x2 - y1 * y2, im = x1 * y2 + y1 * x2;
+#endif
+  const double kappa2 = (double)re, kappa1 = -(double)im;
+  const double gammac = -alpha - a * (1.0 - mus * mus);
+  const double polarpsi = atan2(beta * kappa2 - gammac * kappa1, -beta * kappa1 - gammac * kappa2);
+  s2psi = sin(2.0 * polarpsi);
+  c2psi = cos(2.0 * polarpsi);
+  cosne = rshift * sqrt(q2) / r;
+}
+
 struct OrthoOut {
   double s2xi, c2xi, ang, g, cosne;
 };

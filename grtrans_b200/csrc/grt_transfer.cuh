@@ -392,6 +392,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     Coef c;
     node_coef<ET>(P, R, rec, F, c, jraw);
     double fac = jraw / 1.0;
+    if (HIST) info->fac = fac;
     if (fac / 1e16 > 0.0)
       for (int i = 0; i < neq; i++) out[i] = c.j[i];
     return;
@@ -536,7 +537,11 @@ GRT_HD void ray_extra_t(const TransferParams &P, const double *rec, const double
   for (int c = 0; c < npts; c++) hist[(size_t)c * hs] = 0.0;
   MarchInfo mi;
   ray_transfer_t<ET, MODE, true>(P, rec, npts, nu_obs, out, hist, hs, &mi);
-  if (npts <= 1 || !(mi.fac / 1e16 > 0.0)) return;  // r%tau(:) = 0
+  if (!(mi.fac / 1e16 > 0.0)) return;  // r%tau(:) = 0
+  if (npts == 1) {  // single (disk) point: the record holds the 7 geometric quantities (grtrans_driver.f90:298-312)
+    for (int q = 0; q < 7; q++) xt[q] = xrec[q];
+    return;
+  }
   const int rnpts = mi.rnpts;
   const FreqConst F = freq_const(nu_obs);
   const RunConst R = run_const<ET>(P, nu_obs);

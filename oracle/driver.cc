@@ -54,9 +54,8 @@ struct RayWork {
 };
 }  // namespace
 
-// pgrtrans.f90:107-113: 19 extra quantities per pixel for rays with more than one point, 7 for nup = 1 (the latter need
-// calc_polar_psi and are not restated: extra is ignored for nup = 1)
-static int extra_count(const RunArgs &A) { return (A.extra == 1 && A.nn[2] > 1) ? 19 : 0; }
+// pgrtrans.f90:107-113: 19 extra quantities per pixel for rays with more than one point, 7 for nup = 1
+static int extra_count(const RunArgs &A) { return (A.extra == 1) ? (A.nn[2] > 1 ? 19 : 7) : 0; }
 
 // grtrans_driver.f90:230-292 (EXTRA_QUANTS == 1, npts > 1).  w.ej / w.eK hold the rotated, invariant, scaled coefficients,
 // w.tau the optical depth from the camera, w.intensity the integrator's output columns 1..rnpts.  rt[0..18] = r%tau(1:19).
@@ -297,6 +296,14 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
           // invariant_intensity(e,rshift,3); grtrans_compute_intensity
           double g3 = std::pow(w.rshift[0], 3);
           for (int c = 0; c < std::min(rneq, eneq); c++) o[c] = w.ej[c] * g3;
+          if (nextra == 7) {  // grtrans_driver.f90:298-312: geometry of the single (disk) point
+            double s2psi, c2psi, cosne2;
+            calc_polar_psi(g.x[0].d[1], std::cos(g.x[0].d[2]), g.q2, g.a, g.alpha, g.beta, w.rshift[0], g.mu0, g.k[0].d, c2psi,
+                           s2psi, cosne2);
+            double *rt = o + nvals;
+            rt[0] = w.s2xi[0]; rt[1] = s2psi; rt[2] = cosne2; rt[3] = w.ang[0]; rt[4] = w.cosne[0]; rt[5] = w.c2xi[0];
+            rt[6] = c2psi;
+          }
         }
       }
       if (dump && m == 0) {

@@ -159,6 +159,29 @@ void calc_polvec(double r, double mu, const double *p, double a, double psi, dou
   for (int i = 0; i < 4; i++) f[i] = f[i] / s;
 }
 
+// kerr.f90:954-996 calc_polar_psi + :1047-1063 calc_kappapw: polarisation angle at infinity of a photon emitted with the
+// thin-disk polarisation vector (calc_polvec, psi = 0), by the Penrose-Walker constant.  kappa_pw is a default (single
+// precision) complex in the reference.
+void calc_polar_psi(double r, double muf, double q2, double a, double alpha, double beta, double rshift, double mus,
+                    const double *p, double &c2psi, double &s2psi, double &cosne) {
+  double f[4];
+  calc_polvec(r, muf, p, a, 0.0, f);
+  double al = (p[0] * f[1] - p[1] * f[0]) + a * (1.0 - muf * muf) * (p[1] * f[3] - p[3] * f[1]);
+  double be = (r * r + a * a) * std::sqrt(1.0 - muf * muf) * (p[3] * f[2] - p[2] * f[3]) -
+              a * std::sqrt(1.0 - muf * muf) * (p[0] * f[2] - p[2] * f[0]);
+  // cmplx(alpha,-beta)*cmplx(r,-a*mu) in single precision
+  float x1 = (float)al, y1 = (float)(-be), x2 = (float)r, y2 = (float)(-a * muf);
+  float re = x1 * x2 - y1 * y2, im = x1 * y2 + y1 * x2;
+  double kappa2 = (double)re, kappa1 = -(double)im;
+  double gammac = -alpha - a * (1.0 - mus * mus);
+  double denom = beta * kappa2 - gammac * kappa1;
+  double num = -beta * kappa1 - gammac * kappa2;
+  double polarpsi = std::atan2(denom, num);
+  s2psi = std::sin(2.0 * polarpsi);
+  c2psi = std::cos(2.0 * polarpsi);
+  cosne = rshift * std::sqrt(q2) / r;
+}
+
 // kerr.f90:502-548
 static void transport_perpk(const double *kv, double r, double th, double a, const double *metric, double Kap1,
                             double Kap2, double &f1, double &f2, double &f3) {

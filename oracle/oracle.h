@@ -78,6 +78,8 @@ void initialize_geodesic(Geo &g, const GeokerrArgs &gargs, int i, int &status);
 void blmetric_cov(double r, double th, double a, double *g10);
 void blmetric_cov_real(float r, float th, float a, float *g10);
 double dot4(const double *metric10, const double *a4, const double *b4);
+void calc_polar_psi(double r, double muf, double q2, double a, double alpha, double beta, double rshift, double mus,
+                    const double *p, double &c2psi, double &s2psi, double &cosne);
 void calc_nullp(double q2, double l, double a, double r, double mu, double su, double smu, double *k4);
 void lnrf_frame_inv_real(float vr, float vt, float omega, float r, float a, float th, float &vrl, float &vtl,
                          float &vpl);

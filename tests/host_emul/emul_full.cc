@@ -43,7 +43,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
   tb.ch_mu = th.ch_mu.data(); tb.ch_I = th.ch_I.data(); tb.ch_del = th.ch_del.data();
   fk.tab = tb;
   int nparams = a->nmdot, nfreq = a->nfreq, nv = a->nvals;
-  const int nextra = (a->extra == 1 && a->nn[2] > 1) ? 19 : 0, nout = nv + nextra;  // image: [cam][ray][nvals + nextra]
+  const int nextra = (a->extra == 1) ? (a->nn[2] > 1 ? 19 : 7) : 0, nout = nv + nextra;  // image: [cam][ray][nvals + nextra]
   fk.nparams = nparams; fk.etype = etype;
   for (int m = 0; m < nparams; m++) {
     SourceDev &sp = fk.sp[m];

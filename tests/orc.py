@@ -48,7 +48,7 @@ def run(nthreads=0, **kw):
     a = kw.pop("_args", None) or args_from_kwargs(**kw)
     npix = a.nn[0] * a.nn[1]
     ncams = a.nmdot * a.nfreq * a.nmu * a.nt
-    nv = a.nvals + (19 if (a.extra == 1 and a.nn[2] > 1) else 0)   # extra=1: 19 diagnostics follow the Stokes values
+    nv = a.nvals + ((19 if a.nn[2] > 1 else 7) if a.extra == 1 else 0)   # extra=1: 19 diagnostics follow the Stokes values
     pixvals = np.zeros((ncams, npix, nv), np.float32)
     pixloc = np.zeros((npix, 2), np.float32)
     freqs = np.zeros(a.nfreq)

@@ -215,7 +215,9 @@ EXTRA_CASES = [("harm3d", dict(n=40, nup=100, nfreq=3, fmin=2e11, fmax=2e12)),
                ("harm", dict(n=32, nup=200, nfreq=1)),
                ("sphacc", dict(n=32, nfreq=3)),
                ("ffjet", dict(n=32, nfreq=2, iname='formal')),
-               ("iharm", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12))]
+               ("iharm", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12)),
+               ("thindisk", dict(n=40, nfreq=3)),                                              # nup = 1: 7 geometric quantities
+               ("thindisk", dict(n=32, nfreq=2, ename='BBPOL', nvals=4))]
 
 
 @pytest.mark.parametrize("cfg,over", EXTRA_CASES)
@@ -226,7 +228,7 @@ def test_extra_quantities(cfg, over):
     got = _lib.main(args_from_kwargs(**kw))['ivals']
     ref = orc.run(_args=args_from_kwargs(**kw))['ivals']
     nv = kw['nvals']
-    assert got.shape == ref.shape and got.shape[0] == nv + 19
+    assert got.shape == ref.shape and got.shape[0] == nv + (19 if kw['nn'][2] > 1 else 7)
     (relI, flux, quv, nanok), xerr, xnan = cases.extra_errors(got, ref, nv)
     assert nanok and relI < 1e-4 and flux < 1e-5 and quv < 1e-3, (relI, flux, quv)
     assert xnan
