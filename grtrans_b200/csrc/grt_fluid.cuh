@@ -634,9 +634,7 @@ GRT_HD void tail_gmin(double p, double theta, double eta, double &gmin, double &
   nfrac = eta * atheta * ((p - 2.) / (p - 1.)) * pow(gmin, p - 2.);
 }
 // assign_source_params (fluid.f90:1640-1677), applied after every model's unit conversion (fluid.f90:582)
-GRT_HD void source_params(const SourceDev &sp, CgsVars &o) {
-  o.gmin = sp.gminval;
-  if (!sp.stail) return;
+GRT_HDN void tail_source(const SourceDev &sp, CgsVars &o) {
   const double pcc = 2.99792458e10, pck = 1.38e-16, pcm = 9.10938188e-28;
   double g, x;
   tail_gmin(sp.p2, sp.muval * pck * o.tcgs / pcm / pcc / pcc, sp.jetalphaval, g, x);
@@ -644,6 +642,10 @@ GRT_HD void source_params(const SourceDev &sp, CgsVars &o) {
   o.gmin = in ? g : sp.gmax / 2.0;
   const double factor = in ? 1.0 : pow(sp.gmax / 2.0 / g, sp.p2 - 2.);
   o.ncgsnth = factor * ((x > 0.0) ? x * o.ncgs * pow(o.gmin, 1. - sp.p2) : 0.0);
+}
+GRT_HD void source_params(const SourceDev &sp, CgsVars &o) {
+  o.gmin = sp.gminval;
+  if (sp.stail) tail_source(sp, o);  // (out of line: rarely used, keeps the common path's registers)
 }
 
 GRT_HD void to_cgs(int model, const SourceDev &sp, float rho, float p, float bmag, float kela, float be, float gam,

@@ -72,6 +72,21 @@ GRT_HD void ray_finalize(int npts, size_t i, int maxpts, int usegeor, PointArray
   m.dt1 = pa.dt[i * maxpts];
 }
 
+// extra = 1: the second per-point record (kept out of line: the common path must not pay registers for it)
+GRT_HDN void point_xrec(double *x, int npts, const RayConst &r0, double r, double th, double ph, const double *k4,
+                        const FluidSample &fs, const OrthoOut &oo, const CgsVars &cg) {
+  if (npts != 1) {  // quantities averaged along the ray by the extra = 1 diagnostics (grtrans_driver.f90:262-283)
+    x[0] = r; x[1] = th; x[2] = ph; x[3] = cg.ncgs; x[4] = cg.tcgs; x[5] = cg.bcgs;
+    x[6] = (double)(fs.p * 2.f / (fs.bmag * fs.bmag));  // f%p*2./f%bmag**2. in real(4)
+    x[7] = 0.0;
+  } else {  // single (disk) point: the 7 geometric quantities of grtrans_driver.f90:298-312
+    double c2psi, s2psi, cosne2;
+    polar_psi(r, cos(th), r0.q2, r0.a, r0.alpha, r0.beta, oo.g, r0.mu0, k4, c2psi, s2psi, cosne2);
+    x[0] = oo.s2xi; x[1] = s2psi; x[2] = cosne2; x[3] = oo.ang; x[4] = oo.cosne; x[5] = oo.c2xi; x[6] = c2psi;
+    x[7] = 0.0;
+  }
+}
+
 // x^mu, k^mu, fluid sample, comoving frame, unit conversion and the 128-byte point record(s)
 GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernelArgs &A, int ray, int slot, int nrays,
                          PointArrays pa, double *rec, StageDump sd) {
@@ -165,19 +180,7 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
 #else
     for (int i = 0; i < nrec; i++) q[i] = o[i];
 #endif
-    if (A.xrec) {
-      double *x = A.xrec + ((size_t)mm * nrays * maxpts + dst) * 8;
-      if (m.npts != 1) {  // quantities averaged along the ray by the extra = 1 diagnostics (grtrans_driver.f90:262-283)
-        x[0] = r; x[1] = th; x[2] = ph; x[3] = cg.ncgs; x[4] = cg.tcgs; x[5] = cg.bcgs;
-        x[6] = (double)(fs.p * 2.f / (fs.bmag * fs.bmag));  // f%p*2./f%bmag**2. in real(4)
-        x[7] = 0.0;
-      } else {  // single (disk) point: the 7 geometric quantities of grtrans_driver.f90:298-312
-        double c2psi, s2psi, cosne2;
-        polar_psi(r, cos(th), r0.q2, r0.a, r0.alpha, r0.beta, oo.g, r0.mu0, k4, c2psi, s2psi, cosne2);
-        x[0] = oo.s2xi; x[1] = s2psi; x[2] = cosne2; x[3] = oo.ang; x[4] = oo.cosne; x[5] = oo.c2xi; x[6] = c2psi;
-        x[7] = 0.0;
-      }
-    }
+    if (A.xrec) point_xrec(A.xrec + ((size_t)mm * nrays * maxpts + dst) * 8, m.npts, r0, r, th, ph, k4, fs, oo, cg);
     if (mm == 0 && sd.ncgs) {
       sd.ncgs[dst] = cg.ncgs; sd.ncgsnth[dst] = cg.ncgsnth; sd.bcgs[dst] = cg.bcgs; sd.tcgs[dst] = cg.tcgs;
     }

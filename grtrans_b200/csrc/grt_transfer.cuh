@@ -234,21 +234,24 @@ GRT_HD void delo_step(const Coef &c0, const Coef &c1, double dx, double delta, d
                       double *inew) {
   double rhs[4], t[4];
   kmat_vec(c1.K, iprev, t);
+  // The optically thick and thin forms (radtrans_integrate.f90 delo) differ only in five scalar weights: the lanes of a warp
+  // (32 frequencies of one ray) often straddle delta = thin, so the weights are chosen in the branch and the right-hand
+  // side and the 4x4 solve are issued once, after it, for all lanes together.
+  double wj0, wj1, qi, qt, sc;
   if (delta > thin) {
     const double E = exp_fast(-delta), F = 1.0 - E, G = (1.0 - (1.0 + delta) * E) / delta;
     const double i0 = 1.0 / c0.K[0], i1 = 1.0 / c1.K[0];
-    const double w0 = (F - G) * i0, w1 = G * i1;
     // (F-G) S_k + G S_k+1 + (E*Id - G*Kp1) iprev,  S = j/aI,  Kp1 = K1/aI1 - Id
-    for (int i = 0; i < 4; i++) rhs[i] = w0 * c0.j[i] + w1 * c1.j[i] + ((E + G) * iprev[i] - w1 * t[i]);
     // matrix = Id + (F-G)*(K0/aI0 - Id) = (1-(F-G)) Id + ((F-G)/aI0) K0
-    solve_delo(1.0 - (F - G), w0, c0.K, rhs, inew);
+    wj0 = (F - G) * i0; wj1 = G * i1; qi = E + G; qt = wj1; sc = 1.0 - (F - G);
   } else {
     const double ki = c0.K[0];
-    const double qa = 1.0 - 0.5 * dx * ki + 1.0 / 6.0 * dx * dx * ki * ki, qb = 0.5 * dx - 1.0 / 3.0 * dx * dx;
-    const double wa = 0.5 * dx - 1.0 / 6.0 * dx * dx * ki, wb = 0.5 * dx - 1.0 / 3.0 * dx * dx * ki;
-    for (int i = 0; i < 4; i++) rhs[i] = wa * c0.j[i] + wb * c1.j[i] + (qa * iprev[i] - qb * t[i]);
-    solve_delo(1.0 - delta / 2.0 + delta * delta / 6.0, wa, c0.K, rhs, inew);
+    qi = 1.0 - 0.5 * dx * ki + 1.0 / 6.0 * dx * dx * ki * ki; qt = 0.5 * dx - 1.0 / 3.0 * dx * dx;
+    wj0 = 0.5 * dx - 1.0 / 6.0 * dx * dx * ki; wj1 = 0.5 * dx - 1.0 / 3.0 * dx * dx * ki;
+    sc = 1.0 - delta / 2.0 + delta * delta / 6.0;
   }
+  for (int i = 0; i < 4; i++) rhs[i] = wj0 * c0.j[i] + wj1 * c1.j[i] + (qi * iprev[i] - qt * t[i]);
+  solve_delo(sc, wj0, c0.K, rhs, inew);
 }
 
 // inew = O(dx; a, rho) * v  (Landi Degl'Innocenti & Landi Degl'Innocenti 1985 evolution operator)
