@@ -11,7 +11,7 @@ import numpy as np
 from ._abi import GrtArgs, args_from_kwargs, args_from_inputs, Inputs  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libgrtrans_b200.so")
+SO_PATH = os.environ.get("GRT_B200_LIB", os.path.join(HERE, "libgrtrans_b200.so"))   # (override: kernel-variant experiments)
 
 ERRORS = {1: "no usable CUDA device (GRT_ERR_NO_DEVICE)", 2: "unsupported argument (GRT_ERR_BAD_ARG)",
           3: "input/output file error (GRT_ERR_IO)", 4: "module data state error (GRT_ERR_STATE)",

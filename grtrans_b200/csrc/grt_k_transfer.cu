@@ -9,8 +9,11 @@ namespace grt {
 // 128-byte point record is one broadcast load per step and the lanes never diverge on npts.
 // __launch_bounds__(128, 4): 128 registers, 16 warps / SM.  Measured on the headline kernel <POLSYNCHTH, DELO>: 3 blocks
 // (154 regs) 84.6 ms, 4 blocks 77.1 ms, 5 blocks (96 regs, spills) 76.9 ms, 6 blocks 76.6 ms at nx=256.
+#ifndef GRT_TRANSFER_MINB
+#define GRT_TRANSFER_MINB 4
+#endif
 template <int ET, int MODE>
-__global__ void __launch_bounds__(128, 4) k_transfer(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
+__global__ void __launch_bounds__(128, GRT_TRANSFER_MINB) k_transfer(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
                                                   const double *__restrict__ freqs, int nfreq, int nparams, int nrays, int maxpts,
                                                   const double *__restrict__ rec, float *__restrict__ image, long long ray_off,
                                                   long long nlocal, int cam0) {
