@@ -42,7 +42,10 @@ void launch_geo_points(const RayInv *inv, int nup, int maxpts, long long total, 
   // 1024-thread blocks (one per SM, 64 registers): measured best of {128x6, 256x3, 384x2, 512x1, 768x1, 1024x1} -- the phase
   // barriers of geo_point work per block, so one big block keeps all 32 warps of the SM inside the same code stage
   // (nx=256 bench: 28.3 / 22.9 / 20.5 / 23.3 / 19.5 / 18.3 ms; 59.6 ms before the code was compacted and phased)
-  constexpr int BS = 1024;
+#ifndef GRT_GEO_BS
+#define GRT_GEO_BS 1024
+#endif
+  constexpr int BS = GRT_GEO_BS;
   k_geo_points<BS, 1><<<(unsigned)((total + BS - 1) / BS), BS, 0, st>>>(inv, nup, maxpts, total, pa);
 }
 void launch_ray_finalize(const RayInv *inv, int maxpts, int usegeor, int n, PointArrays pa, RayMeta *meta, cudaStream_t st) {
