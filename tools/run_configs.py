@@ -40,6 +40,14 @@ CONFIGS = [
      cases.cfg_iharm(n=128, nup=400, nfreq=8, mmks=1, fmin=1e11, fmax=1e13), (8001, 9280)),
     ("next-row KORAL3D (synthetic MKS3 dump, T_e from the dump) POLSYNCHTH nn=[128,128,400] nfreq=8 nvals=4 delo",
      cases.cfg_koral(n=128, nup=400, nfreq=8, threed=True), (8001, 9280)),
+    ("next-row time axis: HARM series, 3 dumps resident + t0 offsets, 3 movie frames, nn=[128,128,400] nfreq=2 nvals=4 delo",
+     # (no sub-range for the oracle here: the t0 offsets of an nload > 1 run are normalised over the pixels i1..i2)
+     cases.cfg_series('harm2d', n=128, nup=400, nfreq=2, fnt=3, nload=3, nt=3, dt=10., fmin=1e12, fmax=3e12), None),
+    ("next-row extra=1: HARM3D POLSYNCHTH + 19 diagnostics per pixel, nn=[128,128,400] nfreq=4 nvals=4 delo",
+     cases.cfg_harm3d(n=128, nup=400, nfreq=4, fmin=2e11, fmax=2e12, extra=1), (8001, 8640)),
+    ("next-row stype='tail': HARM3D HYBRIDTHPL, nn=[128,128,400] nfreq=4 nvals=4 delo",
+     cases.cfg_harm3d(n=128, nup=400, nfreq=4, fmin=1e11, fmax=1e13, ename='HYBRIDTHPL', stype='tail', p1=3., p2=3., jetalpha=.05),
+     (8001, 8640)),
 ]
 
 
@@ -61,7 +69,7 @@ def main():
         t0 = time.time()
         ref = orc.run(_args=args_from_kwargs(i1=i1, i2=i2, **kw))
         cpu_s = ref['seconds']
-        g, r = got[:, i1 - 1:i2], ref['ivals'][:, i1 - 1:i2]
+        g, r = got[:a.nvals, i1 - 1:i2], ref['ivals'][:a.nvals, i1 - 1:i2]   # (extra=1: the Stokes block)
         # Cameras in which the reference algorithm itself is numerically unstable are reported separately: at nu << nu_c the
         # polsynchth fits give |j_V| > j_I, the absorption matrix gets a negative eigenvalue and the transfer solution grows
         # exponentially (I < 0, |I| up to 1e27): rounding differences are amplified without bound there.
