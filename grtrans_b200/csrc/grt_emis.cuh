@@ -29,6 +29,12 @@ struct EmisTables {      // device pointers (log-valued tables, built on the hos
   const double *gx, *gy;  // 181, 3*181
   const double *xv, *ya, *yp, *yv, *yap, *yav;  // 81, 5 x 3*81
   const float *ch_mu, *ch_I, *ch_del;           // 21 each
+  // Faraday-fit table (optional, nullptr = evaluate the fits directly): cubic pieces of jffunc(xarg) and of
+  // log(1 + 0.00185777 xarg^1.50316886) on a uniform grid in u = log(xarg); far[k*8 + 0..3] / [4..7] = a,b,c,d of piece k,
+  // value = a + w (b + w (c + w d)), w = (u - far_u0) far_ih - k
+  const double *far;
+  double far_u0, far_ih;
+  int far_n;
 };
 
 GRT_HD double poly7(double x, const double *c) {
@@ -105,6 +111,7 @@ struct ThermalPoint {  // 12 doubles, stored in the point record
   double RQ;           // rho_Q LBH/g = RQ jff / nu_obs^3
   double RV0, RV1;     // rho_V LBH/g = (RV0 - RV1 shgm) / nu_obs^2
   double g;            // redshift
+  double lAx;          // log(Ax): log(xarg) = lAx - 0.5 log(nu_obs), the abscissa of the Faraday-fit table
 };
 
 // Per observed frequency.  Every x**p of the reference with x = (per-point factor) * nu**q is evaluated as
@@ -115,6 +122,7 @@ struct FreqConst {
   double n13, in13;             // nu^(1/3), nu^(-1/3)
   double nm12;                  // nu^(-1/2)
   double nq1, nq2, nq3, nq4;    // nu^(-1.035/2), nu^(-1.2/2), nu^(-1.50316886/2), nu^(+4/3)
+  double lnm12;                 // log(nu^(-1/2))
 };
 GRT_HD FreqConst freq_const(double nu_obs) {
   FreqConst f;
@@ -126,6 +134,7 @@ GRT_HD FreqConst freq_const(double nu_obs) {
   f.n13 = exp(l * (1.0 / 3.0));
   f.in13 = exp(l * (-1.0 / 3.0));
   f.nm12 = exp(-0.5 * l);
+  f.lnm12 = -0.5 * l;
   f.nq1 = exp((-0.5 * 1.035) * l);
   f.nq2 = exp((-0.5 * 1.2) * l);
   f.nq3 = exp((-0.5 * (double)1.50316886f) * l);
@@ -151,6 +160,7 @@ GRT_HD void thermal_point(double n, double b, double t, double theta, double g, 
   // xarg = thetae*sqrt(sqrt(2) sin(theta) 1e3 omega0/(2 pi nu)),  nu = nu_obs/g
   P.Ax = thetae * sqrt(sqrt(2.0) * sinth * (1e3 * omega0 / 2.0 / pi) * g);
   const double lAx = log(P.Ax);
+  P.lAx = lAx;
   P.Ax1 = exp(1.035 * lAx);
   P.Ax2 = exp(1.2 * lAx);
   P.Ax3 = exp((double)1.50316886f * lAx);
@@ -181,7 +191,47 @@ GRT_HD void thermal_point(double n, double b, double t, double theta, double g, 
 // DELO step divides by alpha_I, and "j_inv == 0 but alpha_I != 0" must stay distinguishable from "both 0".
 // Per call: 5 exp, 1 cos, 1 sqrt, 1 reciprocal (+ 1 log where the Faraday-rotation fit is switched on, + 1 division inside
 // the 16 < xarg < 6552 window of the high-frequency correction) and ~110 multiply-adds.
-GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, double *e, double &jraw) {
+// jffunc (with its high-frequency correction) and the logarithm of shgmfunc, evaluated as written (polsynchemis.f90:737-761),
+// from xarg and its powers x1 = xarg^1.035, x2 = xarg^1.2, x3 = xarg^1.50316886, x4 = xarg^(-8/3).  Out of line: with the
+// Faraday-fit table in place this is the rare path (xarg outside the table, or the table switched off).
+GRT_HDN void faraday_fits(double xarg, double x1, double x2, double x3, double x4, bool want_log, double &jff, double &lt) {
+  const double e1 = .011 * exp_fast(xarg * (-1.0 / 47.2));
+  jff = 2.011 * exp_fast(x1 * (-1.0 / 4.7)) - cos(0.5 * xarg) * exp_fast(x2 * (-1.0 / 2.73)) - e1;
+  // extraterm * (0.5 + 0.5 tanh((log(xarg) - log(120))/0.1)) = extraterm * t^20/(1 + t^20), t = xarg/120; the switch is
+  // exactly 0 in FP64 below t = e^-2 and exactly 1 above t = e^4
+  const double t = xarg * (1.0 / 120.0);
+  if (t > 0.1353352832366127) {
+    double sw = 1.0;
+    if (t < 54.598150033144236) {
+      const double t2 = t * t, t4 = t2 * t2, t5 = t4 * t, t10 = t5 * t5, t20 = t10 * t10;
+      sw = t20 / (1.0 + t20);
+    }
+    const double c83 = 0.7937005259840998 / 67.44733739010397 * GRT_PI * 1e4;  // 2^(-1/3) / 3^(23/6) pi 1e4
+    jff += (e1 - c83 * x4) * sw;  // (xarg + 1e-16)^(-8/3): the 1e-16 is below rounding for xarg > 16
+  }
+  lt = want_log ? log_ge1(1.0 + (double)0.00185777f * x3) : 0.0;
+}
+
+GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, double *e, double &jraw,
+                         const EmisTables &FT) {
+  // Faraday-fit table: the eight coefficients of this (point, frequency) are fetched first, with a clamped index so that the
+  // loads need no branch; their latency is hidden behind the synchrotron part below
+  bool tabulated = false;
+  double tw = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0, q5 = 0.0, q6 = 0.0, q7 = 0.0;
+  if (FT.far) {  // (uniform)
+    const double u = (P.lAx + F.lnm12 - FT.far_u0) * FT.far_ih;
+    tabulated = u >= 0.0 && u < (double)FT.far_n;  // (NaN: direct evaluation, which propagates it)
+    const int k = tabulated ? (int)u : 0;
+    tw = u - (double)k;
+#if defined(__CUDA_ARCH__)
+    const double2 *q = reinterpret_cast<const double2 *>(FT.far) + (size_t)k * 4;
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    q0 = a.x; q1 = a.y; q2 = b.x; q3 = b.y; q4 = c.x; q5 = c.y; q6 = d.x; q7 = d.y;
+#else
+    const double *q = FT.far + (size_t)k * 8;
+    q0 = q[0]; q1 = q[1]; q2 = q[2]; q3 = q[3]; q4 = q[4]; q5 = q[5]; q6 = q[6]; q7 = q[7];
+#endif
+  }
   const double x13 = F.n13 * P.xp13;
   const double i13 = F.in13 * P.ixp13, i23 = i13 * i13;
   const double ex = exp_fast(-1.8899 * x13);
@@ -206,26 +256,17 @@ GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, 
   }
   e[0] = ji * g2; e[1] = jq * g2; e[2] = 0.0; e[3] = jv * g2;
   e[4] = ji * ka; e[5] = jq * ka; e[6] = 0.0; e[7] = jv * ka;
-  // Faraday rotation / conversion (Shcherbakov 2008 fits jffunc, shgmfunc)
-  const double xarg = P.Ax * F.nm12;
-  const double e1 = .011 * exp_fast(xarg * (-1.0 / 47.2));
-  double jff = 2.011 * exp_fast((P.Ax1 * F.nq1) * (-1.0 / 4.7)) - cos(0.5 * xarg) * exp_fast((P.Ax2 * F.nq2) * (-1.0 / 2.73)) - e1;
-  // extraterm * (0.5 + 0.5 tanh((log(xarg) - log(120))/0.1)) = extraterm * t^20/(1 + t^20), t = xarg/120; the switch is
-  // exactly 0 in FP64 below t = e^-2 and exactly 1 above t = e^4
-  const double t = xarg * (1.0 / 120.0);
-  if (t > 0.1353352832366127) {
-    double sw = 1.0;
-    if (t < 54.598150033144236) {
-      const double t2 = t * t, t4 = t2 * t2, t5 = t4 * t, t10 = t5 * t5, t20 = t10 * t10;
-      sw = t20 / (1.0 + t20);
-    }
-    const double c83 = 0.7937005259840998 / 67.44733739010397 * GRT_PI * 1e4;  // 2^(-1/3) / 3^(23/6) pi 1e4
-    jff += (e1 - c83 * (P.Ax4 * F.nq4)) * sw;  // (xarg + 1e-16)^(-8/3): the 1e-16 is below rounding for xarg > 16
+  // Faraday rotation / conversion (Shcherbakov 2008 fits jffunc, shgmfunc): both are functions of xarg alone
+  double jff, lt = 0.0;
+  if (tabulated) {
+    jff = q0 + tw * (q1 + tw * (q2 + tw * q3));
+    lt = q4 + tw * (q5 + tw * (q6 + tw * q7));
   }
+  if (!tabulated) faraday_fits(P.Ax * F.nm12, P.Ax1 * F.nq1, P.Ax2 * F.nq2, P.Ax3 * F.nq3, P.Ax4 * F.nq4, P.RV1 != 0.0, jff, lt);
   e[8] = P.RQ * jff * F.inu3;
   e[9] = 0.0;
   double rv = P.RV0;
-  if (P.RV1 != 0.0) rv -= P.RV1 * ((double)0.43793091f * log_ge1(1.0 + (double)0.00185777f * (P.Ax3 * F.nq3)));
+  if (P.RV1 != 0.0) rv -= P.RV1 * ((double)0.43793091f * lt);
   e[10] = rv * F.inu2;
 }
 
@@ -234,7 +275,9 @@ GRT_HD void polsynchth_eval(double nu, double n, double b, double t, double thet
   ThermalPoint P;
   thermal_point(n, b, t, theta, 1.0, 1.0, P);
   double jraw;
-  thermal_eval(P, freq_const(nu), pc::c2 / (2.0 * pc::h), e, jraw);
+  EmisTables none;
+  none.far = nullptr; none.far_u0 = none.far_ih = 0.0; none.far_n = 0;
+  thermal_eval(P, freq_const(nu), pc::c2 / (2.0 * pc::h), e, jraw, none);
 }
 
 // ---- power-law synchrotron ------------------------------------------------------------------------

@@ -321,6 +321,15 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   SCK(own_h2d(s, &tb.ya, th.ya)); SCK(own_h2d(s, &tb.yp, th.yp)); SCK(own_h2d(s, &tb.yv, th.yv));
   SCK(own_h2d(s, &tb.yap, th.yap)); SCK(own_h2d(s, &tb.yav, th.yav));
   SCK(own_h2d(s, &tb.ch_mu, th.ch_mu)); SCK(own_h2d(s, &tb.ch_I, th.ch_I)); SCK(own_h2d(s, &tb.ch_del, th.ch_del));
+  // Faraday-fit table (GRT_FARADAY_EXACT=1: evaluate the fits directly at every (point, frequency) instead)
+  tb.far = nullptr; tb.far_u0 = th.far_u0; tb.far_ih = th.far_ih; tb.far_n = 0;
+  {
+    const char *fe = getenv("GRT_FARADAY_EXACT");
+    if (!(fe && atoi(fe) != 0)) {
+      SCK(own_h2d(s, &tb.far, th.far));
+      tb.far_n = th.far_n;
+    }
+  }
   s->fk.tab = tb;
   s->fk.nparams = s->nparams; s->fk.etype = etype; s->fk.maxpts = s->maxpts; s->fk.xrec = s->d_xrec;
   for (int m = 0; m < s->nparams; m++) {
@@ -880,6 +889,7 @@ static int emis_tables_device(EmisTables &tb, std::vector<void *> &owned) {
   bool ok = up(&tb.gx, th.gx) && up(&tb.gy, th.gy) && up(&tb.xv, th.xv) && up(&tb.ya, th.ya) && up(&tb.yp, th.yp) &&
             up(&tb.yv, th.yv) && up(&tb.yap, th.yap) && up(&tb.yav, th.yav);
   tb.ch_mu = tb.ch_I = tb.ch_del = nullptr;
+  tb.far = nullptr; tb.far_u0 = tb.far_ih = 0.0; tb.far_n = 0;  // unit surfaces evaluate the fits directly
   return ok ? GRT_OK : GRT_ERR_CUDA;
 }
 

@@ -52,6 +52,11 @@ int advance_fluid(FluidHost &f, const grt_args &a, double dt);
 struct EmisTablesHost {
   std::vector<double> gx, gy, xv, ya, yp, yv, yap, yav;
   std::vector<float> ch_mu, ch_I, ch_del;
+  // Faraday-fit table: cubic Hermite pieces of jffunc(xarg) and log(1 + 0.00185777 xarg^1.50316886) on a uniform grid in
+  // log(xarg) (see EmisTables in grt_emis.cuh); far_n pieces of 8 doubles
+  std::vector<double> far;
+  double far_u0 = 0, far_ih = 0;
+  int far_n = 0;
 };
 void build_emis_tables(EmisTablesHost &t);
 

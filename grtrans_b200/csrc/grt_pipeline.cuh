@@ -146,6 +146,7 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
         thermal_point(cg.ncgs, cg.bcgs, cg.tcgs, oo.ang, oo.g, pc::G * A.sp[mm].mbh * pc::msun / pc::c2, T);
         o[4] = T.xp13; o[5] = T.AI; o[6] = T.AV; o[7] = T.hkT_g; o[8] = T.Ax; o[9] = T.Ax1; o[10] = T.Ax2; o[11] = T.Ax3;
         o[12] = T.Ax4; o[13] = T.RQ; o[14] = T.RV0; o[15] = T.RV1; o[16] = T.ixp13; o[17] = T.xpm32;
+        o[em_is_hybrid(A.etype) ? 26 : 18] = T.lAx;
       } break;
       case EM_POLSYNCHPL:
       case EM_SYNCHPL: {

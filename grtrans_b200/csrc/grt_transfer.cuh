@@ -93,7 +93,8 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
     T.xp13 = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.Ax = rec[8]; T.Ax1 = rec[9]; T.Ax2 = rec[10];
     T.Ax3 = rec[11]; T.Ax4 = rec[12]; T.RQ = rec[13]; T.RV0 = rec[14]; T.RV1 = rec[15]; T.ixp13 = rec[16];
     T.xpm32 = rec[17]; T.g = g;
-    thermal_eval(T, F, pc::c2 * P.LBH / (2.0 * pc::h), e, jI_raw);
+    T.lAx = rec[em_is_hybrid(ET) ? 26 : 18];
+    thermal_eval(T, F, pc::c2 * P.LBH / (2.0 * pc::h), e, jI_raw, P.tab);
     invariant = true;
     if (em_is_hybrid(ET)) {  // emis.f90:469-485: add the power-law population (brought to the same invariant form)
       PlPoint Q;

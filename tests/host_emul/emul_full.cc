@@ -1,6 +1,7 @@
 // Debug/test harness: drives the product's __host__ __device__ stage bodies (grt_pipeline.cuh) on the
 // CPU, with the product's own host layer (grt_io.cpp), to compare kernel logic with the oracle without a
 // GPU.  NOT part of the product; never loaded by grtrans_b200.  Built by tests/test_host_emul.py.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,6 +42,11 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
   tb.gx = th.gx.data(); tb.gy = th.gy.data(); tb.xv = th.xv.data(); tb.ya = th.ya.data(); tb.yp = th.yp.data();
   tb.yv = th.yv.data(); tb.yap = th.yap.data(); tb.yav = th.yav.data();
   tb.ch_mu = th.ch_mu.data(); tb.ch_I = th.ch_I.data(); tb.ch_del = th.ch_del.data();
+  {
+    const char *fe = getenv("GRT_FARADAY_EXACT");
+    const bool exact = fe && atoi(fe) != 0;
+    tb.far = exact ? nullptr : th.far.data(); tb.far_u0 = th.far_u0; tb.far_ih = th.far_ih; tb.far_n = exact ? 0 : th.far_n;
+  }
   fk.tab = tb;
   int nparams = a->nmdot, nfreq = a->nfreq, nv = a->nvals;
   const int nextra = (a->extra == 1) ? (a->nn[2] > 1 ? 19 : 7) : 0, nout = nv + nextra;  // image: [cam][ray][nvals + nextra]
