@@ -159,3 +159,21 @@ extern "C" int emul_fluid_series(const grt_args *a, int nsteps, double dt, doubl
 extern "C" void emul_math(int which, int n, const double *x, double *o) {
   for (int i = 0; i < n; i++) o[i] = (which == 0) ? exp_fast(x[i]) : log_ge1(x[i]);
 }
+
+// Faraday-fit table against the direct evaluation of the fits: out[i*4..] = jff_table, log_table, jff_direct, log_direct
+extern "C" void emul_faraday(int n, const double *xarg, double *out) {
+  grt_host::EmisTablesHost th;
+  grt_host::build_emis_tables(th);
+  for (int i = 0; i < n; i++) {
+    const double x = xarg[i], u = (std::log(x) - th.far_u0) * th.far_ih;
+    double *o = out + 4 * (size_t)i;
+    o[0] = o[1] = NAN;
+    if (u >= 0.0 && u < (double)th.far_n) {
+      const int k = (int)u;
+      const double w = u - k, *q = &th.far[(size_t)k * 8];
+      o[0] = q[0] + w * (q[1] + w * (q[2] + w * q[3]));
+      o[1] = q[4] + w * (q[5] + w * (q[6] + w * q[7]));
+    }
+    faraday_fits(x, std::pow(x, 1.035), std::pow(x, 1.2), std::pow(x, (double)1.50316886f), std::pow(x, -8.0 / 3.0), true, o[2], o[3]);
+  }
+}

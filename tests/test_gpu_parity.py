@@ -220,6 +220,23 @@ EXTRA_CASES = [("harm3d", dict(n=40, nup=100, nfreq=3, fmin=2e11, fmax=2e12)),
                ("thindisk", dict(n=32, nfreq=2, ename='BBPOL', nvals=4))]
 
 
+def test_faraday_table_against_direct_evaluation(monkeypatch):
+    """k_transfer takes the Faraday fits of polsynchth from a table in log(xarg) (|error| < 1e-9); GRT_FARADAY_EXACT=1 makes
+    the session evaluate them directly.  Both must give the same image far inside the parity tolerances."""
+    kw = cases.cfg_harm3d(n=48, nup=200, nfreq=6, fmin=1e11, fmax=1e13)
+    tab = _lib.main(args_from_kwargs(**kw))['ivals']
+    monkeypatch.setenv("GRT_FARADAY_EXACT", "1")
+    direct = _lib.main(args_from_kwargs(**kw))['ivals']
+    monkeypatch.delenv("GRT_FARADAY_EXACT")
+    assert not np.array_equal(tab, direct, equal_nan=True)          # the two paths really differ in the last digits
+    relI, flux, quv, nanok = cases.image_errors(tab, direct)
+    assert nanok and relI < 1e-6 and flux < 1e-8 and quv < 1e-6, (relI, flux, quv)
+    ref = orc.run(_args=args_from_kwargs(**kw))['ivals']
+    for img in (tab, direct):
+        relI, flux, quv, nanok = cases.image_errors(img, ref)
+        assert nanok and relI < 1e-4 and flux < 1e-5 and quv < 1e-3, (relI, flux, quv)
+
+
 @pytest.mark.parametrize("cfg,over", EXTRA_CASES)
 def test_extra_quantities(cfg, over):
     """extra=1 (grtrans_driver.f90:230-292): 19 diagnostics per pixel after the Stokes values -- optical / Faraday depths,

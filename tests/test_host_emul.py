@@ -134,6 +134,23 @@ def test_extra_quantities_match_oracle(emul, cfg, over):
     assert np.abs(np.nan_to_num(ref[kw['nvals']:kw['nvals'] + 7][:, lit])).min(axis=1).max() > 0   # not trivially zero
 
 
+def test_faraday_fit_table_accuracy(emul):
+    """The tabulated Faraday fits (jffunc with its high-frequency correction: an O(1) function; log(1 + 0.00185777 x^1.503))
+    against their direct evaluation over the whole table range 1e-4 <= xarg <= 1e5, incl. the tanh switch near xarg = 120."""
+    rng = np.random.RandomState(3)
+    x = np.concatenate([np.exp(rng.uniform(np.log(1.0001e-4), np.log(0.9999e5), 400000)), np.linspace(60., 300., 20001),
+                        np.linspace(0.5, 40., 20001)])
+    out = np.zeros((len(x), 4))
+    emul.emul_faraday(C.c_int(len(x)), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.isfinite(out).all()
+    assert np.abs(out[:, 0] - out[:, 2]).max() < 1e-9, np.abs(out[:, 0] - out[:, 2]).max()
+    assert np.abs(out[:, 1] - out[:, 3]).max() < 1e-10, np.abs(out[:, 1] - out[:, 3]).max()
+    outside = np.array([1e-5, 2e5])
+    o2 = np.zeros((2, 4))
+    emul.emul_faraday(C.c_int(2), outside.ctypes.data_as(C.c_void_p), o2.ctypes.data_as(C.c_void_p))
+    assert np.isnan(o2[:, 0]).all() and np.isfinite(o2[:, 2]).all()   # outside the table: direct evaluation only
+
+
 def test_fast_exp_and_log_are_one_ulp(emul):
     """exp_fast / log_ge1 (grt_math.cuh) replace libm's exp / log inside the emissivity + DELO loop: within 1 ulp of the
     correctly rounded value over their domains (exp: -745..709 including subnormal results; log: finite x >= 1)."""
