@@ -31,7 +31,7 @@ import numpy as np  # noqa: E402
 W_GEO = 5.8e3   # per (pixel, point): geodesic + geometry
 W_RT = 9.4e2    # per (pixel, point, freq): POLSYNCHTH emissivity + rotate/scale + DELO step
 B_GATHER = 320  # bytes per (pixel, point): 8 corners x 10 fields x 4 B (3-D)
-B_RECORD = 160  # bytes per (pixel, point) read by the transfer kernel (one point record)
+B_RECORD = 128  # bytes per (pixel, point) read by the transfer kernel (one point record)
 # from the ncu --set full capture of one k_transfer launch at this configuration (profiles/r1_ncu_summary.md):
 NCU_TRANSFER = {"dram_bytes_per_launch": 4.803515e9 + 0.225904e9, "fp64_pipe_busy_pct": 65.9, "issue_active_pct": 64.9,
                 "launch": "65536-ray tile (32768 blocks x 128 threads), 57.4 ms under ncu",

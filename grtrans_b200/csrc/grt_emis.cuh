@@ -101,17 +101,15 @@ GRT_HD double planck_bnu(double T, double nu) {
 //
 // Output of thermal_eval are the INVARIANT coefficients of frequency nu_obs: j*g^2 and K/g*LBH evaluated at the comoving
 // frequency nu = nu_obs/g (for the unit-level surface g = LBH = 1 gives the plain comoving polsynchth values).
-struct ThermalPoint {  // 12 doubles, stored in the point record
+struct ThermalPoint {  // 10 doubles (+ g), stored in the point record
   double xp13;         // (g nu_c')^(-1/3):  (nu/nu_c')^(1/3) = nu_obs^(1/3) xp13
   double ixp13, xpm32; // 1/xp13 and xp13^(-3/2): (nu/nu_c')^(-1/3), (nu/nu_c')^(-1/2) without a reciprocal / square root
   double AI, AV;       // comoving j_{I,Q} = AI nu_obs {iix,iqx},  j_V = AV nu_obs ivx   (the 1/g of nu = nu_obs/g folded in)
   double hkT_g;        // h/(k T g): h nu/(k T) = hkT_g nu_obs
-  double Ax;           // xarg = Ax nu_obs^(-1/2)
-  double Ax1, Ax2, Ax3, Ax4;  // Ax^1.035, Ax^1.2, Ax^1.50316886, Ax^(-8/3)
   double RQ;           // rho_Q LBH/g = RQ jff / nu_obs^3
   double RV0, RV1;     // rho_V LBH/g = (RV0 - RV1 shgm) / nu_obs^2
   double g;            // redshift
-  double lAx;          // log(Ax): log(xarg) = lAx - 0.5 log(nu_obs), the abscissa of the Faraday-fit table
+  double lAx;          // log(Ax), xarg = Ax nu_obs^(-1/2): log(xarg) = lAx - 0.5 log(nu_obs), the abscissa of the Faraday fits
 };
 
 // Per observed frequency.  Every x**p of the reference with x = (per-point factor) * nu**q is evaluated as
@@ -121,7 +119,6 @@ struct FreqConst {
   double nu, inu2, inu3;
   double n13, in13;             // nu^(1/3), nu^(-1/3)
   double nm12;                  // nu^(-1/2)
-  double nq1, nq2, nq3, nq4;    // nu^(-1.035/2), nu^(-1.2/2), nu^(-1.50316886/2), nu^(+4/3)
   double lnm12;                 // log(nu^(-1/2))
 };
 GRT_HD FreqConst freq_const(double nu_obs) {
@@ -135,10 +132,6 @@ GRT_HD FreqConst freq_const(double nu_obs) {
   f.in13 = exp(l * (-1.0 / 3.0));
   f.nm12 = exp(-0.5 * l);
   f.lnm12 = -0.5 * l;
-  f.nq1 = exp((-0.5 * 1.035) * l);
-  f.nq2 = exp((-0.5 * 1.2) * l);
-  f.nq3 = exp((-0.5 * (double)1.50316886f) * l);
-  f.nq4 = exp((4.0 / 3.0) * l);
   return f;
 }
 
@@ -158,13 +151,7 @@ GRT_HD void thermal_point(double n, double b, double t, double theta, double g, 
   double wp2 = 4.0 * pi * n * ec * ec / m;
   double omega0 = ec * b / m / c;
   // xarg = thetae*sqrt(sqrt(2) sin(theta) 1e3 omega0/(2 pi nu)),  nu = nu_obs/g
-  P.Ax = thetae * sqrt(sqrt(2.0) * sinth * (1e3 * omega0 / 2.0 / pi) * g);
-  const double lAx = log(P.Ax);
-  P.lAx = lAx;
-  P.Ax1 = exp(1.035 * lAx);
-  P.Ax2 = exp(1.2 * lAx);
-  P.Ax3 = exp((double)1.50316886f * lAx);
-  P.Ax4 = exp((-8.0 / 3.0) * lAx);
+  P.lAx = log(thetae * sqrt(sqrt(2.0) * sinth * (1e3 * omega0 / 2.0 / pi) * g));
   double X, Z0, Z1;
   if (thetae > 1e-2) {
     double x = 1.0 / thetae;
@@ -192,9 +179,11 @@ GRT_HD void thermal_point(double n, double b, double t, double theta, double g, 
 // Per call: 5 exp, 1 cos, 1 sqrt, 1 reciprocal (+ 1 log where the Faraday-rotation fit is switched on, + 1 division inside
 // the 16 < xarg < 6552 window of the high-frequency correction) and ~110 multiply-adds.
 // jffunc (with its high-frequency correction) and the logarithm of shgmfunc, evaluated as written (polsynchemis.f90:737-761),
-// from xarg and its powers x1 = xarg^1.035, x2 = xarg^1.2, x3 = xarg^1.50316886, x4 = xarg^(-8/3).  Out of line: with the
+// from lx = log(xarg) (powers xarg^p = exp(p lx)).  Out of line: with the
 // Faraday-fit table in place this is the rare path (xarg outside the table, or the table switched off).
-GRT_HDN void faraday_fits(double xarg, double x1, double x2, double x3, double x4, bool want_log, double &jff, double &lt) {
+GRT_HDN void faraday_fits(double lx, bool want_log, double &jff, double &lt) {
+  const double xarg = exp(lx), x1 = exp(1.035 * lx), x2 = exp(1.2 * lx), x3 = exp((double)1.50316886f * lx),
+               x4 = exp((-8.0 / 3.0) * lx);
   const double e1 = .011 * exp_fast(xarg * (-1.0 / 47.2));
   jff = 2.011 * exp_fast(x1 * (-1.0 / 4.7)) - cos(0.5 * xarg) * exp_fast(x2 * (-1.0 / 2.73)) - e1;
   // extraterm * (0.5 + 0.5 tanh((log(xarg) - log(120))/0.1)) = extraterm * t^20/(1 + t^20), t = xarg/120; the switch is
@@ -262,7 +251,7 @@ GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, 
     jff = q0 + tw * (q1 + tw * (q2 + tw * q3));
     lt = q4 + tw * (q5 + tw * (q6 + tw * q7));
   }
-  if (!tabulated) faraday_fits(P.Ax * F.nm12, P.Ax1 * F.nq1, P.Ax2 * F.nq2, P.Ax3 * F.nq3, P.Ax4 * F.nq4, P.RV1 != 0.0, jff, lt);
+  if (!tabulated) faraday_fits(P.lAx + F.lnm12, P.RV1 != 0.0, jff, lt);
   e[8] = P.RQ * jff * F.inu3;
   e[9] = 0.0;
   double rv = P.RV0;

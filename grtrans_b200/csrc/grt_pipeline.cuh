@@ -135,18 +135,17 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
       case EM_HYBRIDPL: {  // thermal data as below + the power-law population's point data
         PlPoint Q;
         pl_point<true>(cg.ncgsnth, cg.bcgs, oo.ang, oo.g, Q);
-        o[18] = Q.nnth; o[19] = Q.nubperp; o[20] = Q.L; o[21] = Q.itanth;
+        o[14] = Q.nnth; o[15] = Q.nubperp; o[16] = Q.L; o[17] = Q.itanth;
         if (A.sp[mm].stail) {  // gmin varies from point to point: its share of pl_const travels with the record
           const PlConst C = pl_const((double)(float)A.sp[mm].p1, (double)(float)cg.gmin, (double)(float)A.sp[mm].gmax);
-          o[22] = C.l2gmin; o[23] = C.kq; o[24] = C.kv; o[25] = C.cA;
+          o[18] = C.l2gmin; o[19] = C.kq; o[20] = C.kv; o[21] = C.cA;
         }
       }  // fall through
       case EM_POLSYNCHTH: {
         ThermalPoint T;
         thermal_point(cg.ncgs, cg.bcgs, cg.tcgs, oo.ang, oo.g, pc::G * A.sp[mm].mbh * pc::msun / pc::c2, T);
-        o[4] = T.xp13; o[5] = T.AI; o[6] = T.AV; o[7] = T.hkT_g; o[8] = T.Ax; o[9] = T.Ax1; o[10] = T.Ax2; o[11] = T.Ax3;
-        o[12] = T.Ax4; o[13] = T.RQ; o[14] = T.RV0; o[15] = T.RV1; o[16] = T.ixp13; o[17] = T.xpm32;
-        o[em_is_hybrid(A.etype) ? 26 : 18] = T.lAx;
+        o[4] = T.xp13; o[5] = T.AI; o[6] = T.AV; o[7] = T.hkT_g; o[8] = T.lAx; o[9] = T.RQ; o[10] = T.RV0; o[11] = T.RV1;
+        o[12] = T.ixp13; o[13] = T.xpm32;
       } break;
       case EM_POLSYNCHPL:
       case EM_SYNCHPL: {

@@ -22,14 +22,15 @@
 
 namespace grt {
 
-#define GRT_NREC 20      // doubles per point record (160 B) ...
-#define GRT_NREC_MAX 28  // ... 28 for the hybrid thermal + power-law emissivities (thermal and power-law point data)
+#define GRT_NREC 16      // doubles per point record (128 B) ...
+#define GRT_NREC_MAX 24  // ... 24 for the hybrid thermal + power-law emissivities (thermal and power-law point data)
 GRT_HD constexpr bool em_is_hybrid(int et) { return et == EM_HYBRIDTHPL || et == EM_HYBRIDTH || et == EM_HYBRIDPL; }
 GRT_HD constexpr int record_doubles(int etype) { return em_is_hybrid(etype) ? GRT_NREC_MAX : GRT_NREC; }  // (same for every em_slot member)
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
-//   POLSYNCHTH        [4..17] ThermalPoint (xp13, AI, AV, hkT_g, Ax, Ax^1.035, Ax^1.2, Ax^1.503, Ax^-8/3, RQ, RV0, RV1, 1/xp13, xp13^-1.5)
-//   POLSYNCHPL/SYNCHPL [4] n_nth, [5] nu_B,perp, [6] log(g) + log(1.5 nu_B,perp), [7] 1/tan(angle)  (PlPoint)
-//   HYBRIDTHPL/TH/PL  [4..17] ThermalPoint, [18..21] PlPoint (24-double record)
+//   POLSYNCHTH        [4..13] ThermalPoint (xp13, AI, AV, hkT_g, log Ax, RQ, RV0, RV1, 1/xp13, xp13^-1.5)
+//   POLSYNCHPL/SYNCHPL [4] n_nth, [5] nu_B,perp, [6] log(g) + log(1.5 nu_B,perp), [7] 1/tan(angle)  (PlPoint);
+//                     stype = 'tail': [8..11] the gmin-dependent constants of pl_const (2 log gmin, kq, kv, cA)
+//   HYBRIDTHPL/TH/PL  [4..13] ThermalPoint, [14..17] PlPoint, [18..21] tail constants (24-double record)
 //   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
 
 // integration modes (rad_trans.f90:30-38 iflag x neq)
@@ -90,19 +91,17 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
   bool invariant = false;  // e already holds j g^2 and K LBH / g
   if (ET == EM_POLSYNCHTH || em_is_hybrid(ET)) {
     ThermalPoint T;
-    T.xp13 = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.Ax = rec[8]; T.Ax1 = rec[9]; T.Ax2 = rec[10];
-    T.Ax3 = rec[11]; T.Ax4 = rec[12]; T.RQ = rec[13]; T.RV0 = rec[14]; T.RV1 = rec[15]; T.ixp13 = rec[16];
-    T.xpm32 = rec[17]; T.g = g;
-    T.lAx = rec[em_is_hybrid(ET) ? 26 : 18];
+    T.xp13 = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.lAx = rec[8]; T.RQ = rec[9]; T.RV0 = rec[10];
+    T.RV1 = rec[11]; T.ixp13 = rec[12]; T.xpm32 = rec[13]; T.g = g;
     thermal_eval(T, F, pc::c2 * P.LBH / (2.0 * pc::h), e, jI_raw, P.tab);
     invariant = true;
     if (em_is_hybrid(ET)) {  // emis.f90:469-485: add the power-law population (brought to the same invariant form)
       PlPoint Q;
-      Q.nnth = rec[18]; Q.nubperp = rec[19]; Q.L = rec[20]; Q.itanth = rec[21];
+      Q.nnth = rec[14]; Q.nubperp = rec[15]; Q.L = rec[16]; Q.itanth = rec[17];
       double ep[11];
       if (P.stail) {
         PlConst C = R.pl;
-        C.l2gmin = rec[22]; C.kq = rec[23]; C.kv = rec[24]; C.cA = rec[25];
+        C.l2gmin = rec[18]; C.kq = rec[19]; C.kv = rec[20]; C.cA = rec[21];
         pl_eval<true>(P.tab, C, Q, F.nu / g, R.lnu, ep);
       } else {
         pl_eval<true>(P.tab, R.pl, Q, F.nu / g, R.lnu, ep);

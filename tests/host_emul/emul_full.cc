@@ -174,6 +174,6 @@ extern "C" void emul_faraday(int n, const double *xarg, double *out) {
       o[0] = q[0] + w * (q[1] + w * (q[2] + w * q[3]));
       o[1] = q[4] + w * (q[5] + w * (q[6] + w * q[7]));
     }
-    faraday_fits(x, std::pow(x, 1.035), std::pow(x, 1.2), std::pow(x, (double)1.50316886f), std::pow(x, -8.0 / 3.0), true, o[2], o[3]);
+    faraday_fits(std::log(x), true, o[2], o[3]);
   }
 }
