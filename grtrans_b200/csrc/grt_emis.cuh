@@ -13,7 +13,8 @@ namespace grt {
 enum { EM_POLSYNCHTH = 2, EM_SYNCHPL = 3, EM_POLSYNCHPL = 4, EM_BB = 8, EM_BBPOL = 9, EM_SYNCHTHAV = 13,
        EM_HYBRIDTHPL = 20, EM_HYBRIDTH = 21, EM_HYBRIDPL = 22,
        // unpolarised thermal models sharing SYNCHTHAV's point record (n, B, T) and kernel slot (em_slot)
-       EM_BREMS = 5, EM_SYNCHTHAVNOABS = 14, EM_SYNCHTHBREMS = 27 };
+       EM_BREMS = 5, EM_SYNCHTHAVNOABS = 14, EM_SYNCHTHBREMS = 27,
+       EM_POLSYNCHSYMTH = 15 };  // Pandya et al. (2016) fits (sympolemisth)
 // kernel / record slot of an emissivity type: the (n, B, T) scalar models run in the SYNCHTHAV instantiations and pick
 // their formula from TransferParams::etype at run time (a thread-uniform switch)
 GRT_HD constexpr int em_slot(int et) {
@@ -257,6 +258,68 @@ GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, 
   double rv = P.RV0;
   if (P.RV1 != 0.0) rv -= P.RV1 * ((double)0.43793091f * lt);
   e[10] = rv * F.inu2;
+}
+
+// ---- POLSYNCHSYMTH: sympolemisth (polsynchemis.f90:915-1012), Pandya et al. (2016) fits for j_I, j_Q, j_V with the Faraday
+// coefficients of polsynchth.  Per point: everything but the powers of x = nu/(2/9 nu_c thetae^2 sin theta).
+struct SymPoint {
+  double Xs;          // x = nu Xs
+  double A;           // n e^2/c nu_c
+  double S;           // sqrt(2) pi/27 sin(theta)
+  double cq;          // (7 thetae^(24/25) + 35)/(10 thetae^(24/25) + 75) 2^(11/12)
+  double v0, v1;      // (37 - 87 sin(theta - 28/25))/100/(thetae + 1);  thetae^(3/5)/25 + 7/10
+  double T;           // for B_nu
+  double lAx, RQ, RV0, RV1;  // Faraday part as in ThermalPoint (g = LBH = 1)
+};
+GRT_HD void sym_point(double n, double b, double t, double theta, SymPoint &Q) {
+  ThermalPoint P;
+  thermal_point(n, b, t, theta, 1.0, 1.0, P);
+  Q.lAx = P.lAx; Q.RQ = P.RQ; Q.RV0 = P.RV0; Q.RV1 = P.RV1; Q.T = t;
+  const double thetae = pc::k * t / pc::m / (pc::c * pc::c) + 1e-10;
+  const double nuc = pc::e * b / pc::m / pc::c / 2.0 / GRT_PI + 1.0;
+  const double sinth = sin(theta);
+  Q.Xs = 1.0 / (2.0 / 9.0 * nuc * (thetae * thetae) * sinth);
+  Q.A = n * (pc::e * pc::e) / pc::c * nuc;
+  Q.S = sqrt(2.0) * GRT_PI / 27.0 * sinth;
+  const double t2425 = pow(thetae, 24.0 / 25.0);
+  Q.cq = (7.0 * t2425 + 35.0) / (10.0 * t2425 + 75.0) * pow(2.0, 11.0 / 12.0);
+  Q.v0 = (37.0 - 87.0 * sin(theta - 28.0 / 25.0)) / 100.0 / (thetae + 1.0);
+  Q.v1 = pow(thetae, 3.0 / 5.0) / 25.0 + 7.0 / 10.0;
+}
+// comoving coefficients at frequency nu
+GRT_HD void sym_eval(const SymPoint &Q, double nu, const EmisTables &FT, double *e) {
+  for (int i = 0; i < 11; i++) e[i] = 0.0;
+  const double x = nu * Q.Xs, lx = log(x);
+  const double sx = sqrt(x), x16 = exp(lx * (1.0 / 6.0));
+  const double ti = sx + pow(2.0, 11.0 / 12.0) * x16, tq = sx + Q.cq * x16;
+  const double jis = Q.S * (ti * ti), jqs = -Q.S * (tq * tq);
+  const double jvs = -Q.v0 * exp((5.0 / 3.0) * log(1.0 + Q.v1 * exp(lx * (9.0 / 25.0))));
+  const double fac = Q.A * exp(-exp(lx * (1.0 / 3.0)));
+  const double ji = fac * jis, jq = -fac * jqs, jv = -fac * jvs;
+  const double ib = 1.0 / planck_bnu(Q.T, nu);
+  e[0] = ji; e[1] = jq; e[3] = jv;
+  e[4] = ji * ib; e[5] = jq * ib; e[7] = jv * ib;
+  // Faraday coefficients: the fits of polsynchth in xarg = Ax nu^(-1/2) (table or direct, as in thermal_eval)
+  const double lxa = Q.lAx - 0.5 * log(nu);
+  double jff = 0.0, lt = 0.0;
+  bool tabulated = false;
+  if (FT.far) {
+    const double u = (lxa - FT.far_u0) * FT.far_ih;
+    if (u >= 0.0 && u < (double)FT.far_n) {
+      const int k = (int)u;
+      const double w = u - (double)k;
+      const double *q = FT.far + (size_t)k * 8;
+      jff = q[0] + w * (q[1] + w * (q[2] + w * q[3]));
+      lt = q[4] + w * (q[5] + w * (q[6] + w * q[7]));
+      tabulated = true;
+    }
+  }
+  if (!tabulated) faraday_fits(lxa, Q.RV1 != 0.0, jff, lt);
+  const double inu = 1.0 / nu;
+  e[8] = Q.RQ * jff * (inu * inu * inu);
+  double rv = Q.RV0;
+  if (Q.RV1 != 0.0) rv -= Q.RV1 * ((double)0.43793091f * lt);
+  e[10] = rv * (inu * inu);
 }
 
 // plain comoving polsynchth values at frequency nu (the polsynchemis f2py surface): g = LBH = 1

@@ -64,7 +64,7 @@ static void launch_extra_e(int mode, unsigned grid, cudaStream_t st, const RayMe
 #define GRT_PART_ETYPES(OP) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_HYBRIDPL)
 #define GRT_PART_NAME launch_extra_part1
 #else
-#define GRT_PART_ETYPES(OP) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH)
+#define GRT_PART_ETYPES(OP) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_POLSYNCHSYMTH)
 #define GRT_PART_NAME launch_extra_part2
 #endif
 

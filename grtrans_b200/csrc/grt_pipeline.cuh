@@ -163,6 +163,12 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
       case EM_SYNCHTHAV:
         o[4] = cg.ncgs; o[5] = cg.bcgs; o[6] = cg.tcgs;
         break;
+      case EM_POLSYNCHSYMTH: {
+        SymPoint Q;
+        sym_point(cg.ncgs, cg.bcgs, cg.tcgs, oo.ang, Q);
+        o[4] = Q.Xs; o[5] = Q.A; o[6] = Q.S; o[7] = Q.cq; o[8] = Q.v0; o[9] = Q.v1; o[10] = Q.T; o[11] = Q.lAx;
+        o[12] = Q.RQ; o[13] = Q.RV0; o[14] = Q.RV1;
+      } break;
       case EM_BB:
         o[6] = cg.tcgs;
         break;

@@ -32,6 +32,7 @@ GRT_HD constexpr int record_doubles(int etype) { return em_is_hybrid(etype) ? GR
 //                     stype = 'tail': [8..11] the gmin-dependent constants of pl_const (2 log gmin, kq, kv, cA)
 //   HYBRIDTHPL/TH/PL  [4..13] ThermalPoint, [14..17] PlPoint, [18..21] tail constants (24-double record)
 //   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
+//   POLSYNCHSYMTH     [4..14] SymPoint (Xs, A, S, cq, v0, v1, T, log Ax, RQ, RV0, RV1)
 
 // integration modes (rad_trans.f90:30-38 iflag x neq)
 enum { MODE_RK4 = 0, MODE_DELO = 1, MODE_FORMAL = 2, MODE_QUAD = 3, MODE_RK1 = 4 };
@@ -129,6 +130,12 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
         pl_eval<ET == EM_POLSYNCHPL>(P.tab, R.pl, Q, nu, R.lnu, e);
       }
     }
+    else if (ET == EM_POLSYNCHSYMTH) {
+      SymPoint Q;
+      Q.Xs = rec[4]; Q.A = rec[5]; Q.S = rec[6]; Q.cq = rec[7]; Q.v0 = rec[8]; Q.v1 = rec[9]; Q.T = rec[10]; Q.lAx = rec[11];
+      Q.RQ = rec[12]; Q.RV0 = rec[13]; Q.RV1 = rec[14];
+      sym_eval(Q, nu, P.tab, e);
+    }
     else if (ET == EM_SYNCHTHAV) {  // the (n, B, T) scalar models: emis.f90:525-540
       if (P.etype == EM_BREMS) {
         brems_eval(nu, rec[4], rec[6], e);
@@ -158,7 +165,7 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
   for (int i = 0; i < 4; i++) c.j[i] = 0.0;
   for (int i = 0; i < 7; i++) c.K[i] = 0.0;
   constexpr bool POL = (ET == EM_POLSYNCHTH || ET == EM_POLSYNCHPL || ET == EM_BBPOL || ET == EM_HYBRIDTHPL ||
-                        ET == EM_HYBRIDTH || ET == EM_HYBRIDPL);
+                        ET == EM_HYBRIDTH || ET == EM_HYBRIDPL || ET == EM_POLSYNCHSYMTH);
   if (POL) {
     for (int i = 0; i < 4; i++) c.j[i] = e[i];
     for (int i = 0; i < 7; i++)
@@ -614,7 +621,8 @@ GRT_HD void ray_extra_t(const TransferParams &P, const double *rec, const double
 
 // runtime dispatcher (host emulator / generic callers); the CUDA kernels are instantiated per (ET, MODE) directly
 #define GRT_FOR_ETYPES(OP) \
-  OP(EM_POLSYNCHTH) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_HYBRIDPL)
+  OP(EM_POLSYNCHTH) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_HYBRIDPL) \
+  OP(EM_POLSYNCHSYMTH)
 template <int ET>
 GRT_HD void ray_transfer_e(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
   switch (transfer_mode(P)) {

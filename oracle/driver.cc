@@ -202,6 +202,7 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
         const double e_gmin = (double)(float)w.gmin[p];  // ep%gmin=sp%gmin (grtrans_driver.f90:149), real(4)
         switch (etype) {
           case E_POLSYNCHTH: polsynchth(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], K11); break;
+          case E_POLSYNCHSYMTH: sympolemisth(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], K11); break;
           case E_POLSYNCHPL: polsynchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, K11); break;
           case E_HYBRIDTHPL:
           case E_HYBRIDTH:

@@ -148,6 +148,48 @@ void polsynchth(double nu, double n, double b, double t, double theta, double *e
   e[8] = rhoq; e[9] = rhou; e[10] = rhov;
 }
 
+// polsynchemis.f90:915-1012 sympolemisth: Pandya et al. (2016) fits for thermal polarised synchrotron emission, the
+// Faraday coefficients of polsynchth
+void sympolemisth(double nu, double n, double b, double t, double theta, double *e) {
+  using namespace pc;
+  const double ec = pc::e;
+  const double nucminval = 1.0, thetaemin = 1e-10;
+  for (int i = 0; i < 11; i++) e[i] = 0.0;
+  double thetae = k * t / m / std::pow(c, 2.0) + thetaemin;
+  double nuc = ec * b / m / c / 2.0 / pi + nucminval;
+  double x = nu / (2.0 / 9.0 * nuc * std::pow(thetae, 2.0) * std::sin(theta));
+  double jis = std::sqrt(2.0) * pi / 27.0 * std::sin(theta) *
+               std::pow(std::sqrt(x) + std::pow(2.0, 11.0 / 12.0) * std::pow(x, 1.0 / 6.0), 2.0);
+  double jqs = -std::sqrt(2.0) * pi / 27.0 * std::sin(theta) *
+               std::pow(std::sqrt(x) + (7.0 * std::pow(thetae, 24.0 / 25.0) + 35.0) / (10.0 * std::pow(thetae, 24.0 / 25.0) + 75.0) *
+                                           std::pow(2.0, 11.0 / 12.0) * std::pow(x, 1.0 / 6.0),
+                        2.0);
+  double jvs = -(37.0 - 87.0 * std::sin(theta - 28.0 / 25.0)) / 100.0 / (thetae + 1.0) *
+               std::pow(1.0 + (std::pow(thetae, 3.0 / 5.0) / 25.0 + 7.0 / 10.0) * std::pow(x, 9.0 / 25.0), 5.0 / 3.0);
+  double fac = n * std::pow(ec, 2.0) / c * nuc * std::exp(-std::pow(x, 1.0 / 3.0));
+  double ji = fac * jis, jq = -fac * jqs, jv = -fac * jvs;
+  e[0] = ji; e[1] = jq; e[3] = jv;
+  double bnutnu = bnu(t, nu);
+  e[4] = ji / bnutnu; e[5] = jq / bnutnu; e[7] = jv / bnutnu;
+  double wp2 = 4.0 * pi * n * ec * ec / m;
+  double omega0 = ec * b / m / c;
+  double xarg = thetae * std::sqrt(std::sqrt(2.0) * std::sin(theta) * (1e3 * omega0 / 2.0 / pi / nu));
+  double eps11m22, eps12;
+  double w4 = std::pow(2.0 * pi * nu, 4), w3 = std::pow(2.0 * pi * nu, 3);
+  if (thetae > 1e-2) {
+    double k2 = besselkn(2, 1.0 / thetae);
+    eps11m22 = jffunc(xarg) * wp2 * omega0 * omega0 / w4 * (besselk1(1.0 / thetae) / k2 + 6.0 * thetae) *
+               std::sin(theta) * std::sin(theta);
+    double step = 0.5 + 0.5 * std::tanh((thetae - 1.0) / 0.05);
+    eps12 = wp2 * omega0 / w3 * (besselk0(1.0 / thetae) - step * shgmfunc(xarg)) / k2 * std::cos(theta);
+  } else {
+    eps11m22 = jffunc(xarg) * wp2 * omega0 * omega0 / w4 * (1.0 + 6.0 * thetae) * std::sin(theta) * std::sin(theta);
+    eps12 = wp2 * omega0 / w3 * std::cos(theta);
+  }
+  e[10] = 2.0 * pi * nu / c * eps12;
+  e[8] = 2.0 * pi * nu / 2.0 / c * eps11m22;
+}
+
 // ------------------------------------------------------------------ power-law tables
 struct PlTables {
   double gxvals[181], gyvals[543], xvals[81], yavals[243], ypvals[243], yvvals[243], yapvals[243], yavvals[243];
@@ -361,6 +403,7 @@ int emis_type_from_name(const std::string &ename, int &neq) {
   if (ename == "HYBRIDTHPL") { neq = 4; return E_HYBRIDTHPL; }
   if (ename == "HYBRIDTH") { neq = 4; return E_HYBRIDTH; }
   if (ename == "HYBRIDPL") { neq = 4; return E_HYBRIDPL; }
+  if (ename == "POLSYNCHSYMTH") { neq = 4; return E_POLSYNCHSYMTH; }
   if (ename == "BREMS") { neq = 1; return E_BREMS; }
   if (ename == "SYNCHTHBREMS") { neq = 1; return E_SYNCHTHBREMS; }
   if (ename == "SYNCHTHAVNOABS") { neq = 1; return E_SYNCHTHAVNOABS; }
