@@ -332,6 +332,27 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   }
   s->fk.tab = tb;
   s->fk.nparams = s->nparams; s->fk.etype = etype; s->fk.maxpts = s->maxpts; s->fk.xrec = s->d_xrec;
+  // MAXJUTT / MAXCOMP (calc_maxjutt.f90:18-45): ep%otherargs = delta [, selection], weights...
+  s->fk.ncomp = 0;
+  s->tp.ncomp = 0; s->tp.isel = 0;
+  if (etype == EM_MAXJUTT || etype == EM_MAXCOMP) {
+    const int first = (etype == EM_MAXCOMP) ? 2 : 1, nw = std::min(a->nepotherargs, 8) - first;
+    if (nw < 1 || nw > GRT_MAXJUTT_NCOMP) {
+      session_free(s);
+      return GRT_ERR_BAD_ARG;
+    }
+    const double delta = a->epotherargs[0];
+    double wsum = 0.0, dwsum = 0.0;
+    for (int i = 0; i < nw; i++) wsum += a->epotherargs[first + i];
+    for (int i = 0; i < nw; i++) dwsum += a->epotherargs[first + i] / wsum * std::pow(delta, (double)i);
+    for (int i = 0; i < nw; i++) {
+      s->fk.mj_w[i] = a->epotherargs[first + i] / wsum;
+      s->fk.mj_t[i] = std::pow(delta, (double)i) / dwsum;
+    }
+    s->fk.ncomp = nw;
+    s->tp.ncomp = nw;
+    s->tp.isel = (etype == EM_MAXCOMP) ? (int)a->epotherargs[1] : 0;
+  }
   for (int m = 0; m < s->nparams; m++) {
     SourceDev &sp = s->fk.sp[m];
     sp.mdot = s->mdots[m]; sp.mbh = a->mbh; sp.nfac = a->ftscl; sp.bfac = a->frscl; sp.jetalphaval = a->jetalpha;

@@ -61,7 +61,7 @@ static void launch_extra_e(int mode, unsigned grid, cudaStream_t st, const RayMe
 #define GRT_PART_ETYPES(OP) OP(EM_POLSYNCHTH) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL)
 #define GRT_PART_NAME launch_extra_part0
 #elif GRT_EXTRA_PART == 1
-#define GRT_PART_ETYPES(OP) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_HYBRIDPL)
+#define GRT_PART_ETYPES(OP) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_HYBRIDPL) OP(EM_MAXJUTT)
 #define GRT_PART_NAME launch_extra_part1
 #else
 #define GRT_PART_ETYPES(OP) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_POLSYNCHSYMTH)

@@ -26,6 +26,8 @@ struct FluidKernelArgs {
   FluidDev F;
   SourceDev sp[8];
   int nparams, etype, maxpts;
+  int ncomp;                                              // MAXJUTT / MAXCOMP: number of thermal components
+  double mj_w[GRT_MAXJUTT_NCOMP], mj_t[GRT_MAXJUTT_NCOMP];  // their density weights w_i and temperature factors delta^i / sum(w delta^i)
   EmisTables tab;
   double *xrec;  // extra = 1: [nparams][nrays][maxpts][8] = r, theta, phi, n, T, B, plasma beta, unused (else nullptr)
 };
@@ -70,6 +72,18 @@ GRT_HD void ray_finalize(int npts, size_t i, int maxpts, int usegeor, PointArray
   // (sic) LAMBDAI(g%npts): the trimmed COUNT indexes the untrimmed array
   m.lamN = (npts >= 1) ? pa.lam[i * maxpts + (npts - 1)] : 0.0;
   m.dt1 = pa.dt[i * maxpts];
+}
+
+// MAXJUTT / MAXCOMP (calc_maxjutt.f90:8-65): one ThermalPoint per component, density w_i n and temperature T delta^i/sum(w delta^i)
+GRT_HDN void maxjutt_record(double *q, const FluidKernelArgs &A, int mm, const CgsVars &cg, const OrthoOut &oo, double lam) {
+  q[0] = lam; q[1] = oo.g; q[2] = oo.s2xi; q[3] = oo.c2xi;
+  for (int cc = 0; cc < A.ncomp; cc++) {
+    ThermalPoint T;
+    thermal_point(A.mj_w[cc] * cg.ncgs, cg.bcgs, cg.tcgs * A.mj_t[cc], oo.ang, oo.g, pc::G * A.sp[mm].mbh * pc::msun / pc::c2, T);
+    double *qc = q + 4 + 10 * cc;
+    qc[0] = T.xp13; qc[1] = T.AI; qc[2] = T.AV; qc[3] = T.hkT_g; qc[4] = T.lAx; qc[5] = T.RQ; qc[6] = T.RV0; qc[7] = T.RV1;
+    qc[8] = T.ixp13; qc[9] = T.xpm32;
+  }
 }
 
 // extra = 1: the second per-point record (kept out of line: the common path must not pay registers for it)
@@ -126,6 +140,14 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
     to_cgs(A.F.model, A.sp[mm], fs.rho, fs.p, fs.bmag, fs.kela, fs.be, A.F.gam, cg);
     const int nrec = record_doubles(A.etype);
     double *q = rec + ((size_t)mm * nrays * maxpts + dst) * nrec;
+    if (em_slot(A.etype) == EM_MAXJUTT) {  // (out of line, written in place: the record is larger than the staging array)
+      maxjutt_record(q, A, mm, cg, oo, lam);
+      if (A.xrec) point_xrec(A.xrec + ((size_t)mm * nrays * maxpts + dst) * 8, m.npts, r0, r, th, ph, k4, fs, oo, cg);
+      if (mm == 0 && sd.ncgs) {
+        sd.ncgs[dst] = cg.ncgs; sd.ncgsnth[dst] = cg.ncgsnth; sd.bcgs[dst] = cg.bcgs; sd.tcgs[dst] = cg.tcgs;
+      }
+      continue;
+    }
     double o[GRT_NREC_MAX];
     for (int i = 0; i < GRT_NREC_MAX; i++) o[i] = 0.0;
     o[0] = lam; o[1] = oo.g; o[2] = oo.s2xi; o[3] = oo.c2xi;

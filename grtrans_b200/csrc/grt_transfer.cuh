@@ -25,7 +25,10 @@ namespace grt {
 #define GRT_NREC 16      // doubles per point record (128 B) ...
 #define GRT_NREC_MAX 24  // ... 24 for the hybrid thermal + power-law emissivities (thermal and power-law point data)
 GRT_HD constexpr bool em_is_hybrid(int et) { return et == EM_HYBRIDTHPL || et == EM_HYBRIDTH || et == EM_HYBRIDPL; }
-GRT_HD constexpr int record_doubles(int etype) { return em_is_hybrid(etype) ? GRT_NREC_MAX : GRT_NREC; }  // (same for every em_slot member)
+GRT_HD constexpr int record_doubles(int etype) {  // (same for every em_slot member)
+  return em_is_hybrid(etype) ? GRT_NREC_MAX
+                             : ((etype == EM_MAXJUTT || etype == EM_MAXCOMP) ? 4 + 10 * GRT_MAXJUTT_NCOMP + 2 : GRT_NREC);
+}
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
 //   POLSYNCHTH        [4..13] ThermalPoint (xp13, AI, AV, hkT_g, log Ax, RQ, RV0, RV1, 1/xp13, xp13^-1.5)
 //   POLSYNCHPL/SYNCHPL [4] n_nth, [5] nu_B,perp, [6] log(g) + log(1.5 nu_B,perp), [7] 1/tan(angle)  (PlPoint);
@@ -33,6 +36,7 @@ GRT_HD constexpr int record_doubles(int etype) { return em_is_hybrid(etype) ? GR
 //   HYBRIDTHPL/TH/PL  [4..13] ThermalPoint, [14..17] PlPoint, [18..21] tail constants (24-double record)
 //   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
 //   POLSYNCHSYMTH     [4..14] SymPoint (Xs, A, S, cq, v0, v1, T, log Ax, RQ, RV0, RV1)
+//   MAXJUTT/MAXCOMP   [4 + 10 c ..] ThermalPoint of component c < ncomp <= 7 (76-double record)
 
 // integration modes (rad_trans.f90:30-38 iflag x neq)
 enum { MODE_RK4 = 0, MODE_DELO = 1, MODE_FORMAL = 2, MODE_QUAD = 3, MODE_RK1 = 4 };
@@ -44,6 +48,7 @@ struct TransferParams {
   double max_tau, hmax, ortol, oatol, thin;
   int maxsteps;
   int stail;  // stype = 'tail': the power law's gmin-dependent constants come from the point record
+  int ncomp, isel;  // MAXJUTT / MAXCOMP: thermal components in the record; MAXCOMP: component whose emission is kept (0: all)
   EmisTables tab;
 };
 
@@ -90,7 +95,31 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
   const double g = rec[1];
   double e[11];
   bool invariant = false;  // e already holds j g^2 and K LBH / g
-  if (ET == EM_POLSYNCHTH || em_is_hybrid(ET)) {
+  if (ET == EM_MAXJUTT) {  // calc_maxjutt.f90 / calc_maxcomp.f90: sum of thermal components [4 + 10 c ...]
+    for (int i = 0; i < 11; i++) e[i] = 0.0;
+    jI_raw = 0.0;
+    double esel[4] = {0, 0, 0, 0}, jsel = 0.0;
+#pragma unroll 1
+    for (int cc = 0; cc < P.ncomp; cc++) {
+      const double *rc_ = rec + 4 + 10 * cc;
+      ThermalPoint T;
+      T.xp13 = rc_[0]; T.AI = rc_[1]; T.AV = rc_[2]; T.hkT_g = rc_[3]; T.lAx = rc_[4]; T.RQ = rc_[5]; T.RV0 = rc_[6];
+      T.RV1 = rc_[7]; T.ixp13 = rc_[8]; T.xpm32 = rc_[9]; T.g = g;
+      double ec[11], jr;
+      thermal_eval(T, F, pc::c2 * P.LBH / (2.0 * pc::h), ec, jr, P.tab);
+      for (int i = 0; i < 11; i++) e[i] += ec[i];
+      jI_raw += jr;
+      if (cc + 1 == P.isel) {
+        for (int i = 0; i < 4; i++) esel[i] = ec[i];
+        jsel = jr;
+      }
+    }
+    if (P.isel > 0 && P.isel <= P.ncomp) {  // MAXCOMP: emission of the selected component only
+      for (int i = 0; i < 4; i++) e[i] = esel[i];
+      jI_raw = jsel;
+    }
+    invariant = true;
+  } else if (ET == EM_POLSYNCHTH || em_is_hybrid(ET)) {
     ThermalPoint T;
     T.xp13 = rec[4]; T.AI = rec[5]; T.AV = rec[6]; T.hkT_g = rec[7]; T.lAx = rec[8]; T.RQ = rec[9]; T.RV0 = rec[10];
     T.RV1 = rec[11]; T.ixp13 = rec[12]; T.xpm32 = rec[13]; T.g = g;
@@ -165,7 +194,7 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
   for (int i = 0; i < 4; i++) c.j[i] = 0.0;
   for (int i = 0; i < 7; i++) c.K[i] = 0.0;
   constexpr bool POL = (ET == EM_POLSYNCHTH || ET == EM_POLSYNCHPL || ET == EM_BBPOL || ET == EM_HYBRIDTHPL ||
-                        ET == EM_HYBRIDTH || ET == EM_HYBRIDPL || ET == EM_POLSYNCHSYMTH);
+                        ET == EM_HYBRIDTH || ET == EM_HYBRIDPL || ET == EM_POLSYNCHSYMTH || ET == EM_MAXJUTT);
   if (POL) {
     for (int i = 0; i < 4; i++) c.j[i] = e[i];
     for (int i = 0; i < 7; i++)
@@ -392,7 +421,7 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     info->rnpts = npts;
     info->fac = 0.0;
   }
-  constexpr int NREC = em_is_hybrid(ET) ? GRT_NREC_MAX : GRT_NREC;  // record stride of this emissivity model
+  constexpr int NREC = record_doubles(ET);  // record stride of this emissivity model
   for (int i = 0; i < neq; i++) out[i] = 0.0;
   if (npts <= 0) return;
   const FreqConst F = freq_const(nu_obs);
@@ -542,7 +571,7 @@ template <int ET, int MODE>
 GRT_HD void ray_extra_t(const TransferParams &P, const double *rec, const double *xrec, int npts, double nu_obs, double *out,
                         double *xt, double *hist, size_t hs) {
   constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
-  constexpr int NREC = em_is_hybrid(ET) ? GRT_NREC_MAX : GRT_NREC;
+  constexpr int NREC = record_doubles(ET);
   for (int q = 0; q < 19; q++) xt[q] = 0.0;
   for (int c = 0; c < npts; c++) hist[(size_t)c * hs] = 0.0;
   MarchInfo mi;
@@ -622,7 +651,7 @@ GRT_HD void ray_extra_t(const TransferParams &P, const double *rec, const double
 // runtime dispatcher (host emulator / generic callers); the CUDA kernels are instantiated per (ET, MODE) directly
 #define GRT_FOR_ETYPES(OP) \
   OP(EM_POLSYNCHTH) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_HYBRIDPL) \
-  OP(EM_POLSYNCHSYMTH)
+  OP(EM_POLSYNCHSYMTH) OP(EM_MAXJUTT)
 template <int ET>
 GRT_HD void ray_transfer_e(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
   switch (transfer_mode(P)) {

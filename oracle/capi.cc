@@ -23,6 +23,8 @@ static RunArgs to_run(const grt_args *a) {
   r.muval = a->muval; r.gmin = a->gmin; r.gmax = a->gmax; r.p1 = a->p1; r.p2 = a->p2; r.jetalpha = a->jetalpha;
   r.sigcut = a->sigcut; r.ftscl = a->ftscl; r.frscl = a->frscl;
   for (int i = 0; i < 7; i++) r.coefindx[i] = a->epcoefindx[i];
+  r.nepotherargs = a->nepotherargs < 8 ? a->nepotherargs : 8;
+  for (int i = 0; i < 8; i++) r.epotherargs[i] = a->epotherargs[i];
   r.fargs.dfile = a->fdfile; r.fargs.hfile = a->fhfile; r.fargs.gfile = a->fgfile; r.fargs.nt = a->fnt;
   r.fargs.indf = a->findf; r.fargs.mdot = a->fmdot; r.fargs.mbh = a->mbh; r.fargs.rin = a->frin; r.fargs.rout = a->frout; r.fargs.scalefac = a->fscalefac;
   return r;

@@ -203,6 +203,10 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
         switch (etype) {
           case E_POLSYNCHTH: polsynchth(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], K11); break;
           case E_POLSYNCHSYMTH: sympolemisth(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], K11); break;
+          case E_MAXJUTT:
+          case E_MAXCOMP:
+            maxjutt(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], w.ang[p], A.epotherargs, A.nepotherargs, etype == E_MAXCOMP, K11);
+            break;
           case E_POLSYNCHPL: polsynchpl(nu, w.ncgsnth[p], w.bcgs[p], w.ang[p], e_p, e_gmin, e_gmax, K11); break;
           case E_HYBRIDTHPL:
           case E_HYBRIDTH:

@@ -190,6 +190,30 @@ void sympolemisth(double nu, double n, double b, double t, double theta, double 
   e[8] = 2.0 * pi * nu / 2.0 / c * eps11m22;
 }
 
+// calc_maxjutt.f90:8-65 / calc_maxcomp.f90:8-68: a sum of thermal components of densities w_i n and temperatures
+// T delta^i / sum(w delta^i) (args = delta [, selection], weights...).  MAXCOMP takes the emission (columns 1-4) of the one
+// selected component, absorption / rotation of all.
+void maxjutt(double nu, double n, double b, double t, double theta, const double *args, int nargs, bool comp, double *e) {
+  const int first = comp ? 2 : 1, nw = nargs - first;
+  for (int i = 0; i < 11; i++) e[i] = 0.0;
+  if (nw <= 0) return;
+  double delta = args[0], wsum = 0.0, dwsum = 0.0;
+  for (int i = 0; i < nw; i++) wsum += args[first + i];
+  for (int i = 0; i < nw; i++) dwsum += args[first + i] / wsum * std::pow(delta, (double)i);
+  double tmin = t / dwsum, k11[11];
+  for (int i = 0; i < nw; i++) {
+    polsynchth(nu, args[first + i] / wsum * n, b, tmin * std::pow(delta, (double)i), theta, k11);
+    for (int c = 0; c < 11; c++) e[c] += k11[c];
+  }
+  if (comp) {
+    int isel = (int)args[1];
+    if (isel > 0 && isel <= nw) {
+      polsynchth(nu, args[first + isel - 1] / wsum * n, b, tmin * std::pow(delta, (double)(isel - 1)), theta, k11);
+      for (int c = 0; c < 4; c++) e[c] = k11[c];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ power-law tables
 struct PlTables {
   double gxvals[181], gyvals[543], xvals[81], yavals[243], ypvals[243], yvvals[243], yapvals[243], yavvals[243];
@@ -404,6 +428,8 @@ int emis_type_from_name(const std::string &ename, int &neq) {
   if (ename == "HYBRIDTH") { neq = 4; return E_HYBRIDTH; }
   if (ename == "HYBRIDPL") { neq = 4; return E_HYBRIDPL; }
   if (ename == "POLSYNCHSYMTH") { neq = 4; return E_POLSYNCHSYMTH; }
+  if (ename == "MAXJUTT") { neq = 4; return E_MAXJUTT; }
+  if (ename == "MAXCOMP") { neq = 4; return E_MAXCOMP; }
   if (ename == "BREMS") { neq = 1; return E_BREMS; }
   if (ename == "SYNCHTHBREMS") { neq = 1; return E_SYNCHTHBREMS; }
   if (ename == "SYNCHTHAVNOABS") { neq = 1; return E_SYNCHTHAVNOABS; }

@@ -157,13 +157,14 @@ void harm_transform_and_store(FluidData &fd, const std::vector<double> &rho, con
 // ---------------------------------------------------------------------------------------------
 // emissivities (emis.f90 / polsynchemis.f90)
 enum EmisType { E_SYNCHPL = 3, E_POLSYNCHTH = 2, E_POLSYNCHPL = 4, E_BB = 8, E_BBPOL = 9, E_SYNCHTHAV = 13,
-                E_HYBRIDTHPL = 20, E_HYBRIDTH = 21, E_HYBRIDPL = 22, E_BREMS = 5, E_SYNCHTHAVNOABS = 14, E_SYNCHTHBREMS = 27, E_POLSYNCHSYMTH = 15 };
+                E_HYBRIDTHPL = 20, E_HYBRIDTH = 21, E_HYBRIDPL = 22, E_BREMS = 5, E_SYNCHTHAVNOABS = 14, E_SYNCHTHBREMS = 27, E_POLSYNCHSYMTH = 15, E_MAXJUTT = 23, E_MAXCOMP = 24 };
 int emis_type_from_name(const std::string &ename, int &neq);
 void polsynchth(double nu, double n, double b, double t, double theta, double *e11);
 void polsynchpl(double nu, double nnth, double b, double th, double p, double gmin, double gmax, double *e11);
 void synchpl(double nu, double nnth, double b, double th, double p, double gmin, double gmax, double *e11);
 void brememis(double nu, double ne, double T, double *e11);
 void sympolemisth(double nu, double n, double b, double t, double theta, double *e11);
+void maxjutt(double nu, double n, double b, double t, double theta, const double *args, int nargs, bool comp, double *e11);
 void synchemis(double nu, double n, double B, double T, double *e11);
 double bnu(double T, double nu);
 void interp_chandra_tab24(float mu, float &I, float &del);
@@ -198,6 +199,8 @@ struct RunArgs {
          p2 = 3.5, jetalpha = 0.02, sigcut = 1e10;
   double ftscl = 30, frscl = 6;  // nfac, bfac (pgrtrans.f90:129)
   int coefindx[7] = {1, 1, 1, 1, 1, 1, 1};
+  int nepotherargs = 2;                 // ep%otherargs (pgrtrans.f90:119-120): MAXJUTT / MAXCOMP component weights
+  double epotherargs[8] = {1, 1, 0, 0, 0, 0, 0, 0};
   FluidArgs fargs;
   int nthreads = 0;  // OpenMP threads for the pixel loop (0 = default)
 };

@@ -58,6 +58,21 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
     sp.stail = (std::string(a->stype) == "tail") ? 1 : 0; sp.pad = 0;
   }
   P.stail = (std::string(a->stype) == "tail") ? 1 : 0;
+  fk.ncomp = 0; P.ncomp = 0; P.isel = 0;
+  if (etype == EM_MAXJUTT || etype == EM_MAXCOMP) {  // as grt_session_create
+    const int first = (etype == EM_MAXCOMP) ? 2 : 1, nw = (a->nepotherargs < 8 ? a->nepotherargs : 8) - first;
+    if (nw < 1 || nw > GRT_MAXJUTT_NCOMP) return 3;
+    const double delta = a->epotherargs[0];
+    double wsum = 0.0, dwsum = 0.0;
+    for (int i = 0; i < nw; i++) wsum += a->epotherargs[first + i];
+    for (int i = 0; i < nw; i++) dwsum += a->epotherargs[first + i] / wsum * std::pow(delta, (double)i);
+    for (int i = 0; i < nw; i++) {
+      fk.mj_w[i] = a->epotherargs[first + i] / wsum;
+      fk.mj_t[i] = std::pow(delta, (double)i) / dwsum;
+    }
+    fk.ncomp = nw; P.ncomp = nw;
+    P.isel = (etype == EM_MAXCOMP) ? (int)a->epotherargs[1] : 0;
+  }
   P.etype = etype; P.eneq = eneq; P.rneq = nv; P.iflag = iflag; P.model = fh.model; P.npts_is_one = (a->nn[2] == 1);
   for (int i = 0; i < 7; i++) P.coefindx[i] = a->epcoefindx[i];
   P.LBH = pc::G * a->mbh * pc::msun / pc::c2;
@@ -80,7 +95,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
       r.phi0 = c.phi0; r.t0 = 0; r.tpm = c.tpm[ix]; r.tpr = c.tpr[ix];
       RayInv inv;
       geo_setup(r, fl, inv);
-      std::vector<double> bu(mp), bmu(mp), bdt(mp), bdp(mp), bl(mp), rec((size_t)nparams * mp * GRT_NREC_MAX, 0.0);
+      std::vector<double> bu(mp), bmu(mp), bdt(mp), bdp(mp), bl(mp), rec((size_t)nparams * mp * record_doubles(etype), 0.0);
       std::vector<double> xrec(nextra ? (size_t)nparams * mp * 8 : 0, 0.0), hist(nextra ? mp : 0, 0.0);
       FluidKernelArgs fkr = fk;  // (per-thread copy: the extra-quantity record of this ray)
       fkr.xrec = nextra ? xrec.data() : nullptr;

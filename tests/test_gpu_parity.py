@@ -190,6 +190,10 @@ IMAGE_CASES = [
     ("harm3d", dict(n=40, nup=100, nfreq=4, ename='POLSYNCHSYMTH', fmin=1e11, fmax=1e14), 1e-4),
     ("sphacc", dict(n=32, nfreq=3, ename='POLSYNCHSYMTH', iname='formal'), 1e-4),
     ("harm", dict(n=32, nup=200, nfreq=2, ename='POLSYNCHSYMTH', iname='lsoda', fmin=5e11, fmax=2e12), 1e-4),
+    # sums of thermal components (calc_maxjutt.f90, calc_maxcomp.f90): epotherargs = delta [, selection], weights
+    ("harm3d", dict(n=32, nup=100, nfreq=3, ename='MAXJUTT', epotherargs=[2., .6, .3, .1], fmin=2e11, fmax=2e13), 1e-4),
+    ("harm3d", dict(n=32, nup=100, nfreq=2, ename='MAXJUTT', epotherargs=[1.5, 1., 1., 1., 1., 1., 1., 1.], fmin=2e11, fmax=2e12), 1e-4),
+    ("harm3d", dict(n=32, nup=100, nfreq=2, ename='MAXCOMP', epotherargs=[2., 2., .6, .3, .1], fmin=2e11, fmax=2e12, iname='formal'), 1e-4),
     # stype='tail': power law matched to the thermal distribution point by point (calcgmin.f90; fluid.f90:1656-1667)
     ("harm3d", dict(n=32, nup=100, nfreq=3, ename='POLSYNCHPL', stype='tail', p1=3., p2=3., jetalpha=.1, fmin=1e11, fmax=1e14), 1e-4),
     ("harm3d", dict(n=32, nup=100, nfreq=3, ename='HYBRIDTHPL', stype='tail', p1=3.5, p2=3.5, jetalpha=.05, fmin=1e11,
@@ -221,6 +225,7 @@ EXTRA_CASES = [("harm3d", dict(n=40, nup=100, nfreq=3, fmin=2e11, fmax=2e12)),
                ("ffjet", dict(n=32, nfreq=2, iname='formal')),
                ("iharm", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12)),
                ("harm3d", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12, ename='POLSYNCHSYMTH')),
+               ("harm3d", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12, ename='MAXJUTT', epotherargs=[2., .6, .3, .1])),
                ("thindisk", dict(n=40, nfreq=3)),                                              # nup = 1: 7 geometric quantities
                ("thindisk", dict(n=32, nfreq=2, ename='BBPOL', nvals=4))]
 

@@ -79,6 +79,9 @@ EMUL_CASES = [
     # Pandya et al. (2016) fits for the thermal emissivities (sympolemisth, polsynchemis.f90:915-1012)
     ("harm3d", dict(n=20, nup=100, nfreq=4, ename='POLSYNCHSYMTH', fmin=1e11, fmax=1e14)),
     ("sphacc", dict(n=16, nfreq=3, ename='POLSYNCHSYMTH', iname='formal')),
+    # sums of thermal components (calc_maxjutt.f90, calc_maxcomp.f90): epotherargs = delta [, selection], weights
+    ("harm3d", dict(n=16, nup=100, nfreq=3, ename='MAXJUTT', epotherargs=[2., .6, .3, .1], fmin=2e11, fmax=2e13)),
+    ("harm3d", dict(n=16, nup=100, nfreq=2, ename='MAXCOMP', epotherargs=[2., 2., .6, .3, .1], fmin=2e11, fmax=2e12, iname='formal')),
     # stype='tail': power law matched to the thermal distribution point by point (calcgmin.f90; fluid.f90:1656-1667)
     ("harm3d", dict(n=16, nup=100, nfreq=3, ename='POLSYNCHPL', stype='tail', p1=3., p2=3., jetalpha=.1, fmin=1e11, fmax=1e14)),
     ("harm3d", dict(n=16, nup=100, nfreq=3, ename='HYBRIDTHPL', stype='tail', p1=3.5, p2=3.5, jetalpha=.05, fmin=1e11,
