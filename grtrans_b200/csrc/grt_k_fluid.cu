@@ -9,7 +9,10 @@
 
 namespace grt {
 
-__global__ void __launch_bounds__(128, 4) k_fluid_ortho(const RayConst *__restrict__ rc, const RayInv *__restrict__ inv,
+#ifndef GRT_FLUID_MINB
+#define GRT_FLUID_MINB 6   // measured (nx=512 step): 3 blocks/SM 42.0 ms, 4: 35.8, 5: 33.6, 6: 32.6, 8: 34.4, 10: 38.1, 12: 41.4
+#endif
+__global__ void __launch_bounds__(128, GRT_FLUID_MINB) k_fluid_ortho(const RayConst *__restrict__ rc, const RayInv *__restrict__ inv,
                                                      const RayMeta *__restrict__ meta, const __grid_constant__ FluidKernelArgs A, long long total,
                                                      int nrays, PointArrays pa, double *__restrict__ rec, StageDump sd) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
