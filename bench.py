@@ -33,11 +33,11 @@ W_RT = 9.4e2    # per (pixel, point, freq): POLSYNCHTH emissivity + rotate/scale
 B_GATHER = 320  # bytes per (pixel, point): 8 corners x 10 fields x 4 B (3-D)
 B_RECORD = 128  # bytes per (pixel, point) read by the transfer kernel (one point record)
 # from the ncu --set full capture of one k_transfer launch at this configuration (profiles/r1_ncu_summary.md):
-NCU_TRANSFER = {"dram_bytes_per_launch": 3.826068e9 + 0.089951e9, "fp64_pipe_busy_pct": 64.1, "issue_active_pct": 60.4,
-                "launch": "65536-ray tile (32768 blocks x 128 threads), 38.4 ms under ncu",
+NCU_TRANSFER = {"dram_bytes_per_launch": 3.826e9 + 0.090e9, "fp64_pipe_busy_pct": 64.0, "issue_active_pct": 60.3,
+                "launch": "65536-ray tile (32768 blocks x 128 threads), 38.5 ms under ncu",
                 "other_kernels": {"k_geo_points": {"fp64_pipe_busy_pct": 46.9, "ms": 12.5},
-                                  "k_fluid_ortho": {"fp64_pipe_busy_pct": 33.7, "ms": 8.5, "dram_write_gb": 4.23}},
-                "source": "profiles/r1_ncu_summary.md (capture r1_v16)"}
+                                  "k_fluid_ortho": {"fp64_pipe_busy_pct": 37.3, "ms": 7.7, "dram_write_gb": 8.54}},
+                "source": "profiles/r1_ncu_summary.md (capture r1_v19)"}
 
 
 def workload(nx, nfreq, snapdir, grid):

@@ -24,7 +24,11 @@ RUNS = [("thindisk", dict(n=12, nfreq=2)), ("thindisk", dict(n=10, nfreq=2, enam
         # extra = 1 (history scratch + forward pass), the BREMS family, stype = 'tail'
         ("harm3d", dict(n=8, nup=100, nfreq=2, extra=1)), ("harm3d", dict(n=8, nup=100, nfreq=2, extra=1, iname='lsoda')),
         ("sphacc", dict(n=8, nfreq=2, extra=1, nvals=1)), ("harm3d", dict(n=8, nup=100, nfreq=2, ename='SYNCHTHBREMS', nvals=1)),
-        ("harm3d", dict(n=8, nup=100, nfreq=2, ename='POLSYNCHPL', stype='tail', p1=3., p2=3., jetalpha=.1))]
+        ("harm3d", dict(n=8, nup=100, nfreq=2, ename='POLSYNCHPL', stype='tail', p1=3., p2=3., jetalpha=.1)),
+        ("harm3d", dict(n=8, nup=100, nfreq=2, ename='POLSYNCHSYMTH')),
+        ("harm3d", dict(n=8, nup=100, nfreq=2, ename='MAXJUTT', epotherargs=[2., .6, .3, .1])),
+        ("harm3d", dict(n=8, nup=100, nfreq=2, ename='MAXCOMP', epotherargs=[2., 2., .6, .3, .1], extra=1)),
+        ("thindisk", dict(n=10, nfreq=2, extra=1))]
 os.environ["GRT_TILE"] = "64"   # several tiles per run
 for cfg, over in RUNS:
     kw = getattr(cases, "cfg_" + cfg)(**over)
