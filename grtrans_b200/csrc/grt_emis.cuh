@@ -13,14 +13,15 @@ namespace grt {
 enum { EM_POLSYNCHTH = 2, EM_SYNCHPL = 3, EM_POLSYNCHPL = 4, EM_BB = 8, EM_BBPOL = 9, EM_SYNCHTHAV = 13,
        EM_HYBRIDTHPL = 20, EM_HYBRIDTH = 21, EM_HYBRIDPL = 22,
        // unpolarised thermal models sharing SYNCHTHAV's point record (n, B, T) and kernel slot (em_slot)
-       EM_BREMS = 5, EM_SYNCHTHAVNOABS = 14, EM_SYNCHTHBREMS = 27,
+       EM_BREMS = 5, EM_SYNCHTHAVNOABS = 14, EM_SYNCHTHBREMS = 27, EM_RHO = 12,
        EM_POLSYNCHSYMTH = 15,   // Pandya et al. (2016) fits (sympolemisth)
        EM_MAXJUTT = 23, EM_MAXCOMP = 24 };  // sums of thermal components (calc_maxjutt.f90, calc_maxcomp.f90)
 #define GRT_MAXJUTT_NCOMP 7   // at most 7 components (8 ep%otherargs: delta [, selection], weights)
 // kernel / record slot of an emissivity type: the (n, B, T) scalar models run in the SYNCHTHAV instantiations and pick
 // their formula from TransferParams::etype at run time (a thread-uniform switch)
 GRT_HD constexpr int em_slot(int et) {
-  return (et == EM_BREMS || et == EM_SYNCHTHAVNOABS || et == EM_SYNCHTHBREMS) ? EM_SYNCHTHAV : (et == EM_MAXCOMP ? EM_MAXJUTT : et);
+  return (et == EM_BREMS || et == EM_SYNCHTHAVNOABS || et == EM_SYNCHTHBREMS || et == EM_RHO) ? EM_SYNCHTHAV
+                                                                                           : (et == EM_MAXCOMP ? EM_MAXJUTT : et);
 }
 
 namespace pc {

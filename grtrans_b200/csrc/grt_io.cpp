@@ -103,7 +103,7 @@ int emis_type_id(const std::string &e, int *neq) {
     int t, q;
   } tab[] = {{"POLSYNCHTH", 2, 4}, {"SYNCHPL", 3, 1}, {"POLSYNCHPL", 4, 4}, {"BB", 8, 1}, {"BBPOL", 9, 4}, {"SYNCHTHAV", 13, 1},
              {"HYBRIDTHPL", 20, 4}, {"HYBRIDTH", 21, 4}, {"HYBRIDPL", 22, 4},
-             {"BREMS", 5, 1}, {"SYNCHTHAVNOABS", 14, 1}, {"SYNCHTHBREMS", 27, 1}, {"POLSYNCHSYMTH", 15, 4}, {"MAXJUTT", 23, 4}, {"MAXCOMP", 24, 4}};
+             {"BREMS", 5, 1}, {"SYNCHTHAVNOABS", 14, 1}, {"SYNCHTHBREMS", 27, 1}, {"POLSYNCHSYMTH", 15, 4}, {"MAXJUTT", 23, 4}, {"MAXCOMP", 24, 4}, {"RHO", 12, 1}};
   for (auto &x : tab)
     if (e == x.n) {
       *neq = x.q;

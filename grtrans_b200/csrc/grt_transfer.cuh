@@ -168,6 +168,9 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
     else if (ET == EM_SYNCHTHAV) {  // the (n, B, T) scalar models: emis.f90:525-540
       if (P.etype == EM_BREMS) {
         brems_eval(nu, rec[4], rec[6], e);
+      } else if (P.etype == EM_RHO) {  // rhoemis (emis.f90:144-151): j = n g, no absorption (a column-density map)
+        for (int i = 0; i < 11; i++) e[i] = 0.0;
+        e[0] = rec[4] * g;
       } else {
         synchemis_eval(nu, rec[4], rec[5], rec[6], e);
         if (P.etype == EM_SYNCHTHAVNOABS) e[4] = 0.0;

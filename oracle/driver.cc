@@ -227,6 +227,7 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
             for (int c = 4; c < 11; c++) K11[c] = 0.0;
             break;
           case E_BREMS: brememis(nu, w.ncgs[p], w.tcgs[p], K11); break;
+          case E_RHO: K11[0] = w.ncgs[p] * w.rshift[p]; break;  // rhoemis (emis.f90:144-151): density map, no absorption
           case E_SYNCHTHBREMS: {  // emis.f90:531-534
             double Kbr[11];
             synchemis(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], K11);

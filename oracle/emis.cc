@@ -428,6 +428,7 @@ int emis_type_from_name(const std::string &ename, int &neq) {
   if (ename == "HYBRIDTH") { neq = 4; return E_HYBRIDTH; }
   if (ename == "HYBRIDPL") { neq = 4; return E_HYBRIDPL; }
   if (ename == "POLSYNCHSYMTH") { neq = 4; return E_POLSYNCHSYMTH; }
+  if (ename == "RHO") { neq = 1; return E_RHO; }
   if (ename == "MAXJUTT") { neq = 4; return E_MAXJUTT; }
   if (ename == "MAXCOMP") { neq = 4; return E_MAXCOMP; }
   if (ename == "BREMS") { neq = 1; return E_BREMS; }

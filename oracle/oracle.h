@@ -157,7 +157,7 @@ void harm_transform_and_store(FluidData &fd, const std::vector<double> &rho, con
 // ---------------------------------------------------------------------------------------------
 // emissivities (emis.f90 / polsynchemis.f90)
 enum EmisType { E_SYNCHPL = 3, E_POLSYNCHTH = 2, E_POLSYNCHPL = 4, E_BB = 8, E_BBPOL = 9, E_SYNCHTHAV = 13,
-                E_HYBRIDTHPL = 20, E_HYBRIDTH = 21, E_HYBRIDPL = 22, E_BREMS = 5, E_SYNCHTHAVNOABS = 14, E_SYNCHTHBREMS = 27, E_POLSYNCHSYMTH = 15, E_MAXJUTT = 23, E_MAXCOMP = 24 };
+                E_HYBRIDTHPL = 20, E_HYBRIDTH = 21, E_HYBRIDPL = 22, E_BREMS = 5, E_SYNCHTHAVNOABS = 14, E_SYNCHTHBREMS = 27, E_POLSYNCHSYMTH = 15, E_MAXJUTT = 23, E_MAXCOMP = 24, E_RHO = 12 };
 int emis_type_from_name(const std::string &ename, int &neq);
 void polsynchth(double nu, double n, double b, double t, double theta, double *e11);
 void polsynchpl(double nu, double nnth, double b, double th, double p, double gmin, double gmax, double *e11);

@@ -186,6 +186,7 @@ IMAGE_CASES = [
     ("harm3d", dict(n=32, nup=100, nfreq=4, ename='SYNCHTHBREMS', nvals=1, fmin=1e11, fmax=1e17), 1e-4),
     ("harm3d", dict(n=32, nup=100, nfreq=3, ename='SYNCHTHAVNOABS', nvals=1, iname='lsoda'), 1e-4),
     ("sphacc", dict(n=32, nfreq=4, ename='SYNCHTHBREMS', nvals=1), 1e-4),
+    ("harm3d", dict(n=32, nup=100, nfreq=1, ename='RHO', nvals=1), 1e-4),                 # column-density map (rhoemis)
     # Pandya et al. (2016) fits for the thermal emissivities (sympolemisth, polsynchemis.f90:915-1012)
     ("harm3d", dict(n=40, nup=100, nfreq=4, ename='POLSYNCHSYMTH', fmin=1e11, fmax=1e14), 1e-4),
     ("sphacc", dict(n=32, nfreq=3, ename='POLSYNCHSYMTH', iname='formal'), 1e-4),

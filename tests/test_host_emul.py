@@ -76,6 +76,7 @@ EMUL_CASES = [
     ("harm3d", dict(n=16, nup=100, nfreq=3, ename='BREMS', nvals=1, fmin=1e12, fmax=1e18)),
     ("harm3d", dict(n=16, nup=100, nfreq=3, ename='SYNCHTHBREMS', nvals=1, fmin=1e11, fmax=1e17)),
     ("harm3d", dict(n=16, nup=100, nfreq=3, ename='SYNCHTHAVNOABS', nvals=1, iname='lsoda')),
+    ("harm3d", dict(n=16, nup=100, nfreq=1, ename='RHO', nvals=1)),                       # column-density map (rhoemis)
     # Pandya et al. (2016) fits for the thermal emissivities (sympolemisth, polsynchemis.f90:915-1012)
     ("harm3d", dict(n=20, nup=100, nfreq=4, ename='POLSYNCHSYMTH', fmin=1e11, fmax=1e14)),
     ("sphacc", dict(n=16, nfreq=3, ename='POLSYNCHSYMTH', iname='formal')),
