@@ -51,7 +51,9 @@ static cudaError_t h2d(T **p, const std::vector<T> &v) {
 struct grt_session {
   grt_args args;
   int device = 0, rank = 0, nranks = 1;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, up_stream = nullptr;
+  cudaEvent_t up_done = nullptr, up_gate = nullptr;  // snapshot upload overlapped with the geodesic stage of the first tile
+  bool up_pending = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t tile_done = nullptr;
   float *h_image = nullptr;            // pinned host image [ncams][nlocal][nvals] (grt_session_launch_fetch)
@@ -96,6 +98,9 @@ static int session_free(grt_session *s) {
   if (s->tile_done) cudaEventDestroy(s->tile_done);
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  if (s->up_stream) cudaStreamDestroy(s->up_stream);
+  if (s->up_done) cudaEventDestroy(s->up_done);
+  if (s->up_gate) cudaEventDestroy(s->up_gate);
   delete s;
   return GRT_OK;
 }
@@ -395,6 +400,10 @@ static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump 
   launch_geo_points(s->d_inv, s->fl.nup, s->maxpts, total, s->pa, s->stream);
   launch_ray_finalize(s->d_inv, s->maxpts, s->fl.usegeor, n, s->pa, s->d_meta, s->stream);
   if (time_stages) cudaEventRecord(s->ev[2], s->stream);
+  if (s->up_pending) {  // snapshot upload in flight (grt_session_upload)
+    cudaStreamWaitEvent(s->stream, s->up_done, 0);
+    s->up_pending = false;
+  }
   launch_fluid_ortho(s->d_rc[jmu] + off, s->d_inv, s->d_meta, s->fk, total, n, s->pa, s->d_rec, sd, s->stream);
   if (time_stages) cudaEventRecord(s->ev[3], s->stream);
   if (s->nextra)
@@ -413,6 +422,7 @@ static int launch_tile(grt_session *s, int jmu, long long off, int n, StageDump 
 static int reload_dumps(grt_session *s, bool restart, double dt) {
   if (s->fh.cells.empty()) return GRT_OK;
   CK(cudaStreamSynchronize(s->stream));
+  if (s->up_stream) CK(cudaStreamSynchronize(s->up_stream));  // (an upload that no launch has consumed yet)
   int rc;
   if (restart) {
     grt_host::FluidHost fresh;
@@ -500,8 +510,18 @@ extern "C" int grt_session_upload(grt_session *s, long long *bytes) {
     b += (long long)n;
   }
   if (!s->fh.cells.empty()) {
+    // the snapshot goes up on its own stream: only the fluid kernel needs it, so the copy overlaps the geodesic kernels of
+    // the first tile (launch_tile waits for up_done before k_fluid_ortho); up_gate orders it after any earlier pass that is
+    // still reading the cells
     size_t n = s->fh.cells.size() * sizeof(Cell);
-    CK(cudaMemcpyAsync(const_cast<Cell *>(s->fk.F.cells), s->fh.cells.data(), n, cudaMemcpyHostToDevice, s->stream));
+    if (!s->up_stream) CK(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
+    if (!s->up_done) CK(cudaEventCreateWithFlags(&s->up_done, cudaEventDisableTiming));
+    if (!s->up_gate) CK(cudaEventCreateWithFlags(&s->up_gate, cudaEventDisableTiming));
+    CK(cudaEventRecord(s->up_gate, s->stream));
+    CK(cudaStreamWaitEvent(s->up_stream, s->up_gate, 0));
+    CK(cudaMemcpyAsync(const_cast<Cell *>(s->fk.F.cells), s->fh.cells.data(), n, cudaMemcpyHostToDevice, s->up_stream));
+    CK(cudaEventRecord(s->up_done, s->up_stream));
+    s->up_pending = true;
     b += (long long)n;
   }
   CK(cudaMemcpyAsync(s->d_freqs, s->freqs.data(), s->freqs.size() * 8, cudaMemcpyHostToDevice, s->stream));
@@ -531,6 +551,7 @@ extern "C" int grt_session_sync(grt_session *s) {
   if (!s) return GRT_ERR_BAD_ARG;
   cudaError_t e = cudaStreamSynchronize(s->stream);
   if (e == cudaSuccess && s->copy_stream) e = cudaStreamSynchronize(s->copy_stream);
+  if (e == cudaSuccess && s->up_stream) e = cudaStreamSynchronize(s->up_stream);
   if (e != cudaSuccess) {
     fprintf(stderr, "grtrans_b200: %s\n", cudaGetErrorString(e));
     return GRT_ERR_CUDA;
