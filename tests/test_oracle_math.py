@@ -79,3 +79,18 @@ def test_thermal_synchrotron_against_independent_fit():
     assert 0.94 < r.min() and r.max() < 1.01, (r.min(), r.max())
     frac = E[:, 1] / E[:, 0]
     assert frac.min() > 0.5 and frac.max() < 0.92
+
+
+def test_component_sums_reduce_to_polsynchth():
+    """MAXJUTT with a single component, and MAXCOMP with selection 0, are the plain sums (calc_maxjutt.f90, calc_maxcomp.f90):
+    one component of weight 1 at the full temperature is polsynchth itself."""
+    import cases
+    kw = cases.cfg_sphacc(n=10, nfreq=3)
+    ref = orc.run(**kw)['ivals']
+    one = orc.run(**dict(kw, ename='MAXJUTT', epotherargs=[2., 1.]))['ivals']
+    assert np.array_equal(one, ref, equal_nan=True)
+    mj = orc.run(**dict(kw, ename='MAXJUTT', epotherargs=[2., .6, .3, .1]))['ivals']
+    mc0 = orc.run(**dict(kw, ename='MAXCOMP', epotherargs=[2., 0., .6, .3, .1]))['ivals']
+    assert np.array_equal(mj, mc0, equal_nan=True)
+    assert not np.array_equal(mj, ref, equal_nan=True)
+
