@@ -32,13 +32,6 @@ W_GEO = 5.8e3   # per (pixel, point): geodesic + geometry
 W_RT = 9.4e2    # per (pixel, point, freq): POLSYNCHTH emissivity + rotate/scale + DELO step
 B_GATHER = 320  # bytes per (pixel, point): 8 corners x 10 fields x 4 B (3-D)
 B_RECORD = 128  # bytes per (pixel, point) read by the transfer kernel (one point record)
-# from the ncu --set full capture of one k_transfer launch at this configuration (profiles/r1_ncu_summary.md):
-NCU_TRANSFER = {"dram_bytes_per_launch": 3.826e9 + 0.090e9, "fp64_pipe_busy_pct": 64.0, "issue_active_pct": 60.3,
-                "launch": "65536-ray tile (32768 blocks x 128 threads), 38.5 ms under ncu",
-                "other_kernels": {"k_geo_points": {"fp64_pipe_busy_pct": 46.9, "ms": 12.5},
-                                  "k_fluid_ortho": {"fp64_pipe_busy_pct": 37.3, "ms": 7.7, "dram_write_gb": 8.54}},
-                "source": "profiles/r1_ncu_summary.md (capture r1_v19)"}
-
 
 def workload(nx, nfreq, snapdir, grid):
     import make_snapshot as ms
@@ -159,6 +152,7 @@ def main():
     ap.add_argument("--nfreq", type=int, default=64)
     ap.add_argument("--grid", default=os.environ.get("GRT_BENCH_GRID", "288x128x128"))
     ap.add_argument("--cpu-rays", type=int, default=int(os.environ.get("GRT_BENCH_CPU_RAYS", 16384)))
+    ap.add_argument("--ref-seconds", type=float, default=float(os.environ.get("GRT_BENCH_REF_SECONDS", 150.)))
     ap.add_argument("--snapdir", default=os.environ.get("GRT_SNAPDIR", "/tmp/grt_snap"))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -168,7 +162,9 @@ def main():
     kw = workload(args.nx, args.nfreq, args.snapdir, grid) if (rank == 0 or args.impl != "reference") else None
     cfg = {"workload": "config5: synthetic HARM-like 3-D snapshot %s, camera %dx%d x 400 pts x %d freqs, nvals=4, "
                        "POLSYNCHTH, DELO" % (args.grid, args.nx, args.nx, args.nfreq),
-           "sharding": "interleaved 256-ray tiles over %d GPU(s), NCCL gather of the float32 Stokes image" % world,
+           "sharding": "interleaved 256-ray shards over %d GPU(s); value: one process per GPU, every finished tile sent to rank 0 "
+                       "by ncclSend/ncclRecv inside the library behind the next tile's kernels; e2e: one process, one host "
+                       "thread per GPU, tiles stream into the single host image" % world,
            "l2": "per-step working set (point records) >> 126 MB L2; no explicit flush needed"}
     ncores = os.cpu_count() or 1
 
@@ -178,10 +174,17 @@ def main():
             return 0
         t_all = []
         rays = pts = 0
-        for _ in range(args.warmup):
-            cpu_reference_sample(kw, ncores, max(64, args.cpu_rays // 8))
+        # bounded sample: the rays of one step are sized from the first warm-up so that the K timed steps together take
+        # about --ref-seconds (default 150 s) of CPU time; never more than --cpu-rays, never fewer than 512
+        nwarm = max(64, args.cpu_rays // 8)
+        per_step = args.cpu_rays
+        for i in range(max(1, args.warmup)):
+            r_, p_, s_ = cpu_reference_sample(kw, ncores, nwarm)
+            if i == 0 and s_ > 0:
+                budget = args.ref_seconds / max(1, args.steps)
+                per_step = max(8, int(min(args.cpu_rays, max(512, (r_ / s_) * budget))) // 8 * 8)
         for _ in range(args.steps):
-            rays, pts, secs = cpu_reference_sample(kw, ncores, args.cpu_rays)
+            rays, pts, secs = cpu_reference_sample(kw, ncores, per_step)
             t_all.append(secs)
         sec = float(np.mean(t_all))
         value = rays * args.nfreq / sec
@@ -199,39 +202,32 @@ def main():
 
     # ------------------------------------------------------------------ B200 arm
     from grtrans_b200 import _lib, args_from_kwargs
+    from grtrans_b200 import dist as gdist
     dist = None
+    tdev = None
     if world > 1:
         # keep stdout to the single JSON line: the box exports NCCL_DEBUG=VERSION, which prints a banner to stdout
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        import torch
+        # torch.distributed is launcher plumbing only (rendezvous, barrier, three scalar reductions, the 128-byte NCCL id) and
+        # runs over gloo on the host: the data path -- the image gather -- is ncclSend / ncclRecv inside libgrtrans_b200.so,
+        # and a host-side barrier keeps the waiting ranks' GPUs idle while rank 0 times the end-to-end call on all of them
+        import torch  # noqa: F401
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo")
     a = args_from_kwargs(**kw)
     sess = _lib.Session(a, device=local_rank, rank=rank, nranks=world)
-    nlocal = sess.nlocal()
     npix = args.nx * args.nx
-
-    gather = None
     if world > 1:
-        import torch
-        from grtrans_b200.dist import DeviceImage, gather_image
-        dimg = DeviceImage(sess)
-
-        def gather():
-            return gather_image(dimg, npix, world, rank)
+        sess.comm_init(gdist.broadcast_unique_id(_lib.nccl_unique_id, rank, tdev))
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    def step():
-        sess.launch()
-        sess.sync()
-        if gather:
-            gather()
-            torch.cuda.synchronize()
+    def step(n=1):
+        """n passes, device time of this rank (CUDA events on the launching stream; N > 1: up to the end of its gather work)"""
+        return sess.run_timed_gather(n) if world > 1 else sess.run_timed(n)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -240,59 +236,51 @@ def main():
         sampler.start()
     barrier()
     sess.sync()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        if gather:
-            step()
-        else:
-            dev_ms += sess.run_timed(1)   # CUDA events on the launching stream
+    dev_ms = step(args.steps)       # EXACTLY K steps between two events; every step re-reads / re-writes > 3.7 GB per tile
     sess.sync()
     barrier()
-    t1 = time.perf_counter()
     clocks = sampler.stop() if rank == 0 else None
-    wall = t1 - t0
-    step_s = (dev_ms * 1e-3 / args.steps) if (not gather) else wall / args.steps
+    step_s = dev_ms * 1e-3 / args.steps
     if world > 1:
-        import torch
-        t = torch.tensor([step_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_s = float(t.item())
+        step_s = gdist.reduce_max(step_s, tdev)     # max over ranks (rank 0 holds the complete image at its time)
+    launches_per_step = sess.last_launches()
+    tile_rays = sess.tile()
 
     # per-stage device times (one extra untimed pass with CUDA events between the kernels)
     tot_ms, stage_ms = sess.time()
     nr, npts_local = sess.counts()
-    if world > 1:
-        import torch
-        t = torch.tensor([float(npts_local)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t)
-        npts_total = float(t.item())
-    else:
-        npts_total = float(npts_local)
+    npts_total = gdist.reduce_sum(npts_local, tdev) if world > 1 else float(npts_local)
+    launches_total = gdist.reduce_sum(launches_per_step, tdev) if world > 1 else float(launches_per_step)
+    sess.close()
+    barrier()
 
-    # ---- end to end through the public API with HOST buffers: upload inputs, run, read the image back
-    e2e_steps = max(1, min(args.steps, 3))
-    sess.upload(); sess.launch_fetch(); sess.sync()   # untimed warm-up: allocates the pinned host image
+    # ---- end to end through the reference-facing call: grt_main (pgrtrans.grtrans_main) with HOST buffers in and the
+    # real(8) ivals array out, one process driving all N GPUs (one host thread per device).  Per step: camera constants,
+    # fluid snapshot and frequency grid go host -> device, every finished tile comes back to pinned host memory behind the
+    # kernels of the next tile and is widened to ivals.  Under torchrun the other ranks wait at the barrier.
+    e2e = None
+    if rank == 0:
+        e2e_steps = max(1, min(args.steps, 5))
+        _lib.set_devices(list(range(world)))
+        iv = _lib.main_view(a)          # untimed: builds the pooled sessions, pinned buffers and the ivals array
+        _lib.del_data()
+        iv = _lib.main_view(a)
+        _lib.del_data()
+        te0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            iv = _lib.main_view(a)      # returns when ivals is complete in host memory
+            chk = float(iv[0, npix // 2, 0])
+            _lib.del_data()
+        te1 = time.perf_counter()
+        info = _lib.main_info()
+        e2e_s = (te1 - te0) / e2e_steps
+        e2e = {"value": npix * args.nfreq / e2e_s, "unit": "rays*freq/s", "h2d_bytes_per_step": int(info["h2d_bytes"]),
+               "d2h_bytes_per_step": int(info["d2h_bytes"]), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
+               "api": "grt_main (pgrtrans.grtrans_main): host grt_args in, real(8) ivals(nvals,npix,ncams) out, %d device(s) "
+                      "driven by one process" % info["ndevices"],
+               "ivals_bytes": int(iv.size * 8), "gpu_launches_per_step": int(info["launches"]), "check": chk}
+        _lib.release_cache()
     barrier()
-    sess.sync()
-    te0 = time.perf_counter()
-    h2d = 0
-    for _ in range(e2e_steps):
-        h2d = sess.upload()                 # pinned host mirrors -> device (camera constants, snapshot, frequencies)
-        img, d2h = sess.launch_fetch()      # tiles of the image stream back to pinned host memory behind the compute
-        sess.sync()
-        chk = float(img[0, 0, 0])           # the result is host-readable here
-        if gather:
-            gather()
-    barrier()
-    te1 = time.perf_counter()
-    e2e_s = (te1 - te0) / e2e_steps
-    if world > 1:
-        import torch
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    d2h = int(d2h)
 
     if rank == 0:
         value = npix * args.nfreq / step_s
@@ -301,51 +289,78 @@ def main():
             dfma = _lib.dfma_peak(local_rank)
         except Exception:
             dfma = None
-        # dominant kernel: k_transfer (emissivity + DELO march); algorithmic FP64 work of this rank's launch
+        counts = kernel_counts()
+        kt = counts["k_transfer"]
+        # dominant kernel: k_transfer (emissivity + DELO march).  achieved = EXECUTED FP64 flop (ncu opcode counts of the
+        # committed capture: DFMA = 2, DMUL / DADD = 1) per (point, frequency) x the (point, frequency) pairs of this rank's
+        # launches / their measured duration (CUDA events of this run)
         k_s = stage_ms[3] * 1e-3
-        flops = W_RT * float(npts_local) * args.nfreq
-        ach = flops / k_s / 1e12 if k_s > 0 else None
-        nlaunch = max(1, sess.launch_count() // 5)
+        units = float(npts_local) * args.nfreq
+        ach = kt["fp64_flop_per_unit"] * units / k_s / 1e12 if k_s > 0 else None
+        nlaunch = max(1, sess_launch_tiles(nr, tile_rays))
         roof = {"bound": "fp64", "kernel": "k_transfer<POLSYNCHTH,DELO>", "achieved": ach, "peak": dfma, "unit": "TFLOP/s",
                 "frac": (ach / dfma) if (ach and dfma) else None,
-                "traffic": NCU_TRANSFER["dram_bytes_per_launch"] if (args.nx == 1024 and world == 1) else None,
-                "algorithmic_bytes_per_launch": B_RECORD * float(npts_local) / nlaunch, "ncu": NCU_TRANSFER,
+                "traffic": kt.get("dram_bytes_per_launch") if (args.nx == 1024 and world == 1) else None,
+                "algorithmic_bytes_per_launch": B_RECORD * float(npts_local) / nlaunch,
+                "fp64_pipe_busy_pct": kt.get("fp64_pipe_busy_pct"), "issue_active_pct": kt.get("issue_active_pct"),
+                "executed_fp64_flop_per_point_freq": kt["fp64_flop_per_unit"],
+                "executed_fp64_instr_per_point_freq": kt.get("fp64_instr_per_unit"),
+                "algorithmic_equiv": {"ops_per_point_freq": W_RT, "tflops": W_RT * units / k_s / 1e12 if k_s > 0 else None,
+                                      "note": "the reference formulation's operation count (SURVEY 8d); the kernel does the same "
+                                              "job in fewer operations (closed-form DELO solve, per-point / per-frequency "
+                                              "factorisation, tabulated Faraday fits), so this can exceed the DFMA peak"},
                 "launches_per_step": nlaunch, "avg_launch_ms": stage_ms[3] / nlaunch,
-                "peak_source": "FP64 DFMA micro-benchmark run in this process (grt_dfma_peak); no tensor-core / HBM bound applies: "
-                               "the path has no dense contraction and moves ~0.1 byte per FP64 op",
-                "algorithmic_ops_per_point_freq": W_RT,
-                "note": "achieved counts the reference formulation's 940 op per (point, frequency) (SURVEY 8d); the kernel "
-                        "executes ~240 FP64 instructions for them (closed-form DELO solve, Faraday fits read from a table), so "
-                        "achieved / peak can exceed 1 -- ncu.fp64_pipe_busy_pct is the measured utilisation of the pipe",
-                "executed_fp64_instr_per_point_freq": 237,
+                "peak_source": "FP64 DFMA micro-benchmark run in this process (grt_dfma_peak; 148 SM x 64 DFMA/clk x 1.965 GHz = "
+                               "37.2 TFLOP/s nominal); MEASURED_PEAKS.json has no FP64 figure.  No tensor-core / HBM bound "
+                               "applies: the path has no dense contraction and moves ~0.1 byte per FP64 op",
+                "counts_source": counts.get("source"),
                 "kernel_share_of_step": stage_ms[3] / tot_ms if tot_ms else None,
                 "stages_ms": {"ray_setup": stage_ms[0], "geodesic_points": stage_ms[1], "fluid_ortho": stage_ms[2],
                               "transfer": stage_ms[3], "total": tot_ms},
-                "geodesic": {"achieved": W_GEO * float(npts_local) / (stage_ms[1] * 1e-3) / 1e12 if stage_ms[1] else None,
-                             "unit": "TFLOP/s", "algorithmic_ops_per_point": W_GEO},
-                "gather": {"bound": "hbm", "achieved": B_GATHER * float(npts_local) / (stage_ms[2] * 1e-3) / 1e9 if stage_ms[2] else None,
-                           "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_source": peak_src,
-                           "algorithmic_bytes_per_point": B_GATHER}}
+                "other_kernels": {}}
+        for name, st, unit_n in (("k_geo_points", stage_ms[1], float(npts_local)), ("k_fluid_ortho", stage_ms[2], float(npts_local))):
+            kc = counts.get(name, {})
+            t = st * 1e-3
+            fl = kc.get("fp64_flop_per_unit")
+            roof["other_kernels"][name] = {
+                "ms": st, "achieved_tflops": (fl * unit_n / t / 1e12) if (fl and t > 0) else None,
+                "frac": (fl * unit_n / t / 1e12 / dfma) if (fl and t > 0 and dfma) else None,
+                "fp64_pipe_busy_pct": kc.get("fp64_pipe_busy_pct"), "executed_fp64_flop_per_point": fl,
+                "dram_write_gb_per_launch": kc.get("dram_write_gb"), "algorithmic_write_gb_per_launch": kc.get("alg_write_gb")}
+        roof["other_kernels"]["k_fluid_ortho"]["gather"] = {
+            "bound": "hbm", "achieved": B_GATHER * float(npts_local) / (stage_ms[2] * 1e-3) / 1e9 if stage_ms[2] else None,
+            "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_source": peak_src, "algorithmic_bytes_per_point": B_GATHER}
+        roof["other_kernels"]["k_geo_points"]["algorithmic_equiv_ops_per_point"] = W_GEO
         # CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
         cpu = None
         if world == 1 and args.cpu_rays > 0:
             rays, pts, secs = cpu_reference_sample(kw, ncores, args.cpu_rays)
             cpu = {"value": rays * args.nfreq / secs, "unit": "rays*freq/s", "cores": ncores, "kind": "port",
                    "sample": "%d rays in 8 row-blocks spread over the camera, all %d freqs, pixel loop only (%.1f s)" % (
-                       rays, args.nfreq, secs)}
+                       rays, args.nfreq, secs),
+                   "note": "the oracle evaluates the Faraday fits of polsynchth directly; the GPU kernel reads them from a "
+                           "cubic table (|error| < 4e-10, GRT_FARADAY_EXACT=1 switches it off)"}
         line = {"metric": "rays*freq/s", "value": value, "unit": "rays*freq/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "points_per_s": npts_total * args.nfreq / step_s, "mean_points_per_ray": npts_total / npix,
-                "e2e": {"value": npix * args.nfreq / e2e_s, "unit": "rays*freq/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
-                "gpu_launches": int(sess.launch_count() * args.steps), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+                "e2e": e2e, "gpu_launches": int(launches_total * args.steps), "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks}
         out.write(json.dumps(line) + "\n")
         out.flush()
-    sess.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def sess_launch_tiles(nrays, tile):
+    return (int(nrays) + int(tile) - 1) // max(1, int(tile))
+
+
+def kernel_counts():
+    """Executed-instruction counts of the stage kernels from the committed ncu capture (tools/ncu_tables.py --counts)."""
+    p = os.path.join(ROOT, "profiles", "kernel_counts.json")
+    return json.load(open(p))
 
 
 if __name__ == "__main__":

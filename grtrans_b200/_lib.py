@@ -22,7 +22,10 @@ SYMBOLS = ["grt_args_defaults", "grt_main", "grt_get_ivals", "grt_get_ab", "grt_
            "grt_del_data", "grt_run", "grt_program", "grt_read_inputs", "grt_write_output", "grt_geokerr_camera",
            "grt_geokerr_rays", "grt_ray_stage_dump", "grt_polsynchth", "grt_polsynchpl", "grt_synchemis",
            "grt_rt_integrate", "grt_session_create", "grt_session_destroy", "grt_session_launch", "grt_session_sync", "grt_session_launch_fetch", "grt_session_upload", "grt_session_run_timed",
-           "grt_session_time", "grt_session_launch_count", "grt_session_counts", "grt_session_device_image",
+           "grt_session_time", "grt_session_launch_count", "grt_session_counts",
+           "grt_set_devices", "grt_main_info", "grt_release_cache", "grt_shard_rays", "grt_nccl_unique_id",
+           "grt_session_comm_init", "grt_session_launch_gather", "grt_session_run_timed_gather",
+           "grt_session_last_launches", "grt_session_tile", "grt_session_full_image", "grt_session_fetch_full",
            "grt_session_fetch", "grt_session_ncams", "grt_session_nvals", "grt_version", "grt_device_count", "grt_dfma_peak"]
 
 
@@ -41,6 +44,9 @@ def lib():
                            "(there is no CPU fallback)" % SO_PATH)
         _lib = C.CDLL(SO_PATH)
         _lib.grt_version.restype = C.c_char_p
+        _lib.grt_shard_rays.restype = C.c_longlong
+        _lib.grt_release_cache.restype = None
+        _lib.grt_del_data.restype = None
     return _lib
 
 
@@ -61,6 +67,51 @@ def dfma_peak(device=0):
     t = C.c_double()
     check(lib().grt_dfma_peak(C.c_int(device), C.byref(t)), "grt_dfma_peak")
     return t.value
+
+
+def set_devices(devices=None):
+    """Devices grt_main uses (None / empty: GRT_DEVICES, GRT_NGPU or every visible device)."""
+    d = list(devices or [])
+    arr = (C.c_int * max(1, len(d)))(*d)
+    check(lib().grt_set_devices(arr, C.c_int(len(d))), "grt_set_devices")
+
+
+def main_info():
+    nd = C.c_int(); h2d = C.c_longlong(); d2h = C.c_longlong(); nl = C.c_int()
+    check(lib().grt_main_info(C.byref(nd), C.byref(h2d), C.byref(d2h), C.byref(nl)), "grt_main_info")
+    return dict(ndevices=nd.value, h2d_bytes=h2d.value, d2h_bytes=d2h.value, launches=nl.value)
+
+
+def release_cache():
+    lib().grt_release_cache()
+
+
+def shard_rays(i1, i2, rank, nranks):
+    """1-based geodesic indices of `rank`'s rays (grt_shard_rays: host logic, works without a GPU)."""
+    n = lib().grt_shard_rays(C.c_int(i1), C.c_int(i2), C.c_int(rank), C.c_int(nranks), None)
+    idx = np.zeros(n, np.int32)
+    lib().grt_shard_rays(C.c_int(i1), C.c_int(i2), C.c_int(rank), C.c_int(nranks), _p(idx))
+    return idx
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib().grt_nccl_unique_id(buf), "grt_nccl_unique_id")
+    return buf.raw
+
+
+def main_view(a):
+    """grt_main, returning zero-copy views of the module arrays (valid until del_data()): ivals [ncams, npix, nv]."""
+    L = lib()
+    check(L.grt_main(C.byref(a)), "grt_main")
+    p = C.POINTER(C.c_double)()
+    dims = (C.c_int * 3)()
+    check(L.grt_get_ivals(C.byref(p), dims), "grt_get_ivals")
+    return np.ctypeslib.as_array(p, shape=(dims[2], dims[1], dims[0]))
+
+
+def del_data():
+    lib().grt_del_data()
 
 
 def maxpts_of(a):
@@ -210,6 +261,17 @@ class Session(object):
         check(lib().grt_session_run_timed(self._h, C.c_int(nsteps), C.byref(ms)), "grt_session_run_timed")
         return ms.value
 
+    def run_timed_gather(self, nsteps):
+        ms = C.c_float()
+        check(lib().grt_session_run_timed_gather(self._h, C.c_int(nsteps), C.byref(ms)), "grt_session_run_timed_gather")
+        return ms.value
+
+    def last_launches(self):
+        return lib().grt_session_last_launches(self._h)
+
+    def tile(self):
+        return lib().grt_session_tile(self._h)
+
     def time(self):
         tot = C.c_float()
         st = (C.c_float * 4)()
@@ -229,11 +291,20 @@ class Session(object):
         check(lib().grt_session_counts(self._h, C.byref(nr), None), "grt_session_counts")
         return nr.value
 
-    def device_image(self):
-        p = C.c_void_p(); n = C.c_longlong(); pi = C.c_void_p(); nr = C.c_longlong()
-        check(lib().grt_session_device_image(self._h, C.byref(p), C.byref(n), C.byref(pi), C.byref(nr)),
-              "grt_session_device_image")
-        return p.value, n.value, pi.value, nr.value
+    def comm_init(self, uid):
+        """Collective: join the NCCL communicator of the job (uid: the 128 bytes of nccl_unique_id() from rank 0)."""
+        check(lib().grt_session_comm_init(self._h, C.c_char_p(uid)), "grt_session_comm_init")
+
+    def launch_gather(self):
+        """Collective: launch; finished tiles go to rank 0's full device image behind the following tiles' kernels."""
+        check(lib().grt_session_launch_gather(self._h), "grt_session_launch_gather")
+
+    def fetch_full(self):
+        """Rank 0: the gathered image [ncams, npix, nvals] float32."""
+        npix = self.a.nn[0] * self.a.nn[1]
+        img = np.zeros((self.ncams, npix, self.nvals), np.float32)
+        check(lib().grt_session_fetch_full(self._h, _p(img)), "grt_session_fetch_full")
+        return img
 
     def fetch(self):
         nl = self.nlocal()

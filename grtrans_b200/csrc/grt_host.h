@@ -69,8 +69,8 @@ void make_grids(const grt_args &a, std::vector<double> &freqs, std::vector<doubl
 // ---- namelists / output -----------------------------------------------------------------------------
 int read_inputs_file(const char *ifile, grt_args *a);                      // read_inputs.f90:47-100
 int read_files_in(const char *path, std::string &ifile, std::string &ofile);  // grtrans_program.f90
-// camera.f90:156-344 kwrite_raytrace_camera for all cameras; pixvals [ncams][npix][nv] float32
+// camera.f90:156-344 kwrite_raytrace_camera for all cameras; ivals [ncams][npix][nv] = dble() of the real(4) pixel values
 int write_output(const grt_args &a, const char *outfile, int nx, int ny, int nv, int ncams, const float *pixloc,
-                 const float *pixvals, const std::vector<double> &freqs);
+                 const double *ivals, const std::vector<double> &freqs);
 
 }  // namespace grt_host

@@ -935,18 +935,52 @@ void put_be_floats(std::string &out, const float *v, size_t n) {
     out[off + 4 * i + 3] = (char)u;
   }
 }
-void frec(FILE *fp, const void *p, int nbytes) {
-  fwrite(&nbytes, 4, 1, fp);
-  fwrite(p, 1, nbytes, fp);
-  fwrite(&nbytes, 4, 1, fp);
+// checked output: any short write marks the writer as failed (a full disk must not produce a truncated file + GRT_OK)
+struct OutFile {
+  FILE *fp = nullptr;
+  bool ok = true;
+  void put(const void *p, size_t n) {
+    if (ok && n && fwrite(p, 1, n, fp) != n) ok = false;
+  }
+};
+// one Fortran sequential-unformatted record.  gfortran's 4-byte markers cannot describe 2 GiB or more: such a record is
+// written as subrecords of at most 2147483639 bytes whose leading marker is negative when another subrecord follows and
+// whose trailing marker is negative when one precedes (libgfortran io/unix.c, the format gfortran reads back).
+void frec(OutFile &f, const void *p, size_t nbytes) {
+  const size_t MAXSUB = 2147483639u;
+  const char *c = (const char *)p;
+  size_t done = 0;
+  bool first = true;
+  do {
+    const size_t n = std::min(MAXSUB, nbytes - done);
+    const bool more = done + n < nbytes;
+    const int head = more ? -(int)n : (int)n, tail = first ? (int)n : -(int)n;
+    f.put(&head, 4);
+    f.put(c + done, n);
+    f.put(&tail, 4);
+    done += n;
+    first = false;
+  } while (done < nbytes);
+}
+// real(8) image values (exact copies of the real(4) pixel values) -> real(4), in chunks
+template <class F>
+void for_float_chunks(const double *v, size_t n, F &&fn) {
+  const size_t CH = 1u << 20;
+  std::vector<float> buf(std::min(n, CH));
+  for (size_t off = 0; off < n; off += CH) {
+    const size_t m = std::min(CH, n - off);
+    for (size_t i = 0; i < m; i++) buf[i] = (float)v[off + i];
+    fn(buf.data(), m);
+  }
 }
 }  // namespace
 
 int write_output(const grt_args &a, const char *outfile, int nx, int ny, int nv, int ncams, const float *pixloc,
-                 const float *pixvals, const std::vector<double> &freqs) {
+                 const double *ivals, const std::vector<double> &freqs) {
   const size_t npix = (size_t)nx * ny;
-  FILE *fp = fopen(outfile, "wb");
-  if (!fp) return GRT_ERR_IO;
+  OutFile f;
+  f.fp = fopen(outfile, "wb");
+  if (!f.fp) return GRT_ERR_IO;
   if (a.cflag == 1) {
     std::string hdu;
     // primary: FTPHPR(simple=T, bitpix=-32, naxis=1, naxes=[2*npix], pcount=0, gcount=1, extend=T)
@@ -960,8 +994,8 @@ int write_output(const grt_args &a, const char *outfile, int nx, int ny, int nv,
     std::string data;
     put_be_floats(data, pixloc, 2 * npix);
     pad2880(data, '\0');
-    fwrite(hdu.data(), 1, hdu.size(), fp);
-    fwrite(data.data(), 1, data.size(), fp);
+    f.put(hdu.data(), hdu.size());
+    f.put(data.data(), data.size());
     for (int m = 0; m < ncams; m++) {
       std::string h;
       card_str(h, "XTENSION", "IMAGE", "IMAGE extension");
@@ -1008,27 +1042,36 @@ int write_output(const grt_args &a, const char *outfile, int nx, int ny, int nv,
       card_int(h, "cflag", a.cflag, "cflag"); card_int(h, "extra", a.extra, "extra");
       card(h, "END");
       pad2880(h, ' ');
-      std::string d;
-      put_be_floats(d, pixvals + (size_t)m * npix * nv, npix * nv);
-      pad2880(d, '\0');
-      fwrite(h.data(), 1, h.size(), fp);
-      fwrite(d.data(), 1, d.size(), fp);
+      f.put(h.data(), h.size());
+      // big-endian float32 data unit, streamed in chunks, zero padded to a multiple of 2880 bytes
+      for_float_chunks(ivals + (size_t)m * npix * nv, npix * nv, [&](const float *v, size_t n) {
+        std::string d;
+        put_be_floats(d, v, n);
+        f.put(d.data(), d.size());
+      });
+      const size_t rem = (npix * nv * 4) % 2880;
+      if (rem) {
+        const std::string z(2880 - rem, '\0');
+        f.put(z.data(), z.size());
+      }
     }
   } else {
     // Fortran sequential unformatted, 4-byte record markers (camera.f90:322-341)
     for (int m = 0; m < ncams; m++) {
       int dims[3] = {nx, ny, nv};
-      frec(fp, dims, 12);
+      frec(f, dims, 12);
       int nkey = 3;
-      frec(fp, &nkey, 4);
+      frec(f, &nkey, 4);
       float kv[3] = {(float)nx, (float)ny, (float)freqs[m % a.nfreq]};
-      for (int k = 0; k < 3; k++) frec(fp, &kv[k], 4);
-      frec(fp, pixloc, (int)(8 * npix));
-      frec(fp, pixvals + (size_t)m * npix * nv, (int)(4 * npix * nv));
+      for (int k = 0; k < 3; k++) frec(f, &kv[k], 4);
+      frec(f, pixloc, 8 * npix);
+      std::vector<float> pv(npix * nv);
+      for (size_t i = 0; i < pv.size(); i++) pv[i] = (float)ivals[(size_t)m * npix * nv + i];
+      frec(f, pv.data(), 4 * npix * nv);
     }
   }
-  fclose(fp);
-  return GRT_OK;
+  if (fclose(f.fp) != 0) f.ok = false;
+  return f.ok ? GRT_OK : GRT_ERR_IO;
 }
 
 }  // namespace grt_host

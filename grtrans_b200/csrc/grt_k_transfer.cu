@@ -1,5 +1,7 @@
 // grtrans_b200 -- emissivity + polarised transfer kernels and the unit-surface kernels.
 //   k_transfer       thread / (ray, mdot, nu)  emissivity + DELO/FORMAL/quadrature/RK march -> float32 Stokes image
+#include <algorithm>
+
 #include "grt_kernels.h"
 
 namespace grt {
@@ -37,6 +39,30 @@ __global__ void __launch_bounds__(128, GRT_TRANSFER_MINB) k_transfer(const RayMe
     *reinterpret_cast<float4 *>(dst) = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
   else
     dst[0] = (float)out[0];
+}
+
+// Gather: one block [ncamb][n][nv] of rank r's image (local rays off .. off+n-1) -> the full image
+// [ncams][npix][nv] of rank 0.  Rank r owns the 256-ray shards r, r+nranks, ... of the index range starting at i1
+// (grt_shard_rays).  One thread per float: pure HBM traffic (4 B read + 4 B write), coalesced over 256-ray runs.
+__global__ void k_gather_scatter(const float *__restrict__ blk, float *__restrict__ full, int ncamb, int n, int nv, long long npix,
+                                 int cam0, long long off, int r, int nranks, int i1) {
+  const long long per_cam = (long long)n * nv, total = per_cam * ncamb;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cam = (int)(idx / per_cam);
+    const long long rem = idx - (long long)cam * per_cam;
+    const long long q = off + rem / nv;
+    const int k = (int)(rem % nv);
+    const long long pix = (long long)(i1 - 1) + ((q / 256) * nranks + r) * 256 + q % 256;
+    full[((size_t)(cam0 + cam) * npix + pix) * nv + k] = blk[idx];
+  }
+}
+void launch_gather_scatter(const float *blk, float *full, int ncamb, int n, int nv, long long npix, int cam0, long long off,
+                           int r, int nranks, int i1, cudaStream_t st) {
+  const long long total = (long long)ncamb * n * nv;
+  if (total <= 0) return;
+  const int B = 256;
+  const unsigned grid = (unsigned)std::min<long long>((total + B - 1) / B, 148LL * 16);  // a few blocks per SM, grid-stride
+  k_gather_scatter<<<grid, B, 0, st>>>(blk, full, ncamb, n, nv, npix, cam0, off, r, nranks, i1);
 }
 
 // small stand-alone kernels for the unit-level C ABI

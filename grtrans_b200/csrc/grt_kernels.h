@@ -28,6 +28,10 @@ void launch_transfer_extra(const RayMeta *meta, const TransferParams &P, const d
                            int nparams, int nrays, int maxpts, const double *rec, const double *xrec, double *hist, float *image,
                            long long ray_off, long long nlocal, int cam0, int nextra, cudaStream_t st);
 
+// multi-GPU gather: scatter one block [ncamb][n][nv] of rank r (local rays off..off+n-1) into rank 0's full image [ncams][npix][nv]
+void launch_gather_scatter(const float *blk, float *full, int ncamb, int n, int nv, long long npix, int cam0, long long off,
+                           int r, int nranks, int i1, cudaStream_t st);
+
 // unit-level surfaces
 void launch_polsynchth(int n, const double *nu, const double *nc, const double *b, const double *t, const double *th, double *e);
 void launch_polsynchpl(int n, EmisTables tab, const double *nu, const double *nnth, const double *b, const double *th,

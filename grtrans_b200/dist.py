@@ -1,17 +1,28 @@
-"""Multi-GPU plumbing: one process per GPU, pixel range sharded in interleaved tiles, one gather of the
-float32 Stokes image to rank 0 over NCCL/NVLink (torch.distributed is used for the collective only).
+"""Multi-GPU plumbing for launchers that start one process per GPU (torchrun, mpirun).
 
-The path has no data-path exchange step: rays are independent (pgrtrans.f90:198-209), so the only collective is the
-final image gather."""
+The data path is inside libgrtrans_b200.so: rays i1..i2 are sharded over the ranks in interleaved 256-ray shards
+(grt_shard_rays), and grt_session_launch_gather sends every finished tile of the float32 Stokes image to rank 0
+with ncclSend / ncclRecv behind the kernels of the following tiles.  The path has no other exchange step: rays are
+independent (pgrtrans.f90:198-209).  What is left for the launcher -- and all this module does -- is to carry the 128-byte
+NCCL unique id from rank 0 to the other ranks and to reduce a few scalars (timings); torch.distributed (nccl or gloo) is
+used for that and for nothing else.  A single process drives several GPUs without any of this: grt_main() does it with
+one host thread per device.
+"""
 import numpy as np
 
-SHARD = 256  # rays per interleaved tile; must match grt_session_create (grt_engine.cu)
+SHARD = 256  # rays per interleaved shard; must match GRT_SHARD (grt_engine.cu)
 
 
 def shard_indices(i1, i2, rank, nranks, shard=SHARD):
-    """1-based geodesic indices owned by `rank` (same rule as the C++ session)."""
+    """1-based geodesic indices owned by `rank` (numpy mirror of grt_shard_rays)."""
     i = np.arange(i1, i2 + 1, dtype=np.int64)
     return i[((i - i1) // shard) % nranks == rank].astype(np.int32)
+
+
+def shard_pixels(q, rank, nranks, i1=1, shard=SHARD):
+    """0-based pixel of local ray q of `rank`: the scatter rule of k_gather_scatter / convert_block."""
+    q = np.asarray(q, np.int64)
+    return (i1 - 1) + ((q // shard) * nranks + rank) * shard + q % shard
 
 
 def assemble(images, indices, npix):
@@ -24,63 +35,30 @@ def assemble(images, indices, npix):
     return full
 
 
-class _CudaArray(object):
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3,
-                                         "strides": None}
-
-
-class DeviceImage(object):
-    """Zero-copy torch views of the session's device-resident image and ray-index buffers."""
-
-    def __init__(self, sess):
-        import torch
-        p, n, pi, nr = sess.device_image()
-        self.ncams, self.nvals, self.nlocal = sess.ncams, sess.nvals, nr
-        self.image = torch.as_tensor(_CudaArray(p, (max(n, 1),), "<f4"), device="cuda")[:n]
-        self.index = torch.as_tensor(_CudaArray(pi, (max(nr, 1),), "<i4"), device="cuda")[:nr]
-
-
-def gather_blocks(img_flat, idx, ncams, nvals, rank, world):
-    """Gather per-rank flat images [ncams*nlocal*nvals] and index vectors to rank 0 (works with nccl and gloo).
-    torch.distributed.gather needs equal sizes, so blocks are padded to the largest rank's count."""
+def broadcast_unique_id(make_id, rank, device=None):
+    """Rank 0 calls make_id() (-> 128 bytes); every rank returns the same bytes (torch.distributed broadcast)."""
     import torch
     import torch.distributed as dist
-    dev = img_flat.device
-    nloc = int(idx.numel())
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([nloc], dtype=torch.int64, device=dev))
-    counts = [int(c.item()) for c in counts]
-    cmax = max(counts)
-    if nloc == cmax:
-        pimg, pidx = img_flat, idx
-    else:
-        pimg = torch.zeros(ncams * cmax * nvals, dtype=img_flat.dtype, device=dev)
-        pimg.view(ncams, cmax, nvals)[:, :nloc, :] = img_flat.view(ncams, nloc, nvals)
-        pidx = torch.zeros(cmax, dtype=idx.dtype, device=dev)
-        pidx[:nloc] = idx
+    t = torch.zeros(128, dtype=torch.uint8, device=device)
     if rank == 0:
-        imgs = [torch.empty(ncams * cmax * nvals, dtype=img_flat.dtype, device=dev) for _ in range(world)]
-        idxs = [torch.empty(cmax, dtype=idx.dtype, device=dev) for _ in range(world)]
-    else:
-        imgs = idxs = None
-    dist.gather(pimg, imgs, dst=0)
-    dist.gather(pidx, idxs, dst=0)
-    if rank != 0:
-        return None, None, counts
-    imgs = [im.view(ncams, cmax, nvals)[:, :c, :] for im, c in zip(imgs, counts)]
-    idxs = [ix[:c] for ix, c in zip(idxs, counts)]
-    return imgs, idxs, counts
+        t = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).clone()
+        if device is not None:
+            t = t.to(device)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
 
 
-def gather_image(dimg, npix, world, rank):
-    """NCCL gather of every rank's [ncams, nlocal, nvals] block; rank 0 scatters them into the full device image."""
+def reduce_max(x, device=None):
     import torch
-    imgs, idxs, counts = gather_blocks(dimg.image, dimg.index, dimg.ncams, dimg.nvals, rank, world)
-    if rank != 0:
-        return None
-    full = torch.zeros(dimg.ncams, npix, dimg.nvals, dtype=torch.float32, device="cuda")
-    for im, ix, c in zip(imgs, idxs, counts):
-        if c:
-            full[:, ix.long() - 1, :] = im
-    return full
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(x, device=None):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

@@ -66,8 +66,20 @@ void grt_args_defaults(grt_args *a);
 
 /* ---- pgrtrans module surface (pgrtrans.f90:6-8, 12-58, 255-258) -------------------------------- */
 /* grtrans_main: trace i1..i2, all mu0 / mdot / freq cameras.  Results stay owned by the library
- * until grt_del_data() (like the module variables ivals/ab/freqs). */
+ * until grt_del_data() (like the module variables ivals/ab/freqs).
+ * Multi-GPU: the geodesic index range is sharded over every selected device (grt_set_devices, else the
+ * environment GRT_DEVICES="0,2,3" / GRT_NGPU=4, else all visible devices), one host thread per device in
+ * place of the reference's OpenMP pixel loop (pgrtrans.f90:198-209); every finished tile streams into the
+ * single host image.  The result does not depend on the number of devices (bit-identical). */
 int grt_main(const grt_args *a);
+/* devices grt_main uses (n = 0: back to the default) */
+int grt_set_devices(const int *devices, int n);
+/* after grt_main: devices used, host->device / device->host bytes of that call, kernels launched */
+int grt_main_info(int *ndevices, long long *h2d_bytes, long long *d2h_bytes, int *launches);
+/* grt_main pools its device sessions, pinned buffers and the ivals array between calls with identical
+ * arguments (grt_del_data only marks them free, like deallocate); this gives the memory back.
+ * GRT_CACHE=0 in the environment disables the pool. */
+void grt_release_cache(void);
 /* ivals(nvals+nextra, npix, ncams) column-major exactly like the Fortran module array.
  * dims = {nvals+nextra, npix, ncams}.  Returns GRT_ERR_STATE when nothing is allocated. */
 int grt_get_ivals(const double **ivals, int dims[3]);
@@ -146,11 +158,30 @@ int grt_session_run_timed(grt_session *s, int nsteps, float *ms);
 int grt_session_time(grt_session *s, float *total_ms, float stage_ms[4]);
 /* number of kernel launches one grt_session_launch() issues */
 int grt_session_launch_count(const grt_session *s);
+/* kernels launched by the last pass (a gather pass adds rank 0's scatter kernels); rays per tile */
+int grt_session_last_launches(const grt_session *s);
+int grt_session_tile(const grt_session *s);
 /* local rays of this rank and their total number of geodesic points (after a launch+sync) */
 int grt_session_counts(grt_session *s, long long *nrays_local, long long *npoints_local);
-/* device pointer + element count of the local float32 image [cam][local_ray][nvals] and the
- * geodesic indices (1-based, int32 device pointer) of the local rays, for an NVLink gather */
-int grt_session_device_image(grt_session *s, void **d_image, long long *nelem, void **d_ray_index, long long *nrays);
+/* ---- multi-GPU with one process per GPU (torchrun / mpirun): NCCL inside the library ------------ */
+/* geodesic indices (1-based) of rank's rays: the 256-ray shards rank, rank+nranks, ... of i1..i2
+ * (replaces the schedule(static,1) of pgrtrans.f90:198).  Returns the count; ray_index may be NULL.
+ * Pure host logic (no device needed). */
+long long grt_shard_rays(int i1, int i2, int rank, int nranks, int *ray_index);
+/* rank 0 makes the NCCL unique id (128 bytes); the launcher hands it to every rank */
+int grt_nccl_unique_id(char id[128]);
+/* collective: ncclCommInitRank over the nranks sessions created with the same arguments */
+int grt_session_comm_init(grt_session *s, const char id[128]);
+/* collective: launch the whole path; every finished tile goes to rank 0 with ncclSend/ncclRecv on a
+ * second stream, behind the kernels of the following tiles, and is scattered into rank 0's full
+ * device image [ncams][npix][nvals] (zero outside i1..i2).  nranks = 1 needs no communicator. */
+int grt_session_launch_gather(grt_session *s);
+/* grt_session_run_timed with gather passes; the closing event waits for this rank's share of the gather */
+int grt_session_run_timed_gather(grt_session *s, int nsteps, float *ms);
+/* rank 0: the gathered device image (complete after grt_session_sync on every rank) */
+int grt_session_full_image(grt_session *s, const float **d_full, long long *nelem);
+/* rank 0: synchronous copy of the gathered image to host memory, float32 [ncams][npix][nvals] */
+int grt_session_fetch_full(grt_session *s, float *image);
 /* copy the local image to host (float32 [ncams][nrays_local][nvals]) and the ray indices */
 int grt_session_fetch(grt_session *s, float *image, int *ray_index);
 int grt_session_ncams(const grt_session *s);

@@ -32,6 +32,37 @@ static RunArgs to_run(const grt_args *a) {
 
 extern "C" {
 
+// Test-only switches (tests/test_oracle_golden.py): physical constants of an older reference commit and "legacy" code
+// variants, used to pin the oracle against goldens the reference's repository still carries from older commits.
+// name = "h","k","c","e","G","m","mp","sigb","msun","sigt" or a LegacyOptions field; "reset" restores everything.
+int orc_set_option(const char *name, double v) {
+  const std::string n(name);
+  if (n == "reset") {
+    pc::h = 6.626e-27; pc::k = 1.38e-16; pc::c = 2.99792458e10; pc::e = 4.8032e-10; pc::G = 6.67e-8; pc::m = 9.10938188e-28;
+    pc::mp = 1.67262158e-24; pc::sigb = 5.6704e-5; pc::msun = 1.998e33; pc::sigt = 6.6523e-25;
+    legacy = LegacyOptions();
+  } else if (n == "h") pc::h = v;
+  else if (n == "k") pc::k = v;
+  else if (n == "c") pc::c = v;
+  else if (n == "e") pc::e = v;
+  else if (n == "G") pc::G = v;
+  else if (n == "m") pc::m = v;
+  else if (n == "mp") pc::mp = v;
+  else if (n == "sigb") pc::sigb = v;
+  else if (n == "msun") pc::msun = v;
+  else if (n == "sigt") pc::sigt = v;
+  else if (n == "kstarq_sign_old") legacy.kstarq_sign_old = (int)v;
+  else if (n == "pl_rhoq_scale") legacy.pl_rhoq_scale = v;
+  else if (n == "pl_rhov_scale") legacy.pl_rhov_scale = v;
+  else if (n == "pl_jv_scale") legacy.pl_jv_scale = v;
+  else if (n == "pl_av_scale") legacy.pl_av_scale = v;
+  else if (n == "pl_ai_scale") legacy.pl_ai_scale = v;
+  else if (n == "pl_aq_scale") legacy.pl_aq_scale = v;
+  else return 1;
+  pc::c2 = pc::c * pc::c;
+  return 0;
+}
+
 double orc_rf(double x, double y, double z) { return rf(x, y, z); }
 double orc_rc(double x, double y) { return rc(x, y); }
 double orc_rd(double x, double y, double z) { return rd(x, y, z); }

@@ -294,7 +294,10 @@ void polsynchpl(double nu, double nnth, double b, double th, double p, double gm
   double aq = afac * gapfac;
   double av = afac * 4.0 / 3.0 / tanth * gavfac * std::pow(2.0 * omega / 3.0 / omega0, -1.0 / 2.0);
   e[0] = ji; e[1] = jq; e[2] = 0.0; e[3] = jv; e[4] = ai; e[5] = aq; e[6] = 0.0; e[7] = av;
+  if (legacy.kstarq_sign_old) kstarq = -kstarq;  // test-only switches, see oracle.h
   e[8] = kstarq; e[9] = 0.0; e[10] = kstarv;
+  e[8] *= legacy.pl_rhoq_scale; e[10] *= legacy.pl_rhov_scale; e[3] *= legacy.pl_jv_scale; e[7] *= legacy.pl_av_scale;
+  e[4] *= legacy.pl_ai_scale; e[5] *= legacy.pl_aq_scale;
 }
 
 // polsynchemis.f90:633-698

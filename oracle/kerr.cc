@@ -12,7 +12,11 @@ namespace orc {
 
 namespace pc {
 const double pi = std::acos(-1.0);
+// phys_constants.f90:3-6 (current reference values; see oracle.h)
+double h = 6.626e-27, k = 1.38e-16, c = 2.99792458e10, e = 4.8032e-10, G = 6.67e-8, m = 9.10938188e-28,
+       mp = 1.67262158e-24, c2 = c * c, sigb = 5.6704e-5, msun = 1.998e33, sigt = 6.6523e-25;
 }
+LegacyOptions legacy;
 
 static inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }
 

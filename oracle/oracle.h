@@ -7,12 +7,21 @@
 
 namespace orc {
 
-// physical constants exactly as the reference defines them (phys_constants.f90:3-6; NOT CODATA)
+// physical constants exactly as the reference defines them (phys_constants.f90:3-6; NOT CODATA).  They are variables
+// (defined in driver.cc with the current phys_constants.f90 values) so that tests can re-run the oracle with the
+// constant set of an OLDER reference commit when pinning against goldens that predate phys_constants.f90
+// (orc_set_option, capi.cc): the product path always uses the current values.
 namespace pc {
-const double h = 6.626e-27, k = 1.38e-16, c = 2.99792458e10, e = 4.8032e-10, G = 6.67e-8, m = 9.10938188e-28,
-             mp = 1.67262158e-24, c2 = c * c, sigb = 5.6704e-5, msun = 1.998e33, sigt = 6.6523e-25;
+extern double h, k, c, e, G, m, mp, c2, sigb, msun, sigt;
 extern const double pi;  // acos(-1d0)
 }  // namespace pc
+
+// switches for bisecting goldens written by older reference commits (all 0 = the reference as it is today)
+struct LegacyOptions {
+  int kstarq_sign_old = 0;   // polsynchpl: rho_Q with the sign it had before the "JAD changing sign here" edit (polsynchemis.f90:583-585)
+  double pl_rhoq_scale = 1.0, pl_rhov_scale = 1.0, pl_jv_scale = 1.0, pl_av_scale = 1.0, pl_ai_scale = 1.0, pl_aq_scale = 1.0;  // bisecting only
+};
+extern LegacyOptions legacy;
 
 // per-ray cached integrals: the by-reference arguments threaded through GEOMU/GEOR/GEOPHITIME
 // (geokerr_wrapper.f:405-409)

@@ -115,31 +115,61 @@ def test_fits_reader_on_handwritten_file(tmp_path):
 
 
 def test_shard_rule_partitions_range():
+    from grtrans_b200 import _lib
     for nr in (1, 2, 4, 8):
         allidx = np.concatenate([gdist.shard_indices(5, 100003, r, nr) for r in range(nr)])
         assert np.array_equal(np.sort(allidx), np.arange(5, 100004))
         sizes = [len(gdist.shard_indices(1, 1024 * 1024, r, nr)) for r in range(nr)]
         assert max(sizes) - min(sizes) <= gdist.SHARD
+        assert sizes[0] == max(sizes)       # rank 0 owns the most rays: its tile loop covers every rank's tiles (gather)
+        for r in range(nr):
+            # the C rule (grt_shard_rays: session sharding, works without a GPU), its numpy mirror and the scatter rule of
+            # k_gather_scatter / convert_block (local ray q -> pixel) agree
+            c = _lib.shard_rays(5, 100003, r, nr)
+            assert np.array_equal(c, gdist.shard_indices(5, 100003, r, nr))
+            assert np.array_equal(gdist.shard_pixels(np.arange(len(c)), r, nr, i1=5) + 1, c)
 
 
 _WORKER = r'''
 import os, sys, numpy as np
 sys.path.insert(0, %r)
 import torch, torch.distributed as dist
-from grtrans_b200 import dist as gdist
+from grtrans_b200 import dist as gdist, _lib
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
-npix, ncams, nv, i1, i2 = 5000, 3, 4, 11, 4990
-idx = gdist.shard_indices(i1, i2, rank, world)
-# stand-in for the per-rank image: a deterministic function of (cam, pixel, stokes)
+# launcher plumbing: the 128-byte id rank 0 makes reaches every rank unchanged (stand-in id: no GPU / NCCL here)
+uid = gdist.broadcast_unique_id(lambda: bytes(range(128)), rank)
+assert uid == bytes(range(128))
+npix, ncams, nv, i1, i2, tile = 5000, 3, 4, 11, 4990, 1024
+idx = _lib.shard_rays(i1, i2, rank, world)
+# stand-in for this rank's image: a deterministic function of (cam, pixel, stokes)
 img = (idx[None, :, None] * 10.0 + np.arange(ncams)[:, None, None] * 1e6 + np.arange(nv)[None, None, :]).astype(np.float32)
-imgs, idxs, counts = gdist.gather_blocks(torch.from_numpy(img.ravel().copy()), torch.from_numpy(idx), ncams, nv, rank, world)
+# the gather protocol of grt_session_launch_gather on the host: tile by tile, every rank sends its block [cam][n][nv] to
+# rank 0, which scatters it with the shard rule
+full = np.zeros((ncams, npix, nv), np.float32) if rank == 0 else None
+nl0 = len(_lib.shard_rays(i1, i2, 0, world))
+for off in range(0, nl0, tile):
+    blk = np.ascontiguousarray(img[:, off:off + tile, :])
+    if rank == 0:
+        for r in range(world):
+            nlr = len(_lib.shard_rays(i1, i2, r, world))
+            n = max(0, min(tile, nlr - off))
+            if n == 0:
+                continue
+            if r == 0:
+                got = blk
+            else:
+                t = torch.zeros(ncams * n * nv); dist.recv(t, src=r); got = t.numpy().reshape(ncams, n, nv)
+            full[:, gdist.shard_pixels(off + np.arange(n), r, world, i1=i1), :] = got
+    elif blk.shape[1]:
+        dist.send(torch.from_numpy(blk.ravel().copy()), dst=0)
+tot = gdist.reduce_sum(len(idx)); mx = gdist.reduce_max(rank)
 if rank == 0:
-    full = gdist.assemble([g.numpy() for g in imgs], [x.numpy() for x in idxs], npix)
     pix = np.arange(1, npix + 1)
     want = (pix[None, :, None] * 10.0 + np.arange(ncams)[:, None, None] * 1e6 + np.arange(nv)[None, None, :]).astype(np.float32)
     want[:, :i1 - 1] = 0; want[:, i2:] = 0
     assert np.array_equal(full, want)
+    assert tot == i2 - i1 + 1 and mx == world - 1
     print("GLOO_OK")
 dist.destroy_process_group()
 '''
