@@ -58,6 +58,9 @@ int orc_set_option(const char *name, double v) {
   else if (n == "pl_av_scale") legacy.pl_av_scale = v;
   else if (n == "pl_ai_scale") legacy.pl_ai_scale = v;
   else if (n == "pl_aq_scale") legacy.pl_aq_scale = v;
+  else if (n == "rt_perturb") legacy.rt_perturb = v;
+  else if (n == "lambda_perturb_ulp") legacy.lambda_perturb_ulp = v;
+  else if (n == "delo_inverse_lu") legacy.delo_inverse_lu = (int)v;
   else return 1;
   pc::c2 = pc::c * pc::c;
   return 0;

@@ -139,6 +139,17 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
   if (!(status == 1 && g.npts > 0)) return;
   int npts = g.npts;
   if (npoints) *npoints += npts;
+  if (legacy.lambda_perturb_ulp > 0.0) {
+    // test-only (oracle.h): the affine parameter is the difference of two numbers of size 1/u0 (geokerr_wrapper.f LAMBDA
+    // integrals; u0 <= 1e-4), so the reference's own values carry rounding noise of a few ulp(1/u0).  This adds noise of
+    // that size, to measure how far the reference ALGORITHM amplifies it on a given ray.
+    const double ulp = 2.220446049250313e-16 / gargs.u0 * legacy.lambda_perturb_ulp;
+    unsigned long long h = 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    for (int p = 0; p < npts; p++) {
+      h ^= h << 13; h ^= h >> 7; h ^= h << 17;
+      g.lambda[p] += ulp * ((double)(h >> 11) / 9007199254740992.0 * 2.0 - 1.0);
+    }
+  }
   int eneq;
   int etype = emis_type_from_name(A.ename, eneq);
   int enk = 1 + eneq * (eneq - 1) / 2;
@@ -292,6 +303,17 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
           for (int p = 0; p < npts; p++) {
             for (int c = 0; c < rneq; c++) w.j[(size_t)p * rneq + c] = (c < eneq) ? w.ej[(size_t)p * 4 + c] : 0.0;
             for (int c = 0; c < rnk; c++) w.K[(size_t)p * rnk + c] = (c < enk) ? w.eK[(size_t)p * 7 + c] : 0.0;
+          }
+          if (legacy.rt_perturb > 0.0) {
+            // test-only (oracle.h): relative noise of amplitude rt_perturb on the coefficients, to measure how much the
+            // reference ALGORITHM amplifies rounding-level differences on this ray (conditioning of the transfer problem)
+            unsigned long long h = 0x9E3779B97F4A7C15ull * (unsigned long long)(k + 1) + (unsigned long long)npts;
+            auto nz = [&]() {
+              h ^= h << 13; h ^= h >> 7; h ^= h << 17;
+              return 1.0 + legacy.rt_perturb * ((double)(h >> 11) / 9007199254740992.0 * 2.0 - 1.0);
+            };
+            for (size_t q = 0; q < (size_t)npts * rneq; q++) w.j[q] *= nz();
+            for (size_t q = 0; q < (size_t)npts * rnk; q++) w.K[q] *= nz();
           }
           rnpts = rt_integrate(iflag, rneq, npts, g.lambda.data(), w.j.data(), w.K.data(), w.tau.data(),
                                w.intensity.data(), opt);

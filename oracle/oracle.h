@@ -20,6 +20,9 @@ extern const double pi;  // acos(-1d0)
 struct LegacyOptions {
   int kstarq_sign_old = 0;   // polsynchpl: rho_Q with the sign it had before the "JAD changing sign here" edit (polsynchemis.f90:583-585)
   double pl_rhoq_scale = 1.0, pl_rhov_scale = 1.0, pl_jv_scale = 1.0, pl_av_scale = 1.0, pl_ai_scale = 1.0, pl_aq_scale = 1.0;  // bisecting only
+  int delo_inverse_lu = 0;  // DELO: 4x4 inverse by pivoted elimination instead of cofactors (rounding-ambiguity measurements)
+  double lambda_perturb_ulp = 0.0;  // noise on the affine parameter in units of ulp(1/u0) (conditioning measurements)
+  double rt_perturb = 0.0;  // relative noise on the transfer coefficients (conditioning measurements)
 };
 extern LegacyOptions legacy;
 

@@ -30,7 +30,40 @@ void tsum(int n, const double *x, const double *y, double *out) {
 typedef double M4[4][4];
 
 // radtrans_integrate.f90:685-733 (cofactor inverse)
+// test-only alternative (oracle.h: legacy.delo_inverse_lu): the same inverse by Gauss-Jordan elimination with partial
+// pivoting.  Algebraically identical to the cofactor formula; where the two differ in the image, the difference is the
+// rounding-level ambiguity of the reference ALGORITHM (near-singular DELO matrices in cells where the polsynchth fits
+// give |alpha_V| > alpha_I), which no implementation can be held to.
+static void imatrix_4_lu(const M4 a, M4 b) {
+  double w[4][8];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      w[i][j] = a[i][j];
+      w[i][4 + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 4; c++) {
+    int piv = c;
+    for (int r = c + 1; r < 4; r++)
+      if (std::fabs(w[r][c]) > std::fabs(w[piv][c])) piv = r;
+    if (piv != c)
+      for (int j = 0; j < 8; j++) std::swap(w[c][j], w[piv][j]);
+    const double d = w[c][c];
+    for (int j = 0; j < 8; j++) w[c][j] /= d;
+    for (int r = 0; r < 4; r++)
+      if (r != c) {
+        const double f = w[r][c];
+        for (int j = 0; j < 8; j++) w[r][j] -= f * w[c][j];
+      }
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) b[i][j] = w[i][4 + j];
+}
+
 static void imatrix_4(const M4 a, M4 b) {
+  if (legacy.delo_inverse_lu) {
+    imatrix_4_lu(a, b);
+    return;
+  }
   double a11 = a[0][0], a12 = a[0][1], a13 = a[0][2], a14 = a[0][3];
   double a21 = a[1][0], a22 = a[1][1], a23 = a[1][2], a24 = a[1][3];
   double a31 = a[2][0], a32 = a[2][1], a33 = a[2][2], a34 = a[2][3];

@@ -169,3 +169,48 @@ def image_errors(got, ref):
         if r.shape[0] == 4:
             quv = max(quv, np.abs(g[1:, :, k] - r[1:, :, k]).max() / Imax)
     return relI, flux, quv, nanok
+
+
+def image_errors_unmasked(got, ref):
+    """Like image_errors, but the per-pixel criterion runs over EVERY pixel whose reference intensity is a normal float32
+    number with all its mantissa bits (|I| > 1e-30: the image is stored in real(4), camera.f90:28-39, and loses relative
+    precision only in the denormal range below 1.2e-38) -- no I > 1e-4 Imax mask.  Returns (max rel dI, pixels compared)."""
+    import numpy as np
+    g = np.nan_to_num(got); r = np.nan_to_num(ref)
+    w = np.abs(r[0]) > 1e-30
+    if not w.any():
+        return 0., 0
+    return float(np.max(np.abs(g[0][w] - r[0][w]) / np.abs(r[0][w]))), int(w.sum())
+
+
+def conditioned_image_errors(got, ref, ref_noise, k=4.):
+    """Per-pixel criterion with the reference algorithm's own rounding ambiguity taken into account.
+
+    ref_noise is the oracle run with noise of a few ulp(1/u0) on the affine parameter (test-only switch lambda_perturb_ulp:
+    the reference computes lambda as the difference of two numbers of size 1/u0, so its own values carry that noise).  Where
+    the transfer problem amplifies it -- cameras in which the polsynchth fits give |alpha_V| > alpha_I and the solution grows
+    exponentially -- no implementation can be held to 1e-4 of ONE realisation of the reference's rounding.  The tolerance
+    per pixel is  1e-4 |I| + k |ref_noise - ref|  (Q, U, V: 1e-3 Imax + k |ref_noise - ref|).
+    Returns (worst err/tol for I, worst err/tol for QUV, fraction of pixels whose tolerance is dominated by the noise term,
+    per-camera list of the max relative self-deviation of the oracle under the noise)."""
+    import numpy as np
+    g = np.nan_to_num(got); r = np.nan_to_num(ref); rn = np.nan_to_num(ref_noise)
+    worstI = worstQ = 0.
+    ndom = ntot = 0
+    selfdev = []
+    for c in range(r.shape[2]):
+        I = r[0, :, c]
+        Imax = np.abs(I).max()
+        if Imax == 0.:
+            selfdev.append(0.)
+            continue
+        amb = np.abs(rn[0, :, c] - I)
+        tol = 1e-4 * np.abs(I) + k * amb
+        w = tol > 0
+        worstI = max(worstI, float(np.max(np.abs(g[0, w, c] - I[w]) / tol[w])))
+        ndom += int((k * amb > 1e-4 * np.abs(I)).sum()); ntot += I.size
+        selfdev.append(float(np.max(amb[I != 0] / np.abs(I[I != 0]))))
+        if r.shape[0] == 4:
+            tq = 1e-3 * Imax + k * np.abs(rn[1:, :, c] - r[1:, :, c])
+            worstQ = max(worstQ, float(np.max(np.abs(g[1:, :, c] - r[1:, :, c]) / tq)))
+    return worstI, worstQ, ndom / max(1, ntot), selfdev

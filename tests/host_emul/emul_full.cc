@@ -145,6 +145,103 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
   return 0;
 }
 
+// Debug: the transfer coefficients node_coef() hands to the integrator, for one ray at one frequency: out[p*11 ..] =
+// j[4] (invariant, not divided by fac), K[7] (times LBH / g).  Returns the number of points (mu0 index 0, mdot 0).
+extern "C" int emul_ray_coefs(const grt_args *a, int ix1, double nu_obs, double *out, int cap) {
+  grt_host::FluidHost fh;
+  if (grt_host::load_fluid(fh, *a)) return -1;
+  std::vector<double> freqs, mdots, mu0;
+  grt_host::make_grids(*a, freqs, mdots, mu0);
+  int eneq = 1;
+  const int etype = grt_host::emis_type_id(a->ename, &eneq);
+  FluidKernelArgs fk;
+  memset(&fk, 0, sizeof(fk));
+  FluidDev &F = fk.F;
+  F.model = fh.model; F.nx1 = fh.nx1; F.nx2 = fh.nx2; F.nx3 = fh.nx3; F.h = fh.h; F.nslots = fh.nslots; F.ncell = fh.ncell;
+  F.tstep = fh.tstep; F.td_mbh = fh.td_mbh; F.td_mdot = fh.td_mdot; F.td_rin = fh.td_rin; F.td_rout = fh.td_rout;
+  F.ax1 = fh.ax1.data(); F.axr = fh.axr.data(); F.ax2 = fh.ax2.data(); F.axth = fh.axth.data(); F.ax3 = fh.ax3.data();
+  F.uvals = fh.uvals.data(); F.vvals = fh.vvals.data(); F.uv = fh.uv.data(); F.tvals = fh.tvals.data();
+  F.cells = reinterpret_cast<const Cell *>(fh.cells.data());
+  grt_host::EmisTablesHost th;
+  grt_host::build_emis_tables(th);
+  TransferParams P;
+  memset(&P, 0, sizeof(P));
+  EmisTables &tb = P.tab;
+  tb.gx = th.gx.data(); tb.gy = th.gy.data(); tb.xv = th.xv.data(); tb.ya = th.ya.data(); tb.yp = th.yp.data();
+  tb.yv = th.yv.data(); tb.yap = th.yap.data(); tb.yav = th.yav.data();
+  tb.far = nullptr; tb.far_n = 0;
+  fk.tab = tb; fk.nparams = 1; fk.etype = etype;
+  SourceDev &sp = fk.sp[0];
+  sp.mdot = mdots[0]; sp.mbh = a->mbh; sp.nfac = a->ftscl; sp.bfac = a->frscl; sp.jetalphaval = a->jetalpha;
+  sp.gminval = a->gmin; sp.muval = a->muval; sp.gmax = a->gmax; sp.p1 = a->p1; sp.p2 = a->p2; sp.sigcut = a->sigcut;
+  P.etype = etype; P.eneq = eneq; P.rneq = a->nvals; P.npts_is_one = (a->nn[2] == 1);
+  for (int i = 0; i < 7; i++) P.coefindx[i] = a->epcoefindx[i];
+  P.LBH = pc::G * a->mbh * pc::msun / pc::c2;
+  P.gmin = (double)(float)a->gmin; P.gmax = (double)(float)a->gmax; P.p = (double)(float)a->p1;
+  grt_host::Camera c;
+  grt_host::build_camera(c, a->standard, mu0[0], a->phi0, a->spin, a->uout, a->rcut, a->nrotype, a->gridvals, a->nn[0], a->nn[1],
+                         a->nn[2]);
+  const int mp = c.maxpts(), ix = ix1 - 1;
+  fk.maxpts = mp;
+  GeoFlags fl{a->nn[2], c.kext, c.next, c.mufill, c.usegeor, 1, 1};
+  RayConst r;
+  r.a = c.a; r.mu0 = c.mu0; r.u0 = c.u0; r.uout = c.uout; r.alpha = c.alpha[ix]; r.beta = c.beta[ix]; r.q2 = c.q2[ix];
+  r.l = c.l[ix]; r.su = c.su[ix]; r.sm = c.sm[ix]; r.uf = c.uf[ix]; r.muf = c.muf[ix]; r.offset = c.offset; r.phi0 = c.phi0;
+  r.t0 = 0; r.tpm = c.tpm[ix]; r.tpr = c.tpr[ix];
+  RayInv inv;
+  geo_setup(r, fl, inv);
+  std::vector<double> bu(mp), bmu(mp), bdt(mp), bdp(mp), bl(mp), rec((size_t)mp * record_doubles(etype), 0.0);
+  std::vector<signed char> btm(mp), btr(mp);
+  PointArrays pa{bu.data(), bmu.data(), bdt.data(), bdp.data(), bl.data(), btm.data(), btr.data()};
+  for (int s = 0; s < mp; s++) point_store(inv, fl.nup, s, (size_t)s, pa);
+  RayMeta m;
+  ray_finalize(inv.npts, 0, mp, fl.usegeor, pa, m);
+  StageDump sd;
+  memset(&sd, 0, sizeof(sd));
+  for (int s = 0; s < mp; s++) point_record(r, m, fk, 0, s, 1, pa, rec.data(), sd);
+  if (m.status != 1) return 0;
+  const FreqConst Fq = freq_const(nu_obs);
+  for (int p = 0; p < m.npts && p < cap; p++) {
+    Coef cf;
+    double jraw;
+    const double *rk = rec.data() + (size_t)p * record_doubles(etype);
+    if (etype == EM_POLSYNCHTH) {
+      RunConst R = run_const<EM_POLSYNCHTH>(P, nu_obs);
+      node_coef<EM_POLSYNCHTH>(P, R, rk, Fq, cf, jraw);
+    } else {
+      return -2;
+    }
+    for (int i = 0; i < 4; i++) out[p * 11 + i] = cf.j[i];
+    for (int i = 0; i < 7; i++) out[p * 11 + 4 + i] = cf.K[i];
+  }
+  return m.npts;
+}
+
+// The kernel's DELO march (delo_step: closed-form 4x4 solve, merged thick / thin weights) on caller-supplied coefficients:
+// s[npts] (lambda, descending), j[npts][4], K[npts][7]; intensity[npts][4] like grt_rt_integrate (column k = intensity(:,k)).
+extern "C" void emul_delo(int npts, const double *s, const double *j, const double *K, double thin, double *intensity) {
+  double Ip[4] = {0, 0, 0, 0}, In[4];
+  for (int i = 0; i < 4 * npts; i++) intensity[i] = 0.0;
+  auto load = [&](int k, Coef &c) {
+    for (int i = 0; i < 4; i++) c.j[i] = j[(size_t)k * 4 + i];
+    for (int i = 0; i < 7; i++) c.K[i] = K[(size_t)k * 7 + i];
+  };
+  Coef c0, c1;
+  load(npts - 1, c1);
+  for (int k = npts - 2; k >= 0; k--) {
+    load(k, c0);
+    const double dx = s[k] - s[k + 1];
+    const double delta = dx * 0.5 * (fabs(c0.K[0]) + fabs(c1.K[0]));
+    delo_step(c0, c1, dx, delta, thin, Ip, In);
+    const int col = npts - 1 - k;
+    for (int i = 0; i < 4; i++) {
+      Ip[i] = In[i];
+      intensity[(size_t)col * 4 + i] = In[i];
+    }
+    c1 = c0;
+  }
+}
+
 // Host logic of the time axis: load the dump slots, then advance `nsteps` times by dt.  out[(step)*5 + ..] = indf, toffset,
 // tstep, sum_k (k+1) sum_cells rho, sum_k (k+1) sum_cells u0 (slot-weighted, so a slot shift is visible).
 extern "C" int emul_fluid_series(const grt_args *a, int nsteps, double dt, double *out) {

@@ -32,6 +32,24 @@ def lib():
     return _lib
 
 
+class options(object):
+    """with orc.options(name=value, ...): test-only switches of the oracle (orc_set_option, oracle/capi.cc): constants and
+    code variants of older reference commits, noise injections for conditioning measurements.  Reset on exit."""
+
+    def __init__(self, **opts):
+        self.opts = opts
+
+    def __enter__(self):
+        L = lib()
+        L.orc_set_option.argtypes = [C.c_char_p, C.c_double]
+        assert L.orc_set_option(b"reset", 0.) == 0
+        for k, v in self.opts.items():
+            assert L.orc_set_option(k.encode(), float(v)) == 0, k
+
+    def __exit__(self, *a):
+        lib().orc_set_option(b"reset", 0.)
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 

@@ -94,3 +94,48 @@ def test_component_sums_reduce_to_polsynchth():
     assert np.array_equal(mj, mc0, equal_nan=True)
     assert not np.array_equal(mj, ref, equal_nan=True)
 
+
+
+def test_polsynchth_fits_give_jv_above_ji_at_low_frequency():
+    """BASELINE config 2 at the README's fmin = 2.41e10 Hz: along every ray the reference's thermal fits return |j_V| > j_I
+    (and, by Kirchhoff, |alpha_V| > alpha_I: an absorption matrix with a negative eigenvalue, i.e. exponential growth of the
+    transfer solution).  That is a property of the FORMULAE (polsynchemis.f90:717-723, 831-861), shown here with a
+    transcription written independently of the oracle: |j_V| / j_I = 4 / (3 tan(theta) theta_e) * ivx(x) / iix(x), and
+    ivx / iix -> 0.709 x^(-1/3) for x = nu / nu_c -> 0, which is unbounded -- the exact synchrotron emissivities always
+    satisfy |j_V| <= j_I."""
+    h, k, c, e, m = 6.626e-27, 1.38e-16, 2.99792458e10, 4.8032e-10, 9.10938188e-28
+
+    def fits(nu, n, b, t, th):
+        thetae = k * t / m / c / c + 1e-10
+        nuc = 3. * e * b * np.sin(th) / 4. / np.pi / m / c * thetae ** 2 + 1.
+        x = nu / nuc
+        ex = np.exp(-1.8899 * x ** (1. / 3.))
+        iix = 2.5651 * (1. + 1.92 / x ** (1. / 3.) + .9977 / x ** (2. / 3.)) * ex
+        ivx = (1.81384 / x + 3.42319 / x ** (2. / 3.) + 0.0292545 / np.sqrt(x) + 2.03773 / x ** (1. / 3.)) * ex
+        ji = e ** 2 / c / np.sqrt(3.) / 2. * n / thetae ** 2 * nu * iix
+        jv = 4. * e ** 2 / c / 3. / np.sqrt(3.) / np.tan(th) * n / 2. / thetae ** 3 * nu * ivx
+        return x, ji, jv
+
+    # a cell of the SPHACC flow at r ~ 8.6 M (ray dump of the worst pixel of camera 2): T = 4.0e10 K, B = 9.8e3 G,
+    # n = 4.4e10 cm^-3, redshift g = 0.55
+    n_, b_, t_ = 4.39e10, 9.8e3, 4.02e10
+    th = np.linspace(0.05, 1.3, 26)
+    for nu in (2.41e10, 3.68e10, 5.63e10):                  # the three lowest cameras
+        x, ji, jv = fits(nu / 0.55, n_, b_, t_, th)
+        e11 = orc.polsynchth(nu / 0.55, n_, b_, t_, th)
+        assert np.allclose(e11[:, 0], ji, rtol=1e-12) and np.allclose(e11[:, 3], jv, rtol=1e-12)   # the oracle IS the formula
+        small = th < 0.18      # field within ~10 degrees of the line of sight (|j_V| > j_I up to 0.30 / 0.25 / 0.20 rad)
+        assert np.all(np.abs(jv[small]) > ji[small])                           # unphysical: circular above total emission
+        assert np.all(np.abs(e11[small, 7]) > e11[small, 4])                   # and |alpha_V| > alpha_I (Kirchhoff)
+        pol = np.sqrt(e11[:, 5] ** 2 + e11[:, 7] ** 2)                         # the absorption matrix is indefinite where
+        assert np.all(pol[th < 0.22] > e11[th < 0.22, 4])                      # sqrt(aQ^2 + aV^2) > aI
+    # the ratio is unbounded: |j_V| / j_I -> 0.945 x^(-1/3) / (tan(theta) theta_e) as x = nu / nu_c -> 0
+    xs = np.array([1e-2, 1e-4, 1e-6, 1e-8])
+    ex = np.exp(-1.8899 * xs ** (1. / 3.))
+    iix = 2.5651 * (1. + 1.92 / xs ** (1. / 3.) + .9977 / xs ** (2. / 3.)) * ex
+    ivx = (1.81384 / xs + 3.42319 / xs ** (2. / 3.) + 0.0292545 / np.sqrt(xs) + 2.03773 / xs ** (1. / 3.)) * ex
+    r = ivx / iix
+    assert np.all(np.diff(r) > 0) and abs(r[-1] * xs[-1] ** (1. / 3.) / 0.709 - 1.) < 2e-2
+    # at 6.3e11 Hz and above the same cell is fine at every angle of the sample
+    x, ji, jv = fits(6.3e11 / 0.55, n_, b_, t_, th[th > 0.12])
+    assert np.all(np.abs(jv) < ji)
