@@ -15,13 +15,16 @@ enum { EM_POLSYNCHTH = 2, EM_SYNCHPL = 3, EM_POLSYNCHPL = 4, EM_BB = 8, EM_BBPOL
        // unpolarised thermal models sharing SYNCHTHAV's point record (n, B, T) and kernel slot (em_slot)
        EM_BREMS = 5, EM_SYNCHTHAVNOABS = 14, EM_SYNCHTHBREMS = 27, EM_RHO = 12,
        EM_POLSYNCHSYMTH = 15,   // Pandya et al. (2016) fits (sympolemisth)
-       EM_MAXJUTT = 23, EM_MAXCOMP = 24 };  // sums of thermal components (calc_maxjutt.f90, calc_maxcomp.f90)
+       EM_MAXJUTT = 23, EM_MAXCOMP = 24,    // sums of thermal components (calc_maxjutt.f90, calc_maxcomp.f90)
+       // non-thermal electrons in bins of Lorentz factor (KORALNTH; emis.f90:520-526) [+ angle-averaged thermal synchrotron]
+       EM_BINS = 25, EM_HYBRIDTHBINS = 26 };
 #define GRT_MAXJUTT_NCOMP 7   // at most 7 components (8 ep%otherargs: delta [, selection], weights)
+#define GRT_MAXBINS 64        // at most 64 Lorentz-factor bins in a point record (12 + 64 doubles)
 // kernel / record slot of an emissivity type: the (n, B, T) scalar models run in the SYNCHTHAV instantiations and pick
 // their formula from TransferParams::etype at run time (a thread-uniform switch)
 GRT_HD constexpr int em_slot(int et) {
   return (et == EM_BREMS || et == EM_SYNCHTHAVNOABS || et == EM_SYNCHTHBREMS || et == EM_RHO) ? EM_SYNCHTHAV
-                                                                                           : (et == EM_MAXCOMP ? EM_MAXJUTT : et);
+                                                                                           : (et == EM_MAXCOMP ? EM_MAXJUTT : (et == EM_HYBRIDTHBINS ? EM_BINS : et));
 }
 
 namespace pc {
@@ -447,6 +450,45 @@ GRT_HD void synchemis_eval(double nu, double n, double B, double T, double *e) {
   double jnu = 4.43e-30 / 2.0 * nu * n * ipx / (thetae * thetae);
   e[0] = jnu;
   e[4] = (fabs(jnu) > 0.) ? jnu / planck_bnu(T, nu) : 0.0;
+}
+
+// synchbinemis (polsynchemis.f90:1036-1150): unpolarised synchrotron emission / absorption of electrons given as dn/dgamma
+// in logarithmic bins of Lorentz factor.  fx / k53x are the reference's fits to F(x) = x int_x^inf K_5/3 and to K_5/3(x)
+// (:1104-1148; single-precision literals 1./3., -5./3., 1.e-6 promoted as gfortran does).  nb[b] = dn/dgamma of bin b,
+// bins[0..nbin) = bin centres, bins[nbin..2 nbin) = bin widths (emis_model_bins, emis.f90:884-908, built on the host).
+GRT_HD double bins_fx(double x) {
+  if (x >= 1000.) return 0.0;
+  const double third = (double)(1.f / 3.f);
+  const double sx = sqrt(x), cx = pow(x, third);
+  const double d1 = exp(-0.97947838884478688 * x + -0.83333239129525072 * sx + 0.15541796026816246 * cx);
+  const double d2 = 1. - exp(-0.0469247165562628882 * x + -0.7005501805646288 * sx + 0.0103876297841949544 * cx);
+  return 2.149528241534479 * cx * d1 + 1.2533141373155 * sx * exp(-x) * d2;
+}
+GRT_HD double bins_k53x(double x) {
+  if (x >= 1000.) return 0.0;
+  if (x <= (double)1.e-6f) return 6.7e16;
+  const double third = (double)(1.f / 3.f);
+  const double sx = sqrt(x);
+  const double d1 = exp(-1.0194198041210243 * x + 0.28011396300530672 * sx + -0.0771058491739234908 * pow(x, third));
+  const double d2 = 1. - exp(-15.761577796582387 * x);
+  return 1.433018827689652 * pow(x, (double)(-5.f / 3.f)) * d1 + 1.2533141373155 / sx * exp(-x) * d2;
+}
+GRT_HDN void bins_eval(double nu, double B, double theta, const double *nb, int nbin, const double *bins, double *e) {
+  for (int i = 0; i < 11; i++) e[i] = 0.0;
+  const double s3 = (double)sqrtf(3.f), s33 = (double)(3.f * sqrtf(3.f));  // sqrt(3.), 3.*sqrt(3.) are real(4) expressions
+  const double sth = sin(theta);
+  const double prefj = s3 * (pc::e * pc::e * pc::e) * fabs(B) * sth / (4. * (GRT_PI * GRT_PI) * pc::m * (pc::c * pc::c));
+  const double prefa = (fabs(B) > 0.) ? 4. * GRT_PI * pc::e / (s33 * fabs(B) * sth) : 0.0;
+  const double nup = (3.0 * pc::e * B * sth) / (4. * GRT_PI * pc::m * pc::c);
+  double sj = 0.0, sa = 0.0;
+  for (int b = 0; b < nbin; b++) {
+    const double gam = bins[b], dg = bins[nbin + b], g2 = gam * gam;
+    const double xm = nu / (nup * g2);
+    sj += bins_fx(xm) * nb[b] * dg;
+    sa += bins_k53x(xm) * nb[b] * dg / (g2 * g2 * gam);
+  }
+  e[0] = prefj * sj;
+  e[4] = prefa * sa;
 }
 
 // free-free emission / absorption (brememisHEROIC, emis.f90:188-238); literals without d0 are single precision there

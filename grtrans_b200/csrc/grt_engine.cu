@@ -257,6 +257,11 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
   s->ncams = a->nmdot * a->nfreq * a->nmu * a->nt;
   s->npix = a->nn[0] * a->nn[1];
   int rcio = grt_host::load_fluid(s->fh, *a);
+  // BINS / HYBRIDTHBINS need a fluid model that carries electron bins (KORALNTH), at most GRT_MAXBINS of them, and run one
+  // frame (the movie path re-reads cells only)
+  if (rcio == GRT_OK && (etype == EM_BINS || etype == EM_HYBRIDTHBINS) &&
+      (s->fh.nrelbin < 1 || s->fh.nrelbin > GRT_MAXBINS || a->nt > 1))
+    rcio = GRT_ERR_BAD_ARG;
   if (rcio != GRT_OK) {
     delete s;
     return rcio;
@@ -369,6 +374,8 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
       SCK(cudaMemcpy(dc, s->fh.cells.data(), s->fh.cells.size() * sizeof(Cell), cudaMemcpyHostToDevice));
     F.cells = dc;
   }
+  SCK(own_h2d(s, &F.nth, s->fh.nth));
+  F.nrelbin = s->fh.nrelbin;
   // emissivity tables
   grt_host::EmisTablesHost th;
   grt_host::build_emis_tables(th);
@@ -408,6 +415,14 @@ extern "C" int grt_session_create(const grt_args *a, int device, int rank, int n
     s->fk.ncomp = nw;
     s->tp.ncomp = nw;
     s->tp.isel = (etype == EM_MAXCOMP) ? (int)a->epotherargs[1] : 0;
+  }
+  s->tp.nbins = 0; s->tp.bins = nullptr;
+  if (etype == EM_BINS || etype == EM_HYBRIDTHBINS) {
+    const int nb = s->fh.nrelbin;
+    std::vector<double> bins;
+    grt_host::emis_model_bins((double)s->fh.relgammamin, (double)s->fh.relgammamax, nb, bins);
+    SCK(own_h2d(s, &s->tp.bins, bins));
+    s->tp.nbins = nb;
   }
   for (int m = 0; m < s->nparams; m++) {
     SourceDev &sp = s->fk.sp[m];

@@ -41,6 +41,9 @@ struct FluidDev {
   // koral / koral3d MKS3 grid (fluid_model_koral.f90:11-29) and trust region in x2 (minpolecell cells at each pole)
   float kh, kr0, kaa, kbb, kpp, x2mintrust, x2maxtrust;
   int ktype;
+  // KORALNTH (fluid_model_koral.f90:16-30): dn/dgamma of the non-thermal electrons, [ncell][nrelbin] real(4) (else nullptr / 0)
+  const float *nth;
+  int nrelbin;
   // SPHACC tables
   const float *uvals, *vvals, *uv, *tvals;  // 498, 498, 461 (=1/rvals), 461
 };

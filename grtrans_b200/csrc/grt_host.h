@@ -31,6 +31,10 @@ struct FluidHost {
   int is_mmks = 0, eheat = 0;
   float kh = 0, kr0 = 0, kaa = 0, kbb = 0, kpp = 0, x2mintrust = 0, x2maxtrust = 0;  // koral MKS3 grid (fluid_model_koral.f90)
   int ktype = 0;
+  // KORALNTH (fluid_model_koral.f90:16-30, 318-326): non-thermal electron bins nth_arr(cell, bin), real(4)
+  int nrelbin = 0;
+  float relgammamin = 1.f, relgammamax = 1.f;
+  std::vector<float> nth;  // [ncell][nrelbin]
   std::vector<float> ax1, axr, ax2, axth, ax3;
   std::vector<HostCell> cells;  // [nslots][ncell]
   std::vector<float> uvals, vvals, uv, tvals;
@@ -59,6 +63,8 @@ struct EmisTablesHost {
   int far_n = 0;
 };
 void build_emis_tables(EmisTablesHost &t);
+// emis_model_bins (emis.f90:884-908): bins[0..nb) = centres, bins[nb..2nb) = widths of nb logarithmic Lorentz-factor bins
+void emis_model_bins(double relgammamin, double relgammamax, int nb, std::vector<double> &bins);
 
 int fluid_model_id(const std::string &fname);                 // fluid.f90:283-377 (supported subset)
 int emis_type_id(const std::string &ename, int *neq);         // emis.f90:294-367

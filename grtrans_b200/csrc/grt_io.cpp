@@ -92,10 +92,27 @@ int fluid_model_id(const std::string &f) {
   if (f == "FFJET") return 13;
   if (f == "HARM3D") return 19;
   if (f == "IHARM") return 29;
-  if (f == "KORAL") return 22;
+  if (f == "KORAL" || f == "KORALNTH") return 22;  // KORALNTH: f%model = KORAL + the non-thermal bins (fluid.f90:343-349)
   if (f == "KORAL3D") return 25;
   if (f == "KORAL3D_DISK") return 26;
   return -1;
+}
+// emis_model_bins (emis.f90:884-908): logarithmic bin edges between the real(4) limits of the fluid module; centres =
+// geometric means of the edges (built by repeated multiplication, as written), widths = edge differences, the last one
+// closing exactly on relgammamax
+void emis_model_bins(double gmn, double gmx, int nb, std::vector<double> &bins) {
+  bins.assign(2 * (size_t)std::max(nb, 0), 0.0);
+  if (nb < 1) return;
+  std::vector<double> edges(nb + 1);
+  const double logbinspace = (std::log(gmx) - std::log(gmn)) / (double)(float)nb, binspace = std::exp(logbinspace);
+  edges[0] = gmn;
+  bins[0] = std::exp(std::log(gmn) + 0.5 * logbinspace);
+  for (int i = 1; i < nb; i++) {
+    edges[i] = edges[i - 1] * binspace;
+    bins[i] = bins[i - 1] * binspace;
+    bins[nb + i - 1] = edges[i] - edges[i - 1];
+  }
+  bins[2 * nb - 1] = gmx - edges[nb - 1];
 }
 int emis_type_id(const std::string &e, int *neq) {
   struct {
@@ -103,7 +120,8 @@ int emis_type_id(const std::string &e, int *neq) {
     int t, q;
   } tab[] = {{"POLSYNCHTH", 2, 4}, {"SYNCHPL", 3, 1}, {"POLSYNCHPL", 4, 4}, {"BB", 8, 1}, {"BBPOL", 9, 4}, {"SYNCHTHAV", 13, 1},
              {"HYBRIDTHPL", 20, 4}, {"HYBRIDTH", 21, 4}, {"HYBRIDPL", 22, 4},
-             {"BREMS", 5, 1}, {"SYNCHTHAVNOABS", 14, 1}, {"SYNCHTHBREMS", 27, 1}, {"POLSYNCHSYMTH", 15, 4}, {"MAXJUTT", 23, 4}, {"MAXCOMP", 24, 4}, {"RHO", 12, 1}};
+             {"BREMS", 5, 1}, {"SYNCHTHAVNOABS", 14, 1}, {"SYNCHTHBREMS", 27, 1}, {"POLSYNCHSYMTH", 15, 4}, {"MAXJUTT", 23, 4}, {"MAXCOMP", 24, 4}, {"RHO", 12, 1},
+             {"BINS", 25, 1}, {"HYBRIDTHBINS", 26, 1}};
   for (auto &x : tab)
     if (e == x.n) {
       *neq = x.q;
@@ -534,6 +552,14 @@ int load_koral(FluidHost &f, const grt_args &a) {
   f.kr0 = (float)header[5 + o]; f.kh = (float)header[6 + o]; f.kaa = (float)header[7 + o]; f.kbb = (float)header[8 + o];
   f.kpp = (float)header[9 + o];
   f.ktype = (f.model == 26) ? 1 : 0;
+  const bool doingnth = std::string(a.fname) == "KORALNTH";
+  if (doingnth) {  // second header line: nrelbin, relgammamin, relgammamax (fluid_model_koral.f90:318-326)
+    double h2[3];
+    for (int i = 0; i < 3; i++)
+      if (!(hf >> h2[i])) return GRT_ERR_IO;
+    f.nrelbin = (int)h2[0]; f.relgammamin = (float)h2[1]; f.relgammamax = (float)h2[2];
+    if (f.nrelbin < 1) return GRT_ERR_IO;
+  }
   if (f.nx1 < 2 || f.nx2 < 8 || (d3 && f.nx3 < 2)) return GRT_ERR_IO;
   if (std::fabs(f.asim - (float)a.spin) > 1e-4f) return GRT_ERR_BAD_ARG;
   char append[16];
@@ -541,12 +567,18 @@ int load_koral(FluidHost &f, const grt_args &a) {
   std::ifstream df(std::string(a.fdfile) + append);
   if (!df) return GRT_ERR_IO;
   double tmp;
-  for (int i = 0; i < nhead; i++) {
+  for (int i = 0; i < nhead + (doingnth ? 3 : 0); i++) {
     if (!(df >> tmp)) return GRT_ERR_IO;
     if (i == 0) f.tcur = tmp;  // tcur=header(1)
   }
   const size_t n = (size_t)f.nx1 * f.nx2 * f.nx3;
-  const int dlen = d3 ? 23 : 38, rhopos = 10, vpos = 12, bpos = d3 ? 16 : 25, ppos = d3 ? 21 : 33, gridpos = 4, bepos = 22;
+  // (sic) KORALNTH rows hold 41 + nrelbin numbers and bin ie is read from column nthpos + ie - 1 with nthpos = 43
+  // (fluid_model_koral.f90:345-355, 400): the last bin lies one element past the row, which in the column-major
+  // data(dlen, nx2) block is the first column of the next row of the block (past the allocation for the block's last row:
+  // undefined in the reference, 0 here)
+  const int nthpos = 43;
+  if (doingnth) f.nth.assign(n * (size_t)f.nrelbin, 0.f);
+  const int dlen = d3 ? 23 : (doingnth ? 41 + f.nrelbin : 38), rhopos = 10, vpos = 12, bpos = d3 ? 16 : 25, ppos = d3 ? 21 : 33, gridpos = 4, bepos = 22;
   const double scalefac = a.fscalefac, sq = std::sqrt(scalefac);
   std::vector<double> row(dlen);
   std::vector<float> x1(n), x2(n), x3(n);
@@ -579,6 +611,13 @@ int load_koral(FluidHost &f, const grt_args &a) {
     c.u0 = (float)u[0];
     c.vrl = vrl; c.vtl = vtl; c.vpl = vpl;
     c.kela = 0.f;
+    if (doingnth) {
+      for (int ie = 0; ie < f.nrelbin; ie++) {
+        const int col = nthpos + ie;  // 1-based
+        if (col <= dlen) f.nth[i * (size_t)f.nrelbin + ie] = (float)(row[col - 1] * scalefac);
+      }
+      if (i > 0 && (i % (size_t)f.nx2) != 0) f.nth[(i - 1) * (size_t)f.nrelbin + (f.nrelbin - 1)] = (float)(row[0] * scalefac);
+    }
   }
   f.ax1.resize(f.nx1); f.axr.resize(f.nx1); f.ax2.resize(f.nx2); f.axth.assign(f.nx2, 0.f); f.ax3.assign(std::max(f.nx3, 2), 0.f);
   for (int i = 0; i < f.nx2; i++) f.ax2[i] = x2[i];
@@ -632,6 +671,7 @@ int load_fluid(FluidHost &f, const grt_args &a) {
   if (has_time_axis(f.model) && a.fnt > 1) {
     // iharm: t(k) is the header file's time for every slot, so tstep = 0 and the slot index is undefined in the reference
     if (f.model == 29) return GRT_ERR_BAD_ARG;
+    if (f.nrelbin > 0) return GRT_ERR_BAD_ARG;  // KORALNTH: one dump resident
     f.nslots = a.fnt;
     f.tdump.assign(a.fnt, 0.0);
     f.cells.resize(f.ncell * (size_t)a.fnt);

@@ -53,7 +53,7 @@ static void launch_extra_e(int mode, unsigned grid, cudaStream_t st, const RayMe
 #undef GRT_LAUNCH
 }
 
-// The 45 instantiations are split over three objects (-DGRT_EXTRA_PART=0/1/2) so that the build compiles them in parallel.
+// The 60 instantiations are split over three objects (-DGRT_EXTRA_PART=0/1/2) so that the build compiles them in parallel.
 #ifndef GRT_EXTRA_PART
 #error "compile with -DGRT_EXTRA_PART=0, 1 or 2"
 #endif
@@ -64,7 +64,7 @@ static void launch_extra_e(int mode, unsigned grid, cudaStream_t st, const RayMe
 #define GRT_PART_ETYPES(OP) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_HYBRIDPL) OP(EM_MAXJUTT)
 #define GRT_PART_NAME launch_extra_part1
 #else
-#define GRT_PART_ETYPES(OP) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_POLSYNCHSYMTH)
+#define GRT_PART_ETYPES(OP) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_POLSYNCHSYMTH) OP(EM_BINS)
 #define GRT_PART_NAME launch_extra_part2
 #endif
 

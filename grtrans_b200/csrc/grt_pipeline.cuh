@@ -86,6 +86,53 @@ GRT_HDN void maxjutt_record(double *q, const FluidKernelArgs &A, int mm, const C
   }
 }
 
+// BINS / HYBRIDTHBINS on KORALNTH (fluid_model_koral.f90:262-270, fluid.f90:1149-1151): the non-thermal electron spectrum of
+// the point, dn/dgamma per bin, bilinear in (theta, r) between the four cells koral_vals uses for every other field.  Kept
+// out of line and written in place (the record is larger than the staging array of the common models); it repeats the
+// cell location of fluid_sample's FL_KORAL branch (2-D only) instead of carrying indices and weights through the common path.
+GRT_HDN void bins_record(double *q, const FluidKernelArgs &A, const CgsVars &cg, const OrthoOut &oo, double lam, double a_,
+                         double rr, double thh) {
+  const FluidDev &F = A.F;
+  q[0] = lam; q[1] = oo.g; q[2] = oo.s2xi; q[3] = oo.c2xi;
+  q[4] = cg.ncgs; q[5] = cg.bcgs; q[6] = cg.tcgs; q[7] = oo.ang;
+  for (int i = 8; i < 12; i++) q[i] = 0.0;
+  const int nx1 = F.nx1, nx2 = F.nx2;
+  const float a = (float)a_;
+  float theta = (float)thh, zr = (float)rr;
+  float x1 = (float)log((double)zr - (double)F.kr0);
+  float x2 = koral_x2_of_theta(theta, zr, F.kh, F.kaa, F.kbb, F.kpp);
+  int lx1 = (int)floorf((x1 - F.ax1[0]) / (F.ax1[nx1 - 1] - F.ax1[0]) * (float)(nx1 - 1)) + 1;
+  int ux1 = lx1 + 1;
+  lx1 = (lx1 >= 1) ? lx1 : 1;
+  ux1 = (ux1 <= nx1) ? ux1 : nx1;
+  lx1 = lx1 > nx1 ? nx1 : lx1;
+  ux1 = ux1 < 1 ? 1 : ux1;
+  int lx2 = (int)floorf((x2 - F.ax2[0]) / (F.ax2[nx2 - 1] - F.ax2[0]) * (float)(nx2 - 1)) + 1;
+  int ux2 = lx2 + 1;
+  lx2 = (lx2 >= 1) ? lx2 : 1;
+  ux2 = (ux2 <= nx2) ? ux2 : nx2;
+  lx2 = lx2 > nx2 ? nx2 : lx2;
+  ux2 = ux2 < 1 ? 1 : ux2;
+  float rd = (zr - F.axr[lx1 - 1]) / (F.axr[ux1 - 1] - F.axr[lx1 - 1]);
+  float rh = 1.f + sqrtf(1.f - a * a);
+  if (F.axr[lx1 - 1] <= rh || lx1 == 1) rd = 1.f;
+  float thl = koral_theta_of_x2(F.ax2[lx2 - 1], F.axr[lx1 - 1], F.kh, F.kaa, F.kbb, F.kpp);
+  float thu = koral_theta_of_x2(F.ax2[ux2 - 1], F.axr[lx1 - 1], F.kh, F.kaa, F.kbb, F.kpp);
+  float thone = koral_theta_of_x2(F.ax2[0], F.axr[lx1 - 1], F.kh, F.kaa, F.kbb, F.kpp);
+  float td = (ux2 != lx2) ? fabsf((theta - thl) / (thu - thl)) : fabsf((theta - thl) / thone);
+  const size_t nb = (size_t)F.nrelbin;
+  const float *c0 = F.nth + ((size_t)(lx1 - 1) * nx2 + (lx2 - 1)) * nb, *c1 = F.nth + ((size_t)(lx1 - 1) * nx2 + (ux2 - 1)) * nb,
+              *c2 = F.nth + ((size_t)(ux1 - 1) * nx2 + (lx2 - 1)) * nb, *c3 = F.nth + ((size_t)(ux1 - 1) * nx2 + (ux2 - 1)) * nb;
+  // masked below the inner edge and (sic) below the first trusted polar cell only (x2 > x2mintrust, no upper bound)
+  const bool keep = (x1 > F.ax1[0]) && (x2 > F.x2mintrust);
+  for (int ie = 0; ie < F.nrelbin; ie++) {
+    float i1 = c0[ie] * (1.f - td) + c1[ie] * td, i2 = c2[ie] * (1.f - td) + c3[ie] * td;
+    float w1 = i1 * (1.f - rd) + i2 * rd;
+    float v = w1 * (1.f - 0.f) + w1 * 0.f;
+    q[12 + ie] = keep ? (double)v : 0.0;
+  }
+}
+
 // extra = 1: the second per-point record (kept out of line: the common path must not pay registers for it)
 GRT_HDN void point_xrec(double *x, int npts, const RayConst &r0, double r, double th, double ph, const double *k4,
                         const FluidSample &fs, const OrthoOut &oo, const CgsVars &cg) {
@@ -140,8 +187,11 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
     to_cgs(A.F.model, A.sp[mm], fs.rho, fs.p, fs.bmag, fs.kela, fs.be, A.F.gam, cg);
     const int nrec = record_doubles(A.etype);
     double *q = rec + ((size_t)mm * nrays * maxpts + dst) * nrec;
-    if (em_slot(A.etype) == EM_MAXJUTT) {  // (out of line, written in place: the record is larger than the staging array)
-      maxjutt_record(q, A, mm, cg, oo, lam);
+    if (em_slot(A.etype) == EM_MAXJUTT || em_slot(A.etype) == EM_BINS) {  // (out of line, written in place: the record is larger than the staging array)
+      if (em_slot(A.etype) == EM_MAXJUTT)
+        maxjutt_record(q, A, mm, cg, oo, lam);
+      else
+        bins_record(q, A, cg, oo, lam, r0.a, r, th);
       if (A.xrec) point_xrec(A.xrec + ((size_t)mm * nrays * maxpts + dst) * 8, m.npts, r0, r, th, ph, k4, fs, oo, cg);
       if (mm == 0 && sd.ncgs) {
         sd.ncgs[dst] = cg.ncgs; sd.ncgsnth[dst] = cg.ncgsnth; sd.bcgs[dst] = cg.bcgs; sd.tcgs[dst] = cg.tcgs;

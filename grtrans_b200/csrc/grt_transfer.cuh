@@ -27,7 +27,8 @@ namespace grt {
 GRT_HD constexpr bool em_is_hybrid(int et) { return et == EM_HYBRIDTHPL || et == EM_HYBRIDTH || et == EM_HYBRIDPL; }
 GRT_HD constexpr int record_doubles(int etype) {  // (same for every em_slot member)
   return em_is_hybrid(etype) ? GRT_NREC_MAX
-                             : ((etype == EM_MAXJUTT || etype == EM_MAXCOMP) ? 4 + 10 * GRT_MAXJUTT_NCOMP + 2 : GRT_NREC);
+                             : ((etype == EM_MAXJUTT || etype == EM_MAXCOMP) ? 4 + 10 * GRT_MAXJUTT_NCOMP + 2
+                                : ((etype == EM_BINS || etype == EM_HYBRIDTHBINS) ? 12 + GRT_MAXBINS : GRT_NREC));
 }
 // record layout: [0] lambda, [1] g (redshift), [2] sin 2xi, [3] cos 2xi, [4..] emissivity-model inputs:
 //   POLSYNCHTH        [4..13] ThermalPoint (xp13, AI, AV, hkT_g, log Ax, RQ, RV0, RV1, 1/xp13, xp13^-1.5)
@@ -37,6 +38,7 @@ GRT_HD constexpr int record_doubles(int etype) {  // (same for every em_slot mem
 //   SYNCHTHAV         [4] n, [5] B, [6] T          BB [6] T          BBPOL [6] T, [7] I(mu), [8] delta(mu)
 //   POLSYNCHSYMTH     [4..14] SymPoint (Xs, A, S, cq, v0, v1, T, log Ax, RQ, RV0, RV1)
 //   MAXJUTT/MAXCOMP   [4 + 10 c ..] ThermalPoint of component c < ncomp <= 7 (76-double record)
+//   BINS/HYBRIDTHBINS [4] n, [5] B, [6] T, [7] field angle, [12 + b] dn/dgamma of bin b < nbins <= 64 (76-double record)
 
 // integration modes (rad_trans.f90:30-38 iflag x neq)
 enum { MODE_RK4 = 0, MODE_DELO = 1, MODE_FORMAL = 2, MODE_QUAD = 3, MODE_RK1 = 4 };
@@ -49,6 +51,8 @@ struct TransferParams {
   int maxsteps;
   int stail;  // stype = 'tail': the power law's gmin-dependent constants come from the point record
   int ncomp, isel;  // MAXJUTT / MAXCOMP: thermal components in the record; MAXCOMP: component whose emission is kept (0: all)
+  int nbins;           // BINS / HYBRIDTHBINS: Lorentz-factor bins in the record
+  const double *bins;  // [2 nbins] bin centres, bin widths (emis_model_bins, emis.f90:884-908)
   EmisTables tab;
 };
 
@@ -164,6 +168,14 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
       Q.Xs = rec[4]; Q.A = rec[5]; Q.S = rec[6]; Q.cq = rec[7]; Q.v0 = rec[8]; Q.v1 = rec[9]; Q.T = rec[10]; Q.lAx = rec[11];
       Q.RQ = rec[12]; Q.RV0 = rec[13]; Q.RV1 = rec[14];
       sym_eval(Q, nu, P.tab, e);
+    }
+    else if (ET == EM_BINS) {  // emis.f90:520-526
+      bins_eval(nu, rec[5], rec[7], rec + 12, P.nbins, P.bins, e);
+      if (P.etype == EM_HYBRIDTHBINS) {
+        double et[11];
+        synchemis_eval(nu, rec[4], rec[5], rec[6], et);
+        for (int i = 0; i < 11; i++) e[i] = et[i] + e[i];
+      }
     }
     else if (ET == EM_SYNCHTHAV) {  // the (n, B, T) scalar models: emis.f90:525-540
       if (P.etype == EM_BREMS) {
@@ -654,7 +666,7 @@ GRT_HD void ray_extra_t(const TransferParams &P, const double *rec, const double
 // runtime dispatcher (host emulator / generic callers); the CUDA kernels are instantiated per (ET, MODE) directly
 #define GRT_FOR_ETYPES(OP) \
   OP(EM_POLSYNCHTH) OP(EM_POLSYNCHPL) OP(EM_SYNCHPL) OP(EM_SYNCHTHAV) OP(EM_BB) OP(EM_BBPOL) OP(EM_HYBRIDTHPL) OP(EM_HYBRIDTH) OP(EM_HYBRIDPL) \
-  OP(EM_POLSYNCHSYMTH) OP(EM_MAXJUTT)
+  OP(EM_POLSYNCHSYMTH) OP(EM_MAXJUTT) OP(EM_BINS)
 template <int ET>
 GRT_HD void ray_transfer_e(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out) {
   switch (transfer_mode(P)) {

@@ -84,6 +84,14 @@ void orc_polsynchpl(int n, const double *nu, const double *nnth, const double *b
 void orc_synchemis(int n, const double *nu, const double *nc, const double *b, const double *t, double *e) {
   for (int i = 0; i < n; i++) synchemis(nu[i], nc[i], b[i], t[i], e + 11 * i);
 }
+// synchbinemis with the bins of emis_model_bins: n[npt][nbin] electrons per unit gamma
+void orc_synchbinemis(int npt, const double *nu, const double *n, int nbin, double gmin, double gmax, const double *b,
+                      const double *th, double *e, double *gammas, double *dgammas) {
+  std::vector<double> g, dg;
+  emis_model_bins(gmin, gmax, nbin, g, dg);
+  for (int i = 0; i < nbin; i++) { gammas[i] = g[i]; dgammas[i] = dg[i]; }
+  for (int i = 0; i < npt; i++) synchbinemis(nu[i], n + (size_t)i * nbin, nbin, b[i], th[i], g.data(), dg.data(), e + 11 * i);
+}
 
 // one ray: intensity[npts][neq]; returns nptsout
 int orc_rt_integrate(int iflag, int neq, int npts, const double *s, const double *j, const double *K, const double *tau,

@@ -205,6 +205,13 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
       dump->ncgs = w.ncgs; dump->ncgsnth = w.ncgsnth; dump->bcgs = w.bcgs; dump->tcgs = w.tcgs;
     }
     std::fill(w.eK.begin(), w.eK.end(), 0.0);
+    // BINS / HYBRIDTHBINS: bin centres and widths (emis_model_bins, emis.f90:884-908; the limits travel through the real(4)
+    // module variables of fluid.f90:45-46).  Fluid models without bins have nrelbin = 0: the sums are empty.
+    std::vector<double> bin_g, bin_dg, bin_n;
+    if (etype == E_BINS || etype == E_HYBRIDTHBINS) {
+      emis_model_bins((double)(float)fd.relgammamin, (double)(float)fd.relgammamax, fd.nrelbin, bin_g, bin_dg);
+      bin_n.assign(std::max(1, fd.nrelbin), 0.0);
+    }
     for (int k = 0; k < nfreq; k++) {
       // ---- calc_emissivity (emis.f90:461-571)
       for (int p = 0; p < npts; p++) {
@@ -244,6 +251,16 @@ static void drive_ray(const RunArgs &A, const FluidData &fd, const GeokerrArgs &
             synchemis(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], K11);
             brememis(nu, w.ncgs[p], w.tcgs[p], Kbr);
             for (int c = 0; c < 11; c++) K11[c] += Kbr[c];
+          } break;
+          case E_BINS:
+          case E_HYBRIDTHBINS: {  // emis.f90:520-526: binned non-thermal electrons (+ angle-averaged thermal synchrotron)
+            for (int b = 0; b < fd.nrelbin; b++) bin_n[b] = (b < (int)w.f[p].nnth.size()) ? (double)w.f[p].nnth[b] : 0.0;
+            synchbinemis(nu, bin_n.data(), fd.nrelbin, w.bcgs[p], w.ang[p], bin_g.data(), bin_dg.data(), K11);
+            if (etype == E_HYBRIDTHBINS) {
+              double Kth[11];
+              synchemis(nu, w.ncgs[p], w.bcgs[p], w.tcgs[p], Kth);
+              for (int c = 0; c < 11; c++) K11[c] += Kth[c];
+            }
           } break;
           case E_BB: K11[0] = bnu(w.tcgs[p], nu); break;
           case E_BBPOL: {

@@ -876,6 +876,16 @@ static void koral_vals(const FluidData &fd, const Geo &g, std::vector<FluidPt> &
     p.b[3] = ok ? gat(fd.bph_arr) : 1.f;
     p.u[0] = ok ? (double)gat(fd.u0_arr) : 1.0;
     float vpl0 = ok ? gat(fd.vpl_arr) : 0.f;
+    if (fd.doingnth) {  // fluid_model_koral.f90:262-270: masked below the inner edge and (sic) at the first pole only
+      p.nnth.assign(fd.nrelbin, 0.f);
+      for (int ie = 0; ie < fd.nrelbin; ie++) {
+        float v[8];
+        for (int q = 0; q < 4; q++) v[q] = v[4 + q] = fd.nth_arr[idx[q] * (size_t)fd.nrelbin + ie];
+        float nt_ = trilin(v, 0.f, rd, td);
+        nt_ = in ? nt_ : 0.f;
+        p.nnth[ie] = (x2 > x2mintrust) ? nt_ : 0.f;
+      }
+    }
     finish_grid_point(p, zr, (float)g.x[i].d[2], a, vrl0, vtl0, vpl0, 1.0);
   }
 }
@@ -896,18 +906,33 @@ static bool load_koral(FluidData &fd, const FluidArgs &fa, double a) {
   fd.kr0 = (float)header[5 + o]; fd.kh = (float)header[6 + o]; fd.kaa = (float)header[7 + o]; fd.kbb = (float)header[8 + o];
   fd.kpp = (float)header[9 + o];
   fd.scalefac = fa.scalefac;
+  if (fd.doingnth) {  // second header line: nrelbin, relgammamin, relgammamax (fluid_model_koral.f90:318-326)
+    double h2[3];
+    for (int i = 0; i < 3; i++)
+      if (!(hf >> h2[i])) return false;
+    fd.nrelbin = (int)h2[0]; fd.relgammamin = h2[1]; fd.relgammamax = h2[2];
+    if (fd.nrelbin < 1) return false;
+  }
   if (std::fabs(fd.asim - (float)a) > 1e-4f) return false;
   char append[16];
   snprintf(append, sizeof append, d3 ? "%04d" : "%03d", fa.indf);
   std::ifstream df(fa.dfile + append);
   if (!df) return false;
   double tmp;
-  for (int i = 0; i < nhead; i++) {
+  for (int i = 0; i < nhead + (fd.doingnth ? 3 : 0); i++) {
     if (!(df >> tmp)) return false;
     if (i == 0) fd.tcur = tmp;  // tcur=header(1)
   }
   size_t n = (size_t)fd.nx1 * fd.nx2 * fd.nx3;
-  int dlen = d3 ? 23 : 38;
+  int dlen = d3 ? 23 : (fd.nrelbin > 0 ? 41 + fd.nrelbin : 38);
+  // (sic) nthpos = 43 with rows of dlen = 41 + nrelbin numbers (fluid_model_koral.f90:345-355, 400): bin ie is read from
+  // column 42 + ie, so bin nrelbin comes from column dlen + 1 -- in the column-major data(dlen, nx2) block that is column 1
+  // of the NEXT row of the block.  For the last row of a block it lies one element past the allocation (undefined in
+  // the reference); 0 is used there.
+  const int nthpos = 43;
+  if (fd.doingnth) fd.nth_arr.assign(n * (size_t)fd.nrelbin, 0.f);
+  std::vector<double> prevrow;
+  size_t prev_i = 0;
   int rhopos = 10, vpos = 12, bpos = d3 ? 16 : 25, ppos = d3 ? 21 : 33, gridpos = 4, bepos = 22;
   fd.x1_arr.resize(n); fd.x2_arr.resize(n); fd.x3_arr.resize(n); fd.r_arr.resize(n); fd.th_arr.resize(n); fd.ph_arr.resize(n);
   fd.rho_arr.resize(n); fd.p_arr.resize(n); fd.u0_arr.resize(n); fd.vrl_arr.resize(n); fd.vtl_arr.resize(n);
@@ -936,6 +961,17 @@ static bool load_koral(FluidData &fd, const FluidArgs &fa, double a) {
     fd.bph_arr[i] = (float)(b[3] * sq);
     fd.u0_arr[i] = (float)u[0];
     fd.vrl_arr[i] = vrl; fd.vtl_arr[i] = vtl; fd.vpl_arr[i] = vpl;
+    if (fd.doingnth) {
+      for (int ie = 0; ie < fd.nrelbin; ie++) {
+        const int col = nthpos + ie;  // 1-based column of the row
+        if (col <= dlen) fd.nth_arr[i * (size_t)fd.nrelbin + ie] = (float)(row[col - 1] * fd.scalefac);
+      }
+      // the out-of-range last bin of the PREVIOUS row of the same nx2-block is this row's first column
+      if (!prevrow.empty() && (i % (size_t)fd.nx2) != 0)
+        fd.nth_arr[prev_i * (size_t)fd.nrelbin + (fd.nrelbin - 1)] = (float)(row[0] * fd.scalefac);
+      prevrow = row;
+      prev_i = i;
+    }
   }
   return true;
 }
@@ -1117,8 +1153,9 @@ static bool load_fluid_single(FluidData &fd, const std::string &fname, double a,
   } else if (fname == "IHARM") {
     fd.model = F_IHARM;
     fd.ok = load_iharm(fd, fa, a);
-  } else if (fname == "KORAL" || fname == "KORAL3D" || fname == "KORAL3D_DISK") {
-    fd.model = (fname == "KORAL") ? F_KORAL : (fname == "KORAL3D" ? F_KORAL3D : F_KORAL3D_DISK);
+  } else if (fname == "KORAL" || fname == "KORAL3D" || fname == "KORAL3D_DISK" || fname == "KORALNTH") {
+    fd.model = (fname == "KORAL" || fname == "KORALNTH") ? F_KORAL : (fname == "KORAL3D" ? F_KORAL3D : F_KORAL3D_DISK);
+    fd.doingnth = (fname == "KORALNTH");  // fluid.f90:218-220, 343-349: the 2-D koral model with non-thermal electron bins
     fd.ktype = (fname == "KORAL3D_DISK") ? 1 : 0;
     fd.ok = load_koral(fd, fa, a);
   } else {
@@ -1169,6 +1206,7 @@ bool load_fluid_model(FluidData &fd, const std::string &fname, double a, const F
   fd.ncell = fd.rho_arr.size();
   fd.tdump.assign(1, fd.tcur);
   if (has_time_axis(fd.model) && fa.nt > 1) {
+    if (fd.doingnth) return fd.ok = false;  // KORALNTH: one dump resident (the bins have no slot axis here)
     fd.nt = fa.nt;
     fd.tdump.assign(fa.nt, 0.0);
     fd.ok = load_slots(fd, fname, a, fa, fa.nt);

@@ -132,6 +132,11 @@ struct FluidData {  // module-level state of fluid_model_{thindisk,sphacc,ffjet,
   double scalefac = 1.0;
   int ktype = 0, minpolecell = 4;
   std::vector<float> be_arr;
+  // KORALNTH (fluid_model_koral.f90:16-30, 318-326): non-thermal electron bins nth_arr(cell, bin), real(4)
+  bool doingnth = false;
+  int nrelbin = 0;
+  double relgammamin = 1., relgammamax = 1.;
+  std::vector<float> nth_arr;  // [nt][ncell][nrelbin]
   // time axis (fluid_model_harm.f90:13-16,446-546 and the same code in the harm3d / iharm / koral modules): `nt` dump slots of
   // `ncell` cells each, slot k (0-based) = dump file indf-k; tstep / toffset are real(4) module variables (real(8) in iharm)
   size_t ncell = 0;
@@ -146,6 +151,7 @@ struct FluidData {  // module-level state of fluid_model_{thindisk,sphacc,ffjet,
 struct FluidPt {  // one entry of fluid.f90:type fluid
   float rho = 0, p = 0, bmag = 0, kela = 0, be = 0;
   double u[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  std::vector<float> nnth;  // f%nnth(point, 1:nrelbin) (KORALNTH only)
 };
 
 struct SourceParams {  // fluid.f90:69-75
@@ -169,7 +175,8 @@ void harm_transform_and_store(FluidData &fd, const std::vector<double> &rho, con
 // ---------------------------------------------------------------------------------------------
 // emissivities (emis.f90 / polsynchemis.f90)
 enum EmisType { E_SYNCHPL = 3, E_POLSYNCHTH = 2, E_POLSYNCHPL = 4, E_BB = 8, E_BBPOL = 9, E_SYNCHTHAV = 13,
-                E_HYBRIDTHPL = 20, E_HYBRIDTH = 21, E_HYBRIDPL = 22, E_BREMS = 5, E_SYNCHTHAVNOABS = 14, E_SYNCHTHBREMS = 27, E_POLSYNCHSYMTH = 15, E_MAXJUTT = 23, E_MAXCOMP = 24, E_RHO = 12 };
+                E_HYBRIDTHPL = 20, E_HYBRIDTH = 21, E_HYBRIDPL = 22, E_BREMS = 5, E_SYNCHTHAVNOABS = 14, E_SYNCHTHBREMS = 27, E_POLSYNCHSYMTH = 15, E_MAXJUTT = 23, E_MAXCOMP = 24, E_RHO = 12,
+                E_BINS = 25, E_HYBRIDTHBINS = 26 };
 int emis_type_from_name(const std::string &ename, int &neq);
 void polsynchth(double nu, double n, double b, double t, double theta, double *e11);
 void polsynchpl(double nu, double nnth, double b, double th, double p, double gmin, double gmax, double *e11);
@@ -178,6 +185,10 @@ void brememis(double nu, double ne, double T, double *e11);
 void sympolemisth(double nu, double n, double b, double t, double theta, double *e11);
 void maxjutt(double nu, double n, double b, double t, double theta, const double *args, int nargs, bool comp, double *e11);
 void synchemis(double nu, double n, double B, double T, double *e11);
+// synchbinemis (polsynchemis.f90:1036-1150): n[nbin] electrons per bin, bin centres / widths from emis_model_bins
+void synchbinemis(double nu, const double *n, int nbin, double B, double theta, const double *gammas, const double *dgammas,
+                  double *e11);
+void emis_model_bins(double relgammamin, double relgammamax, int nrelbin, std::vector<double> &gammas, std::vector<double> &dgammas);
 double bnu(double T, double nu);
 void interp_chandra_tab24(float mu, float &I, float &del);
 double besselk0(double x);

@@ -113,6 +113,20 @@ def cfg_koral(n=40, nup=100, nfreq=4, iname='delo', threed=True, fname=None, **k
     return d
 
 
+def cfg_koralnth(n=40, nup=100, nfreq=4, iname='delo', ename='HYBRIDTHBINS', nrelbin=12, **kw):
+    """KORALNTH (fluid.f90:218-220, 343-349): the 2-D koral model with non-thermal electrons in nrelbin bins of Lorentz factor,
+    emissivities BINS (bins only) / HYBRIDTHBINS (+ angle-averaged thermal synchrotron), unpolarised (emis.f90:333-337)."""
+    import make_snapshot as ms
+    os.makedirs(SNAPDIR, exist_ok=True)
+    prefix = os.path.join(SNAPDIR, "koralnth%d_" % nrelbin)
+    if not os.path.exists(prefix + "040"):
+        ms.write_koral(prefix, indf=40, threed=False, nrelbin=nrelbin)
+    d = cfg_koral(n=n, nup=nup, nfreq=nfreq, iname=iname, threed=False, fname='KORALNTH', ename=ename, nvals=1)
+    d.update(fdfile=prefix, fhfile=prefix + "header.txt")
+    d.update(kw)
+    return d
+
+
 def cfg_series(kind='harm2d', n=24, nup=100, nfreq=2, fnt=3, nload=1, nt=1, dt=10., **kw):
     """Time axis of the gridded models: dumps 36..46 of a synthetic series (time 10 per dump, the torus moves from dump to
     dump), fnt dumps resident (slow light: each point samples the dump of its own look-back time), nload > 1 = per-pixel

@@ -35,6 +35,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
   F.ax1 = fh.ax1.data(); F.axr = fh.axr.data(); F.ax2 = fh.ax2.data(); F.axth = fh.axth.data(); F.ax3 = fh.ax3.data();
   F.cells = reinterpret_cast<const Cell *>(fh.cells.data());
   F.nslots = fh.nslots; F.ncell = fh.ncell; F.tstep = fh.tstep;
+  F.nth = fh.nth.data(); F.nrelbin = fh.nrelbin;
   F.uvals = fh.uvals.data(); F.vvals = fh.vvals.data(); F.uv = fh.uv.data(); F.tvals = fh.tvals.data();
   TransferParams P;
   memset(&P, 0, sizeof(P));
@@ -72,6 +73,12 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
     }
     fk.ncomp = nw; P.ncomp = nw;
     P.isel = (etype == EM_MAXCOMP) ? (int)a->epotherargs[1] : 0;
+  }
+  std::vector<double> bins;
+  if (etype == EM_BINS || etype == EM_HYBRIDTHBINS) {  // as grt_session_create
+    if (fh.nrelbin < 1 || fh.nrelbin > GRT_MAXBINS) return 3;
+    grt_host::emis_model_bins((double)fh.relgammamin, (double)fh.relgammamax, fh.nrelbin, bins);
+    P.nbins = fh.nrelbin; P.bins = bins.data();
   }
   P.etype = etype; P.eneq = eneq; P.rneq = nv; P.iflag = iflag; P.model = fh.model; P.npts_is_one = (a->nn[2] == 1);
   for (int i = 0; i < 7; i++) P.coefindx[i] = a->epcoefindx[i];

@@ -148,3 +148,14 @@ def synchemis(nu, n, b, t):
     e = np.zeros((arrs[0].size, 11))
     lib().orc_synchemis(C.c_int(arrs[0].size), *[_p(x) for x in arrs], _p(e))
     return e
+
+
+def synchbinemis(nu, nbins, gmin, gmax, b, th):
+    """nbins[npt, nbin] = dn/dgamma per bin.  Returns (e[npt, 11], gammas, dgammas)."""
+    nbins = np.ascontiguousarray(nbins, np.float64)
+    npt, nb = nbins.shape
+    arrs = [np.ascontiguousarray(np.broadcast_to(x, (npt,)), np.float64) for x in (nu, b, th)]
+    e = np.zeros((npt, 11)); g = np.zeros(nb); dg = np.zeros(nb)
+    lib().orc_synchbinemis(C.c_int(npt), _p(arrs[0]), _p(nbins), C.c_int(nb), C.c_double(gmin), C.c_double(gmax), _p(arrs[1]),
+                           _p(arrs[2]), _p(e), _p(g), _p(dg))
+    return e, g, dg

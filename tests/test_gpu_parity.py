@@ -209,6 +209,11 @@ IMAGE_CASES = [
     ("koral", dict(n=50, nup=200, nfreq=4, threed=True), 1e-4),                   # KORAL3D, T_e straight from the dump
     ("koral", dict(n=40, nup=100, nfreq=3, threed=False), 1e-4),                  # KORAL (2-D)
     ("koral", dict(n=40, nup=100, nfreq=3, threed=True, fname='KORAL3D_DISK', gmin=10.), 1e-4),  # Bernoulli cut, R-beta
+    # KORALNTH: non-thermal electrons in Lorentz-factor bins (synchbinemis, polsynchemis.f90:1036-1150; emis.f90:520-526)
+    ("koralnth", dict(n=40, nup=100, nfreq=5, ename='BINS', fmin=1e10, fmax=1e14), 1e-4),
+    ("koralnth", dict(n=40, nup=200, nfreq=5, ename='HYBRIDTHBINS', fmin=1e10, fmax=1e14), 1e-4),
+    ("koralnth", dict(n=32, nup=100, nfreq=3, ename='HYBRIDTHBINS', iname='lsoda', nrelbin=5, fmin=1e10, fmax=1e13), 1e-4),
+    ("koralnth", dict(n=32, nup=100, nfreq=3, ename='BINS', nrelbin=64, fmin=1e10, fmax=1e13), 1e-4),   # GRT_MAXBINS bins
     ("iharm", dict(n=50, nup=200, nfreq=4, mmks=1), 1e-4),                        # FMKS grid, R-beta electrons
     ("iharm", dict(n=50, nup=200, nfreq=4, mmks=0, gmin=-1.), 1e-4),              # MKS grid, electron-entropy T_e
     # (fmin=1e11: at 1e10 Hz nu << nu_c, the polsynchth fits give |j_V| > j_I, the transfer matrix has a growing mode and the
@@ -227,6 +232,7 @@ EXTRA_CASES = [("harm3d", dict(n=40, nup=100, nfreq=3, fmin=2e11, fmax=2e12)),
                ("iharm", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12)),
                ("harm3d", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12, ename='POLSYNCHSYMTH')),
                ("harm3d", dict(n=24, nup=100, nfreq=2, fmin=2e11, fmax=1e12, ename='MAXJUTT', epotherargs=[2., .6, .3, .1])),
+               ("koralnth", dict(n=24, nup=100, nfreq=2, fmin=1e11, fmax=1e12, ename='HYBRIDTHBINS')),
                ("thindisk", dict(n=40, nfreq=3)),                                              # nup = 1: 7 geometric quantities
                ("thindisk", dict(n=32, nfreq=2, ename='BBPOL', nvals=4))]
 

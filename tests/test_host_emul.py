@@ -92,6 +92,10 @@ EMUL_CASES = [
     ("koral", dict(n=24, nup=100, nfreq=3, threed=True)),                                  # KORAL3D, T_e from the dump
     ("koral", dict(n=24, nup=100, nfreq=3, threed=False)),                                 # KORAL (2-D)
     ("koral", dict(n=20, nup=100, nfreq=2, threed=True, fname='KORAL3D_DISK', gmin=10.)),  # Bernoulli cut + R-beta electrons
+    # KORALNTH: non-thermal electrons in Lorentz-factor bins (synchbinemis) [+ angle-averaged thermal synchrotron]
+    ("koralnth", dict(n=20, nup=100, nfreq=4, ename='BINS', fmin=1e10, fmax=1e14)),
+    ("koralnth", dict(n=20, nup=100, nfreq=4, ename='HYBRIDTHBINS', fmin=1e10, fmax=1e14)),
+    ("koralnth", dict(n=16, nup=100, nfreq=3, ename='HYBRIDTHBINS', iname='lsoda', nrelbin=5, fmin=1e10, fmax=1e13)),
 ]
 
 
@@ -122,6 +126,7 @@ EXTRA_CASES = [("harm3d", dict(n=14, nup=100, nfreq=2, fmin=2e11, fmax=1e12)),
                ("harm3d", dict(n=12, nup=100, nfreq=2, fmin=2e11, fmax=1e12, nvals=1)),       # dlp = 0: NaN in 15-19
                ("sphacc", dict(n=14, nfreq=3)),
                ("ffjet", dict(n=14, nfreq=2, iname='formal')),
+               ("koralnth", dict(n=12, nup=100, nfreq=2, fmin=1e11, fmax=1e12, ename='HYBRIDTHBINS')),
                ("thindisk", dict(n=20, nfreq=2)),                                              # nup = 1: 7 geometric quantities
                ("thindisk", dict(n=16, nfreq=2, ename='BBPOL', nvals=4))]
 

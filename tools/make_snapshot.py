@@ -240,12 +240,17 @@ def koral_arrays(threed=True, nx1=48, nx2=40, nx3=16, a=0.9375, h=0.7, r0=0.0, a
                 rho=1e-16 * rho, te=te, be=be, ucon=ks2bl(u), bcon=600. * ks2bl(b))
 
 
-def write_koral(prefix, indf=40, threed=True, time=0.0, **kw):
+def write_koral(prefix, indf=40, threed=True, time=0.0, nrelbin=0, relgammamin=10., relgammamax=1e5, **kw):
     """ASCII dumps read by fluid_model_koral.f90:318-402 (38 columns) / fluid_model_koral3d.f90:397-514 ("shortfile", 23
-    columns): `<prefix>%03d` / `<prefix>%04d` and the header file `<prefix>header.txt`.  Returns (header path, prefix)."""
+    columns): `<prefix>%03d` / `<prefix>%04d` and the header file `<prefix>header.txt`.  Returns (header path, prefix).
+    nrelbin > 0 (2-D only): the KORALNTH layout -- a second header line `nrelbin relgammamin relgammamax` and rows of
+    41 + nrelbin numbers with the non-thermal electron spectrum dn/dgamma of bin ie in column 43 + ie - 1 (1-based; (sic) the
+    reference's nthpos = 43 reads one column to the right of where a 41 + nrelbin row ends, fluid_model_koral.f90:345-355,400,
+    so the last bin comes from the first column of the next row, which is 0 here): a power law gamma^-2.5 whose
+    normalisation follows the magnetisation."""
     d = koral_arrays(threed=threed, **kw)
     n = d['nx1'] * d['nx2'] * d['nx3']
-    dlen = 23 if threed else 38
+    dlen = 23 if threed else (41 + nrelbin if nrelbin > 0 else 38)
     rows = np.zeros((n, dlen))
     rows[:, 3] = d['x1'].ravel(); rows[:, 4] = d['x2'].ravel()
     if threed:
@@ -266,6 +271,22 @@ def write_koral(prefix, indf=40, threed=True, time=0.0, **kw):
         hdr = [time, d['nx1'], d['nx2'], d['a'], 0.0, d['r0'], d['h'], d['aa'], d['bb'], d['pp']]
         path = "%s%03d" % (prefix, indf)
     line = " ".join("%.17g" % v for v in hdr) + "\n"
+    if nrelbin > 0:
+        assert not threed
+        # dn/dgamma [cm^-3 per unit gamma] = f_nth n_e (p-1) gmin^(p-1) gamma^-p with a non-thermal fraction that follows the
+        # magnetisation; bin ie sits in 0-based column 42 + ie (the last one does not fit into the row, see above)
+        edges = relgammamin * (relgammamax / relgammamin) ** (np.arange(nrelbin + 1) / float(nrelbin))
+        gam = np.sqrt(edges[:-1] * edges[1:])
+        ne = d['rho'].ravel() / 1.6726e-24
+        b2 = np.einsum('...i,...i', d['bcon'].reshape(n, 4)[:, 1:], d['bcon'].reshape(n, 4)[:, 1:])
+        fnth = 1.0 * b2 / (b2 + 0.3 * b2.max())
+        pidx = 2.5
+        for ie in range(nrelbin):
+            col = 42 + ie
+            if col < dlen:
+                rows[:, col] = fnth * ne * (pidx - 1.) * relgammamin ** (pidx - 1.) * gam[ie] ** (-pidx)
+        line2 = "%d %.17g %.17g\n" % (nrelbin, relgammamin, relgammamax)
+        line = line + line2
     with open(path, 'w') as f:
         f.write(line)
         np.savetxt(f, rows, fmt="%.9e")
