@@ -1,6 +1,7 @@
 // grtrans_b200 -- emissivity + polarised transfer kernels and the unit-surface kernels.
 //   k_transfer       thread / (ray, mdot, nu)  emissivity + DELO/FORMAL/quadrature/RK march -> float32 Stokes image
 #include <algorithm>
+#include <cstdlib>
 
 #include "grt_kernels.h"
 
@@ -14,7 +15,7 @@ namespace grt {
 #ifndef GRT_TRANSFER_MINB
 #define GRT_TRANSFER_MINB 4
 #endif
-template <int ET, int MODE>
+template <int ET, int MODE, bool STAGE = false>
 __global__ void __launch_bounds__(128, GRT_TRANSFER_MINB) k_transfer(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
                                                   const double *__restrict__ freqs, int nfreq, int nparams, int nrays, int maxpts,
                                                   const double *__restrict__ rec, float *__restrict__ image, long long ray_off,
@@ -31,7 +32,13 @@ __global__ void __launch_bounds__(128, GRT_TRANSFER_MINB) k_transfer(const RayMe
   if (m.status == 1 && m.npts > 0) {
     P.LBH = lbh_m[mm];
     const double *rr = rec + ((size_t)mm * nrays * maxpts + (size_t)ray * maxpts) * record_doubles(ET);
-    ray_transfer_t<ET, MODE>(P, rr, m.npts, freqs[f], out);
+    if (STAGE) {  // (launched only when nfreq is a multiple of 32: the lanes of a warp share ray and mdot)
+      __shared__ __align__(16) double stage[4][GRT_STAGE_DEPTH * record_doubles(ET)];
+      ray_transfer_t<ET, MODE, false, true>(P, rr, m.npts, freqs[f], out, nullptr, 0, nullptr, stage[threadIdx.x >> 5],
+                                            threadIdx.x & 31);
+    } else {
+      ray_transfer_t<ET, MODE>(P, rr, m.npts, freqs[f], out);
+    }
   }
   int cam = cam0 + mm * nfreq + f;
   float *dst = image + ((size_t)cam * nlocal + (ray_off + ray)) * neq;
@@ -39,6 +46,43 @@ __global__ void __launch_bounds__(128, GRT_TRANSFER_MINB) k_transfer(const RayMe
     *reinterpret_cast<float4 *>(dst) = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
   else
     dst[0] = (float)out[0];
+}
+
+// Two frequencies per thread (ray_transfer_delo_nf): thread = (ray, mdot, frequency pair), pair p of a ray = frequencies p and
+// p + ceil(nfreq / 2), pair fastest, so a warp still marches one ray (nfreq = 64: lane l holds frequencies l and l + 32) and
+// the point record stays a broadcast load.  255 registers, two blocks of 128 threads per SM.
+#ifndef GRT_TRANSFER2_MINB
+#define GRT_TRANSFER2_MINB 2
+#endif
+template <int ET>
+__global__ void __launch_bounds__(128, GRT_TRANSFER2_MINB) k_transfer2(const RayMeta *__restrict__ meta, TransferParams P,
+                                                                      const double *__restrict__ lbh_m, const double *__restrict__ freqs,
+                                                                      int nfreq, int nparams, int nrays, int maxpts,
+                                                                      const double *__restrict__ rec, float *__restrict__ image,
+                                                                      long long ray_off, long long nlocal, int cam0) {
+  const int npair = (nfreq + 1) / 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)nrays * nparams * npair;
+  if (idx >= total) return;
+  const int pr = (int)(idx % npair);
+  const int mm = (int)((idx / npair) % nparams);
+  const int ray = (int)(idx / ((long long)npair * nparams));
+  const int f0 = pr, f1 = pr + npair;
+  const bool has1 = f1 < nfreq;
+  RayMeta m = meta[ray];
+  double out[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  if (m.status == 1 && m.npts > 0) {
+    P.LBH = lbh_m[mm];
+    const double *rr = rec + ((size_t)mm * nrays * maxpts + (size_t)ray * maxpts) * GRT_NREC;
+    const double nu[2] = {freqs[f0], freqs[has1 ? f1 : f0]};
+    ray_transfer_delo_nf<ET, 2>(P, rr, m.npts, nu, out);
+  }
+  float *d0 = image + ((size_t)(cam0 + mm * nfreq + f0) * nlocal + (ray_off + ray)) * 4;
+  *reinterpret_cast<float4 *>(d0) = make_float4((float)out[0][0], (float)out[0][1], (float)out[0][2], (float)out[0][3]);
+  if (has1) {
+    float *d1 = image + ((size_t)(cam0 + mm * nfreq + f1) * nlocal + (ray_off + ray)) * 4;
+    *reinterpret_cast<float4 *>(d1) = make_float4((float)out[1][0], (float)out[1][1], (float)out[1][2], (float)out[1][3]);
+  }
 }
 
 // Gather: one block [ncamb][n][nv] of rank r's image (local rays off .. off+n-1) -> the full image
@@ -194,6 +238,20 @@ static void launch_transfer_e(int mode, unsigned grid, cudaStream_t st, const Ra
   const int B = 128;
 #define GRT_LAUNCH(M) \
   k_transfer<ET, M><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0)
+#define GRT_LAUNCH_ST(M) \
+  k_transfer<ET, M, true><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0)
+  // warp-staged records (see stage_issue): every warp must hold 32 frequencies of one ray, and the ring holds records of at
+  // most 64 doubles (GRT_TRANSFER_STAGE=0 switches it off)
+  static const int stage_env = getenv("GRT_TRANSFER_STAGE") ? atoi(getenv("GRT_TRANSFER_STAGE")) : 1;
+  if constexpr (record_doubles(ET) <= 64) {
+    if (stage_env && nfreq % 32 == 0 && (mode == MODE_DELO || mode == MODE_FORMAL)) {
+      if (mode == MODE_DELO)
+        GRT_LAUNCH_ST(MODE_DELO);
+      else
+        GRT_LAUNCH_ST(MODE_FORMAL);
+      return;
+    }
+  }
   switch (mode) {
     case MODE_DELO: GRT_LAUNCH(MODE_DELO); break;
     case MODE_FORMAL: GRT_LAUNCH(MODE_FORMAL); break;
@@ -211,6 +269,14 @@ void launch_transfer(const RayMeta *meta, const TransferParams &P, const double 
   long long tt = (long long)nrays * nparams * nfreq;
   unsigned grid = (unsigned)((tt + B - 1) / B);
   const int mode = transfer_mode(P);
+  // the headline combination marches two frequencies per thread (GRT_TRANSFER_NF=1: one, as every other combination)
+  static const int nf_env = getenv("GRT_TRANSFER_NF") ? atoi(getenv("GRT_TRANSFER_NF")) : 1;
+  if (em_slot(P.etype) == EM_POLSYNCHTH && mode == MODE_DELO && nfreq >= 2 && nf_env == 2) {
+    const long long t2 = (long long)nrays * nparams * ((nfreq + 1) / 2);
+    k_transfer2<EM_POLSYNCHTH><<<(unsigned)((t2 + B - 1) / B), B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec,
+                                                                          image, ray_off, nlocal, cam0);
+    return;
+  }
   switch (em_slot(P.etype)) {
 #define OP(E) \
   case E: launch_transfer_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0); break;

@@ -75,6 +75,35 @@ GRT_HD void prefetch_record(const double *p) {
 #endif
 }
 
+// Record staging (device only): the 32 lanes of a warp march one ray, so the warp streams that ray's records -- 128 / 192
+// contiguous bytes per step -- through a small ring in shared memory with cp.async, GRT_STAGE_DEPTH - 1 steps ahead of
+// their use.  ncu (capture r2_kt_nf1) showed 18 % of the kernel's stall samples on the first uses of the record's 64-bit
+// loads (about 550 cycles per step: the L1 prefetch hint above does not bring the line in time); staged records are there
+// when the step starts and are read with broadcast shared-memory loads.
+#define GRT_STAGE_DEPTH 4
+GRT_HD void stage_issue(double *slot, const double *src, int ndbl, int lane) {  // lanes 0 .. ndbl/2-1 copy 16 bytes each
+#if defined(__CUDA_ARCH__)
+  if (src != nullptr && lane < ndbl / 2) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(slot + 2 * lane);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 2 * lane) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+  (void)slot; (void)src; (void)ndbl; (void)lane;
+#endif
+}
+GRT_HD void stage_wait() {  // the oldest of the GRT_STAGE_DEPTH groups in flight has landed, for every lane of the warp
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(GRT_STAGE_DEPTH - 1) : "memory");
+  __syncwarp();
+#endif
+}
+GRT_HD void stage_release() {
+#if defined(__CUDA_ARCH__)
+  __syncwarp();
+#endif
+}
+
 // record -> invariant, LBH-scaled coefficients at observed frequency F.nu.  jI_raw returns the comoving un-boosted j_I used
 // for the driver's `fac` (grtrans_driver.f90:183-187).  Replaces calc_emissivity + the e%j/e%K copy (emis.f90:461-571),
 // rotate_emis (:797-829), invariant_emis (:831-838) and the K*LBH scaling (grtrans_driver.f90:217).
@@ -428,9 +457,12 @@ struct MarchInfo {
   int rnpts;
   double fac;
 };
-template <int ET, int MODE, bool HIST = false>
+// STAGE (device, DELO / FORMAL only): `stage` is this warp's ring of GRT_STAGE_DEPTH records in shared memory; every lane of
+// the warp must march the same ray.
+template <int ET, int MODE, bool HIST = false, bool STAGE = false>
 GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out,
-                           double *hist = nullptr, size_t hs = 0, MarchInfo *info = nullptr) {
+                           double *hist = nullptr, size_t hs = 0, MarchInfo *info = nullptr, double *stage = nullptr,
+                           int lane = 0) {
   constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
   if (HIST) {
     info->rnpts = npts;
@@ -458,10 +490,19 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     double I[4] = {0, 0, 0, 0}, In[4];
     Coef c1, c0;
     double lam1 = 0.0;
+    if (STAGE)  // prologue: records npts-1 ... npts-DEPTH are on their way
+      for (int j = 0; j < GRT_STAGE_DEPTH; j++)
+        stage_issue(stage + j * NREC, (npts - 1 - j >= 0) ? rec + (size_t)(npts - 1 - j) * NREC : nullptr, NREC, lane);
+    int slot = 0;
 #pragma unroll 1
     for (int k = npts - 1; k >= 0; k--) {
       const double *rk = rec + (size_t)k * NREC;
-      if (k > 0) prefetch_record(rk - NREC);
+      if (STAGE) {
+        stage_wait();
+        rk = stage + slot * NREC;
+      } else if (k > 0) {
+        prefetch_record(rk - NREC);
+      }
       const double lamk = rk[0];
       node_coef<ET>(P, R, rk, F, c0, jraw);
       fac += jraw * (lam0 - lamk);
@@ -483,6 +524,12 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
       }
       c1 = c0;
       lam1 = lamk;
+      if (STAGE) {  // this step's slot is free: refill it with the record GRT_STAGE_DEPTH steps further on
+        stage_release();
+        stage_issue(stage + slot * NREC, (k - GRT_STAGE_DEPTH >= 0) ? rec + (size_t)(k - GRT_STAGE_DEPTH) * NREC : nullptr, NREC,
+                    lane);
+        slot = (slot + 1 == GRT_STAGE_DEPTH) ? 0 : slot + 1;
+      }
     }
     if (HIST) info->fac = fac;
     if (fac / 1e16 > 0.0)
@@ -574,6 +621,86 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     else if (HIST)
       for (int c = 0; c < npts; c++) hist[(size_t)c * hs] = 0.0;  // the failed integration returns zeros (odepack.f90:91-96)
   }
+}
+
+// ---- DELO march of NF frequencies of one ray in one thread ---------------------------------------------------------------
+// The march of one (ray, frequency) is a serial recurrence: every DELO step waits for the previous one, and with 128
+// registers only four warps per scheduler are resident to hide that latency (ncu: 27 % of the stall samples are fixed-latency
+// dependencies, FP64 pipe 64 % busy).  Marching NF = 2 frequencies of the same ray in one thread gives the scheduler two
+// independent dependency chains per warp, and the per-point work that does not depend on the frequency -- the record load
+// (four 256-bit loads instead of sixteen 64-bit ones), its unpacking, the address arithmetic, the FP64 constants that this
+// ISA has to materialise with two moves each -- is issued once for both.  Same arithmetic per frequency as
+// ray_transfer_t<ET, MODE_DELO> (bit-identical results); points with npts == 1 take the single-point form.
+GRT_HD void load_record16(const double *p, double *r) {
+#if defined(__CUDA_ARCH__)
+  // the records were written by the previous kernel of the stream: the non-coherent path is safe here
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[4]), "=d"(r[5]), "=d"(r[6]), "=d"(r[7]) : "l"(p + 4));
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[8]), "=d"(r[9]), "=d"(r[10]), "=d"(r[11]) : "l"(p + 8));
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[12]), "=d"(r[13]), "=d"(r[14]), "=d"(r[15]) : "l"(p + 12));
+#else
+  for (int i = 0; i < 16; i++) r[i] = p[i];
+#endif
+}
+template <int ET, int NF>
+GRT_HD void ray_transfer_delo_nf(const TransferParams &P, const double *rec, int npts, const double *nu_obs, double (*out)[4]) {
+  static_assert(record_doubles(ET) == GRT_NREC, "16-double records only");
+  for (int f = 0; f < NF; f++)
+    for (int i = 0; i < 4; i++) out[f][i] = 0.0;
+  if (npts <= 0) return;
+  FreqConst F[NF];
+  RunConst R[NF];
+  for (int f = 0; f < NF; f++) {
+    F[f] = freq_const(nu_obs[f]);
+    R[f] = run_const<ET>(P, nu_obs[f]);
+  }
+  double jraw;
+  if (npts == 1) {
+    for (int f = 0; f < NF; f++) {
+      Coef c;
+      node_coef<ET>(P, R[f], rec, F[f], c, jraw);
+      if (jraw / 1e16 > 0.0)
+        for (int i = 0; i < 4; i++) out[f][i] = c.j[i];
+    }
+    return;
+  }
+  const double lam0 = rec[0];
+  double fac[NF], I[NF][4];
+  Coef c1[NF], c0[NF];
+  for (int f = 0; f < NF; f++) {
+    fac[f] = 0.0;
+    for (int i = 0; i < 4; i++) I[f][i] = 0.0;
+  }
+  double lam1 = 0.0;
+#pragma unroll 1
+  for (int k = npts - 1; k >= 0; k--) {
+    const double *rk = rec + (size_t)k * GRT_NREC;
+    if (k > 0) prefetch_record(rk - GRT_NREC);
+    double r_[GRT_NREC];
+    load_record16(rk, r_);
+    const double lamk = r_[0];
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      node_coef<ET>(P, R[f], r_, F[f], c0[f], jraw);
+      fac[f] += jraw * (lam0 - lamk);
+    }
+    if (k < npts - 1) {
+      const double dx = lamk - lam1;
+#pragma unroll
+      for (int f = 0; f < NF; f++) {
+        double In[4];
+        const double delta = dx * 0.5 * (fabs(c0[f].K[0]) + fabs(c1[f].K[0]));
+        delo_step(c0[f], c1[f], dx, delta, P.thin, I[f], In);
+        for (int i = 0; i < 4; i++) I[f][i] = In[i];
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) c1[f] = c0[f];
+    lam1 = lamk;
+  }
+  for (int f = 0; f < NF; f++)
+    if (fac[f] / 1e16 > 0.0)
+      for (int i = 0; i < 4; i++) out[f][i] = I[f][i] * P.LBH;
 }
 
 // ---- extra = 1: the 19 diagnostics of grtrans_driver.f90:230-292 (rays with more than one point) ------------------------
