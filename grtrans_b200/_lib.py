@@ -20,7 +20,7 @@ ERRORS = {1: "no usable CUDA device (GRT_ERR_NO_DEVICE)", 2: "unsupported argume
 # every symbol include/grtrans_b200.h declares
 SYMBOLS = ["grt_args_defaults", "grt_main", "grt_get_ivals", "grt_get_ab", "grt_get_freqs", "grt_data_allocated",
            "grt_del_data", "grt_run", "grt_program", "grt_read_inputs", "grt_write_output", "grt_geokerr_camera",
-           "grt_geokerr_rays", "grt_ray_stage_dump", "grt_polsynchth", "grt_polsynchpl", "grt_synchemis",
+           "grt_geokerr_rays", "grt_ray_stage_dump", "grt_geodebug", "grt_polsynchth", "grt_polsynchpl", "grt_synchemis",
            "grt_rt_integrate", "grt_session_create", "grt_session_destroy", "grt_session_launch", "grt_session_sync", "grt_session_launch_fetch", "grt_session_upload", "grt_session_run_timed",
            "grt_session_time", "grt_session_launch_count", "grt_session_counts",
            "grt_set_devices", "grt_main_info", "grt_release_cache", "grt_shard_rays", "grt_nccl_unique_id",
@@ -178,6 +178,28 @@ def ray_stage_dump(a, i1, i2):
                                *[_p(d[k]) for k in order]), "grt_ray_stage_dump")
     d["cap"] = cap
     return d
+
+
+def geodebug(a, pixel, path="geodebug.out"):
+    """debug = 1 dump of one ray (grtrans_driver.f90:86-110, 341-427) in the layout read_geodebug_file.py parses."""
+    check(lib().grt_geodebug(C.byref(a), C.c_int(pixel), path.encode()), "grt_geodebug")
+    return path
+
+
+# field name per line of geodebug.out, in file order (read_geodebug_file.py:16-83; `b` is assigned twice there -- the
+# fluid-frame field strength, then the cgs field -- and keeps the second)
+GEODEBUG_FIELDS = ["header", "lam", "time", "r", "th", "phi", "kt", "kr", "kth", "kphi", "tpr", "tpm", "rho", "p", "bmag",
+                   "ut", "ur", "uth", "uphi", "bt", "br", "bth", "bphi", "n", "t", "b", "g", "incang", "ji", "ki", "jq", "jv",
+                   "kq", "kv", "rhoq", "rhov", "ii", "iq", "iu", "iv", "taui", "ju", "ku", "rhou", "s2xi", "c2xi", "ang", "g2",
+                   "s2xi2", "c2xi2", "aahat", "aat", "aar", "aath", "aaph", "kht", "khr", "khth", "khph", "bht", "bhr", "bhth",
+                   "bhph", "fac"]
+
+
+def read_geodebug(path="geodebug.out"):
+    """The reference's reader (read_geodebug_file.py) as a function: one array per line of the file."""
+    with open(path) as f:
+        lines = f.readlines()
+    return {k: np.array(l.split(), dtype=float) for k, l in zip(GEODEBUG_FIELDS, lines)}
 
 
 def _bc(*xs):

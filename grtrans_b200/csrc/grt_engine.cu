@@ -34,6 +34,7 @@
 
 #include "grt_host.h"
 #include "grt_kernels.h"
+#include "grt_debug.cuh"
 
 using namespace grt;
 
@@ -1122,6 +1123,10 @@ extern "C" int grt_main(const grt_args *a) {
   }
   g_mod.allocated = true;
   if (a->outfile[0]) rc = grt_write_output(a, a->outfile);
+  if (rc == GRT_OK && a->debug == 1) {  // WRITE_GEO (grtrans_driver.f90:86-90): the file holds the last pixel of the run
+    const long long npix = (long long)a->nn[0] * a->nn[1];
+    rc = grt_geodebug(a, (int)((a->i2 < 1 || a->i2 > npix) ? npix : a->i2), "geodebug.out");
+  }
   return rc;
 }
 
@@ -1191,6 +1196,81 @@ template <class T>
 static int fetch(T *host, const T *dev, size_t n) {
   if (!host) return GRT_OK;
   return cudaMemcpy(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost) == cudaSuccess ? GRT_OK : GRT_ERR_CUDA;
+}
+
+// debug = 1 (grtrans_driver.f90:86-110, 341-427): the reference's pixel loop leaves `geodebug.out` holding the internals of
+// the LAST pixel it processed (every pixel overwrites the file; only the first (mdot, frequency) of a pixel is written).
+// Here that ray is re-run in a one-ray session with the stage dump on, k_geodebug adds the frequency-dependent part, and
+// the host formats the text file (grt_io.cpp: write_geodebug).  pixel: 1-based geodesic index; mu0 index = the last one.
+extern "C" int grt_geodebug(const grt_args *a, int pixel, const char *path) {
+  grt_args aa = *a;
+  aa.i1 = aa.i2 = pixel;
+  aa.extra = 0; aa.debug = 0; aa.nt = 1;
+  aa.outfile[0] = 0;
+  grt_session *s = nullptr;
+  int rc = grt_session_create(&aa, 0, 0, 1, &s);
+  if (rc != GRT_OK) return rc;
+  const int mp = s->maxpts, jmu = s->nmu - 1;
+  const size_t NP = (size_t)mp;
+  StageDump sd;
+  memset(&sd, 0, sizeof(sd));
+  double **dbl[] = {&sd.lambda, &sd.t, &sd.r, &sd.th, &sd.ph, &sd.kt, &sd.kr, &sd.kth, &sd.kph, &sd.s2xi, &sd.c2xi,
+                    &sd.ang, &sd.rshift, &sd.cosne, &sd.ncgs, &sd.ncgsnth, &sd.bcgs, &sd.tcgs};
+  bool okm = true;
+  for (auto pp : dbl) okm = okm && own(s, pp, NP) == cudaSuccess && cudaMemset(*pp, 0, NP * 8) == cudaSuccess;
+  okm = okm && own(s, &sd.u, NP * 4) == cudaSuccess && own(s, &sd.b, NP * 4) == cudaSuccess;
+  okm = okm && own(s, &sd.rho, NP) == cudaSuccess && own(s, &sd.p, NP) == cudaSuccess && own(s, &sd.bmag, NP) == cudaSuccess;
+  double *d_rows = nullptr, *d_hist = nullptr, *d_scal = nullptr;
+  okm = okm && own(s, &d_rows, NP * GD_NROWS) == cudaSuccess && own(s, &d_hist, NP * 4) == cudaSuccess &&
+        own(s, &d_scal, (size_t)2) == cudaSuccess;
+  if (okm) {
+    cudaMemset(sd.u, 0, NP * 32); cudaMemset(sd.b, 0, NP * 32);
+    cudaMemset(sd.rho, 0, NP * 4); cudaMemset(sd.p, 0, NP * 4); cudaMemset(sd.bmag, 0, NP * 4);
+    cudaMemset(d_rows, 0, NP * GD_NROWS * 8); cudaMemset(d_scal, 0, 16);
+  }
+  if (!okm) {
+    grt_session_destroy(s);
+    return GRT_ERR_CUDA;
+  }
+  s->fl.skip_t = 0;  // the dump lists the coordinate time along the ray
+  rc = launch_tile(s, jmu, 0, 1, sd, false);
+  if (rc == GRT_OK) {
+    launch_geodebug(s->d_rc[jmu], s->d_meta, mp, s->pa, sd, s->tp, s->d_lbh, s->d_rec, s->freqs[0], d_hist, d_rows, d_scal,
+                    s->stream);
+    rc = grt_session_sync(s);
+  }
+  grt_host::GeoDebugData d;
+  if (rc == GRT_OK) {
+    RayMeta hm;
+    rc = fetch(&hm, s->d_meta, (size_t)1);
+    d.npts = (hm.status == 1) ? hm.npts : 0;
+    d.maxpts = mp;
+    const RayConst &r0 = s->h_rc[jmu][0];
+    d.alpha = r0.alpha; d.beta = r0.beta; d.su = r0.su; d.sm = r0.sm; d.a = r0.a; d.mu0 = r0.mu0;
+    d.mdots = s->mdots;
+    d.mbh.assign(s->mdots.size(), a->mbh);
+    auto pull = [&](std::vector<double> &h, const double *dv, size_t n) {
+      h.assign(n, 0.0);
+      if (rc == GRT_OK) rc = fetch(h.data(), dv, n);
+    };
+    auto pullf = [&](std::vector<float> &h, const float *dv) {
+      h.assign(NP, 0.f);
+      if (rc == GRT_OK) rc = fetch(h.data(), dv, NP);
+    };
+    pull(d.lambda, sd.lambda, NP); pull(d.t, sd.t, NP); pull(d.r, sd.r, NP); pull(d.th, sd.th, NP); pull(d.ph, sd.ph, NP);
+    pull(d.kt, sd.kt, NP); pull(d.kr, sd.kr, NP); pull(d.kth, sd.kth, NP); pull(d.kph, sd.kph, NP);
+    pull(d.u, sd.u, NP * 4); pull(d.b, sd.b, NP * 4);
+    pull(d.ncgs, sd.ncgs, NP); pull(d.tcgs, sd.tcgs, NP); pull(d.bcgs, sd.bcgs, NP); pull(d.rshift, sd.rshift, NP);
+    pull(d.ang, sd.ang, NP); pull(d.s2xi, sd.s2xi, NP); pull(d.c2xi, sd.c2xi, NP);
+    pullf(d.rho, sd.rho); pullf(d.p, sd.p); pullf(d.bmag, sd.bmag);
+    pull(d.rows, d_rows, NP * GD_NROWS);
+    std::vector<double> sc;
+    pull(sc, d_scal, 2);
+    d.fac = sc[0];
+  }
+  grt_session_destroy(s);
+  if (rc == GRT_OK) rc = grt_host::write_geodebug(path, d);
+  return rc;
 }
 
 extern "C" int grt_ray_stage_dump(const grt_args *a, int i1, int i2, int cap_pts, int *maxpts_out, int *npts, double *lambda,

@@ -79,4 +79,15 @@ int read_files_in(const char *path, std::string &ifile, std::string &ofile);  //
 int write_output(const grt_args &a, const char *outfile, int nx, int ny, int nv, int ncams, const float *pixloc,
                  const double *ivals, const std::vector<double> &freqs);
 
+// debug = 1: the text dump `geodebug.out` of one ray (grtrans_driver.f90:86-110, 341-427), one record per line in the
+// order read_geodebug_file.py expects.  rows = the device debug buffer [nrows][maxpts] (grt_debug.cuh).
+struct GeoDebugData {
+  int npts = 0, maxpts = 0;
+  double alpha = 0, beta = 0, su = 0, sm = 0, a = 0, mu0 = 0, fac = 0;
+  std::vector<double> mdots, mbh;
+  std::vector<double> lambda, t, r, th, ph, kt, kr, kth, kph, u, b, ncgs, tcgs, bcgs, rshift, ang, s2xi, c2xi, rows;
+  std::vector<float> rho, p, bmag;
+};
+int write_geodebug(const char *path, const GeoDebugData &d);
+
 }  // namespace grt_host

@@ -1142,3 +1142,62 @@ extern "C" void grt_args_defaults(grt_args *a) {
   for (int i = 0; i < 7; i++) a->epcoefindx[i] = 1;
   a->nepotherargs = 2; a->epotherargs[0] = 1.; a->epotherargs[1] = 1.;
 }
+
+// ------------------------------------------------------------------------------------------ geodebug.out
+namespace grt_host {
+// One list-directed WRITE of the reference per line (gfortran does not wrap list-directed records written to a file), in
+// the order of grtrans_driver.f90:93-110 (geodesic) and :342-418 (fluid, emission, intensities, tetrad); the reader
+// (read_geodebug_file.py) splits every line on white space.  Row indices of `rows` are those of grt_debug.cuh.
+int write_geodebug(const char *path, const GeoDebugData &d) {
+  FILE *f = fopen(path, "w");
+  if (!f) return GRT_ERR_IO;
+  const int n = d.npts, mp = d.maxpts;
+  auto dline = [&](const double *v, int stride = 1) {
+    for (int i = 0; i < n; i++) fprintf(f, " %24.16E", v[(size_t)i * stride]);
+    fputc('\n', f);
+  };
+  auto fline = [&](const float *v) {
+    for (int i = 0; i < n; i++) fprintf(f, " %15.8E", (double)v[i]);
+    fputc('\n', f);
+  };
+  auto iline = [&](const double *v) {
+    for (int i = 0; i < n; i++) fprintf(f, " %11d", (int)v[i]);
+    fputc('\n', f);
+  };
+  auto row = [&](int r) { return d.rows.data() + (size_t)r * mp; };
+  // header: npts, nitems, alpha, beta, su, sm, mdot(:), mbh(:), fac, a, mu0   ((sic) fac is whatever the variable held
+  // before this pixel's frequency loop in the reference; 0 here)
+  fprintf(f, " %11d %11d %24.16E %24.16E %24.16E %24.16E", n, 18, d.alpha, d.beta, d.su, d.sm);
+  for (double m : d.mdots) fprintf(f, " %24.16E", m);
+  for (double m : d.mbh) fprintf(f, " %24.16E", m);
+  fprintf(f, " %24.16E %24.16E %24.16E\n", 0.0, d.a, d.mu0);
+  dline(d.lambda.data()); dline(d.t.data()); dline(d.r.data()); dline(d.th.data()); dline(d.ph.data());
+  dline(d.kt.data()); dline(d.kr.data()); dline(d.kth.data()); dline(d.kph.data());
+  iline(row(35)); iline(row(36));                                     // tprarr, tpmarr
+  if (n > 0) {
+    fline(d.rho.data()); fline(d.p.data()); fline(d.bmag.data());
+    for (int c = 0; c < 4; c++) dline(d.u.data() + c, 4);
+    for (int c = 0; c < 4; c++) dline(d.b.data() + c, 4);
+    dline(d.ncgs.data()); dline(d.tcgs.data()); dline(d.bcgs.data()); dline(d.rshift.data()); dline(d.ang.data());
+    dline(row(0)); dline(row(4));                                     // j_I, alpha_I
+    dline(row(1)); dline(row(3)); dline(row(5)); dline(row(7));       // j_Q, j_V, alpha_Q, alpha_V
+    dline(row(8)); dline(row(10));                                    // rho_Q, rho_V
+    for (int c = 0; c < 4; c++) dline(row(12 + c));                   // I, Q, U, V / fac / LBH along the ray
+    dline(row(11));                                                   // tau
+    dline(row(2)); dline(row(6)); dline(row(9));                      // j_U, alpha_U, rho_U
+    dline(d.s2xi.data()); dline(d.c2xi.data());
+    dline(row(16)); dline(row(17));                                   // calc_kb_ang, calcg
+    dline(row(33)); dline(row(34));                                   // s2xi, c2xi of comoving_ortho_debug
+    for (int c = 0; c < 3; c++)                                       // aahat(npts, 3), column-major, in ONE record
+      for (int i = 0; i < n; i++) fprintf(f, " %24.16E", row(18 + c)[i]);
+    fputc('\n', f);
+    for (int c = 0; c < 4; c++) dline(row(21 + c));                   // aat, aar, aath, aaph
+    for (int c = 0; c < 4; c++) dline(row(25 + c));                   // kht, khr, khth, khph
+    for (int c = 0; c < 4; c++) dline(row(29 + c));                   // bht, bhr, bhth, bhph
+    fprintf(f, " %24.16E\n", d.fac);
+  }
+  const bool bad = ferror(f) != 0;
+  if (fclose(f) != 0 || bad) return GRT_ERR_IO;
+  return GRT_OK;
+}
+}  // namespace grt_host

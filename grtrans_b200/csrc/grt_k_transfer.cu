@@ -10,13 +10,22 @@ namespace grt {
 // image layout: [cam][ray_local][nvals] float32, cam = (mu_index*nparams + m)*nfreq + k.
 // Thread = (ray, mdot, frequency), frequency fastest: the 32 lanes of a warp march the SAME ray at 32 frequencies, so the
 // 128-byte point record is one broadcast load per step and the lanes never diverge on npts.
-// __launch_bounds__(128, 4): 128 registers, 16 warps / SM.  Measured on the headline kernel <POLSYNCHTH, DELO>: 3 blocks
-// (154 regs) 84.6 ms, 4 blocks 77.1 ms, 5 blocks (96 regs, spills) 76.9 ms, 6 blocks 76.6 ms at nx=256.
+// 128 registers, 16 warps / SM (4 per scheduler), one warp per block.  Measured on the headline kernel <POLSYNCHTH, DELO>
+// (config 5, ms per step): blocks of 128 threads 578.6, of 32 threads 569.9; 96 registers (5 warps per scheduler, spills)
+// 664, with the coefficients of node k+1 kept in shared memory (GRT_TRANSFER_CSM=1) 623.6; 80 registers 774.
+// A dependent DFMA issues every 8.7 cycles (tools/ubench/dfma_latency.cu), so four warps of pure dependency chain could
+// keep the pipe 88 % busy; the kernel reaches 68-70 %.
 #ifndef GRT_TRANSFER_MINB
-#define GRT_TRANSFER_MINB 4
+#define GRT_TRANSFER_MINB 16
+#endif
+#ifndef GRT_TRANSFER_BS
+#define GRT_TRANSFER_BS 32
+#endif
+#ifndef GRT_TRANSFER_CSM
+#define GRT_TRANSFER_CSM 0
 #endif
 template <int ET, int MODE, bool STAGE = false>
-__global__ void __launch_bounds__(128, GRT_TRANSFER_MINB) k_transfer(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
+__global__ void __launch_bounds__(GRT_TRANSFER_BS, GRT_TRANSFER_MINB) k_transfer(const RayMeta *__restrict__ meta, TransferParams P, const double *__restrict__ lbh_m,
                                                   const double *__restrict__ freqs, int nfreq, int nparams, int nrays, int maxpts,
                                                   const double *__restrict__ rec, float *__restrict__ image, long long ray_off,
                                                   long long nlocal, int cam0) {
@@ -33,9 +42,15 @@ __global__ void __launch_bounds__(128, GRT_TRANSFER_MINB) k_transfer(const RayMe
     P.LBH = lbh_m[mm];
     const double *rr = rec + ((size_t)mm * nrays * maxpts + (size_t)ray * maxpts) * record_doubles(ET);
     if (STAGE) {  // (launched only when nfreq is a multiple of 32: the lanes of a warp share ray and mdot)
-      __shared__ __align__(16) double stage[4][GRT_STAGE_DEPTH * record_doubles(ET)];
-      ray_transfer_t<ET, MODE, false, true>(P, rr, m.npts, freqs[f], out, nullptr, 0, nullptr, stage[threadIdx.x >> 5],
-                                            threadIdx.x & 31);
+      __shared__ __align__(16) double stage[GRT_TRANSFER_BS / 32][GRT_STAGE_DEPTH * record_doubles(ET)];
+      if (GRT_TRANSFER_CSM && MODE == MODE_DELO) {
+        __shared__ double csm[GRT_TRANSFER_BS / 32][11 * GRT_CSM_STRIDE];
+        ray_transfer_t<ET, MODE, 0, 2>(P, rr, m.npts, freqs[f], out, nullptr, 0, nullptr, stage[threadIdx.x >> 5],
+                                       threadIdx.x & 31, &csm[threadIdx.x >> 5][threadIdx.x & 31]);
+      } else {
+        ray_transfer_t<ET, MODE, 0, 1>(P, rr, m.npts, freqs[f], out, nullptr, 0, nullptr, stage[threadIdx.x >> 5],
+                                       threadIdx.x & 31);
+      }
     } else {
       ray_transfer_t<ET, MODE>(P, rr, m.npts, freqs[f], out);
     }
@@ -46,43 +61,6 @@ __global__ void __launch_bounds__(128, GRT_TRANSFER_MINB) k_transfer(const RayMe
     *reinterpret_cast<float4 *>(dst) = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
   else
     dst[0] = (float)out[0];
-}
-
-// Two frequencies per thread (ray_transfer_delo_nf): thread = (ray, mdot, frequency pair), pair p of a ray = frequencies p and
-// p + ceil(nfreq / 2), pair fastest, so a warp still marches one ray (nfreq = 64: lane l holds frequencies l and l + 32) and
-// the point record stays a broadcast load.  255 registers, two blocks of 128 threads per SM.
-#ifndef GRT_TRANSFER2_MINB
-#define GRT_TRANSFER2_MINB 2
-#endif
-template <int ET>
-__global__ void __launch_bounds__(128, GRT_TRANSFER2_MINB) k_transfer2(const RayMeta *__restrict__ meta, TransferParams P,
-                                                                      const double *__restrict__ lbh_m, const double *__restrict__ freqs,
-                                                                      int nfreq, int nparams, int nrays, int maxpts,
-                                                                      const double *__restrict__ rec, float *__restrict__ image,
-                                                                      long long ray_off, long long nlocal, int cam0) {
-  const int npair = (nfreq + 1) / 2;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)nrays * nparams * npair;
-  if (idx >= total) return;
-  const int pr = (int)(idx % npair);
-  const int mm = (int)((idx / npair) % nparams);
-  const int ray = (int)(idx / ((long long)npair * nparams));
-  const int f0 = pr, f1 = pr + npair;
-  const bool has1 = f1 < nfreq;
-  RayMeta m = meta[ray];
-  double out[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-  if (m.status == 1 && m.npts > 0) {
-    P.LBH = lbh_m[mm];
-    const double *rr = rec + ((size_t)mm * nrays * maxpts + (size_t)ray * maxpts) * GRT_NREC;
-    const double nu[2] = {freqs[f0], freqs[has1 ? f1 : f0]};
-    ray_transfer_delo_nf<ET, 2>(P, rr, m.npts, nu, out);
-  }
-  float *d0 = image + ((size_t)(cam0 + mm * nfreq + f0) * nlocal + (ray_off + ray)) * 4;
-  *reinterpret_cast<float4 *>(d0) = make_float4((float)out[0][0], (float)out[0][1], (float)out[0][2], (float)out[0][3]);
-  if (has1) {
-    float *d1 = image + ((size_t)(cam0 + mm * nfreq + f1) * nlocal + (ray_off + ray)) * 4;
-    *reinterpret_cast<float4 *>(d1) = make_float4((float)out[1][0], (float)out[1][1], (float)out[1][2], (float)out[1][3]);
-  }
 }
 
 // Gather: one block [ncamb][n][nv] of rank r's image (local rays off .. off+n-1) -> the full image
@@ -235,7 +213,7 @@ template <int ET>
 static void launch_transfer_e(int mode, unsigned grid, cudaStream_t st, const RayMeta *meta, const TransferParams &P,
                               const double *lbh_m, const double *freqs, int nfreq, int nparams, int nrays, int maxpts,
                               const double *rec, float *image, long long ray_off, long long nlocal, int cam0) {
-  const int B = 128;
+  const int B = GRT_TRANSFER_BS;
 #define GRT_LAUNCH(M) \
   k_transfer<ET, M><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0)
 #define GRT_LAUNCH_ST(M) \
@@ -265,18 +243,10 @@ static void launch_transfer_e(int mode, unsigned grid, cudaStream_t st, const Ra
 void launch_transfer(const RayMeta *meta, const TransferParams &P, const double *lbh_m, const double *freqs, int nfreq,
                      int nparams, int nrays, int maxpts, const double *rec, float *image, long long ray_off, long long nlocal,
                      int cam0, cudaStream_t st) {
-  const int B = 128;
+  const int B = GRT_TRANSFER_BS;
   long long tt = (long long)nrays * nparams * nfreq;
   unsigned grid = (unsigned)((tt + B - 1) / B);
   const int mode = transfer_mode(P);
-  // the headline combination marches two frequencies per thread (GRT_TRANSFER_NF=1: one, as every other combination)
-  static const int nf_env = getenv("GRT_TRANSFER_NF") ? atoi(getenv("GRT_TRANSFER_NF")) : 1;
-  if (em_slot(P.etype) == EM_POLSYNCHTH && mode == MODE_DELO && nfreq >= 2 && nf_env == 2) {
-    const long long t2 = (long long)nrays * nparams * ((nfreq + 1) / 2);
-    k_transfer2<EM_POLSYNCHTH><<<(unsigned)((t2 + B - 1) / B), B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec,
-                                                                          image, ray_off, nlocal, cam0);
-    return;
-  }
   switch (em_slot(P.etype)) {
 #define OP(E) \
   case E: launch_transfer_e<E>(mode, grid, st, meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0); break;

@@ -28,6 +28,12 @@ void launch_transfer_extra(const RayMeta *meta, const TransferParams &P, const d
                            int nparams, int nrays, int maxpts, const double *rec, const double *xrec, double *hist, float *image,
                            long long ray_off, long long nlocal, int cam0, int nextra, cudaStream_t st);
 
+// debug = 1: per-point internals of ray 0 of a one-ray tile for the geodebug.out dump (grt_debug.cuh): rows [GD_NROWS][maxpts],
+// scal[2] = fac, r%npts; hist = scratch [maxpts][4]
+void launch_geodebug(const RayConst *rc, const RayMeta *meta, int maxpts, PointArrays pa, StageDump sd, const TransferParams &P,
+                     const double *lbh_m, const double *rec, double nu_obs, double *hist, double *rows, double *scal,
+                     cudaStream_t st);
+
 // multi-GPU gather: scatter one block [ncamb][n][nv] of rank r (local rays off..off+n-1) into rank 0's full image [ncams][npix][nv]
 void launch_gather_scatter(const float *blk, float *full, int ncamb, int n, int nv, long long npix, int cam0, long long off,
                            int r, int nranks, int i1, cudaStream_t st);

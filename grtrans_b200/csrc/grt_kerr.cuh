@@ -171,8 +171,11 @@ struct OrthoOut {
 
 // fluid-frame quantities: polarisation-basis rotation (s2xi,c2xi), angle between k and b, redshift
 // g and emission-angle cosine (Kulkarni+2011 tetrad, Walker-Penrose transported basis)
+struct OrthoDebug {  // comoving_ortho_debug (kerr.f90:562-584): the tetrad components the debug dump lists
+  double aahat[3], aa[4], khat[4], bhat[4];
+};
 GRT_HD void comoving_ortho(double r, double th, double a, double alpha, double beta, double mus, const double *u,
-                           const double *b, const double *k, OrthoOut &o) {
+                           const double *b, const double *k, OrthoOut &o, OrthoDebug *dbg = nullptr) {
   Metric m = bl_metric(r, th, a);
   double ut = u[0], ur = u[1], um = u[2], up = u[3];
   double utc = m.tt * ut + m.tp * up, upc = m.pp * up + m.tp * ut, urc = m.rr * ur, umc = um * m.hh;
@@ -235,11 +238,51 @@ GRT_HD void comoving_ortho(double r, double th, double a, double alpha, double b
     o.c2xi = 1.0;
     angnorm = 0.5;
   }
+  if (dbg) {
+    dbg->aahat[0] = a1; dbg->aahat[1] = a2; dbg->aahat[2] = a3;
+    for (int i = 0; i < 4; i++) dbg->aa[i] = aa[i];
+    dbg->khat[0] = kht; dbg->khat[1] = khr; dbg->khat[2] = khm; dbg->khat[3] = khp;
+    dbg->bhat[0] = mdot(m, ekt, b); dbg->bhat[1] = bhr; dbg->bhat[2] = bhm; dbg->bhat[3] = bhp;
+  }
   double t = (angnorm <= 0.99) ? angnorm : 0.99;
   t = (angnorm >= -0.99) ? t : -0.99;
   o.ang = acos(t);
   o.g = 1.0 / kht;
   o.cosne = o.g * sqrt(beta * beta + mus * mus * (alpha * alpha - a * a)) / r;
+}
+
+// calc_kb_ang (kerr.f90:220-252): angle between wave vector and field in the fluid frame, Broderick (2004) covariant form --
+// the debug dump's independent check of comoving_ortho's angle
+GRT_HD double kb_angle(double r, double th, double a, const double *k, const double *b, const double *u) {
+  const Metric m = bl_metric(r, th, a);
+  const double bdotk = mdot(m, b, k), bdotb = mdot(m, b, b), kdotk = mdot(m, k, k), om = -mdot(m, k, u);
+  double cdot2 = bdotk * bdotk / bdotb / (kdotk + om * om);
+  cdot2 = (cdot2 <= 1.0) ? ((cdot2 >= 0.0) ? cdot2 : 0.0) : 1.0;
+  return acos(((bdotk < 0.0 || (bdotk == 0.0 && signbit(bdotk))) ? -1.0 : 1.0) * sqrt(cdot2));
+}
+
+// CALCG (kerr.f90:181-218): redshift from the LNRF velocities of the fluid -- the debug dump's independent check of
+// comoving_ortho's g.  vr, vt, om = u^r/u^t, u^th/u^t, u^ph/u^t (lnrf_frame, :402-425, is applied here).  (sic) ST carries
+// geokerr's sign convention for the polar momentum, opposite to calc_nullp's: the two redshifts agree only for v^theta = 0.
+GRT_HD double calcg_lnrf(double r, double mu, double q2, double l, double a, int tpm, int tpr, double su, double sm, double vr,
+                         double vt, double omf) {
+  const double u = 1.0 / r;
+  const double D = r * r - 2.0 * r + a * a;
+  const double AR = sq(r * r + a * a) - a * a * D * (1.0 - mu * mu);
+  const double RHO = r * r + a * a * mu * mu;
+  const double ENU = sqrt(D * RHO / AR), EMU1 = sqrt(RHO / D), EMU2 = sqrt(RHO), EPSI = sqrt(1.0 - mu * mu) * sqrt(AR / RHO);
+  const double OM = 2.0 * a * r / AR;
+  double vrl = EMU1 / ENU * vr, vtl = EMU2 / ENU * vt, vpl = EPSI / ENU * (omf - OM);
+  if (!(D > 0.0)) vrl = vtl = vpl = 0.0;
+  const double SR = ((tpr & 1) ? -1.0 : 1.0) * su, ST = -((tpm & 1) ? -1.0 : 1.0) * sm;
+  double OMEGA = ENU / EPSI * vpl + OM;
+  if (EPSI == 0.0) OMEGA = 0.0;
+  const double GAM = 1.0 / sqrt(1.0 - (vrl * vrl + vtl * vtl + vpl * vpl));
+  double RR = -a * a * q2 * u * u * u * u + 2.0 * u * u * u * (q2 + (a - l) * (a - l)) + u * u * (a * a - q2 - l * l) + 1.0;
+  double TT = (q2 + mu * mu * (a * a - l * l - q2) - a * a * mu * mu * mu * mu) / (1.0 - mu * mu);
+  TT = (TT >= 0.0) ? sqrt(TT) : 0.0;
+  RR = (RR >= 0.0) ? sqrt(RR) * r * r : 0.0;
+  return ENU / GAM / (1.0 - l * OMEGA - EMU1 * ENU * vrl / RHO * SR * RR - EMU2 * ENU * vtl / RHO * ST * TT);
 }
 
 }  // namespace grt

@@ -52,45 +52,84 @@ GRT_HD float r4acos(float x) { return acosf(x); }
 GRT_HD float r4pow(float x, float y) { return powf(x, y); }
 #endif
 
+GRT_HD double nan_val() {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(0x7ff8000000000000LL);
+#else
+  return __builtin_nan("");
+#endif
+}
+
 // ---- exp() for the transfer hot loop -------------------------------------------------------------
-// The emissivity + DELO loop calls exp() six times per (point, frequency).  libm's device exp spends two UMOV per
-// 64-bit polynomial coefficient (immediates travel through uniform registers) and a branch on the slow path: ~30% of the
-// instructions the loop issued were such moves (ncu, profiles/).  This version keeps the coefficients in constant memory
-// (they become c[bank][offset] operands of the DFMAs), has no branch, and scales by 2^k in two halves so results in the
-// subnormal range round like the reference's (the DELO step has to tell "underflowed to a subnormal" from 0).
-// e^r = 1 + r + r^2 q(r) on |r| <= ln2/2: degree-11 Chebyshev fit, max relative error 1.6e-17 (tools/fit_exp.py).
-// Domain: x <= 709 (callers guarantee it); x < -800 -> 0; NaN -> NaN.  Error <= 1 ulp like libm's.
-#define GRT_EXP_COEFS                                                                                                   \
-  2.510038549551032e-08, 2.7620088445409746e-07, 2.7557268459997064e-06, 2.4801521295954376e-05, 0.00019841269863053618, \
-      0.0013888888917213717, 0.008333333333330062, 0.04166666666662413, 0.16666666666666669, 0.5000000000000001, 1.0, 1.0
+// The emissivity + DELO loop calls exp() three times per (point, frequency).  On this ISA every 64-bit constant of a
+// polynomial costs an issue slot of its own (one LDC, or two UMOV for an immediate), so a long polynomial pays twice: ncu
+// attributed 6 % of k_transfer's issued instructions to the 11 Horner steps of the previous version, half of them constant
+// loads.  This one is table driven:  e^x = 2^k 2^(j/64) e^r,  n = round(x 64/ln2) = 64 k + j,  |r| <= ln2/128, with
+// 2^(j/64) = hi + lo from a 64-entry table (one 16-byte L1 load, issued right after n is known and needed last) and
+// e^r - 1 = r + r^2 (1/2 + r (1/6 + r (1/24 + r/120))) (truncation < 3.5e-17 relative): 6 dependent FP64 operations and 4
+// constants instead of 11 and 12.  No branch; the scaling by 2^k is done in two halves so that results in the subnormal
+// range round once, like the reference's (the DELO step has to tell "underflowed to a subnormal" from 0).
+// Domain: x <= 709 (callers guarantee it); x < -800 -> 0; NaN -> NaN.  Error <= 1 ulp (tests/test_host_emul.py).
+#define GRT_EXP_TAB \
+  1.0, 0.0, 1.0108892860517005, -1.5234778603368577e-17, 1.0218971486541166, 5.109225028973444e-17, \
+  1.0330248790212284, 7.600838874027088e-18, 1.0442737824274138, 8.551889705537965e-17, 1.0556451783605572, \
+  1.759325738772092e-18, 1.0671404006768237, -7.899853966841582e-17, 1.0787607977571199, \
+  -6.656660436056593e-17, 1.0905077326652577, -3.046782079812471e-17, 1.102382583307841, \
+  5.2660368715706944e-17, 1.1143867425958924, 1.0410278456845571e-16, 1.1265216186082418, \
+  5.165856758795457e-17, 1.1387886347566916, 8.912812676025408e-17, 1.1511892299529827, 3.250710218863827e-17, \
+  1.1637248587775775, 3.8292048369240935e-17, 1.1763969916502812, 5.554203254218079e-17, 1.189207115002721, \
+  3.982015231465646e-17, 1.202156731452703, 6.644981499252301e-17, 1.215247359980469, -7.712630692681488e-17, \
+  1.22848053610687, -1.89878163130253e-17, 1.241857812073484, 4.658027591836937e-17, 1.255380757024691, \
+  -6.7113898212968784e-18, 1.2690509571917332, 2.667932131342186e-18, 1.2828700160787783, \
+  1.713594918243561e-17, 1.2968395546510096, 2.5382502794888315e-17, 1.3109612115247644, \
+  -7.181536135519454e-17, 1.3252366431597413, -2.8587312100388614e-17, 1.339667524053303, \
+  8.927282594831732e-17, 1.3542555469368927, 7.70094837980299e-17, 1.3690024229745905, 9.593797919118849e-17, \
+  1.383909881963832, -6.770511658794786e-17, 1.3989796725383112, -9.614213209051323e-17, 1.4142135623730951, \
+  -9.667293313452913e-17, 1.42961333839197, -1.2031642489053655e-17, 1.4451808069770467, \
+  -3.0237581349939873e-17, 1.460917794180647, -5.600377186075216e-17, 1.4768261459394993, \
+  -3.483994556892796e-17, 1.4929077282912648, 1.4192920154284036e-17, 1.5091644275934228, \
+  -1.016455327754295e-16, 1.5255981507445384, -1.1024941712342561e-16, 1.5422108254079407, \
+  7.949834809697621e-17, 1.559004400237837, 3.7812070533575275e-17, 1.5759808451078865, \
+  -1.0136916471278304e-17, 1.593142151342267, -1.0094406542311964e-16, 1.6104903319492543, \
+  2.4707192569797888e-17, 1.6280274218573478, -6.712955084707084e-17, 1.645755478153965, \
+  -1.0125679913674773e-16, 1.6636765803267364, 5.8909926967131e-17, 1.681792830507429, 8.199010020581497e-17, \
+  1.7001063537185235, -8.0237193703977e-18, 1.718619298122478, -1.851380418263111e-17, 1.7373338352737062, \
+  3.164389299292957e-17, 1.7562521603732995, 2.960140695448873e-17, 1.7753764925265212, 6.429731796556572e-17, \
+  1.7947090750031072, 1.8227458427912087e-17, 1.8142521755003989, -9.969531538920349e-17, 1.8340080864093424, \
+  3.283107224245627e-17, 1.8539791250833855, 9.761887490727594e-17, 1.8741676341103, -6.122763413004143e-17, \
+  1.8945759815869656, 3.4034035352165297e-17, 1.9152065613971474, -1.0619946056195963e-16, 1.9360617934922943, \
+  1.0332385960676326e-16, 1.9571441241754002, 8.960767791036668e-17, 1.978456026387951, 4.0388753109278167e-17
 #if defined(__CUDACC__)
-static __constant__ double grt_expc_dev[12] = {GRT_EXP_COEFS};
+static __device__ __align__(16) const double grt_exp_tab_dev[128] = {GRT_EXP_TAB};  // 2^(j/64) as hi, lo pairs
 #endif
 GRT_HD double exp_fast(double x) {
-#if defined(__CUDA_ARCH__)
-  const double *C = grt_expc_dev;
-#else
-  const double C[12] = {GRT_EXP_COEFS};
+#if !defined(__CUDA_ARCH__)
+  static const double grt_exp_tab_host[128] = {GRT_EXP_TAB};
 #endif
   x = (x < -800.0) ? -800.0 : x;  // (keeps NaN)
-  double t = fma(x, 1.4426950408889634, 6755399441055744.0);  // round(x log2 e) in the low mantissa bits
-  int k;
+  double t = fma(x, 92.33248261689366, 6755399441055744.0);  // round(x 64/ln2) in the low mantissa bits
+  int n;
 #if defined(__CUDA_ARCH__)
-  k = __double2loint(t);
+  n = __double2loint(t);
+  const double2 T2 = __ldg(reinterpret_cast<const double2 *>(grt_exp_tab_dev) + (n & 63));
+  const double T = T2.x, Tl = T2.y;
 #else
   {
     long long b;
     memcpy(&b, &t, 8);
-    k = (int)(unsigned)(b & 0xffffffffLL);
+    n = (int)(unsigned)(b & 0xffffffffLL);
   }
+  const double T = grt_exp_tab_host[2 * (n & 63)], Tl = grt_exp_tab_host[2 * (n & 63) + 1];
 #endif
-  double kf = t - 6755399441055744.0;
-  double r = fma(kf, -6.9314718055994529e-1, x);
-  r = fma(kf, -2.3190468138462996e-17, r);
-  double p = C[0];
-#pragma unroll
-  for (int i = 1; i < 12; i++) p = fma(p, r, C[i]);
-  int k1 = k >> 1, k2 = k - k1;
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -0.010830424696249145, x);   // ln2/64 in two parts
+  r = fma(nf, -3.623510646634843e-19, r);
+  double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  const double q = fma(p, r * r, r);
+  const double y = T + fma(T, q, Tl);
+  const int k = n >> 6, k1 = k >> 1, k2 = k - k1;
   double s1, s2;
 #if defined(__CUDA_ARCH__)
   s1 = __hiloint2double((k1 + 1023) << 20, 0);
@@ -102,7 +141,7 @@ GRT_HD double exp_fast(double x) {
     memcpy(&s2, &b2, 8);
   }
 #endif
-  return (p * s1) * s2;
+  return (y * s1) * s2;
 }
 
 // log(x) for finite x >= 1 (the Faraday-rotation fit takes log(1 + positive) once per (point, frequency)): the argument

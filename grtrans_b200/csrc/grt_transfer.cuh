@@ -81,6 +81,9 @@ GRT_HD void prefetch_record(const double *p) {
 // loads (about 550 cycles per step: the L1 prefetch hint above does not bring the line in time); staged records are there
 // when the step starts and are read with broadcast shared-memory loads.
 #define GRT_STAGE_DEPTH 4
+#ifndef GRT_MARCH_UNROLL2
+#define GRT_MARCH_UNROLL2 0
+#endif
 GRT_HD void stage_issue(double *slot, const double *src, int ndbl, int lane) {  // lanes 0 .. ndbl/2-1 copy 16 bytes each
 #if defined(__CUDA_ARCH__)
   if (src != nullptr && lane < ndbl / 2) {
@@ -109,12 +112,15 @@ GRT_HD void stage_release() {
 // rotate_emis (:797-829), invariant_emis (:831-838) and the K*LBH scaling (grtrans_driver.f90:217).
 struct RunConst {  // per-thread constants of the march (emissivity-model constants that do not depend on the point)
   PlConst pl;
-  double lnu;  // log(nu_obs)
+  double lnu;    // log(nu_obs)
+  bool allcoef;  // every absorption / rotation coefficient is switched on (ep%coefindx all 1: the usual case)
 };
 template <int ET>
 GRT_HD RunConst run_const(const TransferParams &P, double nu_obs) {
   RunConst R;
   R.lnu = 0.0;
+  R.allcoef = true;
+  for (int i = 0; i < 7; i++) R.allcoef = R.allcoef && (P.coefindx[i] == 1);
   if (ET == EM_POLSYNCHPL || ET == EM_SYNCHPL || em_is_hybrid(ET)) {
     R.pl = pl_const(P.p, P.gmin, P.gmax);
     R.lnu = log(nu_obs);
@@ -241,16 +247,29 @@ GRT_HD void node_coef(const TransferParams &P, const RunConst &R, const double *
                         ET == EM_HYBRIDTH || ET == EM_HYBRIDPL || ET == EM_POLSYNCHSYMTH || ET == EM_MAXJUTT);
   if (POL) {
     for (int i = 0; i < 4; i++) c.j[i] = e[i];
-    for (int i = 0; i < 7; i++)
-      if (P.coefindx[i] == 1) c.K[i] = e[4 + i];
+    if (R.allcoef) {  // (uniform)
+      for (int i = 0; i < 7; i++) c.K[i] = e[4 + i];
+    } else {
+      for (int i = 0; i < 7; i++)
+        if (P.coefindx[i] == 1) c.K[i] = e[4 + i];
+    }
     const double s2 = rec[2], c2 = rec[3];
     double jq = c.j[1], ju = c.j[2], aq = c.K[1], au = c.K[2], rq = c.K[4], ru = c.K[5];
-    c.j[1] = c2 * jq - s2 * ju;
-    c.j[2] = s2 * jq + c2 * ju;
-    c.K[1] = c2 * aq - s2 * au;
-    c.K[2] = s2 * aq + c2 * au;
-    c.K[4] = c2 * rq - s2 * ru;
-    c.K[5] = s2 * rq + c2 * ru;
+    // the thermal fits have no U components in the field frame (e[2] = e[6] = e[9] = 0): their products with s2 / c2 are
+    // left out (an IEEE multiply by zero cannot be folded by the compiler)
+    constexpr bool UZERO = (ET == EM_POLSYNCHTH || ET == EM_MAXJUTT);
+    if (UZERO) {
+      c.j[1] = c2 * jq; c.j[2] = s2 * jq;
+      c.K[1] = c2 * aq; c.K[2] = s2 * aq;
+      c.K[4] = c2 * rq; c.K[5] = s2 * rq;
+    } else {
+      c.j[1] = c2 * jq - s2 * ju;
+      c.j[2] = s2 * jq + c2 * ju;
+      c.K[1] = c2 * aq - s2 * au;
+      c.K[2] = s2 * aq + c2 * au;
+      c.K[4] = c2 * rq - s2 * ru;
+      c.K[5] = s2 * rq + c2 * ru;
+    }
   } else {
     c.j[0] = e[0];
     c.K[0] = e[4];
@@ -310,17 +329,52 @@ GRT_HD void solve_delo(double c1, double c2, const double *K, const double *x, d
 }
 
 // one DELO step from node k+1 (c1) to node k (c0): returns I at node k
-GRT_HD void delo_step(const Coef &c0, const Coef &c1, double dx, double delta, double thin, const double *iprev,
-                      double *inew) {
+// carry (optional): 1 / alpha_I of node k+1 as the previous step left it (NaN: not available); on return 1 / alpha_I of
+// node k if this step formed it.  Saves one of the two reciprocals of consecutive optically thick steps.
+// The coefficients of node k+1 are read through an accessor: from registers (CoefRegs), or one by one from the shared-memory
+// column where the previous step of this thread left them (CoefSmem, k_transfer's staged kernels: the 22 registers of a
+// second coefficient set are what keeps the kernel from running a fifth warp per scheduler).
+struct CoefRegs {
+  const Coef &c;
+  GRT_HD double j(int i) const { return c.j[i]; }
+  GRT_HD double K(int i) const { return c.K[i]; }
+};
+#define GRT_CSM_STRIDE 32  // one column of 11 doubles per lane, element i of lane l at [i * 32 + l]: conflict-free
+struct CoefSmem {
+  const double *p;
+  GRT_HD double j(int i) const { return p[i * GRT_CSM_STRIDE]; }
+  GRT_HD double K(int i) const { return p[(4 + i) * GRT_CSM_STRIDE]; }
+};
+GRT_HD void coef_to_smem(const Coef &c, double *p) {
+  for (int i = 0; i < 4; i++) p[i * GRT_CSM_STRIDE] = c.j[i];
+  for (int i = 0; i < 7; i++) p[(4 + i) * GRT_CSM_STRIDE] = c.K[i];
+}
+template <class C1>
+GRT_HD void delo_step_t(const Coef &c0, const C1 &c1, double dx, double delta, double thin, const double *iprev, double *inew,
+                        double *carry = nullptr) {
   double rhs[4], t[4];
-  kmat_vec(c1.K, iprev, t);
+  {  // opacity_matrix(K_k+1) * iprev
+    const double k0 = c1.K(0), k1 = c1.K(1), k2 = c1.K(2), k3 = c1.K(3), k4 = c1.K(4), k5 = c1.K(5), k6 = c1.K(6);
+    t[0] = k0 * iprev[0] + k1 * iprev[1] + k2 * iprev[2] + k3 * iprev[3];
+    t[1] = k1 * iprev[0] + k0 * iprev[1] + k6 * iprev[2] - k5 * iprev[3];
+    t[2] = k2 * iprev[0] - k6 * iprev[1] + k0 * iprev[2] + k4 * iprev[3];
+    t[3] = k3 * iprev[0] + k5 * iprev[1] - k4 * iprev[2] + k0 * iprev[3];
+  }
   // The optically thick and thin forms (radtrans_integrate.f90 delo) differ only in five scalar weights: the lanes of a warp
   // (32 frequencies of one ray) often straddle delta = thin, so the weights are chosen in the branch and the right-hand
   // side and the 4x4 solve are issued once, after it, for all lanes together.
   double wj0, wj1, qi, qt, sc;
   if (delta > thin) {
     const double E = exp_fast(-delta), F = 1.0 - E, G = (1.0 - (1.0 + delta) * E) / delta;
-    const double i0 = 1.0 / c0.K[0], i1 = 1.0 / c1.K[0];
+    const double i0 = 1.0 / c0.K[0];
+    double i1;
+    if (carry) {
+      i1 = *carry;
+      if (i1 != i1) i1 = 1.0 / c1.K(0);
+      *carry = i0;
+    } else {
+      i1 = 1.0 / c1.K(0);
+    }
     // (F-G) S_k + G S_k+1 + (E*Id - G*Kp1) iprev,  S = j/aI,  Kp1 = K1/aI1 - Id
     // matrix = Id + (F-G)*(K0/aI0 - Id) = (1-(F-G)) Id + ((F-G)/aI0) K0
     wj0 = (F - G) * i0; wj1 = G * i1; qi = E + G; qt = wj1; sc = 1.0 - (F - G);
@@ -328,10 +382,15 @@ GRT_HD void delo_step(const Coef &c0, const Coef &c1, double dx, double delta, d
     const double ki = c0.K[0];
     qi = 1.0 - 0.5 * dx * ki + 1.0 / 6.0 * dx * dx * ki * ki; qt = 0.5 * dx - 1.0 / 3.0 * dx * dx;
     wj0 = 0.5 * dx - 1.0 / 6.0 * dx * dx * ki; wj1 = 0.5 * dx - 1.0 / 3.0 * dx * dx * ki;
-    sc = 1.0 - delta / 2.0 + delta * delta / 6.0;
+    sc = 1.0 - 0.5 * delta + delta * delta * (1.0 / 6.0);  // (delta^2/6 as a product: an FP64 division costs ~25 instructions)
+    if (carry) *carry = nan_val();
   }
-  for (int i = 0; i < 4; i++) rhs[i] = wj0 * c0.j[i] + wj1 * c1.j[i] + (qi * iprev[i] - qt * t[i]);
+  for (int i = 0; i < 4; i++) rhs[i] = wj0 * c0.j[i] + wj1 * c1.j(i) + (qi * iprev[i] - qt * t[i]);
   solve_delo(sc, wj0, c0.K, rhs, inew);
+}
+GRT_HD void delo_step(const Coef &c0, const Coef &c1, double dx, double delta, double thin, const double *iprev,
+                      double *inew, double *carry = nullptr) {
+  delo_step_t(c0, CoefRegs{c1}, dx, delta, thin, iprev, inew, carry);
 }
 
 // inew = O(dx; a, rho) * v  (Landi Degl'Innocenti & Landi Degl'Innocenti 1985 evolution operator)
@@ -451,18 +510,21 @@ GRT_HD bool ck_interval(int neq, const Coef &ca, const Coef &cb, double la, doub
 // ---- the per-(ray, frequency) march ------------------------------------------------------------------
 // rec: [npts][GRT_NREC] records of this ray.  out: nvals Stokes values in cgs.  One instance per (emissivity, mode) so that
 // the hot loop of each kernel is a few thousand instructions (it has to live in the 32 KB L1.5 instruction cache).
-// HIST (extra = 1 only): the march also records sqrt(I^2 + Q^2) of every output column of the reference's intensity array
+// HIST = 1 (extra = 1): the march also records sqrt(I^2 + Q^2) of every output column of the reference's intensity array
 // (hist[col * hs], col 0-based; the caller zero-fills it), the number of columns r%npts and the emission scale fac.
+// HIST = 4 (debug dump): all neq Stokes components of every column, hist[(col * 4 + i) * hs], as the integrator holds them
+// (DELO / formal: I before the division by fac; RK: the fac-normalised y).
 struct MarchInfo {
   int rnpts;
   double fac;
 };
 // STAGE (device, DELO / FORMAL only): `stage` is this warp's ring of GRT_STAGE_DEPTH records in shared memory; every lane of
 // the warp must march the same ray.
-template <int ET, int MODE, bool HIST = false, bool STAGE = false>
+// STAGE = 2 (DELO): additionally csm = this lane's shared-memory column for the coefficients of node k+1 (CoefSmem).
+template <int ET, int MODE, int HIST = 0, int STAGE = 0>
 GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts, double nu_obs, double *out,
                            double *hist = nullptr, size_t hs = 0, MarchInfo *info = nullptr, double *stage = nullptr,
-                           int lane = 0) {
+                           int lane = 0, double *csm = nullptr) {
   constexpr int neq = (MODE == MODE_QUAD || MODE == MODE_RK1) ? 1 : 4;
   if (HIST) {
     info->rnpts = npts;
@@ -489,13 +551,13 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
     // march from the deepest point to the camera, I = 0 behind the last point
     double I[4] = {0, 0, 0, 0}, In[4];
     Coef c1, c0;
-    double lam1 = 0.0;
+    double lam1 = 0.0, icarry = nan_val();
     if (STAGE)  // prologue: records npts-1 ... npts-DEPTH are on their way
       for (int j = 0; j < GRT_STAGE_DEPTH; j++)
         stage_issue(stage + j * NREC, (npts - 1 - j >= 0) ? rec + (size_t)(npts - 1 - j) * NREC : nullptr, NREC, lane);
     int slot = 0;
-#pragma unroll 1
-    for (int k = npts - 1; k >= 0; k--) {
+    // one step: coefficients of node k into cn, DELO / formal step from node k+1 (co) to node k
+    auto step = [&](int k, Coef &cn, const Coef &co) {
       const double *rk = rec + (size_t)k * NREC;
       if (STAGE) {
         stage_wait();
@@ -504,31 +566,52 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
         prefetch_record(rk - NREC);
       }
       const double lamk = rk[0];
-      node_coef<ET>(P, R, rk, F, c0, jraw);
+      node_coef<ET>(P, R, rk, F, cn, jraw);
       fac += jraw * (lam0 - lamk);
       if (k < npts - 1) {
         const double dx = lamk - lam1;
         if (MODE == MODE_DELO) {
-          double delta = dx * 0.5 * (fabs(c0.K[0]) + fabs(c1.K[0]));
-          delo_step(c0, c1, dx, delta, P.thin, I, In);
+          if (STAGE == 2) {
+            const CoefSmem cs{csm};
+            double delta = dx * 0.5 * (fabs(cn.K[0]) + fabs(cs.K(0)));
+            delo_step_t(cn, cs, dx, delta, P.thin, I, In, &icarry);
+          } else {
+            double delta = dx * 0.5 * (fabs(cn.K[0]) + fabs(co.K[0]));
+            delo_step(cn, co, dx, delta, P.thin, I, In, &icarry);
+          }
         } else {
           double v[4];
-          for (int i = 0; i < 4; i++) v[i] = c0.j[i] * dx + I[i];
-          formal_apply(c0.K, dx, v, In);
+          for (int i = 0; i < 4; i++) v[i] = cn.j[i] * dx + I[i];
+          formal_apply(cn.K, dx, v, In);
         }
-#ifdef GRT_DEBUG_TRANSFER
-        if (In[0] != In[0] && I[0] == I[0]) printf("NaN at k=%d dx=%g j0=%g K0=%g j1=%g K1=%g I=%g rq=%g rv=%g aq=%g\n", k, dx, c0.j[0], c0.K[0], c1.j[0], c1.K[0], I[0], c0.K[4], c0.K[6], c0.K[1]);
-#endif
         for (int i = 0; i < 4; i++) I[i] = In[i];
-        if (HIST) hist[(size_t)(npts - k - 1) * hs] = sqrt(In[0] * In[0] + In[1] * In[1]);  // intensity(:, npts-k) (1-based)
+        if (HIST == 1) hist[(size_t)(npts - k - 1) * hs] = sqrt(In[0] * In[0] + In[1] * In[1]);  // intensity(:, npts-k) (1-based)
+        if (HIST == 4)
+          for (int i = 0; i < 4; i++) hist[((size_t)(npts - k - 1) * 4 + i) * hs] = In[i];
       }
-      c1 = c0;
       lam1 = lamk;
+      if (STAGE == 2 && MODE == MODE_DELO) coef_to_smem(cn, csm);
       if (STAGE) {  // this step's slot is free: refill it with the record GRT_STAGE_DEPTH steps further on
         stage_release();
         stage_issue(stage + slot * NREC, (k - GRT_STAGE_DEPTH >= 0) ? rec + (size_t)(k - GRT_STAGE_DEPTH) * NREC : nullptr, NREC,
                     lane);
         slot = (slot + 1 == GRT_STAGE_DEPTH) ? 0 : slot + 1;
+      }
+    };
+    // GRT_MARCH_UNROLL2: two steps per trip with the roles of the two coefficient sets exchanged, which removes the
+    // 22-register copy c1 = c0 of every step (at twice the loop body)
+    constexpr bool U2 = (GRT_MARCH_UNROLL2 != 0) && !HIST;
+    if (U2) {
+#pragma unroll 1
+      for (int k = npts - 1; k >= 0; k -= 2) {
+        step(k, c0, c1);
+        if (k - 1 >= 0) step(k - 1, c1, c0);
+      }
+    } else {
+#pragma unroll 1
+      for (int k = npts - 1; k >= 0; k--) {
+        step(k, c0, c1);
+        if (!(STAGE == 2 && MODE == MODE_DELO)) c1 = c0;
       }
     }
     if (HIST) info->fac = fac;
@@ -613,94 +696,16 @@ GRT_HD void ray_transfer_t(const TransferParams &P, const double *rec, int npts,
         double la = rec[(size_t)(s_ - 1) * NREC], lb = rec[(size_t)(s_ - 2) * NREC];
         if (lb > la) ok = ck_interval(neq, ca, cb, la, lb, y, h, P);
         // intensity(:, i1 + m), m = i2 - s_ + 1 (1-based column)
-        if (HIST && neq == 4 && ok) hist[(size_t)(i1 + i2 - s_) * hs] = sqrt(y[0] * y[0] + y[1] * y[1]);
+        if (HIST == 1 && neq == 4 && ok) hist[(size_t)(i1 + i2 - s_) * hs] = sqrt(y[0] * y[0] + y[1] * y[1]);
+        if (HIST == 4 && ok)
+          for (int i = 0; i < neq; i++) hist[((size_t)(i1 + i2 - s_) * 4 + i) * hs] = y[i];
       }
     }
     if (ok)
       for (int i = 0; i < neq; i++) out[i] = y[i] * fac * P.LBH;
     else if (HIST)
-      for (int c = 0; c < npts; c++) hist[(size_t)c * hs] = 0.0;  // the failed integration returns zeros (odepack.f90:91-96)
+      for (int c = 0; c < npts * (HIST == 4 ? 4 : 1); c++) hist[(size_t)c * hs] = 0.0;  // the failed integration returns zeros (odepack.f90:91-96)
   }
-}
-
-// ---- DELO march of NF frequencies of one ray in one thread ---------------------------------------------------------------
-// The march of one (ray, frequency) is a serial recurrence: every DELO step waits for the previous one, and with 128
-// registers only four warps per scheduler are resident to hide that latency (ncu: 27 % of the stall samples are fixed-latency
-// dependencies, FP64 pipe 64 % busy).  Marching NF = 2 frequencies of the same ray in one thread gives the scheduler two
-// independent dependency chains per warp, and the per-point work that does not depend on the frequency -- the record load
-// (four 256-bit loads instead of sixteen 64-bit ones), its unpacking, the address arithmetic, the FP64 constants that this
-// ISA has to materialise with two moves each -- is issued once for both.  Same arithmetic per frequency as
-// ray_transfer_t<ET, MODE_DELO> (bit-identical results); points with npts == 1 take the single-point form.
-GRT_HD void load_record16(const double *p, double *r) {
-#if defined(__CUDA_ARCH__)
-  // the records were written by the previous kernel of the stream: the non-coherent path is safe here
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[0]), "=d"(r[1]), "=d"(r[2]), "=d"(r[3]) : "l"(p));
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[4]), "=d"(r[5]), "=d"(r[6]), "=d"(r[7]) : "l"(p + 4));
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[8]), "=d"(r[9]), "=d"(r[10]), "=d"(r[11]) : "l"(p + 8));
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[12]), "=d"(r[13]), "=d"(r[14]), "=d"(r[15]) : "l"(p + 12));
-#else
-  for (int i = 0; i < 16; i++) r[i] = p[i];
-#endif
-}
-template <int ET, int NF>
-GRT_HD void ray_transfer_delo_nf(const TransferParams &P, const double *rec, int npts, const double *nu_obs, double (*out)[4]) {
-  static_assert(record_doubles(ET) == GRT_NREC, "16-double records only");
-  for (int f = 0; f < NF; f++)
-    for (int i = 0; i < 4; i++) out[f][i] = 0.0;
-  if (npts <= 0) return;
-  FreqConst F[NF];
-  RunConst R[NF];
-  for (int f = 0; f < NF; f++) {
-    F[f] = freq_const(nu_obs[f]);
-    R[f] = run_const<ET>(P, nu_obs[f]);
-  }
-  double jraw;
-  if (npts == 1) {
-    for (int f = 0; f < NF; f++) {
-      Coef c;
-      node_coef<ET>(P, R[f], rec, F[f], c, jraw);
-      if (jraw / 1e16 > 0.0)
-        for (int i = 0; i < 4; i++) out[f][i] = c.j[i];
-    }
-    return;
-  }
-  const double lam0 = rec[0];
-  double fac[NF], I[NF][4];
-  Coef c1[NF], c0[NF];
-  for (int f = 0; f < NF; f++) {
-    fac[f] = 0.0;
-    for (int i = 0; i < 4; i++) I[f][i] = 0.0;
-  }
-  double lam1 = 0.0;
-#pragma unroll 1
-  for (int k = npts - 1; k >= 0; k--) {
-    const double *rk = rec + (size_t)k * GRT_NREC;
-    if (k > 0) prefetch_record(rk - GRT_NREC);
-    double r_[GRT_NREC];
-    load_record16(rk, r_);
-    const double lamk = r_[0];
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-      node_coef<ET>(P, R[f], r_, F[f], c0[f], jraw);
-      fac[f] += jraw * (lam0 - lamk);
-    }
-    if (k < npts - 1) {
-      const double dx = lamk - lam1;
-#pragma unroll
-      for (int f = 0; f < NF; f++) {
-        double In[4];
-        const double delta = dx * 0.5 * (fabs(c0[f].K[0]) + fabs(c1[f].K[0]));
-        delo_step(c0[f], c1[f], dx, delta, P.thin, I[f], In);
-        for (int i = 0; i < 4; i++) I[f][i] = In[i];
-      }
-    }
-#pragma unroll
-    for (int f = 0; f < NF; f++) c1[f] = c0[f];
-    lam1 = lamk;
-  }
-  for (int f = 0; f < NF; f++)
-    if (fac[f] / 1e16 > 0.0)
-      for (int i = 0; i < 4; i++) out[f][i] = I[f][i] * P.LBH;
 }
 
 // ---- extra = 1: the 19 diagnostics of grtrans_driver.f90:230-292 (rays with more than one point) ------------------------
@@ -717,7 +722,7 @@ GRT_HD void ray_extra_t(const TransferParams &P, const double *rec, const double
   for (int q = 0; q < 19; q++) xt[q] = 0.0;
   for (int c = 0; c < npts; c++) hist[(size_t)c * hs] = 0.0;
   MarchInfo mi;
-  ray_transfer_t<ET, MODE, true>(P, rec, npts, nu_obs, out, hist, hs, &mi);
+  ray_transfer_t<ET, MODE, 1>(P, rec, npts, nu_obs, out, hist, hs, &mi);
   if (!(mi.fac / 1e16 > 0.0)) return;  // r%tau(:) = 0
   if (npts == 1) {  // single (disk) point: the record holds the 7 geometric quantities (grtrans_driver.f90:298-312)
     for (int q = 0; q < 7; q++) xt[q] = xrec[q];

@@ -112,6 +112,12 @@ int grt_geokerr_rays(int standard, double mu0, double phi0, double a, double uou
                      const double gridvals[4], int nro, int nphi, int nup, int i1, int i2, int *maxpts_out,
                      int *npts, double *lambda, double *t, double *r, double *th, double *ph, double *kt,
                      double *kr, double *kth, double *kph, int *tpm, int *tpr, int cap_pts);
+/* debug = 1 (grtrans_driver.f90:86-110, 341-427): writes the text file the reference leaves behind as `geodebug.out` --
+ * the per-point internals of ONE ray (geodesic, fluid sample, tetrad, emission / absorption / rotation coefficients of
+ * the first (mdot, frequency), optical depth, intensities along the ray), one record per line in the order
+ * read_geodebug_file.py reads them.  pixel = 1-based geodesic index.  grt_main / grt_run call it with the last pixel of
+ * the run and path "geodebug.out" when args.debug == 1 (the reference's pixel loop overwrites the file pixel by pixel). */
+int grt_geodebug(const grt_args *a, int pixel, const char *path);
 /* Stage dump of the frequency-independent per-point quantities for rays i1..i2 of a full setup:
  * fluid sample (fluid.f90:473-526), comoving_ortho (kerr.f90:586-730) and unit conversion
  * (fluid.f90:528-584).  Arrays [nrays][maxpts]; u and b are [nrays][maxpts][4]. */

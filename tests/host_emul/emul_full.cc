@@ -8,8 +8,12 @@
 
 #include "../../grtrans_b200/csrc/grt_host.h"
 #include "../../grtrans_b200/csrc/grt_pipeline.cuh"
+#include "../../grtrans_b200/csrc/grt_debug.cuh"
 
 using namespace grt;
+
+// emul_geodebug: file to write for the (single) ray of the next emul_full call, like grt_geodebug
+static const char *g_geodebug_path = nullptr;
 
 extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncams][n][nvals]*/, int *npts_out,
                          double *stage /* optional [n][maxpts][8]: lam,r,th,ph,s2xi,c2xi,ang,rshift */) {
@@ -92,7 +96,7 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
                            a->nn[1], a->nn[2]);
     int mp = c.maxpts();
     fk.maxpts = mp;
-    GeoFlags fl{a->nn[2], c.kext, c.next, c.mufill, c.usegeor, 1, (fh.nslots <= 1) ? 1 : 0};  // as grt_session_create
+    GeoFlags fl{a->nn[2], c.kext, c.next, c.mufill, c.usegeor, 1, (fh.nslots <= 1 && !g_geodebug_path) ? 1 : 0};  // as grt_session_create / grt_geodebug
 #pragma omp parallel for schedule(dynamic, 4)
     for (int q = 0; q < n; q++) {
       int ix = i1 - 1 + q;
@@ -116,7 +120,8 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
       std::vector<double> sdl(mp), sdt(mp), sdr(mp), sdth(mp), sdph(mp), sk0(mp), sk1(mp), sk2(mp), sk3(mp), su(4 * mp),
           sb(4 * mp), s2(mp), c2(mp), an(mp), rs(mp), cn(mp), n1(mp), n2(mp), n3(mp), n4(mp);
       std::vector<float> fr(mp), fp(mp), fb(mp);
-      if (stage && jm == 0) {
+      const bool dbg = g_geodebug_path != nullptr && jm == a->nmu - 1 && q == n - 1;
+      if ((stage && jm == 0) || dbg) {
         sd.lambda = sdl.data(); sd.t = sdt.data(); sd.r = sdr.data(); sd.th = sdth.data(); sd.ph = sdph.data();
         sd.kt = sk0.data(); sd.kr = sk1.data(); sd.kth = sk2.data(); sd.kph = sk3.data(); sd.u = su.data(); sd.b = sb.data();
         sd.s2xi = s2.data(); sd.c2xi = c2.data(); sd.ang = an.data(); sd.rshift = rs.data(); sd.cosne = cn.data();
@@ -125,6 +130,23 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
       }
       for (int s = 0; s < mp; s++) point_record(r, m, fkr, 0, s, 1, pa, rec.data(), sd);
       if (jm == 0) npts_out[q] = (m.status == 1) ? m.npts : 0;
+      if (dbg) {  // as grt_geodebug + k_geodebug
+        grt_host::GeoDebugData d;
+        d.npts = (m.status == 1) ? m.npts : 0;
+        d.maxpts = mp;
+        d.alpha = r.alpha; d.beta = r.beta; d.su = r.su; d.sm = r.sm; d.a = r.a; d.mu0 = r.mu0;
+        d.mdots = mdots; d.mbh.assign(mdots.size(), a->mbh);
+        d.rows.assign((size_t)GD_NROWS * mp, 0.0);
+        std::vector<double> hist4((size_t)4 * mp, 0.0);
+        double scal[2] = {0.0, 1.0};
+        for (int p = 0; p < d.npts; p++) geodebug_point(r, m, mp, pa, sd, p, d.rows.data());
+        if (d.npts > 0) geodebug_ray(P, rec.data(), d.npts, mp, freqs[0], hist4.data(), d.rows.data(), scal);
+        d.fac = scal[0];
+        d.lambda = sdl; d.t = sdt; d.r = sdr; d.th = sdth; d.ph = sdph; d.kt = sk0; d.kr = sk1; d.kth = sk2; d.kph = sk3;
+        d.u = su; d.b = sb; d.ncgs = n1; d.tcgs = n4; d.bcgs = n3; d.rshift = rs; d.ang = an; d.s2xi = s2; d.c2xi = c2;
+        d.rho = fr; d.p = fp; d.bmag = fb;
+        grt_host::write_geodebug(g_geodebug_path, d);
+      }
       if (stage && jm == 0)
         for (int s = 0; s < mp; s++) {
           double *o = stage + ((size_t)q * mp + s) * 8;
@@ -150,6 +172,18 @@ extern "C" int emul_full(const grt_args *a, int i1, int i2, float *image /*[ncam
     }
   }
   return 0;
+}
+
+extern "C" int emul_geodebug(const grt_args *a, int pixel, const char *path) {
+  grt_args aa = *a;
+  aa.extra = 0;
+  const int ncams = aa.nmdot * aa.nfreq * aa.nmu;
+  std::vector<float> img((size_t)ncams * aa.nvals, 0.f);
+  int npts = 0;
+  g_geodebug_path = path;
+  int rc = emul_full(&aa, pixel, pixel, img.data(), &npts, nullptr);
+  g_geodebug_path = nullptr;
+  return rc;
 }
 
 // Debug: the transfer coefficients node_coef() hands to the integrator, for one ray at one frequency: out[p*11 ..] =

@@ -458,3 +458,27 @@ def test_config5_full_size_against_oracle_sample_and_tiling():
         s2.close()
     finally:
         del os.environ["GRT_TILE"]
+
+
+@pytest.mark.parametrize("cfg,over,pix", [("harm3d", dict(n=24, nup=100, nfreq=1, fmin=2.3e11, fmax=2.3e11), 24 * 11 + 13),
+                                          ("sphacc", dict(n=16, nfreq=1, fmin=1e12, fmax=1e12, iname='formal'), 16 * 7 + 9),
+                                          ("ffjet", dict(n=24, nfreq=1, fmin=3.45e11, fmax=3.45e11, iname='lsoda'), 24 * 12 + 10)])
+def test_geodebug_file(tmp_path, cfg, over, pix):
+    """debug = 1 (grtrans_driver.f90:86-110, 341-427): `geodebug.out` of one ray in the layout read_geodebug_file.py parses,
+    every record the oracle holds compared with it (k_geodebug + the host writer, through grt_geodebug)."""
+    kw = getattr(cases, "cfg_" + cfg)(**over)
+    path = _lib.geodebug(args_from_kwargs(**kw), pix, str(tmp_path / "geodebug.out"))
+    gd = _lib.read_geodebug(path)
+    dump = orc.ray_dump(pix, pix, _args=args_from_kwargs(**kw))
+    cases.check_geodebug(gd, dump, kw)
+
+
+def test_grtrans_main_with_debug_writes_geodebug_out(tmp_path, monkeypatch):
+    """pgrtrans.grtrans_main with debug = 1 leaves `geodebug.out` in the working directory, holding the last pixel of the run."""
+    monkeypatch.chdir(tmp_path)
+    kw = cases.cfg_harm3d(n=16, nup=100, nfreq=1, fmin=2.3e11, fmax=2.3e11, debug=1, i1=1, i2=16 * 7 + 8)
+    _lib.main(args_from_kwargs(**kw))
+    gd = _lib.read_geodebug(str(tmp_path / "geodebug.out"))
+    kw0 = dict(kw); kw0.pop('debug')
+    dump = orc.ray_dump(16 * 7 + 8, 16 * 7 + 8, _args=args_from_kwargs(**kw0))
+    cases.check_geodebug(gd, dump, kw)

@@ -146,6 +146,21 @@ def test_extra_quantities_match_oracle(emul, cfg, over):
     assert np.abs(np.nan_to_num(ref[kw['nvals']:kw['nvals'] + 7][:, lit])).min(axis=1).max() > 0   # not trivially zero
 
 
+@pytest.mark.parametrize("cfg,over,pix", [("harm3d", dict(n=24, nup=100, nfreq=1, fmin=2.3e11, fmax=2.3e11), 24 * 11 + 13),
+                                          ("sphacc", dict(n=16, nfreq=1, fmin=1e12, fmax=1e12, iname='formal'), 16 * 7 + 9),
+                                          ("ffjet", dict(n=24, nfreq=1, fmin=3.45e11, fmax=3.45e11, iname='lsoda'), 24 * 12 + 10)])
+def test_geodebug_file(emul, tmp_path, cfg, over, pix):
+    """debug = 1: the text dump of one ray in the layout of read_geodebug_file.py (kernel bodies + host writer)."""
+    kw = getattr(cases, "cfg_" + cfg)(**over)
+    path = str(tmp_path / "geodebug.out")
+    emul.emul_geodebug.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    a = args_from_kwargs(**kw)
+    assert emul.emul_geodebug(C.byref(a), C.c_int(pix), path.encode()) == 0
+    gd = _lib.read_geodebug(path)
+    dump = orc.ray_dump(pix, pix, _args=args_from_kwargs(**kw))
+    cases.check_geodebug(gd, dump, kw)
+
+
 def test_faraday_fit_table_accuracy(emul):
     """The tabulated Faraday fits (jffunc with its high-frequency correction: an O(1) function; log(1 + 0.00185777 x^1.503))
     against their direct evaluation over the whole table range 1e-4 <= xarg <= 1e5, incl. the tanh switch near xarg = 120."""
