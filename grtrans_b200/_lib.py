@@ -26,7 +26,7 @@ SYMBOLS = ["grt_args_defaults", "grt_main", "grt_get_ivals", "grt_get_ab", "grt_
            "grt_set_devices", "grt_main_info", "grt_release_cache", "grt_shard_rays", "grt_nccl_unique_id",
            "grt_session_comm_init", "grt_session_launch_gather", "grt_session_run_timed_gather",
            "grt_session_last_launches", "grt_session_tile", "grt_session_full_image", "grt_session_fetch_full",
-           "grt_session_fetch", "grt_session_ncams", "grt_session_nvals", "grt_version", "grt_device_count", "grt_dfma_peak"]
+           "grt_session_fetch", "grt_session_ncams", "grt_session_nvals", "grt_version", "grt_device_count", "grt_dfma_peak", "grt_math_probe"]
 
 
 class GrtError(RuntimeError):
@@ -178,6 +178,14 @@ def ray_stage_dump(a, i1, i2):
                                *[_p(d[k]) for k in order]), "grt_ray_stage_dump")
     d["cap"] = cap
     return d
+
+
+def math_probe(which, x):
+    """exp_fast (0) / log_ge1 (1) of grt_math.cuh evaluated on the device."""
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros_like(x)
+    check(lib().grt_math_probe(C.c_int(which), C.c_int(x.size), _p(x), _p(out)), "grt_math_probe")
+    return out
 
 
 def geodebug(a, pixel, path="geodebug.out"):

@@ -237,6 +237,8 @@ GRT_HD void thermal_eval(const ThermalPoint &P, const FreqConst &F, double kcl, 
   const double ji = P.AI * F.nu * iix, jq = P.AI * F.nu * iqx, jv = P.AV * F.nu * ivx;
   jraw = ji;
   // 1/B_nu (bnu, polsynchemis.f90:1014-1032): Rayleigh-Jeans below h nu/kT = 1e-6; B_nu == 0 is replaced by epsilon
+  // (the Planck exponential stays inside its branch: most (point, frequency) pairs of a hot flow are in the Rayleigh-Jeans
+  // regime h nu / k T < 1e-6 and never evaluate it -- hoisting it next to the first exp cost 20 ms per step)
   const double xh = P.hkT_g * F.nu;
   const double g2 = P.g * P.g;
   double ka;  // alpha_S LBH/g = j_S * ka

@@ -1500,6 +1500,28 @@ extern "C" int grt_rt_integrate(int iflag, int neq, int nrays, int npts, const d
   return GRT_OK;
 }
 
+// exp_fast / log_ge1 (grt_math.cuh) as the device evaluates them, for the accuracy tests
+extern "C" int grt_math_probe(int which, int n, const double *x, double *out) {
+  if (grt_device_count() <= 0) return GRT_ERR_NO_DEVICE;
+  if (which < 0 || which > 1 || n < 0) return GRT_ERR_BAD_ARG;
+  if (n == 0) return GRT_OK;
+  double *dx = nullptr, *dy = nullptr;
+  CK(dalloc(&dx, (size_t)n));
+  if (dalloc(&dy, (size_t)n) != cudaSuccess) {
+    cudaFree(dx);
+    return GRT_ERR_CUDA;
+  }
+  int rc = GRT_OK;
+  if (cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice) != cudaSuccess) rc = GRT_ERR_CUDA;
+  if (rc == GRT_OK) {
+    launch_math_probe(which, n, dx, dy);
+    if (cudaMemcpy(out, dy, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = GRT_ERR_CUDA;
+  }
+  cudaFree(dx);
+  cudaFree(dy);
+  return rc;
+}
+
 extern "C" int grt_dfma_peak(int device, double *tflops) {
   if (grt_device_count() <= 0) return GRT_ERR_NO_DEVICE;
   CK(cudaSetDevice(device));

@@ -14,7 +14,10 @@ namespace grt {
 // (config 5, ms per step): blocks of 128 threads 578.6, of 32 threads 569.9; 96 registers (5 warps per scheduler, spills)
 // 664, with the coefficients of node k+1 kept in shared memory (GRT_TRANSFER_CSM=1) 623.6; 80 registers 774.
 // A dependent DFMA issues every 8.7 cycles (tools/ubench/dfma_latency.cu), so four warps of pure dependency chain could
-// keep the pipe 88 % busy; the kernel reaches 68-70 %.
+// keep the pipe 88 % busy; the kernel reaches 65-68 %.  Also measured and dropped: producer / consumer warp pairs (one warp
+// evaluates the coefficients of node k into a shared-memory ring, its partner does the DELO steps; named barriers): 896 ms at
+// 128 registers (8 pairs / SM), 932 ms at 96, 1123 ms at 80 -- the step time follows the number of (ray, frequency) marches
+// in flight per SM, which pairing halves; straight-line reciprocals (MUFU.RCP64H + Newton, no slow-path branch) 592 ms.
 #ifndef GRT_TRANSFER_MINB
 #define GRT_TRANSFER_MINB 16
 #endif
@@ -197,6 +200,14 @@ __global__ void k_rt_integrate(int iflag, int neq, int nrays, int npts, const do
   if (!ok)
     for (int i = 0; i < npts * neq; i++) I[i] = 0.0;
 }
+
+// the hot loop's own elementary functions evaluated on the device, for the accuracy tests (0: exp_fast, 1: log_ge1)
+__global__ void k_math_probe(int which, int n, const double *x, double *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (which == 0) ? exp_fast(x[i]) : log_ge1(x[i]);
+}
+void launch_math_probe(int which, int n, const double *x, double *out) { k_math_probe<<<(n + 127) / 128, 128>>>(which, n, x, out); }
 
 // FP64 FMA peak micro-benchmark: 8 independent chains per thread
 __global__ void k_dfma(double *out, int iters) {

@@ -46,5 +46,6 @@ void launch_synchemis(int n, const double *nu, const double *nc, const double *b
 void launch_rt_integrate(int iflag, int neq, int nrays, int npts, const double *s, const double *j, const double *K,
                          const double *tau, double *intensity, int *nptsout, const TransferParams &P);
 void launch_dfma(double *out, int blocks, int threads, int iters);
+void launch_math_probe(int which, int n, const double *x, double *out);
 
 }  // namespace grt

@@ -199,6 +199,9 @@ const char *grt_version(void);
 int grt_device_count(void);
 /* FP64 FMA micro-benchmark on the current device: returns achieved DFMA TFLOP/s (2 flop per FMA) */
 int grt_dfma_peak(int device, double *tflops);
+/* Test hook: the transfer loop's own elementary functions as the device evaluates them (which = 0: exp, 1: log for
+ * x >= 1), n values. */
+int grt_math_probe(int which, int n, const double *x, double *out);
 
 #ifdef __cplusplus
 }

@@ -482,3 +482,22 @@ def test_grtrans_main_with_debug_writes_geodebug_out(tmp_path, monkeypatch):
     kw0 = dict(kw); kw0.pop('debug')
     dump = orc.ray_dump(16 * 7 + 8, 16 * 7 + 8, _args=args_from_kwargs(**kw0))
     cases.check_geodebug(gd, dump, kw)
+
+
+def test_device_exp_log_are_one_ulp():
+    """The hot loop's elementary functions as the DEVICE evaluates them (table-driven exp_fast with its __ldg table,
+    log_ge1): within 1 ulp of the correctly rounded value."""
+    from mpmath import mp, mpf, exp as mexp, log as mlog
+    mp.dps = 40
+    rng = np.random.RandomState(11)
+    x = np.concatenate([rng.uniform(-745., 709., 3000), rng.uniform(-1., 1., 2000), [-744.4, -708.4, 0., 709., -1e-300]])
+    got = _lib.math_probe(0, x)
+    for xi, g in zip(x, got):
+        t = mexp(mpf(float(xi)))
+        assert abs(mpf(float(g)) - t) <= 1.0 * float(np.spacing(max(float(t), 2.3e-308))), (xi, g)
+    assert _lib.math_probe(0, np.array([-801., -1e5]))[0] < 1e-320 and np.isnan(_lib.math_probe(0, np.array([np.nan])))[0]
+    x = np.concatenate([1. + 10. ** rng.uniform(-15., 12., 3000), rng.uniform(1., 4., 1000), [1., 2., 1e300]])
+    got = _lib.math_probe(1, x)
+    for xi, g in zip(x, got):
+        t = mlog(mpf(float(xi)))
+        assert abs(mpf(float(g)) - t) <= 1.0 * float(np.spacing(abs(float(t)))), (xi, g)
