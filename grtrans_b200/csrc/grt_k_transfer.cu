@@ -231,7 +231,8 @@ static void launch_transfer_e(int mode, unsigned grid, cudaStream_t st, const Ra
   k_transfer<ET, M, true><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0)
   // warp-staged records (see stage_issue): every warp must hold 32 frequencies of one ray, and the ring holds records of at
   // most 64 doubles (GRT_TRANSFER_STAGE=0 switches it off)
-  static const int stage_env = getenv("GRT_TRANSFER_STAGE") ? atoi(getenv("GRT_TRANSFER_STAGE")) : 1;
+  const char *se = getenv("GRT_TRANSFER_STAGE");  // (read per launch: the tests switch it inside one process)
+  const int stage_env = se ? atoi(se) : 1;
   if constexpr (record_doubles(ET) <= 64) {
     if (stage_env && nfreq % 32 == 0 && (mode == MODE_DELO || mode == MODE_FORMAL)) {
       if (mode == MODE_DELO)

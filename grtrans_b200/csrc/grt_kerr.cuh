@@ -15,8 +15,7 @@ struct Metric {  // covariant BL metric
   double tt, tp, rr, hh, pp;
 };
 
-GRT_HD Metric bl_metric(double r, double th, double a) {
-  double cth = cos(th), sth = sin(th);
+GRT_HD Metric bl_metric_cs(double r, double cth, double sth, double a) {  // with cos(theta), sin(theta) supplied
   double delta = r * r - 2.0 * r + a * a;
   double rho2 = r * r + a * a * cth * cth;
   double sigma = sq(r * r + a * a) - a * a * delta * sth * sth;
@@ -28,6 +27,7 @@ GRT_HD Metric bl_metric(double r, double th, double a) {
   g.pp = sigma / rho2 * sth * sth;
   return g;
 }
+GRT_HD Metric bl_metric(double r, double th, double a) { return bl_metric_cs(r, cos(th), sin(th), a); }
 
 struct MetricF {
   float tt, tp, rr, hh, pp;
@@ -176,13 +176,15 @@ struct OrthoDebug {  // comoving_ortho_debug (kerr.f90:562-584): the tetrad comp
 };
 GRT_HD void comoving_ortho(double r, double th, double a, double alpha, double beta, double mus, const double *u,
                            const double *b, const double *k, OrthoOut &o, OrthoDebug *dbg = nullptr) {
-  Metric m = bl_metric(r, th, a);
+  // cos(theta), sin(theta) once for the metric, the polarisation reference vector and the tetrad normalisation (they were
+  // three separate FP64 libm evaluations of the same argument)
+  const double cth = cos(th), sth = sin(th);
+  Metric m = bl_metric_cs(r, cth, sth, a);
   double ut = u[0], ur = u[1], um = u[2], up = u[3];
   double utc = m.tt * ut + m.tp * up, upc = m.pp * up + m.tp * ut, urc = m.rr * ur, umc = um * m.hh;
   double Kap1 = alpha + a * sqrt(1. - mus * mus), Kap2 = -beta;
   double aa[4] = {0.0, 0.0, 0.0, 0.0};
   if (Kap1 != 0.0 || Kap2 != 0.0) {
-    double cth = cos(th), sth = sin(th);
     double k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3];
     double gam1 = a * cth * k0 - a * a * cth * sth * sth * k3;
     double gam2 = r * (r * r + a * a) * sth * k3 - a * r * sth * k0;
@@ -209,7 +211,6 @@ GRT_HD void comoving_ortho(double r, double th, double a, double alpha, double b
   double w = utc * ut + upc * up;
   double nr2 = -m.rr * w * (1. + umc * um);
   double nm2 = m.hh * (1. + umc * um);
-  double sth = sin(th);
   double np2 = -w * delta * sth * sth;
   double snr = sqrt(nr2), snm = sqrt(nm2), snp = sqrt(np2);
   double ekt[4] = {-1.0 * u[0], -1.0 * u[1], -1.0 * u[2], -1.0 * u[3]};

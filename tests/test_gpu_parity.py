@@ -501,3 +501,23 @@ def test_device_exp_log_are_one_ulp():
     for xi, g in zip(x, got):
         t = mlog(mpf(float(xi)))
         assert abs(mpf(float(g)) - t) <= 1.0 * float(np.spacing(abs(float(t)))), (xi, g)
+
+
+@pytest.mark.parametrize("over", [dict(iname='delo'), dict(iname='formal'),
+                                  dict(iname='delo', ename='HYBRIDTHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True),
+                                  dict(iname='delo', ename='POLSYNCHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True),
+                                  dict(iname='formal', ename='POLSYNCHSYMTH', fmin=1e11, fmax=1e13)])
+def test_staged_records_give_the_same_image(monkeypatch, over):
+    """k_transfer streams the point records through a cp.async ring in shared memory whenever a warp holds 32 frequencies of
+    one ray (nfreq a multiple of 32; 16- and 24-double records, DELO and formal marches): bit-identical to the plain loads
+    (GRT_TRANSFER_STAGE=0), and inside the tolerances against the oracle.  Ragged tiles: 3 tiles of 100 rays + 1 of 24."""
+    kw = cases.cfg_harm3d(n=18, nup=100, nfreq=32, fmin=over.pop('fmin', 1e10), fmax=over.pop('fmax', 1e13), **over)
+    monkeypatch.setenv("GRT_TILE", "100")
+    staged = _lib.main(args_from_kwargs(**kw))['ivals']
+    monkeypatch.setenv("GRT_TRANSFER_STAGE", "0")
+    plain = _lib.main(args_from_kwargs(**kw))['ivals']
+    assert np.array_equal(staged, plain, equal_nan=True)
+    assert np.nanmax(np.abs(staged[0])) > 0
+    ref = orc.run(_args=args_from_kwargs(**kw))['ivals']
+    relI, flux, quv, nanok = cases.image_errors(staged, ref)
+    assert nanok and relI < 1e-4 and flux < 1e-5 and quv < 1e-3, (relI, flux, quv)
