@@ -29,29 +29,23 @@ struct CubicReal {
     U22 = sq((X2 * Y1 * Y3 + Y2 * X1 * X3) * inv);
     U32 = sq((X3 * Y1 * Y2 + Y3 * X1 * X2) * inv);
   }
-  // the Carlson argument triple shared by R_F (base), R_D (m4) and R_J (m2), and the fourth argument of m2's R_J: with
-  // them upiece_eval evaluates all the integrals of a piece in one duplication loop (carlson_shared)
-  GRT_HD void triple(double &A, double &B, double &C) const { A = U32; B = U22; C = U12; }
-  GRT_HD double m2_p(double a4, double b4) const { return U12 - b4 * d12 * d13 / (a1 * b4 - a4 * b1); }
   GRT_HD double rff() const { return rf(U32, U22, U12); }
   GRT_HD double base(double r) const { return 2.0 * r; }
-  GRT_HD double m2(double a4, double b4, double r) const { return m2(a4, b4, r, rj(U32, U22, U12, m2_p(a4, b4))); }
-  GRT_HD double m4(double a4, double b4, double r) const { return m4(a4, b4, r, rd(U32, U22, U12)); }
-  GRT_HD double m2(double a4, double b4, double r, double rjv) const {  // p4 = -2; rjv = R_J(triple, m2_p)
+  GRT_HD double m2(double a4, double b4, double r) const {  // p4 = -2
     double d14 = a1 * b4 - a4 * b1, d24 = a2 * b4 - a4 * b2, d34 = a3 * b4 - a4 * b3;
     double X42 = a4 + b4 * x, Y42 = a4 + b4 * y;
     double W22 = U12 - b4 * d12 * d13 / d14;
     double Q22 = X42 * Y42 / sq(X1 * Y1) * W22;
     double P22 = Q22 + b4 * d24 * d34 / d14;
-    double I3c = 2.0 * rc(P22, Q22) - 2.0 * b1 * d12 * d13 / 3.0 / d14 * rjv;
+    double I3c = 2.0 * rc(P22, Q22) - 2.0 * b1 * d12 * d13 / 3.0 / d14 * rj(U32, U22, U12, W22);
     return (b4 * I3c - b1 * 2.0 * r) / d14;
   }
-  GRT_HD double m4(double a4, double b4, double r, double rdv) const {  // p4 = -4; rdv = R_D(triple)
+  GRT_HD double m4(double a4, double b4, double r) const {  // p4 = -4
     double d14 = a1 * b4 - a4 * b1, d24 = a2 * b4 - a4 * b2, d34 = a3 * b4 - a4 * b3;
     double X42 = a4 + b4 * x, Y42 = a4 + b4 * y;
     double r12 = a1 / b1 - a2 / b2, r13 = a1 / b1 - a3 / b3;
     double r24i = b2 * b4 / d24, r34i = b3 * b4 / d34;
-    double I2c = 2.0 / 3.0 * d12 * d13 * rdv + 2.0 * X1 * Y1 / U1c;
+    double I2c = 2.0 / 3.0 * d12 * d13 * rd(U32, U22, U12) + 2.0 * X1 * Y1 / U1c;
     double K2c = b2 * b3 * I2c - 2.0 * b4 * (X1 * X2 * X3 / X42 - Y1 * Y2 * Y3 / Y42);
     return 0.5 * b4 / d14 / d24 / d34 * K2c + sq(b1 / d14) * (1.0 - 0.5 * r12 * r13 * r24i * r34i) * 2.0 * r;
   }
@@ -75,17 +69,9 @@ struct CubicComplex {
     Lp2 = M2 - beta1 + s2h * a11;
     Lm2 = M2 - beta1 - s2h * a11;
   }
-  GRT_HD void triple(double &A, double &B, double &C) const { A = M2; B = Lm2; C = Lp2; }
-  GRT_HD double m2_p(double a4, double b4) const {
-    double c44 = sqrt(2.0 * f * b4 * b4 - 2.0 * g * a4 * b4 + 2.0 * h * a4 * a4);
-    double a142 = 2.0 * f * b1 * b4 - g * (a1 * b4 + a4 * b1) + 2.0 * h * a1 * a4;
-    return M2 - b1 * (a142 + a11 * c44) / (a1 * b4 - a4 * b1);
-  }
   GRT_HD double rff() const { return rf(M2, Lm2, Lp2); }
   GRT_HD double base(double r) const { return 4.0 * r; }
-  GRT_HD double m2(double a4, double b4, double r) const { return m2(a4, b4, r, rj(M2, Lm2, Lp2, m2_p(a4, b4))); }
-  GRT_HD double m4(double a4, double b4, double r) const { return m4(a4, b4, r, rd(M2, Lm2, Lp2)); }
-  GRT_HD double m2(double a4, double b4, double r, double rjv) const {
+  GRT_HD double m2(double a4, double b4, double r) const {
     double d14 = a1 * b4 - a4 * b1;
     double X42 = a4 + b4 * x, Y42 = a4 + b4 * y;
     double c44 = sqrt(2.0 * f * b4 * b4 - 2.0 * g * a4 * b4 + 2.0 * h * a4 * a4);
@@ -95,12 +81,12 @@ struct CubicComplex {
     double W2 = U2 - a11 * a11 * b4 / 2.0 / d14;
     double Q2 = X42 * Y42 / sq(X1 * Y1) * W2;
     double P2 = Q2 + c44 * c44 * b4 / 2.0 / d14;
-    double I3c = (2.0 * a11 / 3.0 / c44) * ((-4.0 * b1 / d14) * (a142 + a11 * c44) * rjv - 6.0 * r + 3.0 * rc(U2, W2)) +
+    double I3c = (2.0 * a11 / 3.0 / c44) * ((-4.0 * b1 / d14) * (a142 + a11 * c44) * rj(M2, Lm2, Lp2, Wp2) - 6.0 * r +
+                                            3.0 * rc(U2, W2)) +
                  2.0 * rc(P2, Q2);
-    (void)Wp2;
     return (b4 * I3c - b1 * 4.0 * r) / d14;
   }
-  GRT_HD double m4(double a4, double b4, double r, double rdv) const {
+  GRT_HD double m4(double a4, double b4, double r) const {
     double d14 = a1 * b4 - a4 * b1;
     double X42 = a4 + b4 * x, Y42 = a4 + b4 * y;
     double c442 = 2.0 * f * b4 * b4 - 2.0 * g * a4 * b4 + 2.0 * h * a4 * a4;
@@ -108,7 +94,7 @@ struct CubicComplex {
     double rho = sqrt(2.0 * h) * a11 - beta1;
     double r24Xr34 = 0.5 * c442 / h / (b4 * b4);
     double r12Xr13 = 0.5 * a11 * a11 / h / (b1 * b1);
-    double N2c = 2.0 / 3.0 * sqrt(2.0 * h) / a11 * (4.0 * rho * rdv - 6.0 * r + 3.0 / U) + 2.0 / X1 / Y1 / U;
+    double N2c = 2.0 / 3.0 * sqrt(2.0 * h) / a11 * (4.0 * rho * rd(M2, Lm2, Lp2) - 6.0 * r + 3.0 / U) + 2.0 / X1 / Y1 / U;
     double K2c = 0.5 * a11 * a11 * N2c - 2.0 * d14 * (xi / X1 / X42 - eta / Y1 / Y42);
     return 0.5 / d14 / (h * b4 * r24Xr34) * K2c + sq(b1 / d14) * (1.0 - 0.5 * r12Xr13 / r24Xr34) * 4.0 * r;
   }
@@ -130,27 +116,21 @@ struct QuarticReal {
     U132 = sq((X1 * X3 * Y2 * Y4 + Y1 * Y3 * X2 * X4) * inv);
     U142 = sq((X1 * X4 * Y2 * Y3 + Y1 * Y4 * X2 * X3) * inv);
   }
-  GRT_HD void triple(double &A, double &B, double &C) const { A = U122; B = U132; C = U142; }
-  GRT_HD double m2_p(double a5, double b5) const {
-    return U122 - d13 * d14 * (a2 * b5 - a5 * b2) / (a1 * b5 - a5 * b1);
-  }
   GRT_HD double rff() const { return rf(U122, U132, U142); }
   GRT_HD double base(double r) const { return 2.0 * r; }
-  GRT_HD double m2(double a5, double b5, double r) const { return m2(a5, b5, r, rj(U122, U132, U142, m2_p(a5, b5))); }
-  GRT_HD double m4(double a5, double b5, double r) const { return m4(a5, b5, r, rd(U122, U132, U142)); }
-  GRT_HD double m2(double a5, double b5, double r, double rjv) const {
+  GRT_HD double m2(double a5, double b5, double r) const {
     double d15 = a1 * b5 - a5 * b1, d25 = a2 * b5 - a5 * b2, d35 = a3 * b5 - a5 * b3, d45 = a4 * b5 - a5 * b4;
     double X52 = a5 + b5 * x, Y52 = a5 + b5 * y;
     double W22 = U122 - d13 * d14 * d25 / d15;
     double Q22 = X52 * Y52 / sq(X1 * Y1) * W22;
     double P22 = Q22 + d25 * d35 * d45 / d15;
-    double I3 = 2.0 * d12 * d13 * d14 / 3.0 / d15 * rjv + 2.0 * rc(P22, Q22);
+    double I3 = 2.0 * d12 * d13 * d14 / 3.0 / d15 * rj(U122, U132, U142, W22) + 2.0 * rc(P22, Q22);
     return (b5 * I3 - b1 * 2.0 * r) / d15;
   }
-  GRT_HD double m4(double a5, double b5, double r, double rdv) const {
+  GRT_HD double m4(double a5, double b5, double r) const {
     double d15 = a1 * b5 - a5 * b1, d25 = a2 * b5 - a5 * b2, d35 = a3 * b5 - a5 * b3, d45 = a4 * b5 - a5 * b4;
     double X52 = a5 + b5 * x, Y52 = a5 + b5 * y;
-    double I2 = 2.0 / 3.0 * d12 * d13 * rdv + 2.0 * X1 * Y1 / X4 / Y4 / sqrt(U142);
+    double I2 = 2.0 / 3.0 * d12 * d13 * rd(U122, U132, U142) + 2.0 * X1 * Y1 / X4 / Y4 / sqrt(U142);
     double r12 = a1 / b1 - a2 / b2, r13 = a1 / b1 - a3 / b3;
     double r25i = b2 * b5 / d25, r35i = b3 * b5 / d35;
     double A111m1m2 = X1 * X2 * X3 / X4 / X52 - Y1 * Y2 * Y3 / Y4 / Y52;
@@ -178,17 +158,9 @@ struct QuarticComplex {
     Lp2 = M2 + a142 + a11 * c44;
     Lm2 = dmax(M2 + a142 - a11 * c44, 0.0);
   }
-  GRT_HD void triple(double &A, double &B, double &C) const { A = M2; B = Lm2; C = Lp2; }
-  GRT_HD double m2_p(double a5, double b5) const {
-    double c55 = sqrt(2.0 * f * b5 * b5 - 2.0 * g * a5 * b5 + 2.0 * h * a5 * a5);
-    double a152 = 2.0 * f * b1 * b5 - g * (a1 * b5 + a5 * b1) + 2.0 * h * a5 * a1;
-    return M2 + (a1 * b4 - a4 * b1) * (a152 + a11 * c55) / (a1 * b5 - a5 * b1);
-  }
   GRT_HD double rff() const { return rf(M2, Lm2, Lp2); }
   GRT_HD double base(double r) const { return 4.0 * r; }
-  GRT_HD double m2(double a5, double b5, double r) const { return m2(a5, b5, r, rj(M2, Lm2, Lp2, m2_p(a5, b5))); }
-  GRT_HD double m4(double a5, double b5, double r) const { return m4(a5, b5, r, rd(M2, Lm2, Lp2)); }
-  GRT_HD double m2(double a5, double b5, double r, double rjv) const {
+  GRT_HD double m2(double a5, double b5, double r) const {
     double d14 = a1 * b4 - a4 * b1, d15 = a1 * b5 - a5 * b1, d45 = a4 * b5 - a5 * b4;
     double X52 = a5 + b5 * x, Y52 = a5 + b5 * y;
     double c552 = 2.0 * f * b5 * b5 - 2.0 * g * a5 * b5 + 2.0 * h * a5 * a5;
@@ -200,17 +172,16 @@ struct QuarticComplex {
     double Q2 = X52 * Y52 / sq(X1 * Y1) * W2;
     double P2 = Q2 + c552 * d45 / 2.0 / d15;
     double I3 = (2.0 * a11 / 3.0 / c55) *
-                    ((4.0 * d14 / d15) * (a152 + a11 * c55) * rjv - 6.0 * r + 3.0 * rc(U2, W2)) +
+                    ((4.0 * d14 / d15) * (a152 + a11 * c55) * rj(M2, Lm2, Lp2, Wp2) - 6.0 * r + 3.0 * rc(U2, W2)) +
                 2.0 * rc(P2, Q2);
-    (void)Wp2;
     return (b5 * I3 - b1 * 4.0 * r) / d15;
   }
-  GRT_HD double m4(double a5, double b5, double r, double rdv) const {
+  GRT_HD double m4(double a5, double b5, double r) const {
     double d15 = a1 * b5 - a5 * b1, d45 = a4 * b5 - a5 * b4;
     double X52 = a5 + b5 * x, Y52 = a5 + b5 * y;
     double c552 = 2.0 * f * b5 * b5 - 2.0 * g * a5 * b5 + 2.0 * h * a5 * a5;
     double U = (X1 * X4 * eta + Y1 * Y4 * xi) / xmy;
-    double I2 = 2.0 * a11 / 3.0 / c44 * (4.0 * (a142 + a11 * c44) * rdv - 6.0 * r) + 2.0 * a11 / c44 / U +
+    double I2 = 2.0 * a11 / 3.0 / c44 * (4.0 * (a142 + a11 * c44) * rd(M2, Lm2, Lp2) - 6.0 * r) + 2.0 * a11 / c44 / U +
                 2.0 * X1 * Y1 / X4 / Y4 / U;
     double A111m1m2 = X1 * xi / X4 / X52 - Y1 * eta / Y4 / Y52;
     return b5 * b5 / (2.0 * d15 * d45) * c44 * c44 / c552 * I2 +

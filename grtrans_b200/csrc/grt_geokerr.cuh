@@ -88,36 +88,6 @@ struct UPiece {
   double t1, t2, t3, t4; // [-4;(0,1)], [-2;(0,1)], [-2;(1,-1/uplus)], [-2;(1,-umi)]
 };
 
-// GRT_GEO_FUSED: R_F, R_D and the R_J's of a piece in one duplication loop (carlson_shared, grt_math.cuh) instead of one
-// loop per integral
-#ifndef GRT_GEO_FUSED
-#define GRT_GEO_FUSED 1
-#endif
-template <bool PHIT, class Fam>
-GRT_HD void upiece_fused(const Fam &F, const RayInv &c, double sgnv, UPiece &o) {
-  const double iup = 1.0 / c.uplus;
-  const double pa[3] = {0.0, 1.0, 1.0}, pb[3] = {1.0, -iup, -c.umi};
-  double A, B, C, rfv = 0.0, rdv = 0.0, rjv[3] = {0.0, 0.0, 0.0}, pw[3] = {0.0, 0.0, 0.0};
-  F.triple(A, B, C);
-  int mask = 0;
-  if (PHIT) {
-#pragma unroll 1
-    for (int q = c.skip_t; q < 3; q++) {
-      pw[q] = F.m2_p(pa[q], pb[q]);
-      mask |= 1 << q;
-    }
-  }
-  carlson_shared(A, B, C, PHIT, mask, pw, rfv, rdv, rjv);
-  o.iu1 = sgnv * F.base(rfv);
-  if (PHIT) {
-    o.t1 = sgnv * F.m4(0.0, 1.0, rfv, rdv);
-    double t[3] = {0.0, 0.0, 0.0};
-#pragma unroll 1
-    for (int q = c.skip_t; q < 3; q++) t[q] = sgnv * F.m2(pa[q], pb[q], rfv, rjv[q]);  // one copy of m2 (code size, see header)
-    o.t2 = t[0]; o.t3 = t[1]; o.t4 = t[2];
-  }
-}
-
 template <bool PHIT>
 GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double sgnv, UPiece &o) {
   // kind: 1 row1 (u<=u2), 2 row2 (u>=u3), 3 cubic complex, 5 quartic complex, 6 double complex, 7 row7, 8 row8
@@ -128,7 +98,6 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
       F.prep(-c.u1, 1.0, c.u2, -1.0, c.u3, -1.0, y, x);
     else
       F.prep(-c.u1, 1.0, -c.u2, 1.0, -c.u3, 1.0, y, x);
-    if (GRT_GEO_FUSED) return upiece_fused<PHIT>(F, c, sgnv, o);
     double r = F.rff();
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {
@@ -143,7 +112,6 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
     CubicComplex F;
     double f = -1.0 / c.dd / c.u1, g = f / c.u1;
     F.prep(-c.u1, 1.0, f, g, 1.0, y, x);
-    if (GRT_GEO_FUSED) return upiece_fused<PHIT>(F, c, sgnv, o);
     double r = F.rff();
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {
@@ -157,7 +125,6 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
   } else if (kind == 5) {
     QuarticComplex F;
     F.prep(-c.u1, 1.0, c.qs * c.u4, -c.qs, c.f5, c.g5, 1.0, y, x);
-    if (GRT_GEO_FUSED) return upiece_fused<PHIT>(F, c, sgnv, o);
     double r = F.rff();
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {
@@ -188,7 +155,6 @@ GRT_HDN void upiece_eval(const RayInv &c, double y, double x, int kind, double s
       F.prep(-c.u1, 1.0, c.u2, -1.0, c.u3, -1.0, c.u4, -1.0, y, x);
     else
       F.prep(-c.u1, 1.0, -c.u2, 1.0, -c.u3, 1.0, c.u4, -1.0, y, x);
-    if (GRT_GEO_FUSED) return upiece_fused<PHIT>(F, c, sgnv, o);
     double r = F.rff();
     o.iu1 = sgnv * F.base(r);
     if (PHIT) {

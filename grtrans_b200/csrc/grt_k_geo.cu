@@ -42,6 +42,11 @@ void launch_geo_points(const RayInv *inv, int nup, int maxpts, long long total, 
   // 1024-thread blocks (one per SM, 64 registers): measured best of {128x6, 256x3, 384x2, 512x1, 768x1, 1024x1} -- the phase
   // barriers of geo_point work per block, so one big block keeps all 32 warps of the SM inside the same code stage
   // (nx=256 bench: 28.3 / 22.9 / 20.5 / 23.3 / 19.5 / 18.3 ms; 59.6 ms before the code was compacted and phased)
+  // Round 2, measured and dropped (config 5, ms per step for this stage; gpurun_out/r2_geo.jsonl): R_F, R_D and the R_J's of
+  // a radial piece in ONE duplication loop that shares the three square roots per iteration (each integral with its own
+  // sum, convergence test and closing series; identical image): 235.0 against 210.0 -- the fused loop's state (three R_J
+  // arguments, sums and principal-value terms) spills at 64 registers; with 768-thread blocks / 80 registers 235.9, with
+  // 512-thread blocks / 128 registers 267.1.  The stage scales with the number of resident warps, not with instructions.
 #ifndef GRT_GEO_BS
 #define GRT_GEO_BS 1024
 #endif

@@ -307,106 +307,6 @@ GRT_HDN double rj(double x, double y, double z, double p) {
   return r;
 }
 
-// ---- R_F, R_D and up to three R_J of ONE argument triple in one duplication loop ---------------------------------------
-// Every radial integral of a geodesic point is a combination of R_F(x,y,z), R_D(x,y,z) and R_J(x,y,z,p_q) of the same
-// (x, y, z) (grt_ellint.cuh), and the duplication sequence x_n+1 = (x_n + lambda_n)/4 of Carlson's algorithms does not
-// depend on which integral is being summed: evaluated one after the other (as the reference does, geokerr_wrapper.f:
-// 3444-3760) the five loops take the same three square roots per iteration five times over -- 17 % of k_geo_points'
-// instructions (ncu).  Here the triple is advanced once per iteration and every integral keeps its own running sum, its own
-// convergence test (R_F 0.0025, R_D / R_J 0.0015 on its own mean) and is finished with the series of its own routine at
-// the iteration where it converges, so each value is what the separate routine returns up to the rounding of lambda (for
-// p <= 0 the separate R_J sorts the triple first; lambda is symmetric, its rounding is not).
-// p_q <= 0: Cauchy principal value through R_J(x,y,z,pt), R_C and R_F(x,y,z) as in rj() -- the R_F is the shared one.
-// mask: bit q set = R_J number q wanted; want_rd: R_D wanted.  Results of unwanted integrals are left untouched.
-GRT_HDN void carlson_shared(double x, double y, double z, bool want_rd, int mask, const double *pin, double &o_rf, double &o_rd,
-                            double *o_rj) {
-  const double D1 = 3.0 / 14.0, D2 = 1.0 / 6.0, D3 = 9.0 / 22.0, D4 = 3.0 / 26.0, D5 = 0.25 * D3, D6 = 1.5 * D4;
-  const double J1 = 3.0 / 14.0, J2 = 1.0 / 3.0, J3 = 3.0 / 22.0, J4 = 3.0 / 26.0, J5 = 0.75 * J3, J6 = 1.5 * J4, J7 = 0.5 * J2,
-               J8 = J3 + J3;
-  double p[3], ja[3], jb[3], jrcx[3], sumj[3], resj[3];
-  bool jneg[3], needj[3];
-#pragma unroll
-  for (int q = 0; q < 3; q++) {
-    needj[q] = (mask >> q) & 1;
-    jneg[q] = false;
-    p[q] = 1.0; ja[q] = jb[q] = jrcx[q] = 0.0; sumj[q] = 0.0; resj[q] = 0.0;
-    if (needj[q]) {
-      p[q] = pin[q];
-      if (!(p[q] > 0.0)) {
-        jneg[q] = true;
-        const double lo = dmin(dmin(x, y), z), hi = dmax(dmax(x, y), z), mid = x + y + z - lo - hi;
-        ja[q] = 1.0 / (mid - p[q]);
-        jb[q] = ja[q] * (hi - mid) * (mid - lo);
-        const double pt = mid + jb[q];
-        jrcx[q] = rc(lo * hi / mid, p[q] * pt / mid);
-        p[q] = pt;
-      }
-    }
-  }
-  bool needf = true, needd = want_rd;
-  double sumd = 0.0, fac = 1.0, resf = 0.0;
-  do {
-    const double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
-    const double lam = sx * (sy + sz) + sy * sz;
-    if (needd) sumd += fac / (sz * (z + lam));
-#pragma unroll
-    for (int q = 0; q < 3; q++)
-      if (needj[q]) {
-        const double sal = p[q] * (sx + sy + sz) + sx * sy * sz;
-        const double be = p[q] * sq(p[q] + lam);
-        sumj[q] += fac * rc_pos(sal * sal, sal, be);
-        p[q] = 0.25 * (p[q] + lam);
-      }
-    fac *= 0.25;
-    x = 0.25 * (x + lam);
-    y = 0.25 * (y + lam);
-    z = 0.25 * (z + lam);
-    if (needf) {  // rf()
-      const double ave = (1.0 / 3.0) * (x + y + z);
-      double dx = 0.0, dy = 0.0, dz = 0.0;
-      if (ave != 0.0) {
-        const double iave = 1.0 / ave;
-        dx = (ave - x) * iave; dy = (ave - y) * iave; dz = (ave - z) * iave;
-      }
-      if (!(dmax(dmax(fabs(dx), fabs(dy)), fabs(dz)) > 0.0025)) {
-        const double e2 = dx * dy - dz * dz, e3 = dx * dy * dz;
-        resf = (1.0 + ((1.0 / 24.0) * e2 - 0.1 - (3.0 / 44.0) * e3) * e2 + (1.0 / 14.0) * e3) / sqrt(ave);
-        needf = false;
-      }
-    }
-    if (needd) {  // rd()
-      const double ave = 0.2 * (x + y + 3.0 * z), iave = 1.0 / ave;
-      const double dx = (ave - x) * iave, dy = (ave - y) * iave, dz = (ave - z) * iave;
-      if (!(dmax(dmax(fabs(dx), fabs(dy)), fabs(dz)) > 0.0015)) {
-        const double ea = dx * dy, eb = dz * dz, ec = ea - eb, ed = ea - 6.0 * eb, ee = ed + ec + ec;
-        o_rd = 3.0 * sumd +
-               fac * (1.0 + ed * (-D1 + D5 * ed - D6 * dz * ee) + dz * (D2 * ee + dz * (-D3 * ec + dz * D4 * ea))) /
-                   (ave * sqrt(ave));
-        needd = false;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 3; q++)
-      if (needj[q]) {  // rj()
-        const double ave = 0.2 * (x + y + z + p[q] + p[q]), iave = 1.0 / ave;
-        const double dx = (ave - x) * iave, dy = (ave - y) * iave, dz = (ave - z) * iave, dp = (ave - p[q]) * iave;
-        if (!(dmax(dmax(fabs(dx), fabs(dy)), dmax(fabs(dz), fabs(dp))) > 0.0015)) {
-          const double ea = dx * (dy + dz) + dy * dz, eb = dx * dy * dz, ec = dp * dp, ed = ea - 3.0 * ec,
-                       ee = eb + 2.0 * dp * (ea - ec);
-          resj[q] = 3.0 * sumj[q] + fac *
-                                        (1.0 + ed * (-J1 + J5 * ed - J6 * ee) + eb * (J7 + dp * (-J8 + dp * J4)) +
-                                         dp * ea * (J2 - dp * J3) - J2 * dp * ec) /
-                                        (ave * sqrt(ave));
-          needj[q] = false;
-        }
-      }
-  } while (needf || needd || needj[0] || needj[1] || needj[2]);
-  o_rf = resf;
-#pragma unroll
-  for (int q = 0; q < 3; q++)
-    if ((mask >> q) & 1) o_rj[q] = jneg[q] ? ja[q] * (jb[q] * resj[q] + 3.0 * (jrcx[q] - resf)) : resj[q];
-}
-
 // ---- Jacobi elliptic functions sn, cn, dn for parameter complement emmc = 1-k^2 ------------------
 GRT_HDN void sncndn(double u, double emc, double &sn, double &cn, double &dn) {
   if (emc == 0.0) {
