@@ -78,6 +78,19 @@
              import :: c_char, c_int
              character(kind=c_char), intent(in) :: ifile(*), ofile(*)
            end function
+           ! grtrans_driver.f90:86-110, 341-427  the debug = 1 dump `geodebug.out` of one pixel
+           integer(c_int) function grt_geodebug(a, pixel, path) bind(C, name='grt_geodebug')
+             import :: grt_args, c_int, c_char
+             type(grt_args), intent(in) :: a
+             integer(c_int), value :: pixel
+             character(kind=c_char), intent(in) :: path(*)
+           end function
+           ! devices grt_main uses (n = 0: every visible device, or GRT_DEVICES / GRT_NGPU)
+           integer(c_int) function grt_set_devices(devices, n) bind(C, name='grt_set_devices')
+             import :: c_int
+             integer(c_int), intent(in) :: devices(*)
+             integer(c_int), value :: n
+           end function
            ! radtrans_integrate.f90:139  integrate (batched over rays)
            integer(c_int) function grt_rt_integrate(iflag, neq, nrays, npts, s, j, K, tau, intensity, nptsout, &
                 max_tau, hmax, oatol, ortol, thin, maxsteps) bind(C, name='grt_rt_integrate')
