@@ -28,7 +28,13 @@ RUNS = [("thindisk", dict(n=12, nfreq=2)), ("thindisk", dict(n=10, nfreq=2, enam
         ("harm3d", dict(n=8, nup=100, nfreq=2, ename='POLSYNCHSYMTH')),
         ("harm3d", dict(n=8, nup=100, nfreq=2, ename='MAXJUTT', epotherargs=[2., .6, .3, .1])),
         ("harm3d", dict(n=8, nup=100, nfreq=2, ename='MAXCOMP', epotherargs=[2., 2., .6, .3, .1], extra=1)),
-        ("thindisk", dict(n=10, nfreq=2, extra=1))]
+        ("thindisk", dict(n=10, nfreq=2, extra=1)),
+        # nfreq a multiple of 32: k_transfer's cp.async record ring in shared memory (16- and 24-double records, DELO / formal)
+        ("harm3d", dict(n=8, nup=100, nfreq=32)), ("harm3d", dict(n=8, nup=100, nfreq=64, iname='formal')),
+        ("harm3d", dict(n=8, nup=100, nfreq=32, ename='HYBRIDTHPL', jetalpha=0.05, p1=3.2, gmin=5., magnetized=True)),
+        ("sphacc", dict(n=8, nfreq=32, nmdot=2, mdotmin=1e19, mdotmax=1e21)),
+        # KORALNTH: binned non-thermal electrons (76-double records, the nth array)
+        ("koralnth", dict(n=8, nup=100, nfreq=2, ename='BINS')), ("koralnth", dict(n=8, nup=100, nfreq=2, ename='HYBRIDTHBINS', extra=1))]
 os.environ["GRT_TILE"] = "64"   # several tiles per run
 for cfg, over in RUNS:
     kw = getattr(cases, "cfg_" + cfg)(**over)
@@ -40,4 +46,6 @@ for cfg, over in RUNS:
 a = args_from_kwargs(**cases.cfg_ffjet(n=8, nup=100))
 g = _lib.geokerr_rays(a, 1, 64)
 d = _lib.ray_stage_dump(a, 1, 64)
-print("unit surfaces ok", g['npts'].sum(), d['npts'].sum())
+_lib.geodebug(args_from_kwargs(**cases.cfg_harm3d(n=8, nup=100, nfreq=1, iname='lsoda')), 30, "/tmp/geodebug_san.out")
+x = _lib.math_probe(0, np.linspace(-700., 700., 1000))
+print("unit surfaces ok", g['npts'].sum(), d['npts'].sum(), len(_lib.read_geodebug("/tmp/geodebug_san.out")), float(x[500]))
