@@ -48,6 +48,8 @@ CONFIGS = [
     ("next-row stype='tail': HARM3D HYBRIDTHPL, nn=[128,128,400] nfreq=4 nvals=4 delo",
      cases.cfg_harm3d(n=128, nup=400, nfreq=4, fmin=1e11, fmax=1e13, ename='HYBRIDTHPL', stype='tail', p1=3., p2=3., jetalpha=.05),
      (8001, 8640)),
+    ("next-row KORALNTH (synthetic 2-D MKS3 dump with 12 electron bins) HYBRIDTHBINS nn=[128,128,400] nfreq=8 nvals=1",
+     cases.cfg_koralnth(n=128, nup=400, nfreq=8, ename='HYBRIDTHBINS', fmin=1e10, fmax=1e14), (8001, 9280)),
 ]
 
 
