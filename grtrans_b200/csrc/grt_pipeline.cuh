@@ -149,27 +149,10 @@ GRT_HDN void point_xrec(double *x, int npts, const RayConst &r0, double r, doubl
 }
 
 // x^mu, k^mu, fluid sample, comoving frame, unit conversion and the 128-byte point record(s)
-// GRT_FLUID_PHASE_BARRIER (k_fluid_ortho built with GRT_FLUID_PHASED): like GRT_PHASE_BARRIER of the geodesic kernel, re-aligns
-// the warps of a block between the stages so that they share the instruction cache; every thread of the block must then
-// call point_record (in_range = false for the padding threads and for slots beyond the ray's last point).
-#if defined(GRT_FLUID_PHASED) && defined(__CUDA_ARCH__)
-#define GRT_FLUID_PHASE_BARRIER() __syncthreads()
-#else
-#define GRT_FLUID_PHASE_BARRIER() ((void)0)
-#endif
 GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernelArgs &A, int ray, int slot, int nrays,
-                         PointArrays pa, double *rec, StageDump sd, bool in_range = true) {
+                         PointArrays pa, double *rec, StageDump sd) {
   const int maxpts = A.maxpts;
-#if defined(GRT_FLUID_PHASED) && defined(__CUDA_ARCH__)
-  const bool active = in_range && m.status == 1 && slot < m.npts;
-  if (!active) {  // take part in the two phase barriers of the active threads below
-    GRT_FLUID_PHASE_BARRIER();
-    GRT_FLUID_PHASE_BARRIER();
-    return;
-  }
-#else
-  if (!in_range || m.status != 1 || slot >= m.npts) return;
-#endif
+  if (m.status != 1 || slot >= m.npts) return;
   size_t src = (size_t)ray * maxpts + (m.i1 - 1) + slot;
   double u = pa.u[src], mu = pa.mu[src];
   double r = 1.0 / u, th = acos(mu);
@@ -196,10 +179,8 @@ GRT_HD void point_record(const RayConst &r0, const RayMeta &m, const FluidKernel
   // radius of the ray's first point: reference of the look-back time that picks the dump slot (nslots > 1)
   const double r1 = (A.F.nslots > 1) ? 1.0 / pa.u[(size_t)ray * maxpts + (m.i1 - 1)] : r;
   fluid_sample(A.F, r0.a, r, th, ph, t, r1, k4, fs);
-  GRT_FLUID_PHASE_BARRIER();
   OrthoOut oo;
   comoving_ortho(r, th, r0.a, r0.alpha, r0.beta, r0.mu0, fs.u, fs.b, k4, oo);
-  GRT_FLUID_PHASE_BARRIER();
   size_t dst = (size_t)ray * maxpts + slot;
   for (int mm = 0; mm < A.nparams; mm++) {
     CgsVars cg;
