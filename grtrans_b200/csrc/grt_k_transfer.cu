@@ -227,8 +227,10 @@ static void launch_transfer_e(int mode, unsigned grid, cudaStream_t st, const Ra
   const int B = GRT_TRANSFER_BS;
 #define GRT_LAUNCH(M) \
   k_transfer<ET, M><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0)
+  // GRT_TRANSFER_DSMEM (experiments only): dynamic shared memory per block, to lower the number of resident warps
+  static const int dsmem = getenv("GRT_TRANSFER_DSMEM") ? atoi(getenv("GRT_TRANSFER_DSMEM")) : 0;
 #define GRT_LAUNCH_ST(M) \
-  k_transfer<ET, M, true><<<grid, B, 0, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0)
+  k_transfer<ET, M, true><<<grid, B, dsmem, st>>>(meta, P, lbh_m, freqs, nfreq, nparams, nrays, maxpts, rec, image, ray_off, nlocal, cam0)
   // warp-staged records (see stage_issue): every warp must hold 32 frequencies of one ray, and the ring holds records of at
   // most 64 doubles (GRT_TRANSFER_STAGE=0 switches it off)
   const char *se = getenv("GRT_TRANSFER_STAGE");  // (read per launch: the tests switch it inside one process)
