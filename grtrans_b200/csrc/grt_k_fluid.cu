@@ -15,7 +15,10 @@ namespace grt {
 // Round 2, measured and dropped (config 5, this stage per step; gpurun_out/r2_fl2.jsonl): block-wide phase barriers between
 // sample / tetrad / record stages as in k_geo_points (ncu shows 9-15 % "no instruction" stalls here: the hot path of one fluid
 // model is ~80 KB of code): 152.8 ms with one 768-thread block per SM, 136.8 ms with two of 384, against 130.7 ms.
-__global__ void __launch_bounds__(128, GRT_FLUID_MINB) k_fluid_ortho(const RayConst *__restrict__ rc, const RayInv *__restrict__ inv,
+#ifndef GRT_FLUID_BS
+#define GRT_FLUID_BS 128
+#endif
+__global__ void __launch_bounds__(GRT_FLUID_BS, GRT_FLUID_MINB) k_fluid_ortho(const RayConst *__restrict__ rc, const RayInv *__restrict__ inv,
                                                      const RayMeta *__restrict__ meta, const __grid_constant__ FluidKernelArgs A, long long total,
                                                      int nrays, PointArrays pa, double *__restrict__ rec, StageDump sd) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,7 +29,7 @@ __global__ void __launch_bounds__(128, GRT_FLUID_MINB) k_fluid_ortho(const RayCo
 
 void launch_fluid_ortho(const RayConst *rc, const RayInv *inv, const RayMeta *meta, const FluidKernelArgs &A, long long total,
                         int nrays, PointArrays pa, double *rec, StageDump sd, cudaStream_t st) {
-  const int B = 128;
+  const int B = GRT_FLUID_BS;
   // 4 blocks / SM (128 registers): 12.0 ms vs 12.8 (3 blocks) / 12.1 (5, 6) / 12.4 (8) at nx=256
   k_fluid_ortho<<<(unsigned)((total + B - 1) / B), B, 0, st>>>(rc, inv, meta, A, total, nrays, pa, rec, sd);
 }

@@ -47,11 +47,17 @@ void launch_geo_points(const RayInv *inv, int nup, int maxpts, long long total, 
   // sum, convergence test and closing series; identical image): 235.0 against 210.0 -- the fused loop's state (three R_J
   // arguments, sums and principal-value terms) spills at 64 registers; with 768-thread blocks / 80 registers 235.9, with
   // 512-thread blocks / 128 registers 267.1.  The stage scales with the number of resident warps, not with instructions.
+  // Round 2: two 512-thread blocks per SM (same 32 warps at 64 registers; the phase barriers synchronise 16 warps instead of
+  // 32): 203.9 ms per config-5 step against 211.2 with one 1024-thread block; 2 x 576 (56 registers) 204.2, 3 x 320 255.1,
+  // 4 x 256 261.9 (gpurun_out/r2_geo2.jsonl).
 #ifndef GRT_GEO_BS
-#define GRT_GEO_BS 1024
+#define GRT_GEO_BS 512
+#endif
+#ifndef GRT_GEO_MINB
+#define GRT_GEO_MINB 2
 #endif
   constexpr int BS = GRT_GEO_BS;
-  k_geo_points<BS, 1><<<(unsigned)((total + BS - 1) / BS), BS, 0, st>>>(inv, nup, maxpts, total, pa);
+  k_geo_points<BS, GRT_GEO_MINB><<<(unsigned)((total + BS - 1) / BS), BS, 0, st>>>(inv, nup, maxpts, total, pa);
 }
 void launch_ray_finalize(const RayInv *inv, int maxpts, int usegeor, int n, PointArrays pa, RayMeta *meta, cudaStream_t st) {
   const int B = 128;
